@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — CoPER-ConvE hot-path throughput on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--shape wn18rr] [--prec fp32] [--impl ours|reference]
+
+A "step" = one full training step of the hot path over one synthetic batch of B (e1, rel) queries with
+1-N labels: lookups -> conv -> fused CPG-FC -> 1-N scorer + label-smoothed BCE -> backward -> global-norm
+clip -> AMSGrad.  `value` = train rows/s with inputs resident in HBM; `eval` = filtered-rank queries/s
+(forward + 1-N scores + filtered rank); `e2e` = the same through the public API from pinned HOST batches
+with the loss / ranks read back every step.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            d["_source"] = "measured (MEASURED_PEAKS.json)"
+            return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback (B200_PROFILING.md)"
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cfg_of(md, H):
+    from oracle import conve_oracle as O
+    return O.OracleConfig(num_ent=md["num_ent"], num_rel=md["num_rel"], ent_emb_size=md["ent_emb_size"],
+                          rel_emb_size=md["rel_emb_size"], context_rel_out=list(md["context_rel_out"]),
+                          conv_in_height=H, hidden_dropout=0.0, output_dropout=0.0,
+                          batch_norm_momentum=md["batch_norm_momentum"],
+                          batch_norm_train_stats=md["batch_norm_train_stats"])
+
+
+def run_cpu_baseline(shape, budget_s, note=""):
+    """Reference algorithm restated on torch-CPU (oracle/torch_port.py; TensorFlow 1.14 is not installable
+    here), all host cores, bounded sample of the same workload."""
+    from coper_b200 import synthetic
+    from oracle import conve_oracle as O
+    from oracle.torch_port import time_cpu_baseline
+    s = synthetic.SHAPES[shape]
+    md = synthetic.descriptors(shape, dropout=False)
+    cfg = oracle_cfg_of(md, s["H"])
+    params = O.init_params(cfg, seed=0)
+    hb = synthetic.make_batches(s["num_ent"], s["num_rel"], s["batch"], 1, seed=1)[0]
+    dense = O.csr_to_dense(hb["e2_multi_rowptr"], hb["e2_multi_col"], s["num_ent"])
+    r = time_cpu_baseline(params, cfg, (hb["e1"], hb["rel"], hb["e2"], dense), budget_s=budget_s)
+    return {"value": r["train_rows_per_s"], "unit": "train rows/s", "eval_value": r["eval_queries_per_s"],
+            "eval_unit": "eval queries/s", "cores": r["cores"], "kind": "port",
+            "sample": "%d train steps + %d eval batches of B=%d at the %s shape, torch-CPU fp32 materialising "
+                      "restatement of models.py/metrics.py (TensorFlow unavailable offline)%s"
+                      % (r["train_steps"], r["eval_batches"], s["batch"], shape, note),
+            "train_ms": r["train_ms"], "eval_ms": r["eval_ms"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--shape", default=os.environ.get("COPER_BENCH_SHAPE", "wn18rr"))
+    ap.add_argument("--prec", default=os.environ.get("COPER_BENCH_PREC", "fp32"))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from coper_b200 import synthetic
+    s = synthetic.SHAPES[args.shape]
+    B = s["batch"]
+    workload = "CoPER-ConvE %s shape (N=%d entities, R'=%d, d=%d, dr=%d, B=%d, full 1-N labels)" % (
+        args.shape, s["num_ent"], s["num_rel"], s["ent_emb_size"], s["rel_emb_size"], B)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = run_cpu_baseline(args.shape, max(args.cpu_budget, 10.0) * 1.5)
+        line = {"impl": "reference", "metric": "train_rows_per_s", "value": cb["value"], "unit": "train rows/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": cb["train_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "note": "CPU restatement of the reference path (oracle port)"},
+                "eval": {"value": cb["eval_value"], "unit": "eval queries/s", "ms_per_batch": cb["eval_ms"]},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "train rows/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0, "eval_value": cb["eval_value"]}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from coper_b200 import _lib
+    from coper_b200.models import ConvE, EntityShard
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    md = synthetic.descriptors(args.shape, dropout=True)
+    shard = EntityShard(s["num_ent"], rank, world)
+    model = ConvE(md, seed=0, prec=args.prec, shard=shard, conv_in_height=s["H"])
+    n_batches = 8
+    host = synthetic.make_batches(s["num_ent"], s["num_rel"], B, n_batches, seed=1)
+    devb = [{k: torch.as_tensor(v).cuda() for k, v in hb.items()} for hb in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        k0 = lib.coper_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, (lib.coper_launch_count() - k0)
+
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident (kernel-side) numbers
+    train_ms, train_launches = timed(lambda i: model.train_step(devb[i % n_batches]), K, W)
+    eval_ms, eval_launches = timed(lambda i: model.filtered_ranks(devb[i % n_batches]), K, W)
+    # ---- end-to-end through the public API: pinned host batches in, loss / ranks read back every step
+    def e2e_train(i):
+        return float(model.train_step(host[i % n_batches]).item())
+
+    def e2e_eval(i):
+        r, _ = model.filtered_ranks(host[i % n_batches])
+        return r.cpu()
+    e2e_train_ms, _ = timed(e2e_train, K, W)
+    e2e_eval_ms, _ = timed(e2e_eval, K, W)
+    clocks = sampler.stop() if rank == 0 else None
+    nnz = float(np.mean([hb["e2_multi_col"].shape[0] for hb in host]))
+    h2d = int(B * 8 * 2 + (B + 1) * 4 + nnz * 4)
+    d2h = 8
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0, N=1 timing of isolated calls)
+    roofline, breakdown = None, None
+    peaks = load_peaks()
+    if not args.no_breakdown and rank == 0 and world == 1:
+        breakdown, roofline = kernel_breakdown(model, devb[0], peaks, args.prec)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = run_cpu_baseline(args.shape, args.cpu_budget)
+        except Exception as exc:  # the CPU leg must never take the GPU numbers down with it
+            cpu = {"value": None, "unit": "train rows/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "failed: %r" % (exc,)}
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ws_mb = working_set_mb(s, B)
+    line = {
+        "metric": "train_rows_per_s", "value": B / train_ms * 1e3, "unit": "train rows/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": train_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "bf16": "bf16", "tf32x3": "tf32x3"}[args.prec],
+        "data": "synthetic",
+        "config": {"workload": workload, "precision": args.prec,
+                   "parallelism": "single GPU" if world == 1 else
+                   "entity-sharded 1-N scorer x%d (rows/GPU=%d), replicated front end" % (world, shard.rows),
+                   "l2": "no flush: per-step working set ~%d MB > 126 MB L2; %d distinct input batches cycled"
+                         % (ws_mb, n_batches),
+                   "dropout": "on (feature-map 0.3, output 0.2)", "batch_norm": "batch statistics (train)"},
+        "eval": {"value": B / eval_ms * 1e3, "unit": "eval queries/s", "ms_per_batch": eval_ms,
+                 "gpu_launches_per_batch": eval_launches / K},
+        "e2e": {"value": B / e2e_train_ms * 1e3, "unit": "train rows/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_train_ms,
+                "eval_value": B / e2e_eval_ms * 1e3, "eval_unit": "eval queries/s", "eval_ms_per_batch": e2e_eval_ms,
+                "eval_d2h_bytes_per_batch": B * 4},
+        "gpu_launches": int(train_launches), "gpu_launches_per_step": train_launches / K,
+        "clocks": clocks, "roofline": roofline, "kernel_ms": breakdown, "cpu_baseline": cpu,
+        "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "_source")},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def working_set_mb(s, B):
+    N, d, dr = s["num_ent"], s["ent_emb_size"], s["rel_emb_size"]
+    H = s["H"]
+    F = (H - 2) * (d // H - 2) * 32
+    return int((3 * N * d * 4 + 3 * dr * F * d * 4 + B * N * 4 + 4 * B * F * 4) / 1e6)
+
+
+def kernel_breakdown(model, batch, peaks, prec, reps=10):
+    """CUDA-event time of each C-ABI stage in isolation (same stream, warm) and the roofline of the dominant one."""
+    import torch
+    from coper_b200._lib import call, ptr
+    b = model.stage_batch(batch)
+    model._train_device(b)                 # populate every buffer
+    torch.cuda.synchronize()
+    B, d, F, C = b.B, model.ent_emb_size, model.F, model.C
+    Ns = model.shard.rows
+    g = model.grads
+    Pw, Pb = model.fc_weights.projections[-1], model.fc_bias.projections[-1]
+    dc = Pw.shape[0]
+    pos, neg = 0.9 + 1.0 / model.num_ent, 1.0 / model.num_ent
+    stages = {
+        "cpg_fc_fwd": (lambda: call("coper_cpg_fc_fwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(b.cb), ptr(Pb), B, dc, F, d,
+                                    Pb.shape[0], 1.0, None, 0, ptr(b.y), ptr(b.ws), b.ws_bytes, model.prec),
+                       2.0 * B * dc * F * d, "tensor"),
+        "cpg_fc_bwd": (lambda: call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(b.cb), ptr(Pb), ptr(b.dy),
+                                    B, dc, F, d, Pb.shape[0], ptr(g["fc_weights/CPG/Projection0"]),
+                                    ptr(g["fc_bias/CPG/Projection0"]), ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws),
+                                    b.ws_bytes, model.prec), 4.0 * B * dc * F * d, "tensor"),
+        "score1n_bce_fwd_bwd": (lambda: call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(model.ent_emb),
+                                             ptr(model.pred_bias), ptr(b.bits), B, Ns, d, pos, neg,
+                                             1.0 / (B * model.num_ent), ptr(b.loss_sum), ptr(b.SG), b.ld, ptr(b.dq),
+                                             ptr(g["ent_emb"]), ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes,
+                                             model.prec), 6.0 * B * d * Ns, "tensor"),
+        "score1n_fwd": (lambda: model._score(b), 2.0 * B * d * Ns, "tensor"),
+        "filtered_rank": (lambda: call("coper_filtered_rank", ptr(b.SG), b.ld, B, Ns, ptr(b.e2), model.shard.lo,
+                                       ptr(b.gold), ptr(b.bits), ptr(b.n_greater), ptr(b.n_equal)),
+                          B * (4.0 * Ns + Ns / 8.0), "hbm"),
+        "clip_and_amsgrad": (lambda: model._clip_and_apply(),
+                             sum(p.numel() for _, p, _ in model.trainables) * 4.0 * 5, "hbm"),
+    }
+    out, best = {}, None
+    for name, (fn, work, bound) in stages.items():
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = ms
+        in_train = name in ("cpg_fc_fwd", "cpg_fc_bwd", "score1n_bce_fwd_bwd", "clip_and_amsgrad")
+        if in_train and (best is None or ms > best[1]):
+            best = (name, ms, work, bound)
+    name, ms, work, bound = best
+    if bound == "tensor":
+        peak = peaks["bf16_tflops"]
+        achieved = work / (ms * 1e-3) / 1e12
+        unit = "TFLOP/s"
+    else:
+        peak = peaks["hbm_gbs"]
+        achieved = work / (ms * 1e-3) / 1e9
+        unit = "GB/s"
+    roof = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "traffic": None, "ms": ms, "algorithmic_work": work,
+            "peak_source": peaks["_source"] + (", bf16 dense burst" if bound == "tensor" else ", copy bandwidth"),
+            "note": "isolated launches, CUDA events on the launching stream; prec=%s" % prec}
+    return out, roof
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+// Shared device/host helpers for libcoper_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/coper.h"
+
+namespace coper {
+
+extern thread_local int g_last_cuda_error;
+extern long long g_launch_count;  // kernels launched by this library (every launch is followed by check_launch)
+
+inline int check_launch() {
+  ++g_launch_count;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    cudaGetLastError();
+    return COPER_ERR_CUDA;
+  }
+  return COPER_OK;
+}
+inline int check_cuda(cudaError_t e) {
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return COPER_ERR_CUDA;
+  }
+  return COPER_OK;
+}
+#define COPER_CHECK_ARG(cond) \
+  do {                        \
+    if (!(cond)) return COPER_ERR_INVALID_ARG; \
+  } while (0)
+
+static inline cudaStream_t as_stream(coper_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Counter-based dropout hash (splitmix64 finaliser): identical on host and device.
+__host__ __device__ __forceinline__ uint32_t hash32(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// keep threshold: element kept iff hash32 < thr (thr == 0xFFFFFFFF and keep>=1 -> always kept, handled by caller)
+__host__ __device__ __forceinline__ uint32_t keep_threshold(float keep) {
+  double t = (double)keep * 4294967296.0;
+  if (t >= 4294967295.0) return 0xFFFFFFFFu;
+  if (t <= 0.0) return 0u;
+  return (uint32_t)t;
+}
+// multiplicative dropout factor for element idx: 0 or 1/keep; keep>=1 -> 1
+__device__ __forceinline__ float drop_factor(float keep, float inv_keep, uint32_t thr, uint64_t seed, uint64_t idx) {
+  if (keep >= 1.0f) return 1.0f;
+  return hash32(seed, idx) < thr ? inv_keep : 0.0f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide deterministic sum (all threads must call; result valid in thread 0). blockDim.x multiple of 32, <= 1024.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem32) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) smem32[w] = v;
+  __syncthreads();
+  T r = T(0);
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    r = lane < nw ? smem32[lane] : T(0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;
+}
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace coper

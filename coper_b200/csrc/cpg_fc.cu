@@ -1,0 +1,298 @@
+// a3 + a6 (K2 + K3): fused contextual-parameter "generate-and-apply".
+//
+// Reference: W_b = reshape(c_b . P, [F, d]) is materialised for every query ([B,F,d] fp32 = 1.9 GB at
+// FB15k-237, models.py:70-73) and then applied with a batched mat-vec (models.py:412).  Here the
+// contraction is evaluated directly as
+//     y = (c (x) f) . P^ + cb . Pb ,   P^ = P viewed [dc*F, d]
+// with the Khatri-Rao operand (c (x) f) synthesised tile-by-tile in shared memory: P^ is streamed once,
+// the per-query weights never exist in HBM.  K = dc*F (36,864 .. 200,704) against an output of only
+// [B, d], so the K range is split across CTAs and reduced in a fixed order (deterministic).
+//
+// Backward (autodiff of the above, models.py:198):
+//     T_k = dy . P[k]^T                      (never stored)
+//     df  = sum_k c[:,k] * T_k               dc[:,k] = rowsum(f * T_k)         (T kernel, epilogue-reduced)
+//     dP[k] = f^T . (c[:,k] * dy)            dPb = cb^T . dy    dcb = dy . Pb^T
+//
+// This file: exact-fp32 CUDA-core engine (COPER_PREC_FP32) + dispatch + the plain sgemm used by the small
+// dense layers.  tcgen05 engine: umma_cpg.cu.
+#include "simt_gemm.cuh"
+
+namespace coper {
+using namespace simt;
+
+// ---------------------------------------------------------------- sources
+struct CpgFwdA {  // (b, kk) -> f[b, i] * c[b, kq],  K-contiguous
+  static constexpr bool kKContig = true;
+  const float* f;
+  const float* c;
+  int B, F, dc, nt;
+  int kq = 0, i0 = 0;
+  __device__ __forceinline__ void tile(int t) { kq = t / nt; i0 = (t - kq * nt) * BK; }
+  __device__ __forceinline__ float at(int b, int kk) const {
+    int i = i0 + kk;
+    return (b < B && i < F) ? __ldg(f + (int64_t)b * F + i) * __ldg(c + (int64_t)b * dc + kq) : 0.f;
+  }
+};
+struct CpgFwdB {  // (j, kk) -> P[kq, i, j],  MN-contiguous
+  static constexpr bool kKContig = false;
+  const float* P;
+  int F, d, nt;
+  int kq = 0, i0 = 0;
+  __device__ __forceinline__ void tile(int t) { kq = t / nt; i0 = (t - kq * nt) * BK; }
+  __device__ __forceinline__ float at(int j, int kk) const {
+    int i = i0 + kk;
+    return (j < d && i < F) ? __ldg(P + ((int64_t)kq * F + i) * d + j) : 0.f;
+  }
+};
+struct ScaledMN {  // (j, kk) -> x[b, j] * s[b, kq] with b = k index,  MN-contiguous
+  static constexpr bool kKContig = false;
+  const float* x;
+  const float* s;
+  int ld, mn_ext, k_ext, lds, kq;
+  int k0 = 0;
+  __device__ __forceinline__ void tile(int t) { k0 = t * BK; }
+  __device__ __forceinline__ float at(int j, int kk) const {
+    int b = k0 + kk;
+    return (j < mn_ext && b < k_ext) ? __ldg(x + (int64_t)b * ld + j) * __ldg(s + (int64_t)b * lds + kq) : 0.f;
+  }
+};
+
+// ---------------------------------------------------------------- forward
+__global__ void __launch_bounds__(THREADS) cpg_fwd_kernel(const float* __restrict__ c, const float* __restrict__ f,
+                                                          const float* __restrict__ P, int B, int dc, int F, int d,
+                                                          int tiles_per_split, float* __restrict__ part) {
+  __shared__ Smem sm;
+  int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, split = blockIdx.z;
+  int nt = (F + BK - 1) / BK;
+  int T = dc * nt;
+  int t0 = split * tiles_per_split;
+  int t1 = min(T, t0 + tiles_per_split);
+  CpgFwdA A{f, c, B, F, dc, nt};
+  CpgFwdB Bs{P, F, d, nt};
+  float acc[8][8];
+  zero_acc(acc);
+  mainloop(A, Bs, m0, n0, t0, t1, acc, sm);
+  float* o = part + (int64_t)split * B * d;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int b = m0 + mt_row(i);
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = n0 + mt_col(j);
+      if (col < d) o[(int64_t)b * d + col] = acc[i][j];
+    }
+  }
+}
+
+// y = sum_s part[s] + cb . Pb, then output dropout (models.py:414-415)
+__global__ void cpg_fwd_finalize_kernel(const float* __restrict__ part, int S, const float* __restrict__ cb,
+                                        const float* __restrict__ Pb, int B, int d, int dcb, float keep,
+                                        float inv_keep, uint32_t thr, const uint64_t* seed_dev, uint64_t salt,
+                                        float* __restrict__ y) {
+  uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)B * d;
+  if (e >= n) return;
+  int b = (int)(e / d), j = (int)(e % d);
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s) acc += (double)part[(int64_t)s * n + e];
+  float bias = 0.f;
+  for (int k = 0; k < dcb; ++k) bias = fmaf(__ldg(cb + (int64_t)b * dcb + k), __ldg(Pb + (int64_t)k * d + j), bias);
+  float v = (float)acc + bias;
+  y[e] = v * drop_factor(keep, inv_keep, thr, seed, (uint64_t)e);
+}
+
+// ---------------------------------------------------------------- backward: T kernel -> df, dc partials
+__global__ void __launch_bounds__(THREADS) cpg_bwd_T_kernel(const float* __restrict__ c, const float* __restrict__ f,
+                                                            const float* __restrict__ P,
+                                                            const float* __restrict__ dy, int B, int dc, int F, int d,
+                                                            float* __restrict__ df, float* __restrict__ dc_part) {
+  __shared__ Smem sm;
+  int n0 = blockIdx.x * BN;  // feature tile
+  int m0 = blockIdx.y * BM;  // batch tile
+  float dfacc[8][8];
+  zero_acc(dfacc);
+  int kt = (d + BK - 1) / BK;
+  for (int kq = 0; kq < dc; ++kq) {
+    SrcK A{dy, d, B, d};
+    SrcK Bs{P + (int64_t)kq * F * d, d, F, d};
+    float acc[8][8];
+    zero_acc(acc);
+    mainloop(A, Bs, m0, n0, 0, kt, acc, sm);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int b = m0 + mt_row(i);
+      float ck = (b < B) ? __ldg(c + (int64_t)b * dc + kq) : 0.f;
+      float rp = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int col = n0 + mt_col(j);
+        float fv = (b < B && col < F) ? __ldg(f + (int64_t)b * F + col) : 0.f;
+        dfacc[i][j] = fmaf(ck, acc[i][j], dfacc[i][j]);
+        rp = fmaf(fv, acc[i][j], rp);
+      }
+      // reduce over the 16 threads (same half-warp) that share this row
+      rp += __shfl_xor_sync(0xffffffffu, rp, 8);
+      rp += __shfl_xor_sync(0xffffffffu, rp, 4);
+      rp += __shfl_xor_sync(0xffffffffu, rp, 2);
+      rp += __shfl_xor_sync(0xffffffffu, rp, 1);
+      if ((threadIdx.x & 15) == 0 && b < B) dc_part[((int64_t)blockIdx.x * B + b) * dc + kq] = rp;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int b = m0 + mt_row(i);
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = n0 + mt_col(j);
+      if (col < F) df[(int64_t)b * F + col] = dfacc[i][j];
+    }
+  }
+}
+
+// dP[kq][i][j] = sum_b f[b,i] c[b,kq] dy[b,j]
+__global__ void __launch_bounds__(THREADS) cpg_bwd_dP_kernel(const float* __restrict__ c, const float* __restrict__ f,
+                                                             const float* __restrict__ dy, int B, int dc, int F,
+                                                             int d, float* __restrict__ dP) {
+  __shared__ Smem sm;
+  int n0 = blockIdx.x * BN;  // output-dim tile
+  int m0 = blockIdx.y * BM;  // feature tile
+  int kq = blockIdx.z;
+  SrcMN A{f, F, F, B};
+  ScaledMN Bs{dy, c, d, d, B, dc, kq};
+  float acc[8][8];
+  zero_acc(acc);
+  mainloop(A, Bs, m0, n0, 0, (B + BK - 1) / BK, acc, sm);
+  float* o = dP + (int64_t)kq * F * d;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int row = m0 + mt_row(i);
+    if (row >= F) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = n0 + mt_col(j);
+      if (col < d) o[(int64_t)row * d + col] = acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- plain sgemm
+template <class SA, class SB>
+__global__ void __launch_bounds__(THREADS) sgemm_kernel(SA A, SB Bs, int M, int N, int K, float* __restrict__ C,
+                                                        int ldc, int accumulate) {
+  __shared__ Smem sm;
+  int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  float acc[8][8];
+  zero_acc(acc);
+  mainloop(A, Bs, m0, n0, 0, (K + BK - 1) / BK, acc, sm);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int r = m0 + mt_row(i);
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = n0 + mt_col(j);
+      if (col < N) {
+        float* p = C + (int64_t)r * ldc + col;
+        *p = accumulate ? *p + acc[i][j] : acc[i][j];
+      }
+    }
+  }
+}
+
+struct CpgLayout {
+  int splits, tiles_per_split;
+  size_t total;
+};
+static CpgLayout cpg_fwd_layout(int B, int dc, int F, int d) {
+  CpgLayout L;
+  int tiles_mn = ceil_div(d, BN) * ceil_div(B, BM);
+  int T = dc * ceil_div(F, BK);
+  int splits = (2 * 148 + tiles_mn - 1) / tiles_mn;
+  if (splits > T) splits = T;
+  if (splits < 1) splits = 1;
+  L.tiles_per_split = (T + splits - 1) / splits;
+  L.splits = (T + L.tiles_per_split - 1) / L.tiles_per_split;
+  L.total = align_up((size_t)L.splits * B * d * sizeof(float), 256);
+  return L;
+}
+}  // namespace coper
+
+using namespace coper;
+
+extern "C" {
+
+int coper_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                float* C, int ldc, int accumulate, coper_stream_t stream) {
+  COPER_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && lda > 0 && ldb > 0 && ldc >= N);
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  cudaStream_t st = as_stream(stream);
+  // operand A(m,k): !transA -> A[m*lda+k] (K-contig); transA -> A[k*lda+m] (MN-contig)
+  // operand B(k,n): !transB -> B[k*ldb+n] (MN-contig); transB -> B[n*ldb+k] (K-contig)
+  if (!transA && !transB)
+    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcK{A, lda, M, K}, SrcMN{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+  else if (!transA && transB)
+    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcK{A, lda, M, K}, SrcK{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+  else if (transA && !transB)
+    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcMN{A, lda, M, K}, SrcMN{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+  else
+    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcMN{A, lda, M, K}, SrcK{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+  return check_launch();
+}
+
+size_t coper_cpg_fc_fwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
+  (void)prec;
+  return cpg_fwd_layout(B, dc, F, d).total;
+}
+
+int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb, int B, int dc,
+                     int F, int d, int dcb, float keep_out, const uint64_t* seed_dev, uint64_t salt_out, float* y,
+                     void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
+  COPER_CHECK_ARG(c && f && P && cb && Pb && y && workspace && B > 0 && dc > 0 && F > 0 && d > 0 && dcb > 0);
+  COPER_CHECK_ARG(keep_out > 0.f);
+  if (prec != COPER_PREC_FP32) return COPER_ERR_UNSUPPORTED;
+  CpgLayout L = cpg_fwd_layout(B, dc, F, d);
+  if (workspace_bytes < L.total) return COPER_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  float* part = static_cast<float*>(workspace);
+  dim3 grid(ceil_div(d, BN), ceil_div(B, BM), L.splits);
+  cpg_fwd_kernel<<<grid, THREADS, 0, st>>>(c, f, P, B, dc, F, d, L.tiles_per_split, part);
+  int rc = check_launch();
+  if (rc) return rc;
+  int64_t n = (int64_t)B * d;
+  cpg_fwd_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, L.splits, cb, Pb, B, d, dcb, keep_out,
+                                                                       1.0f / keep_out, keep_threshold(keep_out),
+                                                                       seed_dev, salt_out, y);
+  return check_launch();
+}
+
+size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
+  (void)prec; (void)d;
+  return align_up((size_t)ceil_div(F, BN) * B * dc * sizeof(float), 256);
+}
+
+int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb,
+                     const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
+                     float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
+                     coper_stream_t stream) {
+  COPER_CHECK_ARG(c && f && P && cb && Pb && dy && dP && dPb && df && dc_out && dcb_out && workspace);
+  COPER_CHECK_ARG(B > 0 && dc > 0 && F > 0 && d > 0 && dcb > 0);
+  if (prec != COPER_PREC_FP32) return COPER_ERR_UNSUPPORTED;
+  if (workspace_bytes < coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, prec)) return COPER_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  float* dc_part = static_cast<float*>(workspace);
+  int ftiles = ceil_div(F, BN);
+  cpg_bwd_T_kernel<<<dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st>>>(c, f, P, dy, B, dc, F, d, df, dc_part);
+  int rc = check_launch();
+  if (rc) return rc;
+  if ((rc = coper_reduce_partials(dc_part, ftiles, (int64_t)B * dc, 1.0f, 0, dc_out, stream))) return rc;
+  cpg_bwd_dP_kernel<<<dim3(ceil_div(d, BN), ceil_div(F, BM), dc), THREADS, 0, st>>>(c, f, dy, B, dc, F, d, dP);
+  if ((rc = check_launch())) return rc;
+  // dPb [dcb, d] = cb^T . dy ;  dcb [B, dcb] = dy . Pb^T
+  if ((rc = coper_sgemm(1, 0, dcb, d, B, cb, dcb, dy, d, dPb, d, 0, stream))) return rc;
+  return coper_sgemm(0, 1, B, dcb, d, dy, d, Pb, d, dcb_out, dcb, 0, stream);
+}
+
+}  // extern "C"

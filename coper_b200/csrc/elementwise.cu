@@ -1,0 +1,510 @@
+// HBM-bound pieces of the CoPER-ConvE hot path: lookups, batch-norm/relu/dropout, label bit rows,
+// deterministic reductions, global-norm clip and AMSGrad.  All kernels are streaming: coalesced,
+// 128-bit vectorised where the shape allows, grids sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace coper {
+thread_local int g_last_cuda_error = 0;
+long long g_launch_count = 0;
+constexpr int kSMs = 148;
+
+// ------------------------------------------------------------------ gather (models.py:176,178)
+__global__ void gather_rows_kernel(const float* __restrict__ table, int64_t row_lo, int64_t row_hi, int width,
+                                   const int64_t* __restrict__ idx, int n_idx, float* __restrict__ out) {
+  int warps_per_block = blockDim.x >> 5;
+  int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= n_idx) return;
+  int64_t id = idx[row];
+  bool owned = id >= row_lo && id < row_hi;
+  const float* src = table + (id - row_lo) * (int64_t)width;
+  float* dst = out + (int64_t)row * width;
+  if ((width & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < (width >> 2); i += 32) d4[i] = owned ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int i = lane; i < width; i += 32) dst[i] = owned ? __ldg(src + i) : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ column statistics
+// mode 0: (x, x^2); mode 1: backward (g1, g1*xhat) with g1 = dout * drop_post * relu'(a x + b)
+constexpr int kStatRows = 512;  // rows per chunk
+struct StatBwdArgs {
+  const float* dout;
+  const float* a;
+  const float* b;
+  const float* mean;
+  const float* invstd;
+  int relu;
+  float keep;
+  float inv_keep;
+  uint32_t thr;
+  const uint64_t* seed_dev;
+  uint64_t salt;
+};
+template <int MODE>
+__global__ void colstats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ partials,
+                                StatBwdArgs bw) {
+  // block (32, 8): x = column in slab, y = row lane
+  __shared__ float s1[8][33], s2[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int64_t r0 = (int64_t)blockIdx.y * kStatRows;
+  int64_t r1 = r0 + kStatRows < R ? r0 + kStatRows : R;
+  float v1 = 0.f, v2 = 0.f;
+  uint64_t seed = 0;
+  if (MODE == 1) seed = (bw.seed_dev ? *bw.seed_dev : 0ull) + bw.salt;
+  if (c < C) {
+    float ac = 0.f, bc = 0.f, mc = 0.f, ic = 0.f;
+    if (MODE == 1) { ac = bw.a[c]; bc = bw.b[c]; mc = bw.mean[c]; ic = bw.invstd[c]; }
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      int64_t e = r * C + c;
+      float xv = x[e];
+      if (MODE == 0) {
+        v1 += xv;
+        v2 += xv * xv;
+      } else {
+        float g = bw.dout[e] * drop_factor(bw.keep, bw.inv_keep, bw.thr, seed, (uint64_t)e);
+        if (bw.relu && !(ac * xv + bc > 0.f)) g = 0.f;
+        v1 += g;
+        v2 += g * ((xv - mc) * ic);
+      }
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = v1;
+  s2[threadIdx.y][threadIdx.x] = v2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+    int64_t o = ((int64_t)blockIdx.y * C + c) * 2;
+    partials[o] = t1;
+    partials[o + 1] = t2;
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* moving_mean, float* moving_var, float momentum, float eps,
+                                   int use_batch, int update_moving, int bessel, float* a, float* b, float* mean,
+                                   float* invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mu, var;
+  if (use_batch) {
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < nchunk; ++k) {
+      s += (double)partials[((int64_t)k * C + c) * 2];
+      ss += (double)partials[((int64_t)k * C + c) * 2 + 1];
+    }
+    double m = s / (double)R;
+    double v = ss / (double)R - m * m;
+    if (v < 0.0) v = 0.0;
+    mu = (float)m;
+    var = (float)v;
+    if (update_moving) {
+      double vm = bessel ? v * ((double)R / (double)(R > 1 ? R - 1 : 1)) : v;
+      moving_mean[c] = moving_mean[c] * momentum + mu * (1.0f - momentum);
+      moving_var[c] = moving_var[c] * momentum + (float)vm * (1.0f - momentum);
+    }
+  } else {
+    mu = moving_mean[c];
+    var = moving_var[c];
+  }
+  float inv = 1.0f / sqrtf(var + eps);
+  float ac = gamma[c] * inv;
+  a[c] = ac;
+  b[c] = beta[c] - mu * ac;
+  mean[c] = mu;
+  invstd[c] = inv;
+}
+
+__global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t n, int C, const float* __restrict__ a,
+                                  const float* __restrict__ b, int relu, float keep, float inv_keep, uint32_t thr,
+                                  const uint64_t* seed_dev, uint64_t salt, float* __restrict__ out) {
+  uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    int c = (int)(e % C);
+    float v = a[c] * x[e] + b[c];
+    if (relu) v = fmaxf(v, 0.f);
+    out[e] = v * drop_factor(keep, inv_keep, thr, seed, (uint64_t)e);
+  }
+}
+// float4 variant (C % 4 == 0, n % 4 == 0)
+__global__ void bn_act_fwd_kernel4(const float4* __restrict__ x, int64_t n4, int C, const float* __restrict__ a,
+                                   const float* __restrict__ b, int relu, float keep, float inv_keep, uint32_t thr,
+                                   const uint64_t* seed_dev, uint64_t salt, float4* __restrict__ out) {
+  uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int64_t e = i * 4;
+    int c = (int)(e % C);
+    float4 xv = __ldg(x + i);
+    float4 av = *reinterpret_cast<const float4*>(a + c);
+    float4 bv = *reinterpret_cast<const float4*>(b + c);
+    float4 o;
+    o.x = av.x * xv.x + bv.x; o.y = av.y * xv.y + bv.y; o.z = av.z * xv.z + bv.z; o.w = av.w * xv.w + bv.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (keep < 1.0f) {
+      o.x *= drop_factor(keep, inv_keep, thr, seed, (uint64_t)e);
+      o.y *= drop_factor(keep, inv_keep, thr, seed, (uint64_t)e + 1);
+      o.z *= drop_factor(keep, inv_keep, thr, seed, (uint64_t)e + 2);
+      o.w *= drop_factor(keep, inv_keep, thr, seed, (uint64_t)e + 3);
+    }
+    out[i] = o;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C,
+                                       int use_batch, float* dgamma, float* dbeta, float* c1, float* c2) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    s += (double)partials[((int64_t)k * C + c) * 2];
+    ss += (double)partials[((int64_t)k * C + c) * 2 + 1];
+  }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)ss;
+  c1[c] = use_batch ? (float)(s / (double)R) : 0.f;
+  c2[c] = use_batch ? (float)(ss / (double)R) : 0.f;
+}
+
+__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ x, int64_t n,
+                                        int C, const float* __restrict__ a, const float* __restrict__ b,
+                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                        const float* __restrict__ c1, const float* __restrict__ c2, int relu,
+                                        float keep_post, float inv_keep_post, uint32_t thr_post,
+                                        const uint64_t* seed_dev, uint64_t salt_post, float keep_pre,
+                                        float inv_keep_pre, uint32_t thr_pre, uint64_t salt_pre,
+                                        float* __restrict__ dx) {
+  uint64_t sd = seed_dev ? *seed_dev : 0ull;
+  uint64_t seed_post = sd + salt_post, seed_pre = sd + salt_pre;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    int c = (int)(e % C);
+    float xv = x[e];
+    float ac = a[c];
+    float g = dout[e] * drop_factor(keep_post, inv_keep_post, thr_post, seed_post, (uint64_t)e);
+    if (relu && !(ac * xv + b[c] > 0.f)) g = 0.f;
+    float xhat = (xv - mean[c]) * invstd[c];
+    float d = ac * (g - c1[c] - xhat * c2[c]);
+    dx[e] = d * drop_factor(keep_pre, inv_keep_pre, thr_pre, seed_pre, (uint64_t)e);
+  }
+}
+
+__global__ void dropout_mask_kernel(int64_t n, uint32_t thr, float keep, const uint64_t* seed_dev, uint64_t salt,
+                                    float* mask) {
+  uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+    mask[e] = (keep >= 1.0f || hash32(seed, (uint64_t)e) < thr) ? 1.0f : 0.0f;
+}
+__global__ void dropout_apply_kernel(float* x, int64_t n, float keep, float inv_keep, uint32_t thr,
+                                     const uint64_t* seed_dev, uint64_t salt) {
+  uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+    x[e] *= drop_factor(keep, inv_keep, thr, seed, (uint64_t)e);
+}
+
+// ------------------------------------------------------------------ label / filter bit rows
+__global__ void csr_to_bits_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int B,
+                                   int64_t lo, int64_t hi, int64_t words, uint32_t* bits) {
+  int b = blockIdx.x;
+  if (b >= B) return;
+  int s = rowptr[b], e = rowptr[b + 1];
+  for (int i = s + threadIdx.x; i < e; i += blockDim.x) {
+    int64_t n = col[i];
+    if (n >= lo && n < hi) {
+      int64_t l = n - lo;
+      atomicOr(bits + (int64_t)b * words + (l >> 5), 1u << (l & 31));
+    }
+  }
+}
+__global__ void dense_to_bits_kernel(const float* __restrict__ dense, int B, int64_t N, int64_t words,
+                                     uint32_t* __restrict__ bits) {
+  // one warp per output word: lane l tests entity w*32 + l (coalesced 128 B read), ballot packs the word
+  int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t total = (int64_t)B * words;
+  if (gw >= total) return;
+  int64_t b = gw / words, w = gw % words;
+  int64_t n = w * 32 + lane;
+  bool on = n < N && dense[b * N + n] == 1.0f;
+  uint32_t m = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) bits[gw] = m;
+}
+
+// ------------------------------------------------------------------ deterministic reductions
+__global__ void reduce_partials_kernel(const float* __restrict__ in, int S, int64_t n, float scale, int accumulate,
+                                       float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s) acc += (double)in[(int64_t)s * n + i];
+  float r = (float)(acc * (double)scale);
+  out[i] = accumulate ? out[i] + r : r;
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
+  __shared__ double sm[32];
+  double acc = 0.0;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    int64_t n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float p = 0.f;
+    int cnt = 0;
+    for (int64_t j = i; j < n4; j += stride) {
+      float4 v = __ldg(x4 + j);
+      p += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      if (++cnt == 64) { acc += (double)p; p = 0.f; cnt = 0; }
+    }
+    acc += (double)p;
+    for (int64_t j = (n4 << 2) + i; j < n; j += stride) acc += (double)x[j] * (double)x[j];
+  } else {
+    for (int64_t j = i; j < n; j += stride) acc += (double)x[j] * (double)x[j];
+  }
+  double t = block_sum<double>(acc, sm);
+  if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+
+__global__ void clip_scale_kernel(const double* __restrict__ partials, int n, float clip, float* out2) {
+  __shared__ double sm[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+  double t = block_sum<double>(acc, sm);
+  if (threadIdx.x == 0) {
+    double norm = sqrt(t);
+    double c = (double)clip;
+    out2[0] = (float)(c / (norm > c ? norm : c));
+    out2[1] = (float)norm;
+  }
+}
+
+// ------------------------------------------------------------------ AMSGrad (utils/amsgrad.py:130-159)
+__global__ void amsgrad_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                               float* __restrict__ v, float* __restrict__ vhat, int64_t n,
+                               const float* __restrict__ step_state, float b1, float b2, float eps,
+                               const float* __restrict__ clip_scale, int bug_compat) {
+  float lr_t = step_state[0];
+  float cs = clip_scale ? *clip_scale : 1.0f;
+  float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float g = grad[i] * cs;
+    float mt, vt;
+    if (bug_compat) {
+      mt = g * omb1;          // slot m == 0 forever (amsgrad.py:142-144)
+      vt = (g * g) * omb2;    // slot v == 0 forever (amsgrad.py:149-151)
+    } else {
+      mt = m[i] * b1 + g * omb1;
+      vt = v[i] * b2 + (g * g) * omb2;
+      m[i] = mt;
+      v[i] = vt;
+    }
+    float vh = fmaxf(vhat[i], vt);
+    vhat[i] = vh;
+    theta[i] -= lr_t * mt / (sqrtf(vh) + eps);
+  }
+}
+
+__global__ void step_state_advance_kernel(float* st, uint64_t* seed_dev, float lr, float b1, float b2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float b1p = st[1], b2p = st[2];
+    st[0] = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);  // amsgrad.py:137
+    st[1] = b1p * b1;                                // amsgrad.py:234-239
+    st[2] = b2p * b2;
+    if (seed_dev) *seed_dev += 1ull;
+  }
+}
+
+static inline int grid_for(int64_t n, int threads, int per_sm = 8) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)kSMs * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+}  // namespace coper
+
+using namespace coper;
+
+extern "C" {
+
+int coper_version(void) { return 100; }
+const char* coper_status_string(int s) {
+  switch (s) {
+    case COPER_OK: return "ok";
+    case COPER_ERR_INVALID_ARG: return "invalid argument";
+    case COPER_ERR_CUDA: return "CUDA error";
+    case COPER_ERR_UNSUPPORTED: return "unsupported configuration";
+    case COPER_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown status";
+  }
+}
+int coper_last_cuda_error(void) { return g_last_cuda_error; }
+long long coper_launch_count(void) { return g_launch_count; }
+int coper_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return COPER_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return COPER_ERR_CUDA;
+  return major == 10 ? 1 : 0;
+}
+
+int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int width, const int64_t* idx, int n_idx,
+                      float* out, coper_stream_t stream) {
+  COPER_CHECK_ARG(table && idx && out && width > 0 && n_idx >= 0 && row_hi >= row_lo);
+  if (n_idx == 0) return COPER_OK;
+  gather_rows_kernel<<<ceil_div(n_idx, 8), 256, 0, as_stream(stream)>>>(table, row_lo, row_hi, width, idx, n_idx, out);
+  return check_launch();
+}
+
+int coper_colstats_chunks(int64_t R) { return R <= 0 ? 0 : (int)((R + kStatRows - 1) / kStatRows); }
+
+int coper_colstats(const float* x, int64_t R, int C, float* partials, coper_stream_t stream) {
+  COPER_CHECK_ARG(x && partials && R > 0 && C > 0);
+  dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
+  StatBwdArgs bw{};
+  colstats_kernel<0><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw);
+  return check_launch();
+}
+
+int coper_bn_finalize(const float* partials, int nchunk, int64_t R, int C, const float* gamma, const float* beta,
+                      float* moving_mean, float* moving_var, float momentum, float eps, int use_batch_stats,
+                      int update_moving, int bessel, float* a, float* b, float* mean, float* invstd,
+                      coper_stream_t stream) {
+  COPER_CHECK_ARG(gamma && beta && moving_mean && moving_var && a && b && mean && invstd && C > 0);
+  COPER_CHECK_ARG(!use_batch_stats || (partials && nchunk > 0 && R > 0));
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nchunk, R, C, gamma, beta, moving_mean,
+                                                                     moving_var, momentum, eps, use_batch_stats,
+                                                                     update_moving, bessel, a, b, mean, invstd);
+  return check_launch();
+}
+
+int coper_bn_act_fwd(const float* x, int64_t R, int C, const float* a, const float* b, int relu, float keep_post,
+                     const uint64_t* seed_dev, uint64_t salt_post, float* out, coper_stream_t stream) {
+  COPER_CHECK_ARG(x && a && b && out && R > 0 && C > 0 && keep_post > 0.f);
+  int64_t n = R * C;
+  float inv = 1.0f / keep_post;
+  uint32_t thr = keep_threshold(keep_post);
+  bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                               reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  if (vec) {
+    int64_t n4 = n / 4;
+    bn_act_fwd_kernel4<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), n4, C, a, b, relu, keep_post, inv, thr, seed_dev, salt_post,
+        reinterpret_cast<float4*>(out));
+  } else {
+    bn_act_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, C, a, b, relu, keep_post, inv, thr,
+                                                                       seed_dev, salt_post, out);
+  }
+  return check_launch();
+}
+
+int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
+                           const float* mean, const float* invstd, int relu, float keep_post,
+                           const uint64_t* seed_dev, uint64_t salt_post, float* partials, coper_stream_t stream) {
+  COPER_CHECK_ARG(dout && x && a && b && mean && invstd && partials && R > 0 && C > 0 && keep_post > 0.f);
+  dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
+  StatBwdArgs bw{dout, a, b, mean, invstd, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post), seed_dev,
+                 salt_post};
+  colstats_kernel<1><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw);
+  return check_launch();
+}
+
+int coper_bn_act_bwd_finalize(const float* partials, int nchunk, int64_t R, int C, int use_batch_stats,
+                              float* dgamma, float* dbeta, float* c1, float* c2, coper_stream_t stream) {
+  COPER_CHECK_ARG(partials && dgamma && dbeta && c1 && c2 && nchunk > 0 && R > 0 && C > 0);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nchunk, R, C, use_batch_stats,
+                                                                         dgamma, dbeta, c1, c2);
+  return check_launch();
+}
+
+int coper_bn_act_bwd_apply(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
+                           const float* mean, const float* invstd, const float* c1, const float* c2, int relu,
+                           float keep_post, const uint64_t* seed_dev, uint64_t salt_post, float keep_pre,
+                           uint64_t salt_pre, float* dx, coper_stream_t stream) {
+  COPER_CHECK_ARG(dout && x && a && b && mean && invstd && c1 && c2 && dx && R > 0 && C > 0);
+  COPER_CHECK_ARG(keep_post > 0.f && keep_pre > 0.f);
+  int64_t n = R * C;
+  bn_act_bwd_apply_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      dout, x, n, C, a, b, mean, invstd, c1, c2, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post),
+      seed_dev, salt_post, keep_pre, 1.0f / keep_pre, keep_threshold(keep_pre), salt_pre, dx);
+  return check_launch();
+}
+
+int coper_dropout_mask(int64_t n, float keep, const uint64_t* seed_dev, uint64_t salt, float* mask,
+                       coper_stream_t stream) {
+  COPER_CHECK_ARG(mask && n >= 0 && keep > 0.f);
+  if (n == 0) return COPER_OK;
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(n, keep_threshold(keep), keep, seed_dev, salt,
+                                                                       mask);
+  return check_launch();
+}
+int coper_dropout_apply(float* x, int64_t n, float keep, const uint64_t* seed_dev, uint64_t salt,
+                        coper_stream_t stream) {
+  COPER_CHECK_ARG(x && n >= 0 && keep > 0.f);
+  if (n == 0 || keep >= 1.0f) return COPER_OK;
+  dropout_apply_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, keep, 1.0f / keep, keep_threshold(keep),
+                                                                        seed_dev, salt);
+  return check_launch();
+}
+
+int coper_csr_to_bits(const int32_t* rowptr, const int32_t* col, int B, int64_t ent_lo, int64_t ent_hi,
+                      uint32_t* bits, coper_stream_t stream) {
+  COPER_CHECK_ARG(rowptr && bits && B > 0 && ent_hi > ent_lo);
+  int64_t words = (ent_hi - ent_lo + 31) / 32;
+  int rc = check_cuda(cudaMemsetAsync(bits, 0, (size_t)B * words * sizeof(uint32_t), as_stream(stream)));
+  if (rc) return rc;
+  if (!col) return COPER_OK;
+  csr_to_bits_kernel<<<B, 64, 0, as_stream(stream)>>>(rowptr, col, B, ent_lo, ent_hi, words, bits);
+  return check_launch();
+}
+int coper_dense_to_bits(const float* dense, int B, int64_t N, uint32_t* bits, coper_stream_t stream) {
+  COPER_CHECK_ARG(dense && bits && B > 0 && N > 0);
+  int64_t words = (N + 31) / 32;
+  int64_t threads = (int64_t)B * words * 32;
+  dense_to_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(dense, B, N, words, bits);
+  return check_launch();
+}
+
+int coper_reduce_partials(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
+                          coper_stream_t stream) {
+  COPER_CHECK_ARG(in && out && S > 0 && n > 0);
+  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate, out);
+  return check_launch();
+}
+int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_stream_t stream) {
+  COPER_CHECK_ARG(x && partials && n >= 0 && slot >= 0);
+  sumsq_kernel<<<COPER_SUMSQ_BLOCKS, 256, 0, as_stream(stream)>>>(x, n, partials + (int64_t)slot * COPER_SUMSQ_BLOCKS);
+  return check_launch();
+}
+int coper_clip_scale(const double* partials, int n_slots, float clip_norm, float* out2, coper_stream_t stream) {
+  COPER_CHECK_ARG(partials && out2 && n_slots > 0 && clip_norm > 0.f);
+  clip_scale_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, n_slots * COPER_SUMSQ_BLOCKS, clip_norm, out2);
+  return check_launch();
+}
+int coper_step_state_advance(float* step_state, uint64_t* seed_dev, float lr, float beta1, float beta2,
+                             coper_stream_t stream) {
+  COPER_CHECK_ARG(step_state);
+  step_state_advance_kernel<<<1, 32, 0, as_stream(stream)>>>(step_state, seed_dev, lr, beta1, beta2);
+  return check_launch();
+}
+int coper_amsgrad_step(float* theta, const float* grad, float* m, float* v, float* vhat, int64_t n,
+                       const float* step_state, float beta1, float beta2, float eps, const float* clip_scale,
+                       int bug_compat, coper_stream_t stream) {
+  COPER_CHECK_ARG(theta && grad && vhat && step_state && n >= 0);
+  COPER_CHECK_ARG(bug_compat || (m && v));
+  if (n == 0) return COPER_OK;
+  amsgrad_kernel<<<grid_for(n, 256, 16), 256, 0, as_stream(stream)>>>(theta, grad, m, v, vhat, n, step_state, beta1,
+                                                                      beta2, eps, clip_scale, bug_compat);
+  return check_launch();
+}
+
+}  // extern "C"

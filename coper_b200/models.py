@@ -1,0 +1,583 @@
+"""Host-side mirror of the reference model object (``qa_cpg/models.py``) driving libcoper_sm100.
+
+``ConvE(model_descriptors)`` takes the same descriptor dict the reference builds at
+``run_cpg.py:115-137`` and exposes the same variable names (``.variables['ent_emb'|'rel_emb'|
+'conv1_weights'|'conv1_bias'|'fc_weights'|'fc_bias'|'pred_bias']``, ``models.py:316-325``).  Where
+the reference returns graph tensors to ``session.run`` (``run_cpg.py:210-219``, ``metrics.py:40-42``),
+this object offers the equivalent eager calls:
+
+    loss = model.train_step(batch)          # == session.run((model.loss, model.train_op), {is_train: True})
+    scores = model.predict_all(batch)       # == session.run(model.predictions_all)
+    ranks, n_equal = model.filtered_ranks(batch)   # metrics.py:44-51 done on device
+
+PyTorch is used only for device memory, streams, CUDA graphs and torch.distributed; every
+arithmetic step of the hot path is a call into the C ABI (``include/coper.h``).  There is no
+CPU / PyTorch fallback: without the CUDA library or a GPU this raises.
+
+Supported configuration = the one every shipped ``*_cpg.yaml`` uses: ``context_rel_conv: null``
+(shared conv filters), ``context_rel_out: [...]`` (g_linear ``[]`` or g_MLP ``[n, ...]``),
+``concat_rel: False``, full 1-N scoring (``num_labels: null``).  Anything else raises
+NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PREC, call, ptr
+
+BN_EPS = 1e-3           # tf.layers.batch_normalization default epsilon (models.py:386-388)
+CLIP_NORM = 5.0         # models.py:199
+SALT_FEATURE_MAP = 1 << 40
+SALT_OUTPUT = 2 << 40
+SALT_CTX = 3 << 40      # + (net_id * 64 + layer) << 32
+
+
+def _xavier_(t: torch.Tensor, gen: torch.Generator):
+    """tf.contrib.layers.xavier_initializer: U(+-sqrt(6/(fan_in+fan_out))) (models.py:208)."""
+    shape = t.shape
+    if len(shape) == 1:
+        fan_in = fan_out = shape[0]
+    else:
+        rec = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+        fan_in, fan_out = shape[-2] * rec, shape[-1] * rec
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    t.copy_((torch.rand(t.shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim)
+
+
+class EntityShard:
+    """Contiguous row range [lo, hi) of the entity table owned by this rank."""
+
+    def __init__(self, num_ent: int, rank: int = 0, world: int = 1, align: int = 128):
+        per = -(-num_ent // world)
+        per = -(-per // align) * align
+        self.num_ent, self.rank, self.world, self.per = num_ent, rank, world, per
+        self.lo = min(num_ent, rank * per)
+        self.hi = min(num_ent, self.lo + per)
+
+    @property
+    def rows(self) -> int:
+        return self.hi - self.lo
+
+    def owner(self, ent: int) -> int:
+        return ent // self.per
+
+
+class _BatchNorm:
+    """Parameters + scratch of one tf.layers.batch_normalization site."""
+
+    def __init__(self, C, dev):
+        f = dict(dtype=torch.float32, device=dev)
+        self.C = C
+        self.gamma, self.beta = torch.ones(C, **f), torch.zeros(C, **f)
+        self.moving_mean, self.moving_var = torch.zeros(C, **f), torch.ones(C, **f)
+        self.a, self.b, self.mean, self.invstd = (torch.empty(C, **f) for _ in range(4))
+        self.dgamma, self.dbeta, self.c1, self.c2 = (torch.zeros(C, **f) for _ in range(4))
+
+
+class ContextualParameterGenerator:
+    """Variables of one CPG (models.py:32-54): ``projections`` [in,n] per layer, optional BN per hidden layer."""
+
+    def __init__(self, context_size: List[int], name: str, shape: List[int], zero_init: bool, use_batch_norm: bool,
+                 dev, gen):
+        self.name, self.shape = name, list(shape)
+        self.num_elements = int(np.prod(shape))
+        sizes = list(context_size) + [self.num_elements]
+        self.projections: List[torch.Tensor] = []
+        for i in range(len(sizes) - 1):
+            t = torch.zeros(sizes[i], sizes[i + 1], dtype=torch.float32)
+            if not zero_init:
+                _xavier_(t, gen)
+            self.projections.append(t.to(dev))
+        self.use_batch_norm = use_batch_norm
+        self.bns = [_BatchNorm(n, dev) for n in context_size[1:]]
+        self.hidden = list(context_size[1:])
+
+
+class ConvE:
+    def __init__(self, model_descriptors: Dict, device: Optional[str] = None, seed: int = 0, prec: str = "fp32",
+                 shard: Optional[EntityShard] = None, reference_bug_compat: bool = True,
+                 conv_in_height: int = 10, process_group=None):
+        md = model_descriptors
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.CoperError("coper_b200.ConvE needs a CUDA device (sm_100a); no CPU fallback exists")
+        self.dev = torch.device(device or "cuda:%d" % torch.cuda.current_device())
+        torch.cuda.set_device(self.dev)
+        # ---- descriptors (models.py:98-128)
+        self.use_negative_sampling = md.get("use_negative_sampling", False)
+        self.label_smoothing_epsilon = float(md["label_smoothing_epsilon"])
+        self.num_ent, self.num_rel = int(md["num_ent"]), int(md["num_rel"])
+        self.ent_emb_size, self.rel_emb_size = int(md["ent_emb_size"]), int(md["rel_emb_size"])
+        self.is_parameter_lookup = md.get("do_parameter_lookup", False)
+        self.conv_filter_height = md.get("conv_filter_height", 3)
+        self.conv_filter_width = md.get("conv_filter_width", 3)
+        self.conv_num_channels = md.get("conv_num_channels", 32)
+        self.concat_rel = md.get("concat_rel", False)
+        self.context_rel_conv = md.get("context_rel_conv", None)
+        self.context_rel_out = md.get("context_rel_out", None)
+        self.context_rel_dropout = float(md.get("context_rel_dropout", 0.0) or 0.0)
+        self.context_rel_use_batch_norm = bool(md.get("context_rel_use_batch_norm", False))
+        self.input_dropout = md.get("input_dropout", 0.0)          # parsed, unused (models.py:366-370)
+        self.hidden_dropout = float(md.get("hidden_dropout", 0.0) or 0.0)
+        self.output_dropout = float(md.get("output_dropout", 0.0) or 0.0)
+        self.batch_norm_momentum = float(md.get("batch_norm_momentum", 0.1))
+        self.batch_norm_train_stats = bool(md.get("batch_norm_train_stats", False))
+        self.learning_rate = float(md.get("learning_rate", 1e-3))
+        if self.use_negative_sampling:
+            raise NotImplementedError("sampled-label training (num_labels != null) is SURVEY §8f-2, not built yet")
+        if self.is_parameter_lookup or self.context_rel_conv is not None or self.context_rel_out is None \
+                or self.concat_rel:
+            raise NotImplementedError("only the CPG-FC configuration (context_rel_conv=null, context_rel_out=[...], "
+                                      "concat_rel=False) of the shipped *_cpg.yaml files is built (SURVEY §8f-4)")
+        self.H = int(conv_in_height)                                # models.py:261 hard-codes 10
+        if self.ent_emb_size % self.H:
+            raise ValueError("entity_embedding_size %d is not a multiple of the conv image height %d "
+                             "(models.py:355 would fail the same way)" % (self.ent_emb_size, self.H))
+        self.W = self.ent_emb_size // self.H
+        self.OH, self.OW = self.H - self.conv_filter_height + 1, self.W - self.conv_filter_width + 1
+        self.C = self.conv_num_channels
+        self.F = self.OH * self.OW * self.C                          # models.py:268
+        self.prec = PREC[prec]
+        self.shard = shard or EntityShard(self.num_ent)
+        self.group = process_group
+        self.world = self.shard.world
+        self.bug_compat = bool(reference_bug_compat)
+        self.beta1, self.beta2, self.adam_eps = 0.9, 0.999, 1e-8    # amsgrad.py:22-24
+
+        # ---- variables (models.py:203-336); entity-sharded rows are initialised from the full-table
+        # stream so that a P-way sharded model holds exactly the rows of the unsharded one.
+        gen = torch.Generator().manual_seed(seed)
+        dev, f32 = self.dev, torch.float32
+        d, dr = self.ent_emb_size, self.rel_emb_size
+        ent = torch.empty(self.num_ent, d, dtype=f32)
+        _xavier_(ent, gen)
+        self.ent_emb = ent[self.shard.lo:self.shard.hi].contiguous().to(dev)
+        del ent
+        self.rel_emb = torch.empty(self.num_rel, dr, dtype=f32)
+        _xavier_(self.rel_emb, gen)
+        self.rel_emb = self.rel_emb.to(dev)
+        w = torch.empty(self.conv_filter_height, self.conv_filter_width, 1, self.C, dtype=f32)
+        _xavier_(w, gen)
+        self.conv1_weights = w.to(dev)
+        self.conv1_bias = torch.zeros(self.C, dtype=f32, device=dev)
+        ctx = [dr] + list(self.context_rel_out)
+        self.fc_weights = ContextualParameterGenerator(ctx, "fc_weights", [self.F, d], False,
+                                                       self.context_rel_use_batch_norm, dev, gen)
+        self.fc_bias = ContextualParameterGenerator(ctx, "fc_bias", [d], True,
+                                                    self.context_rel_use_batch_norm, dev, gen)
+        self.conv1_bn = _BatchNorm(self.C, dev)
+        self.fc_bn = _BatchNorm(d, dev)
+        self.pred_bias = torch.zeros(self.shard.rows, dtype=f32, device=dev)
+        self.variables = {"ent_emb": self.ent_emb, "rel_emb": self.rel_emb, "conv1_weights": self.conv1_weights,
+                          "conv1_bias": self.conv1_bias, "fc_weights": self.fc_weights, "fc_bias": self.fc_bias,
+                          "pred_bias": self.pred_bias}
+        self._identity = {}
+        self._bufs = {}
+        self._graphs = {}
+        self._build_trainables()
+        # device-resident step state: {lr_t, beta1^t, beta2^t, -} and the dropout seed
+        self.step_state = torch.tensor([0.0, self.beta1, self.beta2, 0.0], dtype=f32, device=dev)
+        self.seed_dev = torch.tensor([seed * 1000003 + 12345], dtype=torch.int64, device=dev)
+        self.clip_out = torch.zeros(2, dtype=f32, device=dev)       # {scale, norm}
+        self.global_step = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _build_trainables(self):
+        """(name, param, sharded?) for everything optimizer.compute_gradients would return (models.py:198)."""
+        tr = [("ent_emb", self.ent_emb, True), ("pred_bias", self.pred_bias, True), ("rel_emb", self.rel_emb, False),
+              ("conv1_weights", self.conv1_weights, False), ("conv1_bias", self.conv1_bias, False)]
+        for cpg in (self.fc_weights, self.fc_bias):
+            for i, p in enumerate(cpg.projections):
+                tr.append(("%s/CPG/Projection%d" % (cpg.name, i), p, False))
+            if cpg.use_batch_norm:
+                for i, bn in enumerate(cpg.bns):
+                    tr.append(("%s/CPG/Projection%d/BatchNorm/gamma" % (cpg.name, i), bn.gamma, False))
+                    tr.append(("%s/CPG/Projection%d/BatchNorm/beta" % (cpg.name, i), bn.beta, False))
+        for nm, bn in (("Conv1BN", self.conv1_bn), ("FCBN", self.fc_bn)):
+            tr.append((nm + "/gamma", bn.gamma, False))
+            tr.append((nm + "/beta", bn.beta, False))
+        self.trainables = tr
+        self.grads = {n: torch.zeros_like(p) for n, p, _ in tr}
+        self.vhat = {n: torch.zeros_like(p) for n, p, _ in tr}
+        if not self.bug_compat:
+            self.m = {n: torch.zeros_like(p) for n, p, _ in tr}
+            self.v = {n: torch.zeros_like(p) for n, p, _ in tr}
+        self.sumsq = torch.zeros(len(tr) * _lib.SUMSQ_BLOCKS, dtype=torch.float64, device=self.dev)
+
+    def _ident(self, C):
+        if C not in self._identity:
+            f = dict(dtype=torch.float32, device=self.dev)
+            self._identity[C] = (torch.ones(C, **f), torch.zeros(C, **f))
+        return self._identity[C]
+
+    # ------------------------------------------------------------------------------------------
+    def load_variables(self, params: Dict):
+        """Load variables from the oracle's naming (numpy arrays; full, unsharded tables)."""
+        def put(dst, src):
+            dst.copy_(torch.as_tensor(np.ascontiguousarray(src), dtype=torch.float32).reshape(dst.shape))
+        s = self.shard
+        put(self.ent_emb, params["ent_emb"][s.lo:s.hi])
+        put(self.pred_bias, params["pred_bias"][s.lo:s.hi])
+        put(self.rel_emb, params["rel_emb"])
+        put(self.conv1_weights, params["conv1_weights"])
+        put(self.conv1_bias, params["conv1_bias"])
+        for cpg, key in ((self.fc_weights, "fc_weights"), (self.fc_bias, "fc_bias")):
+            for t, a in zip(cpg.projections, params[key + "_proj"]):
+                put(t, a)
+            for bn, b in zip(cpg.bns, params[key + "_bn"]):
+                self._put_bn(bn, b)
+        self._put_bn(self.conv1_bn, params["Conv1BN"])
+        self._put_bn(self.fc_bn, params["FCBN"])
+
+    @staticmethod
+    def _put_bn(bn, b):
+        for k in ("gamma", "beta", "moving_mean", "moving_var"):
+            getattr(bn, k).copy_(torch.as_tensor(np.asarray(b[k]), dtype=torch.float32))
+
+    # ------------------------------------------------------------------------------------------
+    def _buffers(self, B: int):
+        """Static per-batch-size device buffers (pointer-stable -> CUDA-graph friendly)."""
+        if B in self._bufs:
+            return self._bufs[B]
+        dev, f32 = self.dev, torch.float32
+        d, dr, F, C = self.ent_emb_size, self.rel_emb_size, self.F, self.C
+        Ns = self.shard.rows
+        ld = -(-Ns // 32) * 32
+        words = -(-Ns // 32)
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        lib = _lib.load()
+        b = type("Buf", (), {})()
+        b.B, b.ld, b.words = B, ld, words
+        b.e1, b.rel, b.e2 = z(B, dt=torch.int64), z(B, dt=torch.int64), z(B, dt=torch.int64)
+        b.x0, b.r = z(B, d), z(B, dr)
+        b.z, b.f = z(B, F), z(B, F)
+        b.y, b.q = z(B, d), z(B, d)
+        b.dq, b.dy, b.df, b.dz, b.dx0, b.dr = z(B, d), z(B, d), z(B, F), z(B, F), z(B, d), z(B, dr)
+        R1 = B * self.OH * self.OW
+        nch = max(lib.coper_colstats_chunks(R1), lib.coper_colstats_chunks(B))
+        maxC = max([C, d] + self.fc_weights.hidden)
+        b.stat = z(nch * maxC * 2)
+        b.stat1 = z(maxC * 2)
+        b.SG = z(B, ld)                        # logits (eval) / dL/dS (train); never read by the host
+        b.bits = z(B, words, dt=torch.int32)
+        b.loss_sum = z(1, dt=torch.float64)
+        b.gold = z(B)
+        b.n_greater, b.n_equal = z(B, dt=torch.int32), z(B, dt=torch.int32)
+        b.dwc_part, b.dbc_part = z(B, self.conv_filter_height * self.conv_filter_width * C), z(B, C)
+        dcw = self.fc_weights.projections[-1].shape[0]
+        dcb = self.fc_bias.projections[-1].shape[0]
+        ws = max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dcw, F, d, self.prec),
+                 lib.coper_cpg_fc_bwd_workspace_bytes(B, dcw, F, d, self.prec),
+                 lib.coper_score1n_bce_workspace_bytes(B, Ns, d, self.prec),
+                 lib.coper_score1n_workspace_bytes(B, Ns, d, self.prec),
+                 lib.coper_segscatter_workspace_bytes(B))
+        b.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+        b.ws_bytes = ws
+        # context nets: activations per hidden layer for the two generators
+        b.ctx = {}
+        for cpg in (self.fc_weights, self.fc_bias):
+            b.ctx[cpg.name] = {"pre": [z(B, n) for n in cpg.hidden], "act": [z(B, n) for n in cpg.hidden],
+                               "dact": [z(B, n) for n in cpg.hidden], "dpre": [z(B, n) for n in cpg.hidden]}
+        b.dcw, b.dcb = z(B, dcw), z(B, dcb)
+        b.dr2 = z(B, dr)
+        # pinned staging for host batches
+        b.h_idx = torch.zeros(3, B, dtype=torch.int64).pin_memory()
+        b.csr_cap = 0
+        b.rowptr = z(B + 1, dt=torch.int32)
+        b.h_rowptr = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        b.col = None
+        b.h_col = None
+        b.h2d_event = None
+        self._bufs[B] = b
+        return b
+
+    def _ensure_csr(self, b, nnz):
+        if b.csr_cap < nnz:
+            cap = max(1024, int(nnz * 1.5))
+            b.col = torch.zeros(cap, dtype=torch.int32, device=self.dev)
+            b.h_col = torch.zeros(cap, dtype=torch.int32).pin_memory()
+            b.csr_cap = cap
+
+    # ------------------------------------------------------------------------------------------
+    def stage_batch(self, batch: Dict, need_e2: bool = False):
+        """Host batch -> device buffers.  Schema follows models.py:135-152: int64 ``e1``/``rel``/``e2`` [B];
+        ``e2_multi`` either as the reference's dense fp32 multi-hot [B, N] or, as the TFRecord stores it
+        (data.py:574-594), the list of positive ids in CSR form (``e2_multi_rowptr``, ``e2_multi_col``).
+        Returns (buffers, nnz or None)."""
+        e1 = batch["e1"]
+        B = int(e1.shape[0])
+        b = self._buffers(B)
+        if b.h2d_event is not None:
+            b.h2d_event.synchronize()          # previous async copies out of the pinned staging are done
+        if isinstance(e1, torch.Tensor) and e1.is_cuda:
+            b.e1.copy_(e1)
+            b.rel.copy_(batch["rel"])
+            if need_e2:
+                b.e2.copy_(batch["e2"])
+        else:
+            b.h_idx[0].copy_(torch.as_tensor(np.asarray(e1), dtype=torch.int64))
+            b.h_idx[1].copy_(torch.as_tensor(np.asarray(batch["rel"]), dtype=torch.int64))
+            if need_e2:
+                b.h_idx[2].copy_(torch.as_tensor(np.asarray(batch["e2"]), dtype=torch.int64))
+            b.e1.copy_(b.h_idx[0], non_blocking=True)
+            b.rel.copy_(b.h_idx[1], non_blocking=True)
+            if need_e2:
+                b.e2.copy_(b.h_idx[2], non_blocking=True)
+        s = self.shard
+        if "e2_multi_rowptr" in batch:
+            rp, col = batch["e2_multi_rowptr"], batch["e2_multi_col"]
+            nnz = int(col.shape[0])
+            self._ensure_csr(b, nnz)
+            if isinstance(rp, torch.Tensor) and rp.is_cuda:
+                b.rowptr.copy_(rp)
+                b.col[:nnz].copy_(col)
+            else:
+                b.h_rowptr.copy_(torch.as_tensor(np.asarray(rp), dtype=torch.int32))
+                b.h_col[:nnz].copy_(torch.as_tensor(np.asarray(col), dtype=torch.int32))
+                b.rowptr.copy_(b.h_rowptr, non_blocking=True)
+                b.col[:nnz].copy_(b.h_col[:nnz], non_blocking=True)
+            call("coper_csr_to_bits", ptr(b.rowptr), ptr(b.col), B, s.lo, s.hi, ptr(b.bits))
+        elif "e2_multi" in batch and batch["e2_multi"] is not None:
+            dense = batch["e2_multi"]
+            if not (isinstance(dense, torch.Tensor) and dense.is_cuda):
+                dense = torch.as_tensor(np.asarray(dense), dtype=torch.float32).to(self.dev, non_blocking=True)
+            if s.world > 1:
+                dense = dense[:, s.lo:s.hi].contiguous()
+            dense = dense.contiguous()
+            call("coper_dense_to_bits", ptr(dense), B, s.rows, ptr(b.bits))
+        if b.h2d_event is None:
+            b.h2d_event = torch.cuda.Event()
+        b.h2d_event.record()
+        return b
+
+    # ------------------------------------------------------------------------------------------
+    def _bn_forward(self, bn: _BatchNorm, x, R, C, b, use_batch, is_train, bessel, relu, keep_post, salt, out):
+        lib = _lib.load()
+        nch = 0
+        if use_batch:
+            nch = lib.coper_colstats_chunks(R)
+            call("coper_colstats", ptr(x), R, C, ptr(b.stat))
+        call("coper_bn_finalize", ptr(b.stat), nch, R, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
+             ptr(bn.moving_var), self.batch_norm_momentum, BN_EPS, int(use_batch), int(use_batch and is_train),
+             int(bessel), ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd))
+        call("coper_bn_act_fwd", ptr(x), R, C, ptr(bn.a), ptr(bn.b), int(relu), keep_post, ptr(self.seed_dev), salt,
+             ptr(out))
+
+    def _bn_backward(self, bn: _BatchNorm, dout, x, R, C, b, use_batch, relu, keep_post, salt_post, keep_pre,
+                     salt_pre, dx):
+        lib = _lib.load()
+        nch = lib.coper_colstats_chunks(R)
+        call("coper_bn_act_bwd_stats", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
+             int(relu), keep_post, ptr(self.seed_dev), salt_post, ptr(b.stat))
+        call("coper_bn_act_bwd_finalize", ptr(b.stat), nch, R, C, int(use_batch), ptr(bn.dgamma), ptr(bn.dbeta),
+             ptr(bn.c1), ptr(bn.c2))
+        call("coper_bn_act_bwd_apply", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
+             ptr(bn.c1), ptr(bn.c2), int(relu), keep_post, ptr(self.seed_dev), salt_post, keep_pre, salt_pre, ptr(dx))
+
+    def _ctx_forward(self, cpg: ContextualParameterGenerator, net_id, b, is_train):
+        """Hidden layers of CPG.generate (models.py:59-68): matmul -> [BN] -> relu -> dropout."""
+        h = b.r
+        B = b.B
+        keep = 1.0 - (self.context_rel_dropout if is_train else 0.0)
+        bufs = b.ctx[cpg.name]
+        for i, n in enumerate(cpg.hidden):
+            P = cpg.projections[i]
+            call("coper_sgemm", 0, 0, B, n, P.shape[0], ptr(h), P.shape[0], ptr(P), n, ptr(bufs["pre"][i]), n, 0)
+            salt = SALT_CTX + ((net_id * 64 + i) << 32)
+            if cpg.use_batch_norm:
+                use_batch = self.batch_norm_train_stats and is_train
+                self._bn_forward(cpg.bns[i], bufs["pre"][i], B, n, b, use_batch, is_train, False, True, keep, salt,
+                                 bufs["act"][i])
+            else:
+                one, zero = self._ident(n)
+                call("coper_bn_act_fwd", ptr(bufs["pre"][i]), B, n, ptr(one), ptr(zero), 1, keep,
+                     ptr(self.seed_dev), salt, ptr(bufs["act"][i]))
+            h = bufs["act"][i]
+        return h
+
+    def _ctx_backward(self, cpg: ContextualParameterGenerator, net_id, b, dctx, dr_out, accumulate):
+        """Back through the hidden layers; writes projection/BN grads, accumulates into dr_out [B,dr]."""
+        B = b.B
+        bufs = b.ctx[cpg.name]
+        keep = 1.0 - self.context_rel_dropout
+        dh = dctx
+        for i in reversed(range(len(cpg.hidden))):
+            n = cpg.hidden[i]
+            P = cpg.projections[i]
+            inp = b.r if i == 0 else bufs["act"][i - 1]
+            salt = SALT_CTX + ((net_id * 64 + i) << 32)
+            if cpg.use_batch_norm:
+                bn = cpg.bns[i]
+                use_batch = self.batch_norm_train_stats
+                self._bn_backward(bn, dh, bufs["pre"][i], B, n, b, use_batch, True, keep, salt, 1.0, 0,
+                                  bufs["dpre"][i])
+                self.grads["%s/CPG/Projection%d/BatchNorm/gamma" % (cpg.name, i)].copy_(bn.dgamma)
+                self.grads["%s/CPG/Projection%d/BatchNorm/beta" % (cpg.name, i)].copy_(bn.dbeta)
+            else:
+                one, zero = self._ident(n)
+                call("coper_bn_act_bwd_apply", ptr(dh), ptr(bufs["pre"][i]), B, n, ptr(one), ptr(zero), ptr(zero),
+                     ptr(one), ptr(zero), ptr(zero), 1, keep, ptr(self.seed_dev), salt, 1.0, 0, ptr(bufs["dpre"][i]))
+            k_in = P.shape[0]
+            # dP_i = inp^T . dpre ; dinp = dpre . P_i^T
+            call("coper_sgemm", 1, 0, k_in, n, B, ptr(inp), k_in, ptr(bufs["dpre"][i]), n,
+                 ptr(self.grads["%s/CPG/Projection%d" % (cpg.name, i)]), n, 0)
+            if i == 0:
+                call("coper_sgemm", 0, 1, B, k_in, n, ptr(bufs["dpre"][i]), n, ptr(P), n, ptr(dr_out), k_in,
+                     int(accumulate))
+            else:
+                call("coper_sgemm", 0, 1, B, k_in, n, ptr(bufs["dpre"][i]), n, ptr(P), n, ptr(bufs["dact"][i - 1]),
+                     k_in, 0)
+                dh = bufs["dact"][i - 1]
+        if not cpg.hidden:
+            if accumulate:
+                dr_out.add_(dctx)     # g_linear: context == relation embedding
+            else:
+                dr_out.copy_(dctx)
+
+    # ------------------------------------------------------------------------------------------
+    def _forward_q(self, b, is_train: bool):
+        """Lookups -> conv block -> fused CPG-FC -> FC block; leaves q in b.q (models.py:176-183, 354-426)."""
+        B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
+        s = self.shard
+        call("coper_gather_rows", ptr(self.ent_emb), s.lo, s.hi, d, ptr(b.e1), B, ptr(b.x0))
+        if self.world > 1:
+            torch.distributed.all_reduce(b.x0, group=self.group)
+        call("coper_gather_rows", ptr(self.rel_emb), 0, self.num_rel, dr, ptr(b.rel), B, ptr(b.r))
+        call("coper_conv_fwd", ptr(b.x0), B, self.H, self.W, ptr(self.conv1_weights), ptr(self.conv1_bias),
+             self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.z))
+        use_batch = self.batch_norm_train_stats and is_train
+        keep1 = 1.0 - (self.hidden_dropout if is_train else 0.0)
+        self._bn_forward(self.conv1_bn, b.z, B * self.OH * self.OW, C, b, use_batch, is_train, True, True, keep1,
+                         SALT_FEATURE_MAP, b.f)
+        cw = self._ctx_forward(self.fc_weights, 0, b, is_train)
+        cb = self._ctx_forward(self.fc_bias, 1, b, is_train)
+        Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
+        keep2 = 1.0 - (self.output_dropout if is_train else 0.0)
+        call("coper_cpg_fc_fwd", ptr(cw), ptr(b.f), ptr(Pw), ptr(cb), ptr(Pb), B, Pw.shape[0], F, d, Pb.shape[0],
+             keep2, ptr(self.seed_dev), SALT_OUTPUT, ptr(b.y), ptr(b.ws), b.ws_bytes, self.prec)
+        self._bn_forward(self.fc_bn, b.y, B, d, b, use_batch, is_train, False, True, 1.0, 0, b.q)
+        b.cw, b.cb = cw, cb
+
+    def _train_device(self, b):
+        """fwd + bwd + clip + AMSGrad on staged buffers; everything is enqueued, nothing syncs."""
+        B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
+        s, g = self.shard, self.grads
+        Ns = s.rows
+        call("coper_step_state_advance", ptr(self.step_state), ptr(self.seed_dev), self.learning_rate, self.beta1,
+             self.beta2)
+        self._forward_q(b, True)
+        pos = np.float32(np.float32(1.0 - self.label_smoothing_epsilon) * np.float32(1.0)
+                         + np.float32(1.0 / self.num_ent))                     # models.py:450 in fp32
+        neg = np.float32(1.0 / self.num_ent)
+        inv_count = 1.0 / (float(B) * float(self.num_ent))                   # mean over B*N (models.py:451)
+        call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), ptr(b.bits), B, Ns, d,
+             float(pos), float(neg), inv_count, ptr(b.loss_sum), ptr(b.SG), b.ld, ptr(b.dq), ptr(g["ent_emb"]),
+             ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes, self.prec)
+        if self.world > 1:
+            # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial
+            # loss and the partial dq = G_shard . E_shard; dE / dbias stay local.
+            torch.distributed.all_reduce(b.loss_sum, group=self.group)
+            torch.distributed.all_reduce(b.dq, group=self.group)
+        use_batch = self.batch_norm_train_stats
+        keep1, keep2 = 1.0 - self.hidden_dropout, 1.0 - self.output_dropout
+        # FC block backward: relu -> FCBN -> output dropout (models.py:414-419)
+        self._bn_backward(self.fc_bn, b.dq, b.y, B, d, b, use_batch, True, 1.0, 0, keep2, SALT_OUTPUT, b.dy)
+        g["FCBN/gamma"].copy_(self.fc_bn.dgamma)
+        g["FCBN/beta"].copy_(self.fc_bn.dbeta)
+        Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
+        nw, nb = len(self.fc_weights.projections) - 1, len(self.fc_bias.projections) - 1
+        call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(b.cb), ptr(Pb), ptr(b.dy), B, Pw.shape[0], F, d,
+             Pb.shape[0], ptr(g["fc_weights/CPG/Projection%d" % nw]), ptr(g["fc_bias/CPG/Projection%d" % nb]),
+             ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws), b.ws_bytes, self.prec)
+        self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
+        self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
+        # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)
+        R1 = B * self.OH * self.OW
+        self._bn_backward(self.conv1_bn, b.df, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz)
+        g["Conv1BN/gamma"].copy_(self.conv1_bn.dgamma)
+        g["Conv1BN/beta"].copy_(self.conv1_bn.dbeta)
+        call("coper_conv_bwd", ptr(b.dz), ptr(b.x0), B, self.H, self.W, ptr(self.conv1_weights),
+             self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.dx0), ptr(b.dwc_part), ptr(b.dbc_part))
+        KK = self.conv_filter_height * self.conv_filter_width * C
+        call("coper_reduce_partials", ptr(b.dwc_part), B, KK, 1.0, 0, ptr(g["conv1_weights"]))
+        call("coper_reduce_partials", ptr(b.dbc_part), B, C, 1.0, 0, ptr(g["conv1_bias"]))
+        # gradients of the two embedding gathers (models.py:176-178): deterministic segmented scatter
+        call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(b.ws),
+             b.ws_bytes)
+        g["rel_emb"].zero_()
+        call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]), 0, self.num_rel, ptr(b.ws),
+             b.ws_bytes)
+        self._clip_and_apply()
+
+    def _clip_and_apply(self):
+        """tf.clip_by_global_norm(5.0) (models.py:199) + AMSGrad apply (amsgrad.py:130-159)."""
+        for i, (n, p, _) in enumerate(self.trainables):
+            call("coper_sumsq", ptr(self.grads[n]), p.numel(), i, ptr(self.sumsq))
+        if self.world > 1:
+            # trainables 0,1 (ent_emb, pred_bias) are row-sharded: their squared norms add across ranks;
+            # every other gradient is replicated (identical on all ranks) and is counted once.
+            torch.distributed.all_reduce(self.sumsq[:2 * _lib.SUMSQ_BLOCKS], group=self.group)
+        call("coper_clip_scale", ptr(self.sumsq), len(self.trainables), CLIP_NORM, ptr(self.clip_out))
+        for n, p, _ in self.trainables:
+            m = None if self.bug_compat else self.m[n]
+            v = None if self.bug_compat else self.v[n]
+            call("coper_amsgrad_step", ptr(p), ptr(self.grads[n]), ptr(m), ptr(v), ptr(self.vhat[n]), p.numel(),
+                 ptr(self.step_state), self.beta1, self.beta2, self.adam_eps, ptr(self.clip_out),
+                 int(self.bug_compat))
+
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, batch: Dict, apply_update: bool = True):
+        """One reference training step (run_cpg.py:210-219).  Returns the loss as a 0-d device tensor
+        (float64 -> call .item() to read it; that is the step's only device->host transfer)."""
+        b = self.stage_batch(batch)
+        if not apply_update:
+            saved = self._clip_and_apply
+            self._clip_and_apply = lambda: None
+            try:
+                self._train_device(b)
+            finally:
+                self._clip_and_apply = saved
+        else:
+            self._train_device(b)
+        self.global_step += 1
+        return b.loss_sum[0] / (float(b.B) * float(self.num_ent))
+
+    def predict_all(self, batch: Dict):
+        """Logits of every query against this rank's entity rows: [B, rows] view (metrics.py:40-42)."""
+        b = self.stage_batch(batch)
+        self._forward_q(b, False)
+        self._score(b)
+        return b.SG[:, :self.shard.rows]
+
+    def _score(self, b):
+        call("coper_score1n_fwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), b.B, self.shard.rows,
+             self.ent_emb_size, ptr(b.SG), b.ld, ptr(b.ws), b.ws_bytes, self.prec)
+
+    def filtered_ranks(self, batch: Dict):
+        """Filtered rank of ``e2`` for each query (metrics.py:44-51) computed on device.
+        ``batch['e2_multi*']`` is the filter set (all known true tails).  Returns int32 device tensors
+        (rank, n_equal); rank == the reference's rank whenever n_equal == 0."""
+        if not (isinstance(batch["e2"], torch.Tensor) and batch["e2"].is_cuda):   # host batches are validated
+            e2 = np.asarray(batch["e2"])
+            if int(e2.min()) < 0 or int(e2.max()) >= self.num_ent:
+                raise ValueError("e2 out of range (train rows carry e2 = -1 in the reference; SURVEY Q17)")
+        b = self.stage_batch(batch, need_e2=True)
+        self._forward_q(b, False)
+        self._score(b)
+        s = self.shard
+        call("coper_gold_scores", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold))
+        if self.world > 1:
+            torch.distributed.all_reduce(b.gold, group=self.group)
+        b.n_greater.zero_()
+        b.n_equal.zero_()
+        call("coper_filtered_rank", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits),
+             ptr(b.n_greater), ptr(b.n_equal))
+        if self.world > 1:
+            torch.distributed.all_reduce(b.n_greater, group=self.group)
+            torch.distributed.all_reduce(b.n_equal, group=self.group)
+        return b.n_greater + 1, b.n_equal

@@ -1,0 +1,212 @@
+/*
+ * coper.h — C ABI of libcoper_sm100.so: the B200 (sm_100a) kernels behind the CoPER-ConvE hot path.
+ *
+ * The reference (otiliastr/coper, CoPER_ConvE/qa_cpg) has no FFI: its "operators" are the TensorFlow-1
+ * stock ops called from models.py / metrics.py.  Each entry point below therefore cites the reference
+ * call site (file:line under /root/reference/CoPER_ConvE/qa_cpg/) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 (COPER_OK) or a negative coper_status; no exceptions, no allocation:
+ *     all buffers (inputs, outputs, workspaces) are caller-owned DEVICE pointers; workspace sizes come
+ *     from the matching *_workspace_bytes function.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns
+ *     immediately (no host synchronisation) -> every entry point is CUDA-graph capturable.
+ *   - tensors are dense row-major fp32 unless stated; index tensors are int64 (TF's e1/e2/rel dtype,
+ *     models.py:141-143) or int32 where noted.
+ *   - `prec` selects the arithmetic of the GEMM-shaped kernels: COPER_PREC_FP32 = CUDA-core FFMA,
+ *     fp32 operands and accumulation (parity path, <=1e-5 rel); COPER_PREC_BF16 = tcgen05 kind::f16 with
+ *     bf16 operands / fp32 TMEM accumulators; COPER_PREC_TF32X3 = tcgen05 kind::tf32 with 3-term error
+ *     compensation (hi*hi + hi*lo + lo*hi), fp32-class accuracy on the tensor pipe.
+ *   - dropout is a counter-based hash of (seed, element index): keep iff hash32 < keep * 2^32
+ *     (coper_dropout_mask exports the same mask for the oracle).  keep >= 1 disables it.  The seed is
+ *     (*seed_dev + salt): seed_dev is a device uint64 the step-state kernel bumps once per step (so a
+ *     captured CUDA graph draws fresh masks on every replay); seed_dev may be NULL (= 0).
+ */
+#ifndef COPER_H_
+#define COPER_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* coper_stream_t; /* cudaStream_t */
+
+typedef enum {
+  COPER_OK = 0,
+  COPER_ERR_INVALID_ARG = -1,
+  COPER_ERR_CUDA = -2,
+  COPER_ERR_UNSUPPORTED = -3,
+  COPER_ERR_WORKSPACE = -4
+} coper_status;
+
+enum { COPER_PREC_FP32 = 0, COPER_PREC_BF16 = 1, COPER_PREC_TF32X3 = 2 };
+
+int coper_version(void);
+const char* coper_status_string(int status);
+/* last cudaError_t observed by a failing call on this thread (0 if none) */
+int coper_last_cuda_error(void);
+/* number of kernels this library has launched in this process (bench.py reports the per-step delta) */
+long long coper_launch_count(void);
+/* 1 if the running device is compute capability 10.x (tcgen05 paths usable), 0 otherwise, <0 on error */
+int coper_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * a2 / K1 — tf.nn.embedding_lookup (models.py:176,178): out[i,:] = table[idx[i],:]
+ * With [row_lo,row_hi) != [0,n_rows) only locally-owned rows are written, others are zero-filled
+ * (entity-sharded lookup: an all-reduce(sum) of the outputs then delivers every row exactly). */
+int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int width,
+                      const int64_t* idx, int n_idx, float* out, coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a5 / K4 — tf.nn.conv2d NHWC, 1 input channel, stride 1, VALID (+ bias) (models.py:355,382-385;
+ * per-query filters: models.py:375-380).  x0 [B, H*W] -> z [B, OH*OW*C] in (h,w,c) order.
+ * wc [KH,KW,C] / bc [C], or [B,KH,KW,C] / [B,C] when per_query != 0. */
+int coper_conv_fwd(const float* x0, int B, int H, int W, const float* wc, const float* bc, int KH, int KW,
+                   int C, int per_query, float* z, coper_stream_t stream);
+/* backward of the above: dz [B,OH*OW*C] -> dx0 [B,H*W]; shared filters: per-sample partials
+ * dwc_part [B, KH*KW*C], dbc_part [B, C] (reduce over B with coper_reduce_partials);
+ * per_query: the same buffers ARE the per-query gradients. */
+int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const float* wc, int KH, int KW,
+                   int C, int per_query, float* dx0, float* dwc_part, float* dbc_part, coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5 — tf.layers.batch_normalization (+relu, +dropout) on x [R, C] with C fastest
+ * (Conv1BN models.py:386-391 with R=B*OH*OW; FCBN :416-419 with R=B; CPG hidden BN :60-68).
+ *   coper_colstats      : per-column partial (sum, sumsq) -> partials [nchunk, C, 2]; nchunk = coper_colstats_chunks(R)
+ *   coper_bn_finalize   : use_batch_stats ? batch mean / biased var : moving stats  -> affine a,b
+ *                         (out = a*x + b), mean, invstd; optionally updates moving stats in place with
+ *                         TF semantics moving = moving*momentum + batch*(1-momentum)
+ *                         (bessel != 0: unbiased variance for the moving update, the fused 4-D path).
+ *   coper_bn_act_fwd    : out = dropout_post(relu?(a[c]*x + b[c]))
+ *   coper_bn_act_bwd_*  : g1 = dout * dropout_post * relu'(a*x+b); stats (sum g1, sum g1*xhat) ->
+ *                         dgamma, dbeta, and dx = a*(g1 - c1 - xhat*c2) [* dropout_pre]. */
+int coper_colstats_chunks(int64_t R);
+int coper_colstats(const float* x, int64_t R, int C, float* partials, coper_stream_t stream);
+int coper_bn_finalize(const float* partials, int nchunk, int64_t R, int C, const float* gamma, const float* beta,
+                      float* moving_mean, float* moving_var, float momentum, float eps, int use_batch_stats,
+                      int update_moving, int bessel, float* a, float* b, float* mean, float* invstd,
+                      coper_stream_t stream);
+int coper_bn_act_fwd(const float* x, int64_t R, int C, const float* a, const float* b, int relu,
+                     float keep_post, const uint64_t* seed_dev, uint64_t salt_post, float* out, coper_stream_t stream);
+int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
+                           const float* mean, const float* invstd, int relu, float keep_post,
+                           const uint64_t* seed_dev, uint64_t salt_post, float* partials, coper_stream_t stream);
+int coper_bn_act_bwd_finalize(const float* partials, int nchunk, int64_t R, int C, int use_batch_stats,
+                              float* dgamma, float* dbeta, float* c1, float* c2, coper_stream_t stream);
+int coper_bn_act_bwd_apply(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
+                           const float* mean, const float* invstd, const float* c1, const float* c2, int relu,
+                           float keep_post, const uint64_t* seed_dev, uint64_t salt_post, float keep_pre,
+                           uint64_t salt_pre, float* dx, coper_stream_t stream);
+/* mask[i] = 1.0f if element i is kept (same hash as the kernels) — exported for the oracle/tests */
+int coper_dropout_mask(int64_t n, float keep, const uint64_t* seed_dev, uint64_t salt, float* mask,
+                       coper_stream_t stream);
+/* x[i] = x[i] * mask(i)/keep (used for the CPG hidden-layer dropout, models.py:67-68) */
+int coper_dropout_apply(float* x, int64_t n, float keep, const uint64_t* seed_dev, uint64_t salt,
+                        coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a3+a6 / K2+K3 — fused contextual-parameter generate-and-apply (models.py:70-73 + :412):
+ *     y[b,:] = f[b,:] . reshape(c[b,:] . P, [F,d]) + cb[b,:] . Pb   ==   (c (x) f) . P^ + cb . Pb
+ * c [B,dc] (relation embedding, or last CPG hidden activation), f [B,F], P [dc, F*d] (viewed [dc,F,d]),
+ * cb [B,dcb], Pb [dcb,d].  The per-query weights [B,F,d] are never formed.  Output-dropout
+ * (models.py:414-415) is applied to y when keep_out < 1.  workspace: coper_cpg_fc_fwd_workspace_bytes. */
+size_t coper_cpg_fc_fwd_workspace_bytes(int B, int dc, int F, int d, int prec);
+int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb, int B,
+                     int dc, int F, int d, int dcb, float keep_out, const uint64_t* seed_dev, uint64_t salt_out,
+                     float* y, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
+/* backward (models.py:198 autodiff of the above): given dy [B,d] (already through the dropout mask)
+ *   dP [dc,F*d], dPb [dcb,d], df [B,F], dc_out [B,dc], dcb_out [B,dcb]. */
+size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec);
+int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb,
+                     const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
+                     float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
+                     coper_stream_t stream);
+
+/* plain C = op(A) . op(B) (+C) for the small dense layers around the path (CPG hidden projections,
+ * models.py:60): row-major; transX != 0 means the stored matrix is the transpose of the operand. */
+int coper_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                float* C, int ldc, int accumulate, coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a7 / K6 — 1-N scorer logits (models.py:433-437): scores[b,n] = q[b,:].E[n,:] + bias[n]
+ * E is this rank's shard [Ns, d] (rows of the entity table), scores [B, ld_scores]. */
+size_t coper_score1n_workspace_bytes(int B, int64_t Ns, int d, int prec);
+int coper_score1n_fwd(const float* q, const float* E, const float* bias, int B, int64_t Ns, int d, float* scores,
+                      int64_t ld_scores, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
+
+/* a7+a9+a10 / K6-K8 — scorer + label-smoothed sigmoid-BCE + its gradient (models.py:433-437,448-453,198):
+ *   s = q.E^T + bias;  z' = bit ? pos_target : neg_target   (pos = (1-eps)+1/N, neg = 1/N; models.py:450)
+ *   loss_sum = sum_{b,n} max(s,0) - s z' + log1p(exp(-|s|))   (caller divides by B*N_total)
+ *   G[b,n]   = (sigmoid(s) - z') * inv_count                    (inv_count = 1/(B*N_total))
+ *   dq = G.E, dE = G^T.q, dbias = sum_b G.
+ * label_bits [B, words] (words = ceil(Ns/32), bit n of row b = 1 iff entity n is a positive of query b);
+ * G [B, ldG] is caller-provided scratch (never read by the host).  loss_sum is a device double. */
+size_t coper_score1n_bce_workspace_bytes(int B, int64_t Ns, int d, int prec);
+int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const float* bias, const uint32_t* label_bits,
+                              int B, int64_t Ns, int d, float pos_target, float neg_target, float inv_count,
+                              double* loss_sum, float* G, int64_t ldG, float* dq, float* dE, float* dbias,
+                              void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
+
+/* labels / filters: CSR positives (rowptr int32 [B+1], col int32 [nnz], global entity ids) -> bit rows for
+ * the shard [ent_lo, ent_hi); replaces the dense fp32 multi-hot of data.py:182-186,318-322. */
+int coper_csr_to_bits(const int32_t* rowptr, const int32_t* col, int B, int64_t ent_lo, int64_t ent_hi,
+                      uint32_t* bits, coper_stream_t stream);
+/* dense fp32 multi-hot [B, N] (the reference batch schema, models.py:144) -> bits (value == 1.0f) */
+int coper_dense_to_bits(const float* dense, int B, int64_t N, uint32_t* bits, coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a11 / K10 — filtered rank (metrics.py:44-51): for each query b over this shard's scores [B, ld]
+ *   n_greater[b] += #{n : n != gold, !filter[b,n], s[b,n] >  gold_score[b]}
+ *   n_equal[b]   += #{n : n != gold, !filter[b,n], s[b,n] == gold_score[b]}
+ * rank = 1 + sum over shards of n_greater.  gold_local[b] = e2[b] - ent_lo (may be out of range).
+ * coper_gold_scores extracts gold_score[b] = scores[b, gold_local[b]] (0 if not owned). Counts are
+ * ACCUMULATED into n_greater / n_equal (zero them first). */
+int coper_gold_scores(const float* scores, int64_t ld, int B, int64_t Ns, const int64_t* e2, int64_t ent_lo,
+                      float* gold, coper_stream_t stream);
+int coper_filtered_rank(const float* scores, int64_t ld, int B, int64_t Ns, const int64_t* e2, int64_t ent_lo,
+                        const float* gold, const uint32_t* filter_bits, int32_t* n_greater, int32_t* n_equal,
+                        coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a10 scatter / K8(3) — gradient of the embedding gathers (IndexedSlices -> dense, models.py:198):
+ *   dst[idx[i] - row_lo, :] += src[i, :] for row_lo <= idx[i] < row_hi; one writer per destination row
+ *   (sort by key, warp per segment, fixed summation order) -> deterministic. */
+size_t coper_segscatter_workspace_bytes(int M);
+int coper_segscatter_add(const int64_t* idx, int M, const float* src, int width, float* dst, int64_t row_lo,
+                         int64_t row_hi, void* workspace, size_t workspace_bytes, coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * generic deterministic reductions
+ *   coper_reduce_partials: out[n] = (accumulate ? out[n] : 0) + scale * sum_s in[s, n]   (fixed order, fp64 acc)
+ *   coper_sumsq          : partials[slot*COPER_SUMSQ_BLOCKS + blk] = sum of squares of a strided chunk of x
+ *   coper_clip_scale     : norm = sqrt(sum of partials[0 .. n_slots*COPER_SUMSQ_BLOCKS)); out[0] = clip / max(norm, clip);
+ *                          out[1] = norm  (tf.clip_by_global_norm, models.py:199). */
+#define COPER_SUMSQ_BLOCKS 256
+int coper_reduce_partials(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
+                          coper_stream_t stream);
+int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_stream_t stream);
+int coper_clip_scale(const double* partials, int n_slots, float clip_norm, float* out2, coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * f-1 — AMSGrad dense apply (utils/amsgrad.py:130-159) with the clip scale read from device memory:
+ *   g = grad * clip_scale[0];
+ *   bug_compat != 0 (reference as written: m, v slots never accumulate; m/v may be NULL):
+ *       vhat = max(vhat, (1-b2) g^2);  theta -= lr_t * (1-b1) g / (sqrt(vhat) + eps)
+ *   else (textbook): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; vhat = max(vhat, v); theta -= lr_t m/(sqrt(vhat)+eps)
+ * lr_t = lr * sqrt(1-b2^t)/(1-b1^t) (amsgrad.py:137) is read from step_state[0] on the device.
+ * coper_step_state_advance (1 thread): step_state = {lr_t, beta1_power, beta2_power, unused};
+ *   lr_t <- lr*sqrt(1-b2p)/(1-b1p); then b1p *= b1, b2p *= b2 (amsgrad.py:230-241; powers start at b1, b2);
+ *   *seed_dev += 1 (fresh dropout masks).  Call once per step BEFORE the update kernels. */
+int coper_step_state_advance(float* step_state, uint64_t* seed_dev, float lr, float beta1, float beta2,
+                             coper_stream_t stream);
+int coper_amsgrad_step(float* theta, const float* grad, float* m, float* v, float* vhat, int64_t n,
+                       const float* step_state, float beta1, float beta2, float eps, const float* clip_scale,
+                       int bug_compat, coper_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COPER_H_ */

@@ -1,0 +1,48 @@
+"""The C-ABI library builds, loads without a GPU and exports exactly what include/coper.h declares."""
+import os
+import re
+
+from coper_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "coper.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(coper_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_builds_and_loads():
+    build.build()
+    lib = _lib.load()
+    assert lib.coper_version() >= 100
+    assert lib.coper_status_string(-3) == b"unsupported configuration"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    build.build()
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "declared in coper.h but not exported: " + n
+        assert n in _lib.SIGNATURES, "declared in coper.h but not bound in _lib.SIGNATURES: " + n
+    for n in _lib.SIGNATURES:
+        assert n in names, "bound but not declared in coper.h: " + n
+
+
+def test_workspace_queries_run_without_gpu():
+    lib = _lib.load()
+    assert lib.coper_colstats_chunks(1000) == 2
+    assert lib.coper_cpg_fc_fwd_workspace_bytes(512, 8, 4608, 200, 0) > 0
+    assert lib.coper_score1n_bce_workspace_bytes(512, 40943, 200, 0) > 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "coper_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

@@ -1,0 +1,324 @@
+"""Per-kernel GPU parity through the C ABI at BASELINE shapes (WN18RR / FB15k-237 dims) and edge cases.
+
+Checker = numpy fp64 restatements from ``oracle`` (small enough to finish in seconds) plus size-independent
+properties (linearity, count identities, permutation invariance) at the larger sizes.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import conve_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+@pytest.fixture(scope="module")
+def L():
+    from coper_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def ws_buf(nbytes):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------ gather / scatter
+def test_gather_rows_full_and_sharded(L):
+    rng = np.random.default_rng(0)
+    N, w, M = 1000, 200, 77
+    tab = rng.normal(size=(N, w)).astype(np.float32)
+    idx = rng.integers(0, N, M)
+    out = torch.zeros(M, w, device="cuda")
+    L.call("coper_gather_rows", L.ptr(dev(tab)), 0, N, w, L.ptr(dev(idx, torch.int64)), M, L.ptr(out))
+    assert np.array_equal(out.cpu().numpy(), tab[idx])
+    lo, hi = 256, 640
+    L.call("coper_gather_rows", L.ptr(dev(tab[lo:hi])), lo, hi, w, L.ptr(dev(idx, torch.int64)), M, L.ptr(out))
+    exp = np.where(((idx >= lo) & (idx < hi))[:, None], tab[idx], 0)
+    assert np.array_equal(out.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("M,rows,w", [(512, 97, 200), (1, 5, 8), (4096, 11, 37), (300, 100000, 256)])
+def test_segscatter_deterministic_and_exact(L, M, rows, w):
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, rows, M)
+    idx[: M // 3] = idx[0]                                         # a hub row
+    src = rng.normal(size=(M, w)).astype(np.float32)
+    base = rng.normal(size=(rows, w)).astype(np.float32)
+    ws = ws_buf(L.load().coper_segscatter_workspace_bytes(M))
+    outs = []
+    for _ in range(2):
+        dst = dev(base)
+        L.call("coper_segscatter_add", L.ptr(dev(idx, torch.int64)), M, L.ptr(dev(src)), w, L.ptr(dst), 0, rows,
+               L.ptr(ws), ws.numel())
+        outs.append(dst.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    exp = base.astype(np.float64)
+    np.add.at(exp, idx, src.astype(np.float64))
+    assert np.abs(outs[0] - exp).max() < 1e-4 * max(1.0, np.abs(exp).max())
+    # sharded: only rows in [lo, hi) are touched
+    lo, hi = rows // 4, rows // 4 + max(1, rows // 2)
+    dst = dev(base[lo:hi])
+    L.call("coper_segscatter_add", L.ptr(dev(idx, torch.int64)), M, L.ptr(dev(src)), w, L.ptr(dst), lo, hi,
+           L.ptr(ws), ws.numel())
+    assert np.abs(dst.cpu().numpy() - exp[lo:hi]).max() < 1e-4 * max(1.0, np.abs(exp).max())
+
+
+# ------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("B,H,W", [(5, 10, 20), (64, 16, 16), (3, 10, 4)])
+def test_conv_fwd_bwd(L, B, H, W):
+    rng = np.random.default_rng(2)
+    KH = KW = 3
+    C = 32
+    OH, OW = H - 2, W - 2
+    x = rng.normal(size=(B, H, W))
+    wc = rng.normal(size=(KH, KW, C))
+    bc = rng.normal(size=C)
+    z = torch.zeros(B, OH * OW * C, device="cuda")
+    L.call("coper_conv_fwd", L.ptr(dev(x, torch.float32)), B, H, W, L.ptr(dev(wc, torch.float32)),
+           L.ptr(dev(bc, torch.float32)), KH, KW, C, 0, L.ptr(z))
+    Z = O._conv_valid(x, wc) + bc
+    assert relerr(z.cpu().numpy().reshape(Z.shape), Z) < 1e-5
+    dz = rng.normal(size=Z.shape)
+    dx = torch.zeros(B, H * W, device="cuda")
+    dwp = torch.zeros(B, KH * KW * C, device="cuda")
+    dbp = torch.zeros(B, C, device="cuda")
+    L.call("coper_conv_bwd", L.ptr(dev(dz, torch.float32)), L.ptr(dev(x, torch.float32)), B, H, W,
+           L.ptr(dev(wc, torch.float32)), KH, KW, C, 0, L.ptr(dx), L.ptr(dwp), L.ptr(dbp))
+    dW = np.zeros_like(wc)
+    dX = np.zeros_like(x)
+    for i in range(KH):
+        for j in range(KW):
+            dW[i, j] = np.einsum("bhw,bhwc->c", x[:, i:i + OH, j:j + OW], dz)
+            dX[:, i:i + OH, j:j + OW] += dz @ wc[i, j]
+    assert relerr(dx.cpu().numpy().reshape(dX.shape), dX) < 1e-5
+    assert relerr(dwp.cpu().numpy().sum(0).reshape(dW.shape), dW) < 1e-4
+    assert relerr(dbp.cpu().numpy().sum(0), dz.sum(axis=(0, 1, 2))) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ fused CPG-FC
+def _cpg_ref(c, f, P, cb, Pb):
+    B, dc = c.shape
+    F = f.shape[1]
+    d = Pb.shape[1]
+    kr = (c[:, :, None] * f[:, None, :]).reshape(B, dc * F)
+    return kr @ P.reshape(dc * F, d) + cb @ Pb
+
+
+@pytest.mark.parametrize("B,dc,F,d", [(512, 8, 4608, 200), (7, 5, 192, 40), (130, 3, 1000, 72), (64, 32, 512, 200)])
+def test_cpg_fc_fwd_bwd(L, B, dc, F, d):
+    rng = np.random.default_rng(3)
+    c = rng.normal(size=(B, dc))
+    f = np.maximum(rng.normal(size=(B, F)), 0)
+    P = rng.normal(size=(dc, F * d)) * 0.01
+    cb = rng.normal(size=(B, dc))
+    Pb = rng.normal(size=(dc, d))
+    lib = L.load()
+    ws = ws_buf(max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dc, F, d, 0), lib.coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, 0)))
+    tc, tf, tP, tcb, tPb = (dev(a, torch.float32) for a in (c, f, P, cb, Pb))
+    y = torch.zeros(B, d, device="cuda")
+    L.call("coper_cpg_fc_fwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), L.ptr(tcb), L.ptr(tPb), B, dc, F, d, dc, 1.0, None, 0,
+           L.ptr(y), L.ptr(ws), ws.numel(), 0)
+    yr = _cpg_ref(c, f, P, cb, Pb)
+    assert relerr(y.cpu().numpy(), yr) < 1e-5
+    dy = rng.normal(size=(B, d))
+    dP = torch.zeros(dc, F * d, device="cuda")
+    dPb = torch.zeros(dc, d, device="cuda")
+    df = torch.zeros(B, F, device="cuda")
+    dcw = torch.zeros(B, dc, device="cuda")
+    dcb = torch.zeros(B, dc, device="cuda")
+    L.call("coper_cpg_fc_bwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), L.ptr(tcb), L.ptr(tPb), L.ptr(dev(dy, torch.float32)),
+           B, dc, F, d, dc, L.ptr(dP), L.ptr(dPb), L.ptr(df), L.ptr(dcw), L.ptr(dcb), L.ptr(ws), ws.numel(), 0)
+    P3 = P.reshape(dc, F, d)
+    T = np.einsum("bj,kij->bki", dy, P3)
+    assert relerr(df.cpu().numpy(), np.einsum("bk,bki->bi", c, T)) < 2e-5
+    assert relerr(dcw.cpu().numpy(), np.einsum("bi,bki->bk", f, T)) < 2e-5
+    kr = (c[:, :, None] * f[:, None, :]).reshape(B, dc * F)
+    assert relerr(dP.cpu().numpy(), (kr.T @ dy).reshape(dc, F * d)) < 2e-5
+    assert relerr(dPb.cpu().numpy(), cb.T @ dy) < 2e-5
+    assert relerr(dcb.cpu().numpy(), dy @ Pb.T) < 2e-5
+
+
+def test_cpg_fc_fb15k_shape_linearity(L):
+    """FB15k-237 shape (dc=32, F=4608, d=200, B=512): y is linear in c and in f (size-independent property)."""
+    B, dc, F, d = 512, 32, 4608, 200
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    c1, c2, f, P = r(B, dc), r(B, dc), r(B, F).clamp_(min=0), r(dc, F * d) * 0.01
+    cb, Pb = torch.zeros(B, dc, device="cuda"), torch.zeros(dc, d, device="cuda")
+    lib = L.load()
+    ws = ws_buf(lib.coper_cpg_fc_fwd_workspace_bytes(B, dc, F, d, 0))
+
+    def run(c, ff):
+        y = torch.zeros(B, d, device="cuda")
+        L.call("coper_cpg_fc_fwd", L.ptr(c), L.ptr(ff), L.ptr(P), L.ptr(cb), L.ptr(Pb), B, dc, F, d, dc, 1.0, None, 0,
+               L.ptr(y), L.ptr(ws), ws.numel(), 0)
+        return y
+    y1, y2, y12 = run(c1, f), run(c2, f), run((c1 + 2 * c2).contiguous(), f)
+    assert relerr(y12.cpu().numpy(), (y1 + 2 * y2).cpu().numpy()) < 2e-5
+    # spot-check 8 rows against fp64
+    rows = [0, 1, 77, 128, 255, 300, 510, 511]
+    yr = _cpg_ref(c1[rows].double().cpu().numpy(), f[rows].double().cpu().numpy(), P.double().cpu().numpy(),
+                  cb[rows].double().cpu().numpy(), Pb.double().cpu().numpy())
+    assert relerr(y1[rows].cpu().numpy(), yr) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ scorer + BCE
+@pytest.mark.parametrize("B,N,d", [(512, 40943, 200), (7, 97, 40), (130, 1003, 200), (33, 5000, 256)])
+def test_score1n_fwd_and_bce(L, B, N, d):
+    rng = np.random.default_rng(4)
+    q = np.maximum(rng.normal(size=(B, d)), 0)
+    E = rng.uniform(-0.05, 0.05, size=(N, d))
+    bias = rng.normal(size=N) * 0.1
+    ld = -(-N // 32) * 32
+    tq, tE, tb = dev(q, torch.float32), dev(E, torch.float32), dev(bias, torch.float32)
+    S = torch.zeros(B, ld, device="cuda")
+    L.call("coper_score1n_fwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), B, N, d, L.ptr(S), ld, None, 0, 0)
+    Sr = q.astype(np.float32).astype(np.float64) @ E.astype(np.float32).astype(np.float64).T + bias.astype(np.float32)
+    assert relerr(S[:, :N].cpu().numpy(), Sr) < 1e-5
+    # BCE + gradient
+    cfg = O.OracleConfig(num_ent=N, num_rel=2, ent_emb_size=d, rel_emb_size=2, conv_in_height=d // 4 if d % 10 else 10)
+    _, _, _, rowptr, col = O.synthetic_batch(cfg, B, seed=9, mean_pos=4.0)
+    words = -(-N // 32)
+    bits = torch.zeros(B, words, dtype=torch.int32, device="cuda")
+    L.call("coper_csr_to_bits", L.ptr(dev(rowptr, torch.int32)), L.ptr(dev(col, torch.int32)), B, 0, N, L.ptr(bits))
+    z = O.csr_to_dense(rowptr, col, N, np.float64)
+    pos = np.float32(np.float32(0.9) + np.float32(1.0 / N))
+    neg = np.float32(1.0 / N)
+    zs = np.where(z > 0, np.float64(pos), np.float64(neg))
+    lib = L.load()
+    ws = ws_buf(lib.coper_score1n_bce_workspace_bytes(B, N, d, 0))
+    G = torch.zeros(B, ld, device="cuda")
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dq, dE, db = torch.zeros(B, d, device="cuda"), torch.zeros(N, d, device="cuda"), torch.zeros(N, device="cuda")
+    inv = 1.0 / (B * N)
+    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
+           inv, L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE), L.ptr(db), L.ptr(ws), ws.numel(), 0)
+    el = np.maximum(Sr, 0) - Sr * zs + np.log1p(np.exp(-np.abs(Sr)))
+    Gr = (O.sigmoid(Sr) - zs) * inv
+    assert abs(loss.item() - el.sum()) < 1e-6 * el.sum()
+    assert relerr(G[:, :N].cpu().numpy(), Gr) < 1e-5
+    q32, E32 = q.astype(np.float32).astype(np.float64), E.astype(np.float32).astype(np.float64)
+    assert relerr(dq.cpu().numpy(), Gr @ E32) < 1e-4
+    assert relerr(dE.cpu().numpy(), Gr.T @ q32) < 1e-4
+    assert relerr(db.cpu().numpy(), Gr.sum(0)) < 1e-4
+    # dense multi-hot schema builds the same bit rows
+    bits2 = torch.zeros_like(bits)
+    L.call("coper_dense_to_bits", L.ptr(dev(z, torch.float32)), B, N, L.ptr(bits2))
+    assert torch.equal(bits, bits2)
+
+
+# ------------------------------------------------------------------------------------------ filtered rank
+@pytest.mark.parametrize("B,N", [(512, 40943), (3, 5), (64, 1000003), (17, 4096), (1, 33)])
+def test_filtered_rank_bit_exact(L, B, N):
+    rng = np.random.default_rng(5)
+    ld = -(-N // 32) * 32
+    S = rng.normal(size=(B, ld)).astype(np.float32)
+    if N >= 4096:
+        S[:, ::7] = S[:, [0]]                                    # plenty of exact ties
+    e2 = rng.integers(0, N, B)
+    filt = rng.random((B, N)) < 0.03
+    filt[np.arange(B), e2] = True                                # the gold is always a known true tail
+    words = -(-N // 32)
+    packed = np.zeros((B, words * 32), bool)
+    packed[:, :N] = filt
+    bits = np.packbits(packed.reshape(B, words, 32), axis=2, bitorder="little").view(np.uint32).reshape(B, words)
+    tS, te2, tb = dev(S), dev(e2, torch.int64), dev(bits.view(np.int32))
+    gold = torch.zeros(B, device="cuda")
+    L.call("coper_gold_scores", L.ptr(tS), ld, B, N, L.ptr(te2), 0, L.ptr(gold))
+    assert np.array_equal(gold.cpu().numpy(), S[np.arange(B), e2])
+    ng = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ne = torch.zeros(B, dtype=torch.int32, device="cuda")
+    L.call("coper_filtered_rank", L.ptr(tS), ld, B, N, L.ptr(te2), 0, L.ptr(gold), L.ptr(tb), L.ptr(ng), L.ptr(ne))
+    rc, eq = O.rank_count(S[:, :N], e2, filt.astype(np.float32))
+    assert np.array_equal(ng.cpu().numpy() + 1, rc)
+    assert np.array_equal(ne.cpu().numpy(), eq)
+    # sharding property: integer partial counts over any split of the entity range add up exactly
+    cut = (N // 3) // 32 * 32
+    if cut > 0:
+        ng2 = torch.zeros(B, dtype=torch.int32, device="cuda")
+        ne2 = torch.zeros(B, dtype=torch.int32, device="cuda")
+        for lo, hi in ((0, cut), (cut, N)):
+            Ss = dev(np.ascontiguousarray(S[:, lo:hi]))
+            fb = np.zeros((B, -(-(hi - lo) // 32) * 32), bool)
+            fb[:, :hi - lo] = filt[:, lo:hi]
+            bs = np.packbits(fb.reshape(B, -1, 32), axis=2, bitorder="little").view(np.uint32).reshape(B, -1)
+            L.call("coper_filtered_rank", L.ptr(Ss), hi - lo, B, hi - lo, L.ptr(te2), lo, L.ptr(gold),
+                   L.ptr(dev(bs.view(np.int32))), L.ptr(ng2), L.ptr(ne2))
+        assert torch.equal(ng, ng2) and torch.equal(ne, ne2)
+
+
+# ------------------------------------------------------------------------------------------ BN / optimizer pieces
+def test_bn_train_and_eval_paths(L):
+    rng = np.random.default_rng(6)
+    R, C = 73728 // 8, 32
+    x = rng.normal(1.0, 2.0, size=(R, C))
+    bn = {"gamma": rng.normal(1, 0.1, C), "beta": rng.normal(0, 0.1, C), "moving_mean": rng.normal(0, 0.1, C),
+          "moving_var": rng.uniform(0.5, 1.5, C)}
+    lib = L.load()
+    nch = lib.coper_colstats_chunks(R)
+    tx = dev(x, torch.float32)
+    part = torch.zeros(nch * C * 2, device="cuda")
+    t = {k: dev(v, torch.float32) for k, v in bn.items()}
+    a, b, mean, inv = (torch.zeros(C, device="cuda") for _ in range(4))
+    out = torch.zeros(R, C, device="cuda")
+    for use_batch in (1, 0):
+        L.call("coper_colstats", L.ptr(tx), R, C, L.ptr(part))
+        L.call("coper_bn_finalize", L.ptr(part), nch, R, C, L.ptr(t["gamma"]), L.ptr(t["beta"]),
+               L.ptr(t["moving_mean"]), L.ptr(t["moving_var"]), 0.9, 1e-3, use_batch, 0, 1, L.ptr(a), L.ptr(b),
+               L.ptr(mean), L.ptr(inv))
+        L.call("coper_bn_act_fwd", L.ptr(tx), R, C, L.ptr(a), L.ptr(b), 1, 1.0, None, 0, L.ptr(out))
+        ref, cache, mm, mv = O._bn_forward(x, bn, bool(use_batch), True, 0.9)
+        assert relerr(out.cpu().numpy(), np.maximum(ref, 0)) < 1e-5
+
+
+def test_amsgrad_and_clip(L):
+    rng = np.random.default_rng(7)
+    n = 100003
+    th, g = rng.normal(size=n).astype(np.float32), (rng.normal(size=n) * 3).astype(np.float32)
+    tth, tg = dev(th), dev(g)
+    vhat = torch.zeros(n, device="cuda")
+    part = torch.zeros(256, dtype=torch.float64, device="cuda")
+    clip = torch.zeros(2, device="cuda")
+    state = torch.tensor([0.0, 0.9, 0.999, 0.0], device="cuda")
+    seed = torch.zeros(1, dtype=torch.int64, device="cuda")
+    L.call("coper_step_state_advance", L.ptr(state), L.ptr(seed), 1e-3, 0.9, 0.999)
+    L.call("coper_sumsq", L.ptr(tg), n, 0, L.ptr(part))
+    L.call("coper_clip_scale", L.ptr(part), 1, 5.0, L.ptr(clip))
+    norm = np.sqrt((g.astype(np.float64) ** 2).sum())
+    assert abs(clip[1].item() - norm) < 1e-6 * norm
+    assert abs(clip[0].item() - 5.0 / norm) < 1e-6
+    L.call("coper_amsgrad_step", L.ptr(tth), L.ptr(tg), None, None, L.ptr(vhat), n, L.ptr(state), 0.9, 0.999, 1e-8,
+           L.ptr(clip), 1)
+    opt = O.AMSGradOracle(1e-3)
+    th64 = th.astype(np.float64)
+    opt.apply({"x": (th64, g.astype(np.float64) * (5.0 / norm))})
+    assert relerr(tth.cpu().numpy(), th64) < 1e-6
+    assert seed.item() == 1 and abs(state[1].item() - 0.81) < 1e-6
+
+
+def test_sgemm_all_layouts(L):
+    rng = np.random.default_rng(8)
+    M, N, K = 130, 77, 301
+    A, Bm = rng.normal(size=(M, K)), rng.normal(size=(K, N))
+    ref = A @ Bm
+    for ta in (0, 1):
+        for tb in (0, 1):
+            a = dev(A.T if ta else A, torch.float32).contiguous()
+            b = dev(Bm.T if tb else Bm, torch.float32).contiguous()
+            c = torch.zeros(M, N, device="cuda")
+            L.call("coper_sgemm", ta, tb, M, N, K, L.ptr(a), a.shape[1], L.ptr(b), b.shape[1], L.ptr(c), N, 0)
+            assert relerr(c.cpu().numpy(), ref) < 1e-5

@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 path, ``prec='fp32'``):
+  * logits / activations: max|gpu - oracle64| <= 1e-5 * max|oracle64|   (BASELINE north_star: 1e-5 rel)
+  * loss: 1e-6 relative
+  * gradients: <= 2e-4 * max|grad| (fp32 accumulation over B*N / B*F*dc products vs the fp64 oracle)
+  * filtered ranks, MR/MRR/Hits: bit-exact against the oracle ranking of the SAME device logits.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import conve_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def descriptors(cfg: O.OracleConfig, lr=1e-3):
+    return {"use_negative_sampling": False, "label_smoothing_epsilon": cfg.label_smoothing_epsilon,
+            "num_ent": cfg.num_ent, "num_rel": cfg.num_rel, "ent_emb_size": cfg.ent_emb_size,
+            "rel_emb_size": cfg.rel_emb_size, "concat_rel": False, "context_rel_conv": None,
+            "context_rel_out": list(cfg.context_rel_out), "context_rel_dropout": cfg.context_rel_dropout,
+            "context_rel_use_batch_norm": cfg.context_rel_use_batch_norm, "input_dropout": 0.2,
+            "hidden_dropout": cfg.hidden_dropout, "output_dropout": cfg.output_dropout, "learning_rate": lr,
+            "batch_size": 0, "add_loss_summaries": False, "add_variable_summaries": False,
+            "add_tensor_summaries": False, "batch_norm_momentum": cfg.batch_norm_momentum,
+            "batch_norm_train_stats": cfg.batch_norm_train_stats, "do_parameter_lookup": False}
+
+
+def make(cfg, params, **kw):
+    from coper_b200.models import ConvE
+    m = ConvE(descriptors(cfg, kw.pop("lr", 1e-3)), conv_in_height=cfg.conv_in_height, **kw)
+    m.load_variables(params)
+    return m
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+def export_masks(model, cfg, B):
+    """Dropout keep-masks of the step that just ran, from the library's own hash (coper_dropout_mask)."""
+    from coper_b200._lib import call, ptr
+    from coper_b200 import models as M
+
+    def mask(n, keep, salt):
+        t = torch.zeros(n, dtype=torch.float32, device=model.dev)
+        call("coper_dropout_mask", n, keep, ptr(model.seed_dev), salt, ptr(t))
+        return t.cpu().numpy() > 0.5
+    OH, OW = cfg.conv_out_hw
+    C = cfg.conv_num_channels
+    masks = {}
+    if cfg.hidden_dropout > 0:
+        masks["feature_map"] = mask(B * OH * OW * C, 1 - cfg.hidden_dropout, M.SALT_FEATURE_MAP).reshape(B, OH, OW, C)
+    if cfg.output_dropout > 0:
+        masks["output"] = mask(B * cfg.ent_emb_size, 1 - cfg.output_dropout, M.SALT_OUTPUT).reshape(B, -1)
+    if cfg.context_rel_dropout > 0 and cfg.context_rel_out:
+        for key, net in (("ctx_w", 0), ("ctx_b", 1)):
+            masks[key] = [mask(B * n, 1 - cfg.context_rel_dropout, M.SALT_CTX + ((net * 64 + i) << 32)).reshape(B, n)
+                          for i, n in enumerate(cfg.context_rel_out)]
+    return masks
+
+
+def batch_of(e1, rel, e2, rowptr, col, dense=None):
+    b = {"e1": e1, "rel": rel, "e2": e2}
+    if dense is not None:
+        b["e2_multi"] = dense
+    else:
+        b["e2_multi_rowptr"], b["e2_multi_col"] = rowptr, col
+    return b
+
+
+def grads_by_name(model):
+    g = {k: v.detach().cpu().numpy() for k, v in model.grads.items()}
+    return g
+
+
+def compare_grads(model, g, cfg, tol=2e-4):
+    mg = grads_by_name(model)
+    nw = len(g["fc_weights_proj"])
+    checks = [("ent_emb", g["ent_emb"]), ("pred_bias", g["pred_bias"]), ("rel_emb", g["rel_emb"]),
+              ("conv1_weights", g["conv1_weights"]), ("conv1_bias", g["conv1_bias"]),
+              ("FCBN/gamma", g["FCBN"]["gamma"]), ("FCBN/beta", g["FCBN"]["beta"]),
+              ("Conv1BN/gamma", g["Conv1BN"]["gamma"]), ("Conv1BN/beta", g["Conv1BN"]["beta"])]
+    for i in range(nw):
+        checks.append(("fc_weights/CPG/Projection%d" % i, g["fc_weights_proj"][i]))
+        checks.append(("fc_bias/CPG/Projection%d" % i, g["fc_bias_proj"][i]))
+    if cfg.context_rel_use_batch_norm:
+        for i in range(nw - 1):
+            checks.append(("fc_weights/CPG/Projection%d/BatchNorm/gamma" % i, g["fc_weights_bn"][i]["gamma"]))
+            checks.append(("fc_bias/CPG/Projection%d/BatchNorm/beta" % i, g["fc_bias_bn"][i]["beta"]))
+    scale = max(np.abs(v).max() for _, v in checks)
+    for name, ref in checks:
+        got = mg[name].reshape(ref.shape)
+        # gradients that are analytically ~0 (e.g. conv bias under batch-stat BN) are compared on the global scale
+        err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-4 * scale)
+        assert err < tol, "%s: rel err %.3e" % (name, err)
+
+
+CASES = {
+    # name: (cfg kwargs, B)
+    "toy_glinear_eval_stats": (dict(num_ent=97, num_rel=6, ent_emb_size=40, rel_emb_size=5, context_rel_out=[],
+                                    batch_norm_train_stats=False), 7),
+    "toy_glinear_batch_stats": (dict(num_ent=97, num_rel=6, ent_emb_size=40, rel_emb_size=5, context_rel_out=[],
+                                     batch_norm_train_stats=True, batch_norm_momentum=0.9), 7),
+    "toy_glinear_dropout": (dict(num_ent=131, num_rel=6, ent_emb_size=40, rel_emb_size=5, context_rel_out=[],
+                                 batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 33),
+    "toy_gmlp_bn_dropout": (dict(num_ent=97, num_rel=6, ent_emb_size=40, rel_emb_size=5, context_rel_out=[6],
+                                 context_rel_use_batch_norm=True, context_rel_dropout=0.2,
+                                 batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 19),
+    "toy_gmlp_nobn": (dict(num_ent=97, num_rel=6, ent_emb_size=40, rel_emb_size=5, context_rel_out=[6, 4],
+                           context_rel_use_batch_norm=False, context_rel_dropout=0.2,
+                           batch_norm_train_stats=False), 19),
+    "ragged_mid": (dict(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[],
+                        batch_norm_train_stats=True, batch_norm_momentum=0.1, hidden_dropout=0.3,
+                        output_dropout=0.2), 130),
+    "d256_16x16": (dict(num_ent=515, num_rel=10, ent_emb_size=256, rel_emb_size=4, context_rel_out=[],
+                        conv_in_height=16, batch_norm_train_stats=True), 40),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_train_step_parity(name):
+    kw, B = CASES[name]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5)
+    # duplicate head entities / relations in the batch (segmented scatter)
+    e1[B // 2:] = e1[: B - B // 2]
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    model = make(cfg, params)
+    loss = model.train_step(batch_of(e1, rel, e2, rowptr, col), apply_update=False)
+    loss = float(loss.item())
+    masks = export_masks(model, cfg, B)
+    out = O.forward(params, cfg, e1, rel, True, masks, dense, np.float64)
+    g = O.backward(out, cfg)
+    b = model._bufs[B]
+    assert relerr(b.x0.cpu().numpy(), out["x0"]) < 1e-7
+    assert relerr(b.f.cpu().numpy(), out["f"]) < 1e-5
+    assert relerr(b.q.cpu().numpy(), out["q"]) < 1e-5
+    assert abs(loss - out["loss"]) < 1e-6 * abs(out["loss"])
+    assert relerr(b.SG[:, :cfg.num_ent].cpu().numpy(), g["_G"]) < 1e-5
+    assert relerr(b.dq.cpu().numpy(), g["_dq"]) < 1e-4
+    assert relerr(b.dy.cpu().numpy(), g["_dy"]) < 1e-4
+    assert relerr(b.df.cpu().numpy(), g["_df"]) < 1e-4
+    assert relerr(b.dr.cpu().numpy(), g["_dr"]) < 2e-4
+    assert relerr(b.dx0.cpu().numpy(), g["_dx0"]) < 2e-4
+    compare_grads(model, g, cfg)
+    # moving statistics (TF momentum semantics; Bessel only on the fused 4-D Conv1BN)
+    mm, mv = out["moving"]["Conv1BN"]
+    assert relerr(model.conv1_bn.moving_mean.cpu().numpy(), mm) < 1e-5
+    assert relerr(model.conv1_bn.moving_var.cpu().numpy(), mv) < 1e-5
+    mm, mv = out["moving"]["FCBN"]
+    assert relerr(model.fc_bn.moving_mean.cpu().numpy(), mm) < 1e-5
+    assert relerr(model.fc_bn.moving_var.cpu().numpy(), mv) < 1e-5
+
+
+def test_dense_label_schema_equals_csr():
+    """The reference's dense fp32 e2_multi [B,N] (models.py:144) and the CSR id lists give the same step."""
+    kw, B = CASES["toy_glinear_batch_stats"]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5)
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    m1, m2 = make(cfg, params), make(cfg, params)
+    l1 = m1.train_step(batch_of(e1, rel, e2, rowptr, col), apply_update=False).item()
+    l2 = m2.train_step(batch_of(e1, rel, e2, None, None, dense), apply_update=False).item()
+    assert l1 == l2
+    for k in m1.grads:
+        assert torch.equal(m1.grads[k], m2.grads[k]), k
+
+
+@pytest.mark.parametrize("name", ["toy_glinear_eval_stats", "toy_gmlp_bn_dropout", "ragged_mid", "d256_16x16"])
+def test_eval_scores_and_ranks(name):
+    kw, B = CASES[name]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=4, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=6, mean_pos=6.0)
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    model = make(cfg, params)
+    batch = batch_of(e1, rel, e2, rowptr, col)
+    S = model.predict_all(batch).cpu().numpy()
+    out = O.forward(params, cfg, e1, rel, False, None, None, np.float64)
+    assert relerr(S, out["scores"]) < 1e-5
+    rank, n_equal = model.filtered_ranks(batch)
+    rank, n_equal = rank.cpu().numpy(), n_equal.cpu().numpy()
+    # bit-exact vs the reference's literal argsort ranking of the device logits
+    lit = O.rank_literal(S, e2, dense)
+    cnt, ne = O.rank_count(S, e2, dense)
+    assert (n_equal == ne).all()
+    assert (rank == cnt).all()
+    if ne.sum() == 0:
+        assert (rank == lit).all()
+
+
+def test_ranking_and_hits_matches_reference_metrics():
+    from coper_b200.metrics import ranking_and_hits
+    kw, _ = CASES["ragged_mid"]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=8, bias_noise=0.05)
+    model = make(cfg, params)
+    batches, all_ranks = [], []
+    for i, B in enumerate([64, 64, 17]):                       # ragged last batch
+        e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=20 + i, mean_pos=5.0)
+        batches.append(batch_of(e1, rel, e2, rowptr, col))
+        S = model.predict_all(batches[-1]).cpu().numpy()
+        all_ranks.append(O.rank_literal(S, e2, O.csr_to_dense(rowptr, col, cfg.num_ent)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        mr, mrr, hits = ranking_and_hits(model, td, iter(batches), "test")
+    emr, emrr, ehits = O.summarize_ranks(np.concatenate(all_ranks))
+    assert mr == emr and mrr == emrr
+    assert all(hits[k] == ehits[k] for k in ehits)
+
+
+def test_multi_step_training_matches_oracle_amsgrad():
+    """5 full steps (fwd, bwd, clip 5.0, AMSGrad as written in the reference) track the fp64 oracle."""
+    kw, B = CASES["toy_glinear_batch_stats"]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    model = make(cfg, params, lr=1e-2)
+    p64 = O.cast_params(params, np.float64)
+    opt = O.AMSGradOracle(1e-2)
+    for step in range(5):
+        e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=50 + step)
+        dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+        loss = model.train_step(batch_of(e1, rel, e2, rowptr, col)).item()
+        out = O.forward(p64, cfg, e1, rel, True, None, dense, np.float64)
+        g = O.backward(out, cfg)
+        assert abs(loss - out["loss"]) < 2e-5 * abs(out["loss"]), step
+        flat = {"ent_emb": g["ent_emb"], "rel_emb": g["rel_emb"], "conv1_weights": g["conv1_weights"],
+                "conv1_bias": g["conv1_bias"], "pred_bias": g["pred_bias"], "fcw": g["fc_weights_proj"][0],
+                "fcb": g["fc_bias_proj"][0], "bn1g": g["Conv1BN"]["gamma"], "bn1b": g["Conv1BN"]["beta"],
+                "bn2g": g["FCBN"]["gamma"], "bn2b": g["FCBN"]["beta"]}
+        clipped, norm = O.clip_by_global_norm(list(flat.values()), 5.0)
+        assert abs(float(model.clip_out[1].item()) - norm) < 1e-4 * norm
+        th = {"ent_emb": p64["ent_emb"], "rel_emb": p64["rel_emb"], "conv1_weights": p64["conv1_weights"],
+              "conv1_bias": p64["conv1_bias"], "pred_bias": p64["pred_bias"], "fcw": p64["fc_weights_proj"][0],
+              "fcb": p64["fc_bias_proj"][0], "bn1g": p64["Conv1BN"]["gamma"], "bn1b": p64["Conv1BN"]["beta"],
+              "bn2g": p64["FCBN"]["gamma"], "bn2b": p64["FCBN"]["beta"]}
+        opt.apply({k: (th[k], c) for k, c in zip(flat.keys(), clipped)})
+        for nm in ("Conv1BN", "FCBN"):
+            p64[nm]["moving_mean"], p64[nm]["moving_var"] = out["moving"][nm]
+    assert relerr(model.ent_emb.cpu().numpy(), p64["ent_emb"]) < 5e-4
+    assert relerr(model.fc_weights.projections[0].cpu().numpy(), p64["fc_weights_proj"][0]) < 5e-4
+    assert relerr(model.rel_emb.cpu().numpy(), p64["rel_emb"]) < 5e-4
+
+
+def test_train_step_is_deterministic():
+    kw, B = CASES["ragged_mid"]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5)
+    e1[:] = e1[0]                                            # worst case: one hub entity
+    outs = []
+    for _ in range(2):
+        m = make(cfg, params)
+        m.train_step(batch_of(e1, rel, e2, rowptr, col), apply_update=False)
+        outs.append({k: v.clone() for k, v in m.grads.items()})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
