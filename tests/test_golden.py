@@ -1,0 +1,268 @@
+"""Golden-vector tests.  tests/golden/*.npz were minted by ``oracle/gen_golden.py`` from the reference's own,
+unmodified ``metrics.py`` (real NumPy) and ``models.py`` + ``utils/amsgrad.py`` (on the TF-1 API shim).
+
+CPU part (``-m "not gpu"``): pins the oracle to those vectors.
+GPU part (``-m gpu``): compares the CUDA path (through the C ABI) with the same vectors directly.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import conve_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODEL_CASES = sorted(os.path.basename(p)[len("ref_model_"):-4] for p in glob.glob(os.path.join(GOLD, "ref_model_*.npz")))
+METRIC_CASES = sorted(os.path.basename(p)[len("ref_metrics_"):-4]
+                      for p in glob.glob(os.path.join(GOLD, "ref_metrics_*.npz")))
+# mirrors oracle/gen_golden.py CASES
+CASE_CFG = {
+    "glinear_eval": dict(ctx=[], bn_train=False, usebn=False, drop=(0.0, 0.0, 0.0), is_train=False, d=40, C=32),
+    "glinear_train": dict(ctx=[], bn_train=True, usebn=False, drop=(0.3, 0.2, 0.0), is_train=True, d=30, C=8),
+    "glinear_train_movingstats": dict(ctx=[], bn_train=False, usebn=False, drop=(0.3, 0.2, 0.0), is_train=True,
+                                      d=30, C=8),
+    "gmlp_train": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, d=30, C=8),
+    "gmlp_eval": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, d=30, C=8),
+}
+LR = 1e-2
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+def assert_grads_close(grads, z, case, tol=2e-4):
+    scale = max(np.abs(v).max() for v in grads.values())
+    for k, v in grads.items():
+        ref = z["step0/grad/" + k]
+        if k == "conv1_bias" and case["bn_train"] and case["is_train"]:
+            # analytically zero under batch-statistics BN: both sides are fp32 rounding noise
+            assert np.abs(v).max() < 1e-4 * scale and np.abs(ref).max() < 1e-4 * scale
+            continue
+        err = np.abs(v.reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-3 * scale)
+        assert err < tol, (k, err)
+
+
+def cfg_of(case):
+    return O.OracleConfig(num_ent=97, num_rel=6, ent_emb_size=case["d"], rel_emb_size=5, context_rel_out=case["ctx"],
+                          conv_num_channels=case["C"], hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
+                          context_rel_dropout=case["drop"][2], context_rel_use_batch_norm=case["usebn"],
+                          batch_norm_train_stats=case["bn_train"], batch_norm_momentum=0.9)
+
+
+def _bn(z, pre, name, n):
+    if pre + name + "/gamma" in z.files:
+        return {"gamma": z[pre + name + "/gamma"], "beta": z[pre + name + "/beta"],
+                "moving_mean": z[pre + name + "/moving_mean"], "moving_var": z[pre + name + "/moving_variance"]}
+    return O._bn_init(n)
+
+
+def params_of(z, pre, case):
+    n = len(case["ctx"]) + 1
+    p = {k: z[pre + k] for k in ("ent_emb", "rel_emb", "conv1_weights", "conv1_bias", "pred_bias")}
+    for which in ("fc_weights", "fc_bias"):
+        p[which + "_proj"] = [z[pre + "%s/CPG/Projection%d" % (which, i)] for i in range(n)]
+        p[which + "_bn"] = [_bn(z, pre, "%s/CPG/Projection%d/BatchNorm" % (which, i), case["ctx"][i])
+                            for i in range(n - 1)]
+    p["Conv1BN"] = _bn(z, pre, "Conv1BN", case["C"])
+    p["FCBN"] = _bn(z, pre, "FCBN", case["d"])
+    return p
+
+
+def masks_of(z, step, case):
+    pre = "step%d/" % step
+    m = {"feature_map": z[pre + "mask_fm"], "output": z[pre + "mask_out"]}
+    m["ctx_w"] = [z[pre + "mask_cw%d" % i] for i in range(len(case["ctx"]))]
+    m["ctx_b"] = [z[pre + "mask_cb%d" % i] for i in range(len(case["ctx"]))]
+    return m
+
+
+def named_grads(g, case):
+    """oracle.backward output keyed by the reference's variable names."""
+    out = {"ent_emb": g["ent_emb"], "rel_emb": g["rel_emb"], "conv1_weights": g["conv1_weights"],
+           "conv1_bias": g["conv1_bias"], "pred_bias": g["pred_bias"], "Conv1BN/gamma": g["Conv1BN"]["gamma"],
+           "Conv1BN/beta": g["Conv1BN"]["beta"], "FCBN/gamma": g["FCBN"]["gamma"], "FCBN/beta": g["FCBN"]["beta"]}
+    for which in ("fc_weights", "fc_bias"):
+        for i, a in enumerate(g[which + "_proj"]):
+            out["%s/CPG/Projection%d" % (which, i)] = a
+        if case["usebn"]:
+            for i, t in enumerate(g[which + "_bn"]):
+                out["%s/CPG/Projection%d/BatchNorm/gamma" % (which, i)] = t["gamma"]
+                out["%s/CPG/Projection%d/BatchNorm/beta" % (which, i)] = t["beta"]
+    return out
+
+
+def named_params(p, case):
+    out = {k: p[k] for k in ("ent_emb", "rel_emb", "conv1_weights", "conv1_bias", "pred_bias")}
+    for nm in ("Conv1BN", "FCBN"):
+        out[nm + "/gamma"], out[nm + "/beta"] = p[nm]["gamma"], p[nm]["beta"]
+    for which in ("fc_weights", "fc_bias"):
+        for i, a in enumerate(p[which + "_proj"]):
+            out["%s/CPG/Projection%d" % (which, i)] = a
+        if case["usebn"]:
+            for i, t in enumerate(p[which + "_bn"]):
+                out["%s/CPG/Projection%d/BatchNorm/gamma" % (which, i)] = t["gamma"]
+                out["%s/CPG/Projection%d/BatchNorm/beta" % (which, i)] = t["beta"]
+    return out
+
+
+# ================================================================================================ CPU: oracle pinned
+@pytest.mark.parametrize("name", METRIC_CASES)
+def test_oracle_ranking_matches_reference_metrics(name):
+    z = np.load(os.path.join(GOLD, "ref_metrics_%s.npz" % name))
+    lit = O.rank_literal(z["pred"], z["e2"], z["e2_multi"])
+    cnt, ne = O.rank_count(z["pred"], z["e2"], z["e2_multi"])
+    assert ne.sum() == 0
+    assert np.array_equal(lit, z["ranks"]) and np.array_equal(cnt, z["ranks"])
+    mr, mrr, hits = O.summarize_ranks(lit, tuple(int(k) for k in z["hits_levels"]))
+    assert mr == float(z["mr"]) and mrr == float(z["mrr"])
+    assert [hits[int(k)] for k in z["hits_levels"]] == list(z["hits_values"])
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_oracle_forward_backward_matches_reference_model(name):
+    case = CASE_CFG[name]
+    cfg = cfg_of(case)
+    z = np.load(os.path.join(GOLD, "ref_model_%s.npz" % name))
+    p = params_of(z, "init/", case)
+    e1, rel = z["step0/e1"], z["step0/rel"]
+    dense = O.csr_to_dense(z["step0/rowptr"], z["step0/col"], cfg.num_ent)
+    out = O.forward(p, cfg, e1, rel, case["is_train"], masks_of(z, 0, case), dense, np.float64)
+    assert relerr(out["scores"], z["step0/predictions_all"]) < 1e-5
+    assert relerr(out["q"], z["step0/predicted_e2_emb"]) < 1e-5
+    assert abs(out["loss"] - float(z["step0/loss"])) < 2e-6 * abs(out["loss"])
+    assert_grads_close(named_grads(O.backward(out, cfg), case), z, case)
+
+
+@pytest.mark.parametrize("name", [n for n in MODEL_CASES if CASE_CFG[n]["is_train"]])
+def test_oracle_multi_step_training_matches_reference(name):
+    """fwd + bwd + clip_by_global_norm(5.0) + AMSGrad exactly as the reference's optimizer code executes it."""
+    case = CASE_CFG[name]
+    cfg = cfg_of(case)
+    z = np.load(os.path.join(GOLD, "ref_model_%s.npz" % name))
+    p = O.cast_params(params_of(z, "init/", case), np.float64)
+    opt = O.AMSGradOracle(LR, reference_bug_compat=True)
+    for step in range(3):
+        pre = "step%d/" % step
+        dense = O.csr_to_dense(z[pre + "rowptr"], z[pre + "col"], cfg.num_ent)
+        out = O.forward(p, cfg, z[pre + "e1"], z[pre + "rel"], True, masks_of(z, step, case), dense, np.float64)
+        assert abs(out["loss"] - float(z[pre + "loss"])) < 1e-4 * abs(out["loss"]), step
+        g = named_grads(O.backward(out, cfg), case)
+        names = list(g)
+        clipped, _ = O.clip_by_global_norm([g[k] for k in names], 5.0)
+        th = named_params(p, case)
+        opt.apply({k: (th[k], c.reshape(th[k].shape)) for k, c in zip(names, clipped)})
+        for nm in ("Conv1BN", "FCBN"):
+            p[nm]["moving_mean"], p[nm]["moving_var"] = out["moving"][nm]
+        for which, key in (("fc_weights", "ctx_w"), ("fc_bias", "ctx_b")):
+            for i, upd in enumerate(out["moving"][key]):
+                if upd is not None:
+                    p[which + "_bn"][i]["moving_mean"], p[which + "_bn"][i]["moving_var"] = upd
+        after = params_of(z, pre + "after/", case)
+        for k, v in named_params(p, case).items():
+            if k == "conv1_bias" and case["bn_train"]:
+                continue   # its gradient is pure rounding noise under batch-stat BN; AMSGrad's g/sqrt(g^2) amplifies it
+            ref = named_params(after, case)[k]
+            assert relerr(v, ref) < 2e-4, (step, k)
+        assert relerr(p["Conv1BN"]["moving_var"], after["Conv1BN"]["moving_var"]) < 1e-5
+        assert relerr(p["FCBN"]["moving_mean"], after["FCBN"]["moving_mean"]) < 1e-5
+        # the reference's dense AMSGrad never accumulates m / v (amsgrad.py:142-151)
+        assert np.abs(z[pre + "after/ent_emb/AMSGrad/m"]).max() == 0.0
+        assert np.abs(z[pre + "after/ent_emb/AMSGrad/v"]).max() == 0.0
+
+
+def test_dropout_hash_restatement_is_uniform():
+    from oracle import dropout_hash as DH
+    m = DH.keep_mask(200000, 0.7, 12346, DH.SALT_FEATURE_MAP)
+    assert abs(m.mean() - 0.7) < 5e-3
+    assert DH.keep_mask(10, 1.0, 1, 2).all()
+
+
+# ================================================================================================ GPU: CUDA vs goldens
+def _model(case, p, lr=LR):
+    from coper_b200.models import ConvE
+    md = {"use_negative_sampling": False, "label_smoothing_epsilon": 0.1, "num_ent": 97, "num_rel": 6,
+          "ent_emb_size": case["d"], "rel_emb_size": 5, "concat_rel": False, "conv_num_channels": case["C"],
+          "context_rel_conv": None, "context_rel_out": case["ctx"], "context_rel_dropout": case["drop"][2],
+          "context_rel_use_batch_norm": case["usebn"], "input_dropout": 0.2, "hidden_dropout": case["drop"][0],
+          "output_dropout": case["drop"][1], "learning_rate": lr, "batch_size": 0, "add_loss_summaries": False,
+          "add_variable_summaries": False, "add_tensor_summaries": False, "batch_norm_momentum": 0.9,
+          "batch_norm_train_stats": case["bn_train"], "do_parameter_lookup": False}
+    m = ConvE(md, seed=0)
+    m.load_variables(p)
+    return m
+
+
+def _batch(z, step):
+    pre = "step%d/" % step
+    return {"e1": z[pre + "e1"], "rel": z[pre + "rel"], "e2": z[pre + "e2"], "e2_multi_rowptr": z[pre + "rowptr"],
+            "e2_multi_col": z[pre + "col"]}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in MODEL_CASES if not CASE_CFG[n]["is_train"]])
+def test_cuda_eval_scores_match_reference_model(name):
+    case = CASE_CFG[name]
+    z = np.load(os.path.join(GOLD, "ref_model_%s.npz" % name))
+    m = _model(case, params_of(z, "init/", case))
+    S = m.predict_all(_batch(z, 0)).cpu().numpy()
+    assert relerr(S, z["step0/predictions_all"]) < 1e-5
+    assert relerr(m._bufs[len(z["step0/e1"])].q.cpu().numpy(), z["step0/predicted_e2_emb"]) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in MODEL_CASES if CASE_CFG[n]["is_train"]])
+def test_cuda_training_matches_reference_model(name):
+    """Gradients of step 0 and three full optimizer steps (same dropout masks: the goldens were generated with the
+    library's hash masks for ConvE(seed=0))."""
+    case = CASE_CFG[name]
+    z = np.load(os.path.join(GOLD, "ref_model_%s.npz" % name))
+    p0 = params_of(z, "init/", case)
+    m = _model(case, p0)
+    loss = m.train_step(_batch(z, 0), apply_update=False).item()
+    assert abs(loss - float(z["step0/loss"])) < 2e-6 * abs(loss)
+    assert_grads_close({k: v.cpu().numpy() for k, v in m.grads.items()}, z, case)
+    m = _model(case, p0)
+    for step in range(3):
+        loss = m.train_step(_batch(z, step)).item()
+        assert abs(loss - float(z["step%d/loss" % step])) < 1e-4 * abs(loss), step
+    after = named_params(params_of(z, "step2/after/", case), case)
+    got = {n: t.cpu().numpy() for n, t, _ in m.trainables}
+    for k, ref in after.items():
+        if k == "conv1_bias" and case["bn_train"]:
+            continue       # noise-driven under batch-stat BN (see the CPU test above)
+        assert relerr(got[k].reshape(ref.shape), ref) < 5e-4, k
+    assert relerr(m.conv1_bn.moving_var.cpu().numpy(), z["step2/after/Conv1BN/moving_variance"]) < 1e-4
+    assert relerr(m.fc_bn.moving_mean.cpu().numpy(), z["step2/after/FCBN/moving_mean"]) < 1e-4
+    assert relerr(m.vhat["ent_emb"].cpu().numpy(), z["step2/after/ent_emb/AMSGrad/v_hat"]) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", METRIC_CASES)
+def test_cuda_filtered_rank_matches_reference_metrics(name):
+    import torch
+    from coper_b200 import _lib as L
+    z = np.load(os.path.join(GOLD, "ref_metrics_%s.npz" % name))
+    pred, e2, filt = z["pred"], z["e2"], z["e2_multi"]
+    B, N = pred.shape
+    ld = -(-N // 32) * 32
+    S = np.zeros((B, ld), np.float32)
+    S[:, :N] = pred
+    tS, te2 = torch.as_tensor(S).cuda(), torch.as_tensor(e2).cuda()
+    tdense = torch.as_tensor(filt).cuda()
+    words = -(-N // 32)
+    bits = torch.zeros(B, words, dtype=torch.int32, device="cuda")
+    L.call("coper_dense_to_bits", L.ptr(tdense), B, N, L.ptr(bits))
+    gold = torch.zeros(B, device="cuda")
+    ng = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ne = torch.zeros(B, dtype=torch.int32, device="cuda")
+    L.call("coper_gold_scores", L.ptr(tS), ld, B, N, L.ptr(te2), 0, L.ptr(gold))
+    L.call("coper_filtered_rank", L.ptr(tS), ld, B, N, L.ptr(te2), 0, L.ptr(gold), L.ptr(bits), L.ptr(ng), L.ptr(ne))
+    assert int(ne.sum().item()) == 0
+    ranks = (ng + 1).cpu().numpy()
+    assert np.array_equal(ranks, z["ranks"])
+    mr, mrr, hits = O.summarize_ranks(ranks, tuple(int(k) for k in z["hits_levels"]))
+    assert mr == float(z["mr"]) and mrr == float(z["mrr"])
+    assert [hits[int(k)] for k in z["hits_levels"]] == list(z["hits_values"])

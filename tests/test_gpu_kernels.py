@@ -12,11 +12,23 @@ from oracle import conve_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+_ALIVE = []     # device tensors created inline as call arguments must outlive the (asynchronous) call
+
+
+@pytest.fixture(autouse=True)
+def _release_tensors():
+    yield
+    torch.cuda.synchronize()
+    _ALIVE.clear()
+
+
 def dev(a, dtype=None):
     t = torch.as_tensor(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
-    return t.cuda()
+    t = t.cuda()
+    _ALIVE.append(t)
+    return t
 
 
 def relerr(a, b):

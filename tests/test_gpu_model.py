@@ -94,6 +94,10 @@ def compare_grads(model, g, cfg, tol=2e-4):
     scale = max(np.abs(v).max() for _, v in checks)
     for name, ref in checks:
         got = mg[name].reshape(ref.shape)
+        if name == "conv1_bias" and cfg.batch_norm_train_stats:
+            # analytically zero (batch-stat BN removes the per-channel mean): both sides are rounding noise
+            assert np.abs(got).max() < 1e-4 * scale and np.abs(ref).max() < 1e-4 * scale
+            continue
         # gradients that are analytically ~0 (e.g. conv bias under batch-stat BN) are compared on the global scale
         err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-4 * scale)
         assert err < tol, "%s: rel err %.3e" % (name, err)
