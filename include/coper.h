@@ -137,6 +137,16 @@ size_t coper_score1n_workspace_bytes(int B, int64_t Ns, int d, int prec);
 int coper_score1n_fwd(const float* q, const float* E, const float* bias, int B, int64_t Ns, int d, float* scores,
                       int64_t ld_scores, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
 
+/* Tensor-pipe operand preparation (COPER_PREC_BF16 / COPER_PREC_TF32X3).  The tcgen05 kernels consume operands in
+ * "prepared" form: a bf16 copy [rows, ldp] (ldp = cols rounded up to 8), or two fp32 planes (hi = tf32-rounded value,
+ * lo = x - hi) of [rows, ldp] (ldp = cols rounded up to 4).  Prepare the entity table once per evaluation pass /
+ * optimizer step and reuse it across calls with coper_score1n_fwd_prepared (coper_score1n_fwd prepares per call). */
+size_t coper_prepared_bytes(int64_t rows, int cols, int prec);
+int coper_prepare_operand(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst,
+                          coper_stream_t stream);
+int coper_score1n_fwd_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
+                               float* scores, int64_t ld_scores, int prec, coper_stream_t stream);
+
 /* a7+a9+a10 / K6-K8 — scorer + label-smoothed sigmoid-BCE + its gradient (models.py:433-437,448-453,198):
  *   s = q.E^T + bias;  z' = bit ? pos_target : neg_target   (pos = (1-eps)+1/N, neg = 1/N; models.py:450)
  *   loss_sum = sum_{b,n} max(s,0) - s z' + log1p(exp(-|s|))   (caller divides by B*N_total)

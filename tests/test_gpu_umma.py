@@ -1,0 +1,57 @@
+"""tcgen05/TMEM engine parity (through the C ABI).
+
+Tolerances:
+  * COPER_PREC_TF32X3 (3-term error-compensated tf32): max|S - S64| <= 1e-5 * max|S64|  (fp32-class; the BASELINE bar)
+  * COPER_PREC_BF16: vs an fp64 product of the bf16-ROUNDED operands <= 1e-5 (the tensor pipe accumulates in fp32);
+    vs the unrounded fp64 product <= 1e-2 (the stated tolerance of the bf16 path).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+PREC = {"bf16": 1, "tf32x3": 2}
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+def bf16_round(x):
+    return torch.as_tensor(x, dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("B,N,d", [(512, 40943, 200), (7, 97, 40), (130, 1003, 200), (33, 5000, 256), (512, 70001, 256),
+                                   (128, 256, 64), (1, 1, 8)])
+def test_score1n_fwd_tensor_pipe(prec, B, N, d):
+    from coper_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(B + N + d)
+    q = np.maximum(rng.normal(size=(B, d)), 0).astype(np.float32)
+    E = rng.uniform(-0.05, 0.05, size=(N, d)).astype(np.float32)
+    bias = (rng.normal(size=N) * 0.1).astype(np.float32)
+    ld = -(-N // 32) * 32
+    tq, tE, tb = torch.as_tensor(q).cuda(), torch.as_tensor(E).cuda(), torch.as_tensor(bias).cuda()
+    S = torch.full((B, ld), float("nan"), device="cuda")
+    p = PREC[prec]
+    ws = torch.empty(lib.coper_score1n_workspace_bytes(B, N, d, p), dtype=torch.uint8, device="cuda")
+    L.call("coper_score1n_fwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), B, N, d, L.ptr(S), ld, L.ptr(ws), ws.numel(), p)
+    got = S[:, :N].cpu().numpy()
+    assert np.isfinite(got).all()
+    exact = q.astype(np.float64) @ E.astype(np.float64).T + bias
+    if prec == "tf32x3":
+        assert relerr(got, exact) < 1e-5
+    else:
+        rounded = bf16_round(q) @ bf16_round(E).T + bias
+        assert relerr(got, rounded) < 1e-5
+        assert relerr(got, exact) < 1e-2
+    # prepared-operand entry point gives bit-identical results
+    qp = torch.empty(lib.coper_prepared_bytes(B, d, p), dtype=torch.uint8, device="cuda")
+    Ep = torch.empty(lib.coper_prepared_bytes(N, d, p), dtype=torch.uint8, device="cuda")
+    L.call("coper_prepare_operand", L.ptr(tq), B, d, d, p, L.ptr(qp))
+    L.call("coper_prepare_operand", L.ptr(tE), N, d, d, p, L.ptr(Ep))
+    S2 = torch.zeros(B, ld, device="cuda")
+    L.call("coper_score1n_fwd_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(tb), B, N, d, L.ptr(S2), ld, p)
+    assert torch.equal(S2[:, :N], S[:, :N])
