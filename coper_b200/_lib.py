@@ -44,6 +44,8 @@ SIGNATURES = {
     "coper_prepared_bytes": (sz, [i64, i32, i32]),
     "coper_prepare_operand": (i32, [vp, i64, i32, i64, i32, vp, vp]),
     "coper_score1n_fwd_prepared": (i32, [vp, vp, vp, i32, i64, i32, vp, i64, i32, vp]),
+    "coper_tc_gemm_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "coper_tc_gemm": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, sz, vp]),
     "coper_score1n_bce_workspace_bytes": (sz, [i32, i64, i32, i32]),
     "coper_score1n_bce_fwd_bwd": (i32, [vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
                                         sz, i32, vp]),

@@ -101,6 +101,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ descriptors
@@ -108,13 +117,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major : tile stored [rows][128 B]; 8-row groups are 1024 B apart (SBO); LBO unused (1)
 //   MN-major: tile stored as atoms of [8 k-rows][128 B of MN]; SBO = byte distance between consecutive
 //             8-row k groups, LBO = byte distance between consecutive 128-B MN chunks
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   32-bit (tf32) MN-major operands must use the 128B swizzle with 32-byte atoms (layout_type 1, TMA mode
+//   SWIZZLE_128B_ATOM_32B): k-atoms are 4 rows (512 B), so SBO = 512.
+enum : uint32_t { LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1 };
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = LAYOUT_SW128) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;   // version = 1
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) { return make_desc(smem_addr, 16, 1024); }
@@ -134,7 +147,7 @@ EncodeTiledFn get_encode_fn();  // umma_host.cu (cudaGetDriverEntryPoint: no lin
 // Row-major matrix [rows, cols] with row pitch `pitch_elems`; box = {box_cols (128 bytes worth), box_rows};
 // 128-byte swizzle; out-of-bounds elements read as zero.
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, bool is_bf16, uint64_t rows, uint64_t cols,
-                 uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows);
+                 uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows, bool atom32 = false);
 
 }  // namespace umma
 }  // namespace coper

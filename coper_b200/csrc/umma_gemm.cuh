@@ -19,8 +19,12 @@ constexpr int PREC_BF16 = COPER_PREC_BF16, PREC_TF32X3 = COPER_PREC_TF32X3;
 constexpr int BLOCK_M = 128;
 constexpr int NUM_NON_EPI_THREADS = 128;
 
-template <int PREC_, int BLOCK_N_, int STAGES_, int EPI_WARPS_, bool A_MN_, bool B_MN_>
+// PROMOTE_KB > 0: the tensor core accumulates in fp32 with truncation, so a long chain of MMAs drifts (~2^-25 per
+// accumulate, linear in chain length).  Chains are therefore cut every PROMOTE_KB k-blocks; each partial chain is
+// read back from TMEM and added in fp32 registers (round-to-nearest) by the epilogue warps ("promotion").
+template <int PREC_, int BLOCK_N_, int STAGES_, int EPI_WARPS_, bool A_MN_, bool B_MN_, int PROMOTE_KB_ = 0>
 struct GemmCfg {
+  static constexpr int PROMOTE_KB = PROMOTE_KB_;
   static constexpr int PREC = PREC_, BLOCK_N = BLOCK_N_, STAGES = STAGES_, EPI_WARPS = EPI_WARPS_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   static constexpr int ELEM = (PREC == PREC_BF16) ? 2 : 4;
@@ -36,6 +40,11 @@ struct GemmCfg {
   static constexpr int THREADS = NUM_NON_EPI_THREADS + EPI_WARPS * 32;
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t FMT = (PREC == PREC_BF16) ? FMT_BF16 : FMT_TF32;
+  // MN-major smem layout: 16-bit types use the plain 128B swizzle (8-row k atoms); tf32 must use the
+  // 128B swizzle with 32-byte atoms (4-row k atoms)
+  static constexpr bool MN_ATOM32 = (PREC == PREC_TF32X3);
+  static constexpr uint32_t MN_LAYOUT = MN_ATOM32 ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
+  static constexpr uint32_t MN_SBO = MN_ATOM32 ? 512 : 1024;
   static constexpr uint32_t IDESC = make_idesc(FMT, BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
   static_assert(2 * BLOCK_N <= 512, "TMEM double buffer");
@@ -144,8 +153,10 @@ __device__ __forceinline__ void issue_stage(const SmemLayout<Cfg>& sm, int stage
     uint64_t da[2], db[2];
 #pragma unroll
     for (int t = 0; t < Cfg::TERMS; ++t) {
-      da[t] = Cfg::A_MN ? make_desc(a_addr[t] + a_off, Cfg::BLOCK_K * 128, 1024) : make_desc_kmajor(a_addr[t] + a_off);
-      db[t] = Cfg::B_MN ? make_desc(b_addr[t] + b_off, Cfg::BLOCK_K * 128, 1024) : make_desc_kmajor(b_addr[t] + b_off);
+      da[t] = Cfg::A_MN ? make_desc(a_addr[t] + a_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                        : make_desc_kmajor(a_addr[t] + a_off);
+      db[t] = Cfg::B_MN ? make_desc(b_addr[t] + b_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                        : make_desc_kmajor(b_addr[t] + b_off);
     }
     uint32_t acc = (first && k == 0) ? 0u : 1u;
     if (Cfg::PREC == PREC_BF16) {
@@ -158,6 +169,39 @@ __device__ __forceinline__ void issue_stage(const SmemLayout<Cfg>& sm, int stage
   }
 }
 
+// same as issue_stage but with a run-time instruction descriptor (N of the last tile may be < BLOCK_N)
+template <class Cfg>
+__device__ __forceinline__ void issue_stage_rt(const SmemLayout<Cfg>& sm, int stage, uint32_t tmem_d, int kvalid,
+                                               bool first, uint32_t idesc) {
+  int nk = (kvalid + Cfg::UMMA_K - 1) / Cfg::UMMA_K;
+  uint32_t a_addr[2], b_addr[2];
+#pragma unroll
+  for (int t = 0; t < Cfg::TERMS; ++t) {
+    a_addr[t] = smem_u32(sm.a_plane(stage, t));
+    b_addr[t] = smem_u32(sm.b_plane(stage, t));
+  }
+  for (int k = 0; k < nk; ++k) {
+    uint32_t a_off = Cfg::A_MN ? k * Cfg::UMMA_K * 128 : k * 32;
+    uint32_t b_off = Cfg::B_MN ? k * Cfg::UMMA_K * 128 : k * 32;
+    uint64_t da[2], db[2];
+#pragma unroll
+    for (int t = 0; t < Cfg::TERMS; ++t) {
+      da[t] = Cfg::A_MN ? make_desc(a_addr[t] + a_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                        : make_desc_kmajor(a_addr[t] + a_off);
+      db[t] = Cfg::B_MN ? make_desc(b_addr[t] + b_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
+                        : make_desc_kmajor(b_addr[t] + b_off);
+    }
+    uint32_t acc = (first && k == 0) ? 0u : 1u;
+    if (Cfg::PREC == PREC_BF16) {
+      mma_bf16(tmem_d, da[0], db[0], idesc, acc);
+    } else {
+      mma_tf32(tmem_d, da[1], db[0], idesc, acc);   // lo * hi
+      mma_tf32(tmem_d, da[0], db[1], idesc, 1u);    // hi * lo
+      mma_tf32(tmem_d, da[0], db[0], idesc, 1u);    // hi * hi
+    }
+  }
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -165,6 +209,291 @@ struct PipeState {
   __device__ __forceinline__ void advance() {
     if (++stage == STAGES) { stage = 0; phase ^= 1; }
   }
+};
+
+}  // namespace umma
+}  // namespace coper
+
+// ================================================================================================
+// Generic persistent kernel: grouped / split-K GEMM with a pluggable epilogue.
+// ================================================================================================
+namespace coper {
+namespace umma {
+
+struct GemmProblem {
+  int M, N, K;                  // per-group extents: M -> TMEM lanes (rows), N -> TMEM columns, K reduction
+  int m_tiles, n_tiles;
+  int splits, kb_per_split;     // split-K in units of BLOCK_K blocks (every split must be non-empty)
+  int groups;                   // number of groups (e.g. context index kq)
+  int groups_inner;             // 0: groups are independent work items; 1: a CTA loops over all groups of one
+                                //    (m_blk, n_blk, split) consecutively (epilogue may accumulate across groups)
+  int a_group_mn, a_group_k;    // per-group coordinate offsets into the operand tensor maps
+  int b_group_mn, b_group_k;
+};
+struct TileCoord {
+  int group, split, m_blk, n_blk, kb0, kb1;
+};
+
+__device__ __forceinline__ long long gemm_supers(const GemmProblem& p) {
+  return (long long)p.m_tiles * p.n_tiles * p.splits * (p.groups_inner ? 1 : p.groups);
+}
+__device__ __forceinline__ TileCoord gemm_decode(const GemmProblem& p, long long s, int g_inner, int block_k) {
+  TileCoord t;
+  t.m_blk = (int)(s % p.m_tiles); s /= p.m_tiles;
+  t.n_blk = (int)(s % p.n_tiles); s /= p.n_tiles;
+  t.split = (int)(s % p.splits);  s /= p.splits;
+  t.group = p.groups_inner ? g_inner : (int)s;
+  int kb_total = (p.K + block_k - 1) / block_k;
+  t.kb0 = t.split * p.kb_per_split;
+  t.kb1 = min(kb_total, t.kb0 + p.kb_per_split);
+  return t;
+}
+
+// Epi concept:
+//   __device__ void chunk(const GemmProblem&, const TileCoord&, int row, int col, const uint32_t (&acc)[32]);
+//       row = global M index of this thread's TMEM lane, col = global N index of acc[0]; called for every 32-column
+//       chunk this warp owns (warp-uniform), also for rows >= M (mask inside).
+//   __device__ void tile_done(const GemmProblem&, const TileCoord&, int row, int col_group, int col_groups);
+//   __device__ void finish(int epi_thread, int epi_threads);   // once per CTA, after the last tile
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__ CUtensorMap tAlo,
+                 const __grid_constant__ CUtensorMap tB, const __grid_constant__ CUtensorMap tBlo,
+                 const GemmProblem p, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout<Cfg> sm(smem_raw);
+  uint32_t tmem_base = cta_setup<Cfg>(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long supers = gemm_supers(p);
+  const int g_loop = p.groups_inner ? p.groups : 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tA);
+      tma_prefetch_desc(&tB);
+      PipeState ps;
+      for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
+        for (int g = 0; g < g_loop; ++g) {
+          TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
+          int a_mn0 = t.m_blk * BLOCK_M + t.group * p.a_group_mn;
+          int b_mn0 = t.n_blk * Cfg::BLOCK_N + t.group * p.b_group_mn;
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
+            mbar_wait(&sm.empty[ps.stage], ps.phase ^ 1);
+            produce_stage<Cfg>(sm, ps.stage, &tA, &tAlo, &tB, &tBlo, a_mn0, b_mn0,
+                               kb * Cfg::BLOCK_K + t.group * p.a_group_k, kb * Cfg::BLOCK_K + t.group * p.b_group_k);
+            ps.template advance<Cfg::STAGES>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
+        for (int g = 0; g < g_loop; ++g) {
+          TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
+          int n_rem = p.N - t.n_blk * Cfg::BLOCK_N;
+          int n_eff = min(Cfg::BLOCK_N, (n_rem + 15) & ~15);
+          uint32_t idesc = make_idesc(Cfg::FMT, BLOCK_M, (uint32_t)n_eff, Cfg::A_MN ? 1u : 0u, Cfg::B_MN ? 1u : 0u);
+          const int chain = Cfg::PROMOTE_KB > 0 ? Cfg::PROMOTE_KB : (t.kb1 - t.kb0);
+          for (int kc = t.kb0; kc < t.kb1; kc += chain) {
+            int kce = min(t.kb1, kc + chain);
+            mbar_wait(&sm.tempty[as], aphase ^ 1);
+            tc_fence_after();
+            for (int kb = kc; kb < kce; ++kb) {
+              mbar_wait(&sm.full[ps.stage], ps.phase);
+              tc_fence_after();
+              int kvalid = min(Cfg::BLOCK_K, p.K - kb * Cfg::BLOCK_K);
+              issue_stage_rt<Cfg>(sm, ps.stage, tmem_base + as * Cfg::BLOCK_N, kvalid, kb == kc, idesc);
+              mma_commit(&sm.empty[ps.stage]);
+              ps.template advance<Cfg::STAGES>();
+            }
+            mma_commit(&sm.tfull[as]);
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const int group_c = (warp - 4) >> 2;
+    constexpr int GROUPS = Cfg::EPI_WARPS / 4;
+    constexpr int COLS = Cfg::BLOCK_N / GROUPS;
+    static_assert(COLS % 32 == 0, "epilogue column split");
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
+      for (int g = 0; g < g_loop; ++g) {
+        TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
+        int row = t.m_blk * BLOCK_M + quarter * 32 + lane;
+        if (Cfg::PROMOTE_KB == 0) {
+          mbar_wait(&sm.tfull[as], aphase);
+          tc_fence_after();
+          for (int c = group_c * COLS; c < (group_c + 1) * COLS; c += 32) {
+            int col = t.n_blk * Cfg::BLOCK_N + c;
+            if (col >= p.N) break;
+            uint32_t r[32];
+            tmem_ld32(tmem_base + as * Cfg::BLOCK_N + c + ((uint32_t)(quarter * 32) << 16), r);
+            tmem_ld_wait();
+            epi.chunk(p, t, row, col, r);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.tempty[as]);
+          as ^= 1;
+          if (as == 0) aphase ^= 1;
+        } else {
+          // promotion: sum the partial chains in fp32 registers (round-to-nearest adds)
+          constexpr int NCH = COLS / 32;
+          float accr[NCH][32];
+#pragma unroll
+          for (int i = 0; i < NCH; ++i)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accr[i][j] = 0.f;
+          const int chain = Cfg::PROMOTE_KB > 0 ? Cfg::PROMOTE_KB : 1;
+          for (int kc = t.kb0; kc < t.kb1; kc += chain) {
+            mbar_wait(&sm.tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+              int c = group_c * COLS + i * 32;
+              if (t.n_blk * Cfg::BLOCK_N + c < p.N) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  uint32_t r[16];
+                  tmem_ld16(tmem_base + as * Cfg::BLOCK_N + c + h * 16 + ((uint32_t)(quarter * 32) << 16), r);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) accr[i][h * 16 + j] += __uint_as_float(r[j]);
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tempty[as]);
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+          }
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            int col = t.n_blk * Cfg::BLOCK_N + group_c * COLS + i * 32;
+            if (col < p.N) {
+              uint32_t r[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(accr[i][j]);
+              epi.chunk(p, t, row, col, r);
+            }
+          }
+        }
+        epi.tile_done(p, t, row, group_c, GROUPS);
+      }
+    }
+    epi.finish(threadIdx.x - NUM_NON_EPI_THREADS, Cfg::EPI_WARPS * 32);
+  }
+  cta_teardown<Cfg>(tmem_base);
+}
+
+// Host-side description of a prepared operand (see coper_prepare_operand)
+struct TcOperand {
+  const void* main;
+  const void* lo;        // tf32x3 only
+  uint64_t rows, cols;   // extents of the stored row-major matrix (cols contiguous)
+  uint64_t pitch;        // elements between rows
+};
+
+// Build the 4 tensor maps for a configuration.  K-major operand: stored [MN, K], box {BLOCK_K, tile rows};
+// MN-major operand: stored [K, MN], box {CHUNK, BLOCK_K}.
+template <class Cfg>
+int make_gemm_tmaps(const TcOperand& A, const TcOperand& B, CUtensorMap* tA, CUtensorMap* tAlo, CUtensorMap* tB,
+                    CUtensorMap* tBlo) {
+  constexpr bool bf16 = Cfg::PREC == PREC_BF16;
+  int rc;
+  uint32_t a_box_rows = Cfg::A_MN ? Cfg::BLOCK_K : BLOCK_M;
+  uint32_t b_box_rows = Cfg::B_MN ? Cfg::BLOCK_K : Cfg::BLOCK_N;
+  const bool a32 = Cfg::A_MN && Cfg::MN_ATOM32, b32 = Cfg::B_MN && Cfg::MN_ATOM32;
+  if ((rc = make_tmap_2d(tA, A.main, Cfg::ELEM, bf16, A.rows, A.cols, A.pitch, Cfg::CHUNK, a_box_rows, a32))) return rc;
+  if ((rc = make_tmap_2d(tB, B.main, Cfg::ELEM, bf16, B.rows, B.cols, B.pitch, Cfg::CHUNK, b_box_rows, b32))) return rc;
+  *tAlo = *tA;
+  *tBlo = *tB;
+  if (!bf16) {
+    if (!A.lo || !B.lo) return COPER_ERR_INVALID_ARG;
+    if ((rc = make_tmap_2d(tAlo, A.lo, 4, false, A.rows, A.cols, A.pitch, Cfg::CHUNK, a_box_rows, a32))) return rc;
+    if ((rc = make_tmap_2d(tBlo, B.lo, 4, false, B.rows, B.cols, B.pitch, Cfg::CHUNK, b_box_rows, b32))) return rc;
+  }
+  return COPER_OK;
+}
+
+template <class Cfg, class Epi>
+int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, const Epi& epi, cudaStream_t st) {
+  CUtensorMap tA, tAlo, tB, tBlo;
+  int rc = make_gemm_tmaps<Cfg>(A, B, &tA, &tAlo, &tB, &tBlo);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    rc = check_cuda(cudaFuncSetAttribute(umma_gemm_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES));
+    if (rc) return rc;
+    attr_done = true;
+  }
+  long long supers = (long long)p.m_tiles * p.n_tiles * p.splits * (p.groups_inner ? 1 : p.groups);
+  int grid = (int)(supers < 148 ? supers : 148);
+  if (grid < 1) return COPER_ERR_INVALID_ARG;
+  umma_gemm_kernel<Cfg, Epi><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tAlo, tB, tBlo, p, epi);
+  return check_launch();
+}
+
+// Fill the tiling fields of a problem; split-K chosen so that ~`target_ctas` work items exist.
+template <class Cfg>
+inline void plan_gemm(GemmProblem& p, bool allow_split, int target_ctas = 148) {
+  p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
+  int kb_total = (p.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
+  long long base = (long long)p.m_tiles * p.n_tiles * (p.groups_inner ? 1 : p.groups);
+  int splits = 1;
+  if (allow_split && base < target_ctas) {
+    splits = (int)((target_ctas + base - 1) / base);
+    if (splits > kb_total) splits = kb_total;
+  }
+  p.kb_per_split = (kb_total + splits - 1) / splits;
+  p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+}
+
+// Plain store epilogue: out[(group, split)][row, col] = acc * row_scale[row, group] (+ col_bias[col])
+struct StoreEpi {
+  float* out;
+  long long ld, group_stride, split_stride;
+  const float* row_scale;   // optional [M, row_scale_ld]; indexed [row, group]
+  int row_scale_ld;
+  const float* col_bias;    // optional [N]
+  int extra_col;            // if >= 0: column index whose values go to extra_out[row] instead (e.g. dbias)
+  float* extra_out;
+  __device__ __forceinline__ void chunk(const GemmProblem& p, const TileCoord& t, int row, int col,
+                                        const uint32_t (&r)[32]) const {
+    if (row >= p.M) return;
+    float sc = row_scale ? __ldg(row_scale + (long long)row * row_scale_ld + t.group) : 1.0f;
+    float* o = out + t.group * group_stride + t.split * split_stride + (long long)row * ld + col;
+    int n_out = extra_col >= 0 ? min(p.N, extra_col) : p.N;
+    bool vec = (col + 31 < n_out) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && !col_bias;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) =
+            make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc, __uint_as_float(r[j + 2]) * sc,
+                        __uint_as_float(r[j + 3]) * sc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        int cj = col + j;
+        if (cj < n_out) o[j] = __uint_as_float(r[j]) * sc + (col_bias ? __ldg(col_bias + cj) : 0.f);
+        else if (cj == extra_col && cj < p.N) extra_out[row] = __uint_as_float(r[j]) * sc;
+      }
+    }
+  }
+  __device__ __forceinline__ void tile_done(const GemmProblem&, const TileCoord&, int, int, int) const {}
+  __device__ __forceinline__ void finish(int, int) const {}
 };
 
 }  // namespace umma

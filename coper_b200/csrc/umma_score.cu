@@ -211,6 +211,11 @@ int umma_score1n_fwd(const float* q, const float* E, const float* bias, int B, i
   if ((rc = prepare(E, Ns, d, d, prec, Ep, st))) return rc;
   return umma_score1n_fwd_prepared(qp, Ep, bias, B, Ns, d, scores, ld, prec, st);
 }
+size_t tc_prepared_bytes(int64_t rows, int cols, int prec) { return prepared_bytes(rows, cols, prec); }
+int tc_prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst, cudaStream_t st) {
+  return prepare(src, rows, cols, ld_src, prec, dst, st);
+}
+int64_t tc_prepared_ld(int cols, int prec) { return prepared_ld(cols, prec); }
 }  // namespace coper
 
 using namespace coper;

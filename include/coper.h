@@ -147,6 +147,12 @@ int coper_prepare_operand(const float* src, int64_t rows, int cols, int64_t ld_s
 int coper_score1n_fwd_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
                                float* scores, int64_t ld_scores, int prec, coper_stream_t stream);
 
+/* C = op(A).op(B) on the tensor pipe (tcgen05, fp32 accumulate in TMEM); same layout flags as coper_sgemm.
+ * Operands are prepared into the workspace on every call (bf16 copy or tf32 hi/lo planes). */
+size_t coper_tc_gemm_workspace_bytes(int M, int N, int K, int prec);
+int coper_tc_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                  float* C, int ldc, int prec, void* workspace, size_t workspace_bytes, coper_stream_t stream);
+
 /* a7+a9+a10 / K6-K8 — scorer + label-smoothed sigmoid-BCE + its gradient (models.py:433-437,448-453,198):
  *   s = q.E^T + bias;  z' = bit ? pos_target : neg_target   (pos = (1-eps)+1/N, neg = 1/N; models.py:450)
  *   loss_sum = sum_{b,n} max(s,0) - s z' + log1p(exp(-|s|))   (caller divides by B*N_total)

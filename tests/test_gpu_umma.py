@@ -55,3 +55,32 @@ def test_score1n_fwd_tensor_pipe(prec, B, N, d):
     S2 = torch.zeros(B, ld, device="cuda")
     L.call("coper_score1n_fwd_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(tb), B, N, d, L.ptr(S2), ld, p)
     assert torch.equal(S2[:, :N], S[:, :N])
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("M,N,K", [(130, 77, 301), (512, 200, 4608), (128, 200, 512), (300, 201, 100), (5, 8, 8),
+                                   (1000, 256, 64)])
+def test_tc_gemm_all_layouts(prec, M, N, K):
+    """C = op(A).op(B) with K-major and MN-major operands (transA / transB) on the tensor pipe."""
+    from coper_b200 import _lib as L
+    lib = L.load()
+    p = PREC[prec]
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.normal(size=(M, K)).astype(np.float32)
+    Bm = rng.normal(size=(K, N)).astype(np.float32)
+    exact = A.astype(np.float64) @ Bm.astype(np.float64)
+    rounded = bf16_round(A) @ bf16_round(Bm)
+    ws = torch.empty(lib.coper_tc_gemm_workspace_bytes(M, N, K, p), dtype=torch.uint8, device="cuda")
+    for ta in (0, 1):
+        for tb in (0, 1):
+            a = torch.as_tensor(np.ascontiguousarray(A.T if ta else A)).cuda()
+            b = torch.as_tensor(np.ascontiguousarray(Bm.T if tb else Bm)).cuda()
+            c = torch.full((M, N), float("nan"), device="cuda")
+            L.call("coper_tc_gemm", ta, tb, M, N, K, L.ptr(a), a.shape[1], L.ptr(b), b.shape[1], L.ptr(c), N, p,
+                   L.ptr(ws), ws.numel())
+            got = c.cpu().numpy()
+            assert np.isfinite(got).all(), (ta, tb)
+            if prec == "tf32x3":
+                assert relerr(got, exact) < 1e-5, (ta, tb, relerr(got, exact))
+            else:
+                assert relerr(got, rounded) < 1e-5, (ta, tb, relerr(got, rounded))
