@@ -27,8 +27,9 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from ._lib import PREC, call, ptr
+from .sharding import EntityShard
 
 BN_EPS = 1e-3           # tf.layers.batch_normalization default epsilon (models.py:386-388)
 CLIP_NORM = 5.0         # models.py:199
@@ -47,24 +48,6 @@ def _xavier_(t: torch.Tensor, gen: torch.Generator):
         fan_in, fan_out = shape[-2] * rec, shape[-1] * rec
     lim = math.sqrt(6.0 / (fan_in + fan_out))
     t.copy_((torch.rand(t.shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim)
-
-
-class EntityShard:
-    """Contiguous row range [lo, hi) of the entity table owned by this rank."""
-
-    def __init__(self, num_ent: int, rank: int = 0, world: int = 1, align: int = 128):
-        per = -(-num_ent // world)
-        per = -(-per // align) * align
-        self.num_ent, self.rank, self.world, self.per = num_ent, rank, world, per
-        self.lo = min(num_ent, rank * per)
-        self.hi = min(num_ent, self.lo + per)
-
-    @property
-    def rows(self) -> int:
-        return self.hi - self.lo
-
-    def owner(self, ent: int) -> int:
-        return ent // self.per
 
 
 class _BatchNorm:
@@ -445,8 +428,7 @@ class ConvE:
         B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
         s = self.shard
         call("coper_gather_rows", ptr(self.ent_emb), s.lo, s.hi, d, ptr(b.e1), B, ptr(b.x0))
-        if self.world > 1:
-            torch.distributed.all_reduce(b.x0, group=self.group)
+        sharding.exchange_rows(b.x0, self.world, self.group)
         call("coper_gather_rows", ptr(self.rel_emb), 0, self.num_rel, dr, ptr(b.rel), B, ptr(b.r))
         call("coper_conv_fwd", ptr(b.x0), B, self.H, self.W, ptr(self.conv1_weights), ptr(self.conv1_bias),
              self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.z))
@@ -478,11 +460,9 @@ class ConvE:
         call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), ptr(b.bits), B, Ns, d,
              float(pos), float(neg), inv_count, ptr(b.loss_sum), ptr(b.SG), b.ld, ptr(b.dq), ptr(g["ent_emb"]),
              ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes, self.prec)
-        if self.world > 1:
-            # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial
-            # loss and the partial dq = G_shard . E_shard; dE / dbias stay local.
-            torch.distributed.all_reduce(b.loss_sum, group=self.group)
-            torch.distributed.all_reduce(b.dq, group=self.group)
+        # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial loss and
+        # the partial dq = G_shard . E_shard; dE / dbias stay local.
+        sharding.reduce_scorer_partials(b.loss_sum, b.dq, self.world, self.group)
         use_batch = self.batch_norm_train_stats
         keep1, keep2 = 1.0 - self.hidden_dropout, 1.0 - self.output_dropout
         # FC block backward: relu -> FCBN -> output dropout (models.py:414-419)
@@ -518,10 +498,9 @@ class ConvE:
         """tf.clip_by_global_norm(5.0) (models.py:199) + AMSGrad apply (amsgrad.py:130-159)."""
         for i, (n, p, _) in enumerate(self.trainables):
             call("coper_sumsq", ptr(self.grads[n]), p.numel(), i, ptr(self.sumsq))
-        if self.world > 1:
-            # trainables 0,1 (ent_emb, pred_bias) are row-sharded: their squared norms add across ranks;
-            # every other gradient is replicated (identical on all ranks) and is counted once.
-            torch.distributed.all_reduce(self.sumsq[:2 * _lib.SUMSQ_BLOCKS], group=self.group)
+        # trainables 0,1 (ent_emb, pred_bias) are row-sharded: their squared norms add across ranks;
+        # every other gradient is replicated (identical on all ranks) and is counted once.
+        sharding.reduce_sharded_sumsq(self.sumsq[:2 * _lib.SUMSQ_BLOCKS], self.world, self.group)
         call("coper_clip_scale", ptr(self.sumsq), len(self.trainables), CLIP_NORM, ptr(self.clip_out))
         for n, p, _ in self.trainables:
             m = None if self.bug_compat else self.m[n]
@@ -571,13 +550,10 @@ class ConvE:
         self._score(b)
         s = self.shard
         call("coper_gold_scores", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold))
-        if self.world > 1:
-            torch.distributed.all_reduce(b.gold, group=self.group)
+        sharding.reduce_gold(b.gold, self.world, self.group)
         b.n_greater.zero_()
         b.n_equal.zero_()
         call("coper_filtered_rank", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits),
              ptr(b.n_greater), ptr(b.n_equal))
-        if self.world > 1:
-            torch.distributed.all_reduce(b.n_greater, group=self.group)
-            torch.distributed.all_reduce(b.n_equal, group=self.group)
+        sharding.reduce_counts(b.n_greater, b.n_equal, self.world, self.group)
         return b.n_greater + 1, b.n_equal

@@ -1,0 +1,105 @@
+"""Entity-sharded CUDA path on >= 2 GPUs (NCCL): the sharded model must reproduce the unsharded oracle —
+loss to fp32 round-off, local rows of dE / updated table, and filtered ranks bit-exactly equal to the
+single-GPU ranks.  Skipped when fewer than 2 devices are visible (run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import conve_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _descr(cfg):
+    return {"use_negative_sampling": False, "label_smoothing_epsilon": 0.1, "num_ent": cfg.num_ent,
+            "num_rel": cfg.num_rel, "ent_emb_size": cfg.ent_emb_size, "rel_emb_size": cfg.rel_emb_size,
+            "concat_rel": False, "context_rel_conv": None, "context_rel_out": [], "context_rel_dropout": 0.0,
+            "context_rel_use_batch_norm": False, "input_dropout": 0.0, "hidden_dropout": cfg.hidden_dropout,
+            "output_dropout": cfg.output_dropout, "learning_rate": 1e-2, "batch_size": 0, "add_loss_summaries": False,
+            "add_variable_summaries": False, "add_tensor_summaries": False,
+            "batch_norm_momentum": cfg.batch_norm_momentum, "batch_norm_train_stats": cfg.batch_norm_train_stats,
+            "do_parameter_lookup": False}
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from coper_b200.models import ConvE
+    from coper_b200.sharding import EntityShard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg = O.OracleConfig(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[],
+                             batch_norm_train_stats=True, batch_norm_momentum=0.1, hidden_dropout=0.3,
+                             output_dropout=0.2)
+        params = O.init_params(cfg, seed=3, bias_noise=0.05)
+        B = 130
+        e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5, mean_pos=5.0)
+        batch = {"e1": e1, "rel": rel, "e2": e2, "e2_multi_rowptr": rowptr, "e2_multi_col": col}
+        sh = EntityShard(cfg.num_ent, rank, world)
+        m = ConvE(_descr(cfg), device="cuda:%d" % rank, seed=0, shard=sh)
+        m.load_variables(params)
+        ranks, n_equal = m.filtered_ranks(batch)
+        S_local = m._bufs[B].SG[:, :sh.rows].cpu().numpy().copy()
+        loss = float(m.train_step(batch).item())
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), ranks=ranks.cpu().numpy(), n_equal=n_equal.cpu().numpy(),
+                 S=S_local, loss=loss, dE=m.grads["ent_emb"].cpu().numpy(), ent=m.ent_emb.cpu().numpy(),
+                 rel_emb=m.rel_emb.cpu().numpy(), P=m.fc_weights.projections[0].cpu().numpy(), lo=sh.lo, hi=sh.hi,
+                 norm=float(m.clip_out[1].item()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_entity_sharded_matches_single_gpu(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    _worker_single(str(tmp_path))
+    ref = np.load(os.path.join(str(tmp_path), "single.npz"))
+    outs = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    S = np.concatenate([o["S"] for o in outs], axis=1)
+    assert np.array_equal(S, ref["S"])                               # same kernels, same rows -> bit-identical logits
+    for o in outs:
+        assert np.array_equal(o["ranks"], ref["ranks"]) and np.array_equal(o["n_equal"], ref["n_equal"])
+        assert abs(o["loss"] - float(ref["loss"])) < 1e-6 * abs(float(ref["loss"]))
+        assert abs(o["norm"] - float(ref["norm"])) < 1e-5 * float(ref["norm"])
+        lo, hi = int(o["lo"]), int(o["hi"])
+        assert np.abs(o["dE"] - ref["dE"][lo:hi]).max() < 1e-5 * np.abs(ref["dE"]).max()
+        assert np.abs(o["ent"] - ref["ent"][lo:hi]).max() < 1e-5 * np.abs(ref["ent"]).max()
+        assert np.abs(o["rel_emb"] - ref["rel_emb"]).max() < 1e-5 * np.abs(ref["rel_emb"]).max()
+        assert np.abs(o["P"] - ref["P"]).max() < 1e-5 * np.abs(ref["P"]).max()
+    # replicated variables stay bit-identical across ranks without any gradient all-reduce
+    assert np.array_equal(outs[0]["P"], outs[1]["P"]) and np.array_equal(outs[0]["rel_emb"], outs[1]["rel_emb"])
+
+
+def _worker_single(out_dir):
+    from coper_b200.models import ConvE
+    cfg = O.OracleConfig(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[],
+                         batch_norm_train_stats=True, batch_norm_momentum=0.1, hidden_dropout=0.3, output_dropout=0.2)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    B = 130
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5, mean_pos=5.0)
+    batch = {"e1": e1, "rel": rel, "e2": e2, "e2_multi_rowptr": rowptr, "e2_multi_col": col}
+    m = ConvE(_descr(cfg), device="cuda:0", seed=0)
+    m.load_variables(params)
+    ranks, n_equal = m.filtered_ranks(batch)
+    S = m._bufs[B].SG[:, :cfg.num_ent].cpu().numpy().copy()
+    loss = float(m.train_step(batch).item())
+    np.savez(os.path.join(out_dir, "single.npz"), ranks=ranks.cpu().numpy(), n_equal=n_equal.cpu().numpy(), S=S,
+             loss=loss, dE=m.grads["ent_emb"].cpu().numpy(), ent=m.ent_emb.cpu().numpy(),
+             rel_emb=m.rel_emb.cpu().numpy(), P=m.fc_weights.projections[0].cpu().numpy(),
+             norm=float(m.clip_out[1].item()))
