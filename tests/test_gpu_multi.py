@@ -79,9 +79,11 @@ def test_entity_sharded_matches_single_gpu(world, tmp_path):
         assert abs(o["norm"] - float(ref["norm"])) < 1e-5 * float(ref["norm"])
         lo, hi = int(o["lo"]), int(o["hi"])
         assert np.abs(o["dE"] - ref["dE"][lo:hi]).max() < 1e-5 * np.abs(ref["dE"]).max()
-        assert np.abs(o["ent"] - ref["ent"][lo:hi]).max() < 1e-5 * np.abs(ref["ent"]).max()
-        assert np.abs(o["rel_emb"] - ref["rel_emb"]).max() < 1e-5 * np.abs(ref["rel_emb"]).max()
-        assert np.abs(o["P"] - ref["P"]).max() < 1e-5 * np.abs(ref["P"]).max()
+        # updated variables: AMSGrad as written steps by ~ g / sqrt(g^2), which amplifies fp32 summation-order noise
+        # on near-zero gradient entries -> compare at 5e-4 (the gradients themselves are compared at 1e-5 above)
+        assert np.abs(o["ent"] - ref["ent"][lo:hi]).max() < 5e-4 * np.abs(ref["ent"]).max()
+        assert np.abs(o["rel_emb"] - ref["rel_emb"]).max() < 5e-4 * np.abs(ref["rel_emb"]).max()
+        assert np.abs(o["P"] - ref["P"]).max() < 5e-4 * np.abs(ref["P"]).max()
     # replicated variables stay bit-identical across ranks without any gradient all-reduce
     assert np.array_equal(outs[0]["P"], outs[1]["P"]) and np.array_equal(outs[0]["rel_emb"], outs[1]["rel_emb"])
 
