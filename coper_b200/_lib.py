@@ -37,7 +37,8 @@ SIGNATURES = {
     "coper_cpg_fc_fwd_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
     "coper_cpg_fc_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, u64, vp, vp, sz, i32, vp]),
     "coper_cpg_fc_bwd_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
-    "coper_cpg_fc_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, i32, vp]),
+    "coper_cpg_fc_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, i32, i32,
+                               vp]),
     "coper_sgemm": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp]),
     "coper_score1n_workspace_bytes": (sz, [i32, i64, i32, i32]),
     "coper_score1n_fwd": (i32, [vp, vp, vp, i32, i64, i32, vp, i64, vp, sz, i32, vp]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "coper_tc_gemm_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "coper_tc_gemm": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, sz, vp]),
     "coper_score1n_bce_workspace_bytes": (sz, [i32, i64, i32, i32]),
+    "coper_score1n_bce_G_bytes": (sz, [i32, i64, i32]),
     "coper_score1n_bce_fwd_bwd": (i32, [vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
                                         sz, i32, vp]),
     "coper_csr_to_bits": (i32, [vp, vp, i32, i64, i64, vp, vp]),

@@ -20,6 +20,15 @@
 namespace coper {
 using namespace simt;
 
+// tcgen05 engine (umma_cpg.cu)
+size_t umma_cpg_fwd_workspace_bytes(int B, int dc, int F, int d, int prec);
+size_t umma_cpg_bwd_workspace_bytes(int B, int dc, int F, int d, int prec);
+int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, int B, int dc, int F, int d, void* ws,
+                          size_t ws_bytes, int prec, cudaStream_t st, float** slabs, int* n_slabs);
+int umma_cpg_bwd(const float* c, const float* f, const float* P, const float* dy, int B, int dc, int F, int d,
+                 float* dP, float* df, float* dc_out, void* ws, size_t ws_bytes, int prec, int reuse_fwd_operands,
+                 cudaStream_t st);
+
 // ---------------------------------------------------------------- sources
 struct CpgFwdA {  // (b, kk) -> f[b, i] * c[b, kq],  K-contiguous
   static constexpr bool kKContig = true;
@@ -243,7 +252,7 @@ int coper_sgemm(int transA, int transB, int M, int N, int K, const float* A, int
 }
 
 size_t coper_cpg_fc_fwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
-  (void)prec;
+  if (prec != COPER_PREC_FP32) return umma_cpg_fwd_workspace_bytes(B, dc, F, d, prec);
   return cpg_fwd_layout(B, dc, F, d).total;
 }
 
@@ -252,44 +261,60 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const float
                      void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
   COPER_CHECK_ARG(c && f && P && cb && Pb && y && workspace && B > 0 && dc > 0 && F > 0 && d > 0 && dcb > 0);
   COPER_CHECK_ARG(keep_out > 0.f);
-  if (prec != COPER_PREC_FP32) return COPER_ERR_UNSUPPORTED;
-  CpgLayout L = cpg_fwd_layout(B, dc, F, d);
-  if (workspace_bytes < L.total) return COPER_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  float* part = static_cast<float*>(workspace);
-  dim3 grid(ceil_div(d, BN), ceil_div(B, BM), L.splits);
-  cpg_fwd_kernel<<<grid, THREADS, 0, st>>>(c, f, P, B, dc, F, d, L.tiles_per_split, part);
-  int rc = check_launch();
-  if (rc) return rc;
+  float* part = nullptr;
+  int n_slabs = 0;
+  int rc;
+  if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3) {
+    if ((rc = umma_cpg_fwd_partials(c, f, P, B, dc, F, d, workspace, workspace_bytes, prec, st, &part, &n_slabs)))
+      return rc;
+  } else if (prec == COPER_PREC_FP32) {
+    CpgLayout L = cpg_fwd_layout(B, dc, F, d);
+    if (workspace_bytes < L.total) return COPER_ERR_WORKSPACE;
+    part = static_cast<float*>(workspace);
+    n_slabs = L.splits;
+    dim3 grid(ceil_div(d, BN), ceil_div(B, BM), L.splits);
+    cpg_fwd_kernel<<<grid, THREADS, 0, st>>>(c, f, P, B, dc, F, d, L.tiles_per_split, part);
+    if ((rc = check_launch())) return rc;
+  } else {
+    return COPER_ERR_UNSUPPORTED;
+  }
   int64_t n = (int64_t)B * d;
-  cpg_fwd_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, L.splits, cb, Pb, B, d, dcb, keep_out,
+  cpg_fwd_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n_slabs, cb, Pb, B, d, dcb, keep_out,
                                                                        1.0f / keep_out, keep_threshold(keep_out),
                                                                        seed_dev, salt_out, y);
   return check_launch();
 }
 
 size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
-  (void)prec; (void)d;
+  if (prec != COPER_PREC_FP32) return umma_cpg_bwd_workspace_bytes(B, dc, F, d, prec);
   return align_up((size_t)ceil_div(F, BN) * B * dc * sizeof(float), 256);
 }
 
 int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb,
                      const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
                      float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
-                     coper_stream_t stream) {
+                     int reuse_fwd_operands, coper_stream_t stream) {
   COPER_CHECK_ARG(c && f && P && cb && Pb && dy && dP && dPb && df && dc_out && dcb_out && workspace);
   COPER_CHECK_ARG(B > 0 && dc > 0 && F > 0 && d > 0 && dcb > 0);
-  if (prec != COPER_PREC_FP32) return COPER_ERR_UNSUPPORTED;
   if (workspace_bytes < coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, prec)) return COPER_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  float* dc_part = static_cast<float*>(workspace);
-  int ftiles = ceil_div(F, BN);
-  cpg_bwd_T_kernel<<<dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st>>>(c, f, P, dy, B, dc, F, d, df, dc_part);
-  int rc = check_launch();
-  if (rc) return rc;
-  if ((rc = coper_reduce_partials(dc_part, ftiles, (int64_t)B * dc, 1.0f, 0, dc_out, stream))) return rc;
-  cpg_bwd_dP_kernel<<<dim3(ceil_div(d, BN), ceil_div(F, BM), dc), THREADS, 0, st>>>(c, f, dy, B, dc, F, d, dP);
-  if ((rc = check_launch())) return rc;
+  int rc;
+  if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3) {
+    if ((rc = umma_cpg_bwd(c, f, P, dy, B, dc, F, d, dP, df, dc_out, workspace, workspace_bytes, prec,
+                           reuse_fwd_operands, st)))
+      return rc;
+  } else if (prec == COPER_PREC_FP32) {
+    float* dc_part = static_cast<float*>(workspace);
+    int ftiles = ceil_div(F, BN);
+    cpg_bwd_T_kernel<<<dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st>>>(c, f, P, dy, B, dc, F, d, df, dc_part);
+    if ((rc = check_launch())) return rc;
+    if ((rc = coper_reduce_partials(dc_part, ftiles, (int64_t)B * dc, 1.0f, 0, dc_out, stream))) return rc;
+    cpg_bwd_dP_kernel<<<dim3(ceil_div(d, BN), ceil_div(F, BM), dc), THREADS, 0, st>>>(c, f, dy, B, dc, F, d, dP);
+    if ((rc = check_launch())) return rc;
+  } else {
+    return COPER_ERR_UNSUPPORTED;
+  }
   // dPb [dcb, d] = cb^T . dy ;  dcb [B, dcb] = dy . Pb^T
   if ((rc = coper_sgemm(1, 0, dcb, d, B, cb, dcb, dy, d, dPb, d, 0, stream))) return rc;
   return coper_sgemm(0, 1, B, dcb, d, dy, d, Pb, d, dcb_out, dcb, 0, stream);

@@ -81,7 +81,7 @@ int coper_tc_gemm(int transA, int transB, int M, int N, int K, const float* A, i
   if ((rc = tc_prepare(B, b_rows, (int)b_cols, ldb, prec, Bp, st))) return rc;
   GemmProblem g{};
   g.M = M; g.N = N; g.K = K; g.groups = 1; g.groups_inner = 0;
-  StoreEpi epi{C, ldc, 0, 0, nullptr, 0, nullptr, -1, nullptr};
+  StoreEpi epi = make_store_epi(C, ldc, 0, 0);
   return tc_gemm_store(prec, transA != 0, transB == 0, tc_operand(Ap, a_rows, (int)a_cols, prec),
                        tc_operand(Bp, b_rows, (int)b_cols, prec), g, false, epi, st);
 }

@@ -234,6 +234,17 @@ struct TileCoord {
   int group, split, m_blk, n_blk, kb0, kb1;
 };
 
+struct EpiBase {
+  static constexpr bool kAccumulate = false;
+  __device__ __forceinline__ void tile_begin(const GemmProblem&, const TileCoord&, int, int) {}
+  __device__ __forceinline__ float group_scale(const GemmProblem&, const TileCoord&, int) const { return 1.0f; }
+  __device__ __forceinline__ void group_vals(const GemmProblem&, const TileCoord&, int, int, const uint32_t (&)[16],
+                                             int) {}
+  __device__ __forceinline__ void group_done(const GemmProblem&, const TileCoord&, int, int, int) {}
+  __device__ __forceinline__ void tile_done(const GemmProblem&, const TileCoord&, int, int, int) {}
+  __device__ __forceinline__ void finish(int, int) {}
+};
+
 __device__ __forceinline__ long long gemm_supers(const GemmProblem& p) {
   return (long long)p.m_tiles * p.n_tiles * p.splits * (p.groups_inner ? 1 : p.groups);
 }
@@ -249,12 +260,19 @@ __device__ __forceinline__ TileCoord gemm_decode(const GemmProblem& p, long long
   return t;
 }
 
-// Epi concept:
-//   __device__ void chunk(const GemmProblem&, const TileCoord&, int row, int col, const uint32_t (&acc)[32]);
+// Epi concept (derive from EpiBase for the no-op defaults):
+//   static constexpr bool kAccumulate   the output tile is the sum over the inner group loop (groups_inner = 1) of
+//                                       group_scale(row, group) * partial tile, accumulated in fp32 registers
+//   void tile_begin(p, t, row, col0)    before waiting for the accumulators (issue global prefetches here);
+//                                       col0 = first N index of this warp's column range
+//   float group_scale(p, t, row)        kAccumulate: multiplier of this group's partial tile for this row
+//   void group_vals(p, t, row, col, const uint32_t (&v)[16], int half_idx)   kAccumulate: raw partial values
+//   void group_done(p, t, row, col_group, col_groups)                         kAccumulate: after each group
+//   void chunk(p, t, row, col, const uint32_t (&acc)[32], int chunk_idx)
 //       row = global M index of this thread's TMEM lane, col = global N index of acc[0]; called for every 32-column
 //       chunk this warp owns (warp-uniform), also for rows >= M (mask inside).
-//   __device__ void tile_done(const GemmProblem&, const TileCoord&, int row, int col_group, int col_groups);
-//   __device__ void finish(int epi_thread, int epi_threads);   // once per CTA, after the last tile
+//   void tile_done(p, t, row, col_group, col_groups);
+//   void finish(int epi_thread, int epi_threads);   // once per CTA, after the last tile
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__ CUtensorMap tAlo,
@@ -322,52 +340,61 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
     const int group_c = (warp - 4) >> 2;
     constexpr int GROUPS = Cfg::EPI_WARPS / 4;
     constexpr int COLS = Cfg::BLOCK_N / GROUPS;
+    constexpr int NCH = COLS / 32;
     static_assert(COLS % 32 == 0, "epilogue column split");
     int as = 0;
     uint32_t aphase = 0;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
-      for (int g = 0; g < g_loop; ++g) {
-        TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
-        int row = t.m_blk * BLOCK_M + quarter * 32 + lane;
-        if (Cfg::PROMOTE_KB == 0) {
-          mbar_wait(&sm.tfull[as], aphase);
-          tc_fence_after();
-          for (int c = group_c * COLS; c < (group_c + 1) * COLS; c += 32) {
-            int col = t.n_blk * Cfg::BLOCK_N + c;
-            if (col >= p.N) break;
+      TileCoord t = gemm_decode(p, s, 0, Cfg::BLOCK_K);
+      const int row = t.m_blk * BLOCK_M + quarter * 32 + lane;
+      const int col0 = t.n_blk * Cfg::BLOCK_N + group_c * COLS;
+      epi.tile_begin(p, t, row, col0);
+      if constexpr (Cfg::PROMOTE_KB == 0 && !Epi::kAccumulate) {
+        // one accumulation chain per tile: TMEM -> registers -> epi.chunk
+        mbar_wait(&sm.tfull[as], aphase);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int col = col0 + i * 32;
+          if (col < p.N) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + as * Cfg::BLOCK_N + c + ((uint32_t)(quarter * 32) << 16), r);
+            tmem_ld32(tmem_base + as * Cfg::BLOCK_N + group_c * COLS + i * 32 + lane_base, r);
             tmem_ld_wait();
-            epi.chunk(p, t, row, col, r);
+            epi.chunk(p, t, row, col, r, i);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.tempty[as]);
-          as ^= 1;
-          if (as == 0) aphase ^= 1;
-        } else {
-          // promotion: sum the partial chains in fp32 registers (round-to-nearest adds)
-          constexpr int NCH = COLS / 32;
-          float accr[NCH][32];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.tempty[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      } else {
+        // several partial chains per output tile (promotion of truncating TMEM chains and / or accumulation
+        // over the inner group loop): summed in fp32 registers with round-to-nearest, optionally scaled per group
+        float accr[NCH][32];
 #pragma unroll
-          for (int i = 0; i < NCH; ++i)
+        for (int i = 0; i < NCH; ++i)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) accr[i][j] = 0.f;
-          const int chain = Cfg::PROMOTE_KB > 0 ? Cfg::PROMOTE_KB : 1;
+          for (int j = 0; j < 32; ++j) accr[i][j] = 0.f;
+        for (int g = 0; g < g_loop; ++g) {
+          t = gemm_decode(p, s, g, Cfg::BLOCK_K);
+          const float scale = epi.group_scale(p, t, row);
+          const int chain = Cfg::PROMOTE_KB > 0 ? Cfg::PROMOTE_KB : (t.kb1 - t.kb0);
           for (int kc = t.kb0; kc < t.kb1; kc += chain) {
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll
             for (int i = 0; i < NCH; ++i) {
-              int c = group_c * COLS + i * 32;
-              if (t.n_blk * Cfg::BLOCK_N + c < p.N) {
+              if (col0 + i * 32 < p.N) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   uint32_t r[16];
-                  tmem_ld16(tmem_base + as * Cfg::BLOCK_N + c + h * 16 + ((uint32_t)(quarter * 32) << 16), r);
+                  tmem_ld16(tmem_base + as * Cfg::BLOCK_N + group_c * COLS + i * 32 + h * 16 + lane_base, r);
                   tmem_ld_wait();
+                  epi.group_vals(p, t, row, col0 + i * 32 + h * 16, r, i * 2 + h);
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) accr[i][h * 16 + j] += __uint_as_float(r[j]);
+                  for (int j = 0; j < 16; ++j) accr[i][h * 16 + j] = fmaf(scale, __uint_as_float(r[j]), accr[i][h * 16 + j]);
                 }
               }
             }
@@ -377,19 +404,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
             as ^= 1;
             if (as == 0) aphase ^= 1;
           }
+          epi.group_done(p, t, row, group_c, GROUPS);
+        }
 #pragma unroll
-          for (int i = 0; i < NCH; ++i) {
-            int col = t.n_blk * Cfg::BLOCK_N + group_c * COLS + i * 32;
-            if (col < p.N) {
-              uint32_t r[32];
+        for (int i = 0; i < NCH; ++i) {
+          const int col = col0 + i * 32;
+          if (col < p.N) {
+            uint32_t r[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(accr[i][j]);
-              epi.chunk(p, t, row, col, r);
-            }
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(accr[i][j]);
+            epi.chunk(p, t, row, col, r, i);
           }
         }
-        epi.tile_done(p, t, row, group_c, GROUPS);
       }
+      epi.tile_done(p, t, row, group_c, GROUPS);
     }
     epi.finish(threadIdx.x - NUM_NON_EPI_THREADS, Cfg::EPI_WARPS * 32);
   }
@@ -428,6 +456,7 @@ int make_gemm_tmaps(const TcOperand& A, const TcOperand& B, CUtensorMap* tA, CUt
 
 template <class Cfg, class Epi>
 int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, const Epi& epi, cudaStream_t st) {
+  if (p.groups_inner && !Epi::kAccumulate) return COPER_ERR_INVALID_ARG;
   CUtensorMap tA, tAlo, tB, tBlo;
   int rc = make_gemm_tmaps<Cfg>(A, B, &tA, &tAlo, &tB, &tBlo);
   if (rc) return rc;
@@ -462,7 +491,7 @@ inline void plan_gemm(GemmProblem& p, bool allow_split, int target_ctas = 148) {
 }
 
 // Plain store epilogue: out[(group, split)][row, col] = acc * row_scale[row, group] (+ col_bias[col])
-struct StoreEpi {
+struct StoreEpi : EpiBase {
   float* out;
   long long ld, group_stride, split_stride;
   const float* row_scale;   // optional [M, row_scale_ld]; indexed [row, group]
@@ -471,7 +500,7 @@ struct StoreEpi {
   int extra_col;            // if >= 0: column index whose values go to extra_out[row] instead (e.g. dbias)
   float* extra_out;
   __device__ __forceinline__ void chunk(const GemmProblem& p, const TileCoord& t, int row, int col,
-                                        const uint32_t (&r)[32]) const {
+                                        const uint32_t (&r)[32], int) const {
     if (row >= p.M) return;
     float sc = row_scale ? __ldg(row_scale + (long long)row * row_scale_ld + t.group) : 1.0f;
     float* o = out + t.group * group_stride + t.split * split_stride + (long long)row * ld + col;
@@ -492,9 +521,14 @@ struct StoreEpi {
       }
     }
   }
-  __device__ __forceinline__ void tile_done(const GemmProblem&, const TileCoord&, int, int, int) const {}
-  __device__ __forceinline__ void finish(int, int) const {}
 };
+
+inline StoreEpi make_store_epi(float* out, long long ld, long long group_stride, long long split_stride) {
+  StoreEpi e;
+  e.out = out; e.ld = ld; e.group_stride = group_stride; e.split_stride = split_stride;
+  e.row_scale = nullptr; e.row_scale_ld = 0; e.col_bias = nullptr; e.extra_col = -1; e.extra_out = nullptr;
+  return e;
+}
 
 }  // namespace umma
 }  // namespace coper

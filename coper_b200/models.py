@@ -125,7 +125,7 @@ class ConvE:
         self.OH, self.OW = self.H - self.conv_filter_height + 1, self.W - self.conv_filter_width + 1
         self.C = self.conv_num_channels
         self.F = self.OH * self.OW * self.C                          # models.py:268
-        self.prec = PREC[prec]
+        self.prec = PREC[prec]                                       # scorer / CPG contraction arithmetic
         self.shard = shard or EntityShard(self.num_ent)
         self.group = process_group
         self.world = self.shard.world
@@ -246,7 +246,10 @@ class ConvE:
         maxC = max([C, d] + self.fc_weights.hidden)
         b.stat = z(nch * maxC * 2)
         b.stat1 = z(maxC * 2)
-        b.SG = z(B, ld)                        # logits (eval) / dL/dS (train); never read by the host
+        # logits (eval, fp32 [B, ld]) / dL/dS in the scorer's operand form (train); never read by the host
+        sg_bytes = max(B * ld * 4, lib.coper_score1n_bce_G_bytes(B, Ns, self.prec))
+        b.SG_store = z(-(-sg_bytes // 4))
+        b.SG = b.SG_store[:B * ld].view(B, ld)
         b.bits = z(B, words, dt=torch.int32)
         b.loss_sum = z(1, dt=torch.float64)
         b.gold = z(B)
@@ -254,9 +257,12 @@ class ConvE:
         b.dwc_part, b.dbc_part = z(B, self.conv_filter_height * self.conv_filter_width * C), z(B, C)
         dcw = self.fc_weights.projections[-1].shape[0]
         dcb = self.fc_bias.projections[-1].shape[0]
-        ws = max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dcw, F, d, self.prec),
-                 lib.coper_cpg_fc_bwd_workspace_bytes(B, dcw, F, d, self.prec),
-                 lib.coper_score1n_bce_workspace_bytes(B, Ns, d, self.prec),
+        # the CPG workspace is kept apart: the backward reuses the operands the forward prepared in it
+        ws_cpg = max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dcw, F, d, self.prec),
+                     lib.coper_cpg_fc_bwd_workspace_bytes(B, dcw, F, d, self.prec))
+        b.ws_cpg = torch.empty(ws_cpg, dtype=torch.uint8, device=dev)
+        b.ws_cpg_bytes = ws_cpg
+        ws = max(lib.coper_score1n_bce_workspace_bytes(B, Ns, d, self.prec),
                  lib.coper_score1n_workspace_bytes(B, Ns, d, self.prec),
                  lib.coper_segscatter_workspace_bytes(B))
         b.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
@@ -441,7 +447,7 @@ class ConvE:
         Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
         keep2 = 1.0 - (self.output_dropout if is_train else 0.0)
         call("coper_cpg_fc_fwd", ptr(cw), ptr(b.f), ptr(Pw), ptr(cb), ptr(Pb), B, Pw.shape[0], F, d, Pb.shape[0],
-             keep2, ptr(self.seed_dev), SALT_OUTPUT, ptr(b.y), ptr(b.ws), b.ws_bytes, self.prec)
+             keep2, ptr(self.seed_dev), SALT_OUTPUT, ptr(b.y), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec)
         self._bn_forward(self.fc_bn, b.y, B, d, b, use_batch, is_train, False, True, 1.0, 0, b.q)
         b.cw, b.cb = cw, cb
 
@@ -473,7 +479,7 @@ class ConvE:
         nw, nb = len(self.fc_weights.projections) - 1, len(self.fc_bias.projections) - 1
         call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(b.cb), ptr(Pb), ptr(b.dy), B, Pw.shape[0], F, d,
              Pb.shape[0], ptr(g["fc_weights/CPG/Projection%d" % nw]), ptr(g["fc_bias/CPG/Projection%d" % nb]),
-             ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws), b.ws_bytes, self.prec)
+             ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec, int(self.prec != 0))
         self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
         self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
         # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)

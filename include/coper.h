@@ -118,12 +118,14 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const float
                      int dc, int F, int d, int dcb, float keep_out, const uint64_t* seed_dev, uint64_t salt_out,
                      float* y, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
 /* backward (models.py:198 autodiff of the above): given dy [B,d] (already through the dropout mask)
- *   dP [dc,F*d], dPb [dcb,d], df [B,F], dc_out [B,dc], dcb_out [B,dcb]. */
+ *   dP [dc,F*d], dPb [dcb,d], df [B,F], dc_out [B,dc], dcb_out [B,dcb].
+ * reuse_fwd_operands != 0 (tensor-pipe precisions only): `workspace` is the buffer the matching
+ * coper_cpg_fc_fwd call used and still holds its prepared f and P operands (f, P unchanged since). */
 size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec);
 int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb,
                      const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
                      float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
-                     coper_stream_t stream);
+                     int reuse_fwd_operands, coper_stream_t stream);
 
 /* plain C = op(A) . op(B) (+C) for the small dense layers around the path (CPG hidden projections,
  * models.py:60): row-major; transX != 0 means the stored matrix is the transpose of the operand. */
@@ -159,11 +161,16 @@ int coper_tc_gemm(int transA, int transB, int M, int N, int K, const float* A, i
  *   G[b,n]   = (sigmoid(s) - z') * inv_count                    (inv_count = 1/(B*N_total))
  *   dq = G.E, dE = G^T.q, dbias = sum_b G.
  * label_bits [B, words] (words = ceil(Ns/32), bit n of row b = 1 iff entity n is a positive of query b);
- * G [B, ldG] is caller-provided scratch (never read by the host).  loss_sum is a device double. */
+ * G is caller-provided scratch of coper_score1n_bce_G_bytes (never read by the host; 128-byte aligned) holding
+ * dL/dS with row pitch ldG (a multiple of 32, >= Ns): fp32 [B, ldG] (FP32), bf16 [B, ldG] (BF16) or tf32
+ * hi/lo planes 2 x fp32 [B, ldG] (TF32X3) - on the tensor-pipe paths G is written by the scorer epilogue
+ * directly in operand form and consumed by the dq / dE GEMMs through TMA.  workspace must be 256-byte
+ * aligned.  loss_sum is a device double. */
 size_t coper_score1n_bce_workspace_bytes(int B, int64_t Ns, int d, int prec);
+size_t coper_score1n_bce_G_bytes(int B, int64_t Ns, int prec);
 int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const float* bias, const uint32_t* label_bits,
                               int B, int64_t Ns, int d, float pos_target, float neg_target, float inv_count,
-                              double* loss_sum, float* G, int64_t ldG, float* dq, float* dE, float* dbias,
+                              double* loss_sum, void* G, int64_t ldG, float* dq, float* dE, float* dbias,
                               void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
 
 /* labels / filters: CSR positives (rowptr int32 [B+1], col int32 [nnz], global entity ids) -> bit rows for

@@ -130,8 +130,20 @@ def _cpg_ref(c, f, P, cb, Pb):
     return kr @ P.reshape(dc * F, d) + cb @ Pb
 
 
-@pytest.mark.parametrize("B,dc,F,d", [(512, 8, 4608, 200), (7, 5, 192, 40), (130, 3, 1000, 72), (64, 32, 512, 200)])
-def test_cpg_fc_fwd_bwd(L, B, dc, F, d):
+def _bf16r(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "bf16"])
+@pytest.mark.parametrize("B,dc,F,d", [(512, 8, 4608, 200), (7, 5, 192, 40), (130, 3, 1000, 72), (64, 32, 512, 200),
+                                      (512, 32, 6272, 256)])
+def test_cpg_fc_fwd_bwd(L, B, dc, F, d, prec):
+    """fused generate-and-apply + backward.  fp32 (CUDA cores) and tf32x3 (tcgen05, 3-term compensated) are held to
+    the fp32 bar; bf16 (tcgen05) is compared with fp64 arithmetic on the bf16-rounded operands it actually consumes
+    (f, P, dy and c*dy are rounded to bf16; c scales in fp32)."""
+    p = L.PREC[prec]
+    if prec != "fp32" and F % 32:
+        pytest.skip("tensor-pipe CPG kernels need F % 32 == 0 (F = OH*OW*32 in the model)")
     rng = np.random.default_rng(3)
     c = rng.normal(size=(B, dc))
     f = np.maximum(rng.normal(size=(B, F)), 0)
@@ -139,27 +151,41 @@ def test_cpg_fc_fwd_bwd(L, B, dc, F, d):
     cb = rng.normal(size=(B, dc))
     Pb = rng.normal(size=(dc, d))
     lib = L.load()
-    ws = ws_buf(max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dc, F, d, 0), lib.coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, 0)))
+    ws = ws_buf(max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dc, F, d, p), lib.coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, p)))
+    c, f, P, cb, Pb = (a.astype(np.float32).astype(np.float64) for a in (c, f, P, cb, Pb))
     tc, tf, tP, tcb, tPb = (dev(a, torch.float32) for a in (c, f, P, cb, Pb))
-    y = torch.zeros(B, d, device="cuda")
+    y = torch.full((B, d), float("nan"), device="cuda")
     L.call("coper_cpg_fc_fwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), L.ptr(tcb), L.ptr(tPb), B, dc, F, d, dc, 1.0, None, 0,
-           L.ptr(y), L.ptr(ws), ws.numel(), 0)
-    yr = _cpg_ref(c, f, P, cb, Pb)
+           L.ptr(y), L.ptr(ws), ws.numel(), p)
+    dy = rng.normal(size=(B, d)).astype(np.float32).astype(np.float64)
+    if prec == "bf16":
+        fr, Pr = _bf16r(f), _bf16r(P)
+    else:
+        fr, Pr = f, P
+    yr = _cpg_ref(c, fr, Pr, cb, Pb)
     assert relerr(y.cpu().numpy(), yr) < 1e-5
-    dy = rng.normal(size=(B, d))
+    if prec == "bf16":
+        assert relerr(y.cpu().numpy(), _cpg_ref(c, f, P, cb, Pb)) < 1e-2
     dP = torch.zeros(dc, F * d, device="cuda")
     dPb = torch.zeros(dc, d, device="cuda")
     df = torch.zeros(B, F, device="cuda")
     dcw = torch.zeros(B, dc, device="cuda")
     dcb = torch.zeros(B, dc, device="cuda")
     L.call("coper_cpg_fc_bwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), L.ptr(tcb), L.ptr(tPb), L.ptr(dev(dy, torch.float32)),
-           B, dc, F, d, dc, L.ptr(dP), L.ptr(dPb), L.ptr(df), L.ptr(dcw), L.ptr(dcb), L.ptr(ws), ws.numel(), 0)
-    P3 = P.reshape(dc, F, d)
-    T = np.einsum("bj,kij->bki", dy, P3)
+           B, dc, F, d, dc, L.ptr(dP), L.ptr(dPb), L.ptr(df), L.ptr(dcw), L.ptr(dcb), L.ptr(ws), ws.numel(), p,
+           int(prec != "fp32"))
+    dyr = _bf16r(dy) if prec == "bf16" else dy
+    P3 = Pr.reshape(dc, F, d)
+    T = np.einsum("bj,kij->bki", dyr, P3)
     assert relerr(df.cpu().numpy(), np.einsum("bk,bki->bi", c, T)) < 2e-5
-    assert relerr(dcw.cpu().numpy(), np.einsum("bi,bki->bk", f, T)) < 2e-5
-    kr = (c[:, :, None] * f[:, None, :]).reshape(B, dc * F)
-    assert relerr(dP.cpu().numpy(), (kr.T @ dy).reshape(dc, F * d)) < 2e-5
+    assert relerr(dcw.cpu().numpy(), np.einsum("bi,bki->bk", f, T)) < 2e-5       # f enters the row sums in fp32
+    if prec == "bf16":
+        dyc = _bf16r((c[:, :, None] * dy[:, None, :]).astype(np.float32))       # [B, dc, d] rounded as consumed
+        dPr = np.einsum("bi,bkj->kij", fr, dyc).reshape(dc, F * d)
+    else:
+        kr = (c[:, :, None] * f[:, None, :]).reshape(B, dc * F)
+        dPr = (kr.T @ dy).reshape(dc, F * d)
+    assert relerr(dP.cpu().numpy(), dPr) < 2e-5
     assert relerr(dPb.cpu().numpy(), cb.T @ dy) < 2e-5
     assert relerr(dcb.cpu().numpy(), dy @ Pb.T) < 2e-5
 

@@ -84,3 +84,57 @@ def test_tc_gemm_all_layouts(prec, M, N, K):
                 assert relerr(got, exact) < 1e-5, (ta, tb, relerr(got, exact))
             else:
                 assert relerr(got, rounded) < 1e-5, (ta, tb, relerr(got, rounded))
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("B,N,d", [(512, 40943, 200), (7, 97, 40), (130, 1003, 200), (33, 5000, 256), (128, 70001, 256)])
+def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
+    """scorer + label-smoothed BCE + gradient on tcgen05 (models.py:433-437,448-453,198): loss, dq, dE, dbias.
+    tf32x3: fp32-class (loss 1e-5 rel, gradients 2e-5 of max); bf16: vs fp64 arithmetic on bf16-rounded q, E
+    (loss 1e-5; gradients additionally carry the bf16 rounding of G -> 1e-2 of max)."""
+    from coper_b200 import _lib as L
+    from oracle import conve_oracle as O
+    lib = L.load()
+    p = PREC[prec]
+    rng = np.random.default_rng(B * 3 + N + d)
+    q = np.maximum(rng.normal(size=(B, d)), 0).astype(np.float32)
+    E = rng.uniform(-0.05, 0.05, size=(N, d)).astype(np.float32)
+    bias = (rng.normal(size=N) * 0.1).astype(np.float32)
+    cfg = O.OracleConfig(num_ent=N, num_rel=2, ent_emb_size=d, rel_emb_size=2, conv_in_height=d // 4 if d % 10 else 10)
+    _, _, _, rowptr, col = O.synthetic_batch(cfg, B, seed=9, mean_pos=4.0)
+    words, ld = -(-N // 32), -(-N // 32) * 32
+    bits = torch.zeros(B, words, dtype=torch.int32, device="cuda")
+    trp, tcol = torch.as_tensor(rowptr.astype(np.int32)).cuda(), torch.as_tensor(col.astype(np.int32)).cuda()
+    L.call("coper_csr_to_bits", L.ptr(trp), L.ptr(tcol), B, 0, N, L.ptr(bits))
+    z = O.csr_to_dense(rowptr, col, N, np.float64)
+    pos, neg = np.float32(np.float32(0.9) + np.float32(1.0 / N)), np.float32(1.0 / N)
+    zs = np.where(z > 0, np.float64(pos), np.float64(neg))
+    inv = 1.0 / (B * N)
+    tq, tE, tb = torch.as_tensor(q).cuda(), torch.as_tensor(E).cuda(), torch.as_tensor(bias).cuda()
+    ws = torch.empty(lib.coper_score1n_bce_workspace_bytes(B, N, d, p), dtype=torch.uint8, device="cuda")
+    G = torch.empty(lib.coper_score1n_bce_G_bytes(B, N, p), dtype=torch.uint8, device="cuda")
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    nan = float("nan")
+    dq, dE, db = (torch.full(s, nan, device="cuda") for s in ((B, d), (N, d), (N,)))
+    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
+           inv, L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE), L.ptr(db), L.ptr(ws), ws.numel(), p)
+    torch.cuda.synchronize()
+    if prec == "tf32x3":
+        qq, EE = q.astype(np.float64), E.astype(np.float64)
+    else:
+        qq, EE = bf16_round(q), bf16_round(E)
+    Sr = qq @ EE.T + bias
+    el = np.maximum(Sr, 0) - Sr * zs + np.log1p(np.exp(-np.abs(Sr)))
+    Gr = (O.sigmoid(Sr) - zs) * inv
+    assert abs(loss.item() - el.sum()) < 1e-5 * el.sum()
+    gtol = 2e-5 if prec == "tf32x3" else 1e-2
+    for got, ref in ((dq, Gr @ EE), (dE, Gr.T @ qq), (db, Gr.sum(0))):
+        got = got.cpu().numpy()
+        assert np.isfinite(got).all()
+        assert relerr(got, ref) < gtol
+    # determinism: a second call is bit-identical
+    dq2, dE2, db2 = (torch.zeros_like(t) for t in (dq, dE, db))
+    loss2 = torch.zeros_like(loss)
+    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
+           inv, L.ptr(loss2), L.ptr(G), ld, L.ptr(dq2), L.ptr(dE2), L.ptr(db2), L.ptr(ws), ws.numel(), p)
+    assert torch.equal(dq, dq2) and torch.equal(dE, dE2) and torch.equal(db, db2) and torch.equal(loss, loss2)

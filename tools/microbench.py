@@ -50,7 +50,59 @@ def tcgemm(M, N, K, ta, tb):
     print("   simt sgemm %.3f ms %.1f TF/s" % (t, fl / t / 1e9))
 
 
+def bce(B, N, d, precs=("fp32", "bf16", "tf32x3")):
+    q = torch.randn(B, d, device="cuda").clamp_(min=0)
+    E = (torch.rand(N, d, device="cuda") - 0.5) * 0.1
+    bias = torch.zeros(N, device="cuda")
+    ld = -(-N // 32) * 32
+    bits = torch.zeros(B, ld // 32, dtype=torch.int32, device="cuda")
+    bits[:, ::97] = 5
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dq, dE, db = torch.zeros(B, d, device="cuda"), torch.zeros(N, d, device="cuda"), torch.zeros(N, device="cuda")
+    fl = 6.0 * B * N * d
+    for name in precs:
+        p = L.PREC[name]
+        ws = torch.empty(lib.coper_score1n_bce_workspace_bytes(B, N, d, p), dtype=torch.uint8, device="cuda")
+        G = torch.empty(lib.coper_score1n_bce_G_bytes(B, N, p), dtype=torch.uint8, device="cuda")
+        t = timeit(lambda: L.call("coper_score1n_bce_fwd_bwd", L.ptr(q), L.ptr(E), L.ptr(bias), L.ptr(bits), B, N, d,
+                                  0.9, 1.0 / N, 1.0 / (B * N), L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE),
+                                  L.ptr(db), L.ptr(ws), ws.numel(), p))
+        print("score1n_bce_fwd_bwd B=%d N=%d d=%d %-7s %.3f ms %.1f TF/s" % (B, N, d, name, t, fl / t / 1e9))
+
+
+def cpg(B, dc, F, d, precs=("fp32", "bf16", "tf32x3")):
+    c, f = torch.randn(B, dc, device="cuda"), torch.randn(B, F, device="cuda").clamp_(min=0)
+    P, Pb = torch.randn(dc, F * d, device="cuda") * 0.01, torch.randn(dc, d, device="cuda")
+    dy = torch.randn(B, d, device="cuda")
+    y, df, dcw, dcb = (torch.zeros(s, device="cuda") for s in ((B, d), (B, F), (B, dc), (B, dc)))
+    dP, dPb = torch.zeros_like(P), torch.zeros_like(Pb)
+    fl = 2.0 * B * dc * F * d
+    for name in precs:
+        p = L.PREC[name]
+        ws = torch.empty(max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dc, F, d, p),
+                             lib.coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, p)), dtype=torch.uint8, device="cuda")
+        t1 = timeit(lambda: L.call("coper_cpg_fc_fwd", L.ptr(c), L.ptr(f), L.ptr(P), L.ptr(c), L.ptr(Pb), B, dc, F, d, dc,
+                                   1.0, None, 0, L.ptr(y), L.ptr(ws), ws.numel(), p))
+        t2 = timeit(lambda: L.call("coper_cpg_fc_bwd", L.ptr(c), L.ptr(f), L.ptr(P), L.ptr(c), L.ptr(Pb), L.ptr(dy), B, dc,
+                                   F, d, dc, L.ptr(dP), L.ptr(dPb), L.ptr(df), L.ptr(dcw), L.ptr(dcb), L.ptr(ws),
+                                   ws.numel(), p, int(p != 0)))
+        print("cpg_fc B=%d dc=%d F=%d d=%d %-7s fwd %.3f ms %.1f TF/s | bwd %.3f ms %.1f TF/s" % (
+            B, dc, F, d, name, t1, fl / t1 / 1e9, t2, 2 * fl / t2 / 1e9))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cpg":
+        cpg(512, 8, 4608, 200)
+        cpg(512, 32, 4608, 200)
+        cpg(512, 32, 6272, 256)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":
+        bce(512, 40943, 200, precs=(sys.argv[2],))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "bce":
+        bce(512, 40943, 200)
+        bce(512, 1250000, 256, precs=("bf16", "tf32x3"))
+        sys.exit(0)
     score(512, 40943, 200)
     score(512, 1000000, 256)
     tcgemm(40943, 200, 512, 1, 0)     # dE-like
