@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--shape", default=os.environ.get("COPER_BENCH_SHAPE", "wn18rr"))
-    ap.add_argument("--prec", default=os.environ.get("COPER_BENCH_PREC", "fp32"))
+    ap.add_argument("--prec", default=os.environ.get("COPER_BENCH_PREC", "tf32x3"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -265,3 +265,68 @@ def test_train_step_is_deterministic():
         outs.append({k: v.clone() for k, v in m.grads.items()})
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+# ------------------------------------------------------------------------------------------ tensor-pipe engines
+TC_TOL = {  # prec: (q, loss, dq/dy/df, parameter grads)
+    "tf32x3": (1e-5, 1e-5, 1e-4, 2e-4),       # fp32-class: same bars as the CUDA-core fp32 engine
+    "bf16": (2e-2, 2e-3, 5e-2, 5e-2),         # stated tolerance of the bf16 path (operands rounded to 8 mantissa bits)
+}
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("name", ["toy_glinear_batch_stats", "toy_gmlp_bn_dropout", "ragged_mid", "d256_16x16"])
+def test_train_step_parity_tensor_pipe(name, prec):
+    """Same step as test_train_step_parity with the CPG contraction and the scorer on tcgen05."""
+    kw, B = CASES[name]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5)
+    e1[B // 2:] = e1[: B - B // 2]
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    model = make(cfg, params, prec=prec)
+    loss = float(model.train_step(batch_of(e1, rel, e2, rowptr, col), apply_update=False).item())
+    masks = export_masks(model, cfg, B)
+    out = O.forward(params, cfg, e1, rel, True, masks, dense, np.float64)
+    g = O.backward(out, cfg)
+    b = model._bufs[B]
+    tq, tl, ta, tg = TC_TOL[prec]
+    assert relerr(b.q.cpu().numpy(), out["q"]) < tq
+    assert abs(loss - out["loss"]) < tl * abs(out["loss"])
+    assert relerr(b.dq.cpu().numpy(), g["_dq"]) < ta
+    mg = grads_by_name(model)
+    if prec == "bf16":
+        # dL/dS is carried in bf16: the scorer-side gradients meet the stated bar; everything behind the batch-stat
+        # FCBN backward sees the per-query variation of dq (the common part cancels) and is only required to point
+        # the same way as the oracle gradient.
+        assert relerr(mg["pred_bias"], g["pred_bias"]) < tg
+        cos = lambda a, r: float((a.ravel() * r.ravel()).sum() / (np.linalg.norm(a) * np.linalg.norm(r) + 1e-30))
+        assert cos(mg["ent_emb"], g["ent_emb"]) > 0.99
+        assert cos(b.dy.cpu().numpy(), g["_dy"]) > 0.9
+        assert cos(mg["fc_weights/CPG/Projection%d" % (len(g["fc_weights_proj"]) - 1)].reshape(-1),
+                   g["fc_weights_proj"][-1].reshape(-1)) > 0.9
+        return
+    assert relerr(b.dy.cpu().numpy(), g["_dy"]) < ta
+    assert relerr(b.df.cpu().numpy(), g["_df"]) < ta
+    compare_grads(model, g, cfg, tol=tg)
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("name", ["toy_glinear_eval_stats", "ragged_mid", "d256_16x16"])
+def test_eval_scores_and_ranks_tensor_pipe(name, prec):
+    kw, B = CASES[name]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=4, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=6, mean_pos=6.0)
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    model = make(cfg, params, prec=prec)
+    batch = batch_of(e1, rel, e2, rowptr, col)
+    S = model.predict_all(batch).cpu().numpy()
+    out = O.forward(params, cfg, e1, rel, False, None, None, np.float64)
+    assert relerr(S, out["scores"]) < (1e-5 if prec == "tf32x3" else 2e-2)
+    rank, n_equal = model.filtered_ranks(batch)
+    cnt, ne = O.rank_count(S, e2, dense)                      # ranks are bit-exact given the device logits
+    assert (n_equal.cpu().numpy() == ne).all() and (rank.cpu().numpy() == cnt).all()
+    if prec == "tf32x3" and ne.sum() == 0:
+        ref_rank = O.rank_literal(out["scores"].astype(np.float32), e2, dense)
+        assert (rank.cpu().numpy() == ref_rank).mean() > 0.98  # fp32-class logits: ranks agree except near-ties
