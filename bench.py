@@ -283,14 +283,14 @@ def kernel_breakdown(model, batch, peaks, prec, reps=10):
     dc = Pw.shape[0]
     pos, neg = 0.9 + 1.0 / model.num_ent, 1.0 / model.num_ent
     stages = {
-        "cpg_fc_fwd": (lambda: call("coper_cpg_fc_fwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(b.cb), ptr(Pb), B, dc, F, d,
+        "cpg_fc_fwd": (lambda: call("coper_cpg_fc_fwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(model.P_prep), ptr(b.cb), ptr(Pb), B, dc, F, d,
                                     Pb.shape[0], 1.0, None, 0, ptr(b.y), ptr(b.ws_cpg), b.ws_cpg_bytes, model.prec),
                        2.0 * B * dc * F * d, "tensor"),
-        "cpg_fc_bwd": (lambda: call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(b.cb), ptr(Pb), ptr(b.dy),
+        "cpg_fc_bwd": (lambda: call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(model.P_prep), ptr(b.cb), ptr(Pb), ptr(b.dy),
                                     B, dc, F, d, Pb.shape[0], ptr(g["fc_weights/CPG/Projection0"]),
                                     ptr(g["fc_bias/CPG/Projection0"]), ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg),
                                     b.ws_cpg_bytes, model.prec, 0), 4.0 * B * dc * F * d, "tensor"),
-        "score1n_bce_fwd_bwd": (lambda: call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(model.ent_emb),
+        "score1n_bce_fwd_bwd": (lambda: call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(model.ent_emb), ptr(model.E_prep),
                                              ptr(model.pred_bias), ptr(b.bits), B, Ns, d, pos, neg,
                                              1.0 / (B * model.num_ent), ptr(b.loss_sum), ptr(b.SG), b.ld, ptr(b.dq),
                                              ptr(g["ent_emb"]), ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes,

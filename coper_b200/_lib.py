@@ -35,9 +35,9 @@ SIGNATURES = {
     "coper_dropout_mask": (i32, [i64, f32, vp, u64, vp, vp]),
     "coper_dropout_apply": (i32, [vp, i64, f32, vp, u64, vp]),
     "coper_cpg_fc_fwd_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
-    "coper_cpg_fc_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, u64, vp, vp, sz, i32, vp]),
+    "coper_cpg_fc_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, u64, vp, vp, sz, i32, vp]),
     "coper_cpg_fc_bwd_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
-    "coper_cpg_fc_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, i32, i32,
+    "coper_cpg_fc_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, i32, i32,
                                vp]),
     "coper_sgemm": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp]),
     "coper_score1n_workspace_bytes": (sz, [i32, i64, i32, i32]),
@@ -49,7 +49,7 @@ SIGNATURES = {
     "coper_tc_gemm": (i32, [i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, sz, vp]),
     "coper_score1n_bce_workspace_bytes": (sz, [i32, i64, i32, i32]),
     "coper_score1n_bce_G_bytes": (sz, [i32, i64, i32]),
-    "coper_score1n_bce_fwd_bwd": (i32, [vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
+    "coper_score1n_bce_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
                                         sz, i32, vp]),
     "coper_csr_to_bits": (i32, [vp, vp, i32, i64, i64, vp, vp]),
     "coper_dense_to_bits": (i32, [vp, i32, i64, vp, vp]),
@@ -61,9 +61,13 @@ SIGNATURES = {
     "coper_sumsq": (i32, [vp, i64, i32, vp, vp]),
     "coper_clip_scale": (i32, [vp, i32, f32, vp, vp]),
     "coper_step_state_advance": (i32, [vp, vp, f32, f32, f32, vp]),
+    "coper_mt_sumsq": (i32, [vp, i32, vp, i32, vp, vp, vp, vp]),
+    "coper_clip_scale_n": (i32, [vp, i32, f32, vp, vp]),
+    "coper_mt_amsgrad": (i32, [vp, vp, i32, vp, f32, f32, f32, vp, i32, vp]),
     "coper_amsgrad_step": (i32, [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, vp, i32, vp]),
 }
 SUMSQ_BLOCKS = 256
+MT_CHUNK = 16384
 
 _lib = None
 launch_count = 0  # number of C-ABI compute calls issued by this process (bench.py reports it)

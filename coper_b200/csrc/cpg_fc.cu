@@ -23,11 +23,11 @@ using namespace simt;
 // tcgen05 engine (umma_cpg.cu)
 size_t umma_cpg_fwd_workspace_bytes(int B, int dc, int F, int d, int prec);
 size_t umma_cpg_bwd_workspace_bytes(int B, int dc, int F, int d, int prec);
-int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, int B, int dc, int F, int d, void* ws,
-                          size_t ws_bytes, int prec, cudaStream_t st, float** slabs, int* n_slabs);
-int umma_cpg_bwd(const float* c, const float* f, const float* P, const float* dy, int B, int dc, int F, int d,
-                 float* dP, float* df, float* dc_out, void* ws, size_t ws_bytes, int prec, int reuse_fwd_operands,
-                 cudaStream_t st);
+int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, const void* P_prepared, int B, int dc, int F,
+                          int d, void* ws, size_t ws_bytes, int prec, cudaStream_t st, float** slabs, int* n_slabs);
+int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* dy, int B, int dc,
+                 int F, int d, float* dP, float* df, float* dc_out, void* ws, size_t ws_bytes, int prec,
+                 int reuse_fwd_operands, cudaStream_t st);
 
 // ---------------------------------------------------------------- sources
 struct CpgFwdA {  // (b, kk) -> f[b, i] * c[b, kq],  K-contiguous
@@ -187,6 +187,37 @@ __global__ void __launch_bounds__(THREADS) cpg_bwd_dP_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------- bias-generator gradients (tiny: dcb, d <= a few hundred)
+// dPb[k, j] = sum_b cb[b,k] dy[b,j] : block = (k, 32-column slab), 8 batch lanes, fixed-order combine
+__global__ void __launch_bounds__(256) cpg_dPb_kernel(const float* __restrict__ cb, const float* __restrict__ dy,
+                                                      int B, int d, int dcb, float* __restrict__ dPb) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.y, j = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (j < d)
+    for (int b = ty; b < B; b += 8) acc = fmaf(__ldg(cb + (int64_t)b * dcb + k), __ldg(dy + (int64_t)b * d + j), acc);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < d) {
+    float t = red[0][tx];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) t += red[r][tx];
+    dPb[(int64_t)k * d + j] = t;
+  }
+}
+// dcb[b, k] = sum_j dy[b,j] Pb[k,j] : one warp per (b, k)
+__global__ void __launch_bounds__(256) cpg_dcb_kernel(const float* __restrict__ dy, const float* __restrict__ Pb, int B,
+                                                      int d, int dcb, float* __restrict__ dcb_out) {
+  int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= B * dcb) return;
+  int b = w / dcb, k = w - b * dcb;
+  float acc = 0.f;
+  for (int j = lane; j < d; j += 32) acc = fmaf(__ldg(dy + (int64_t)b * d + j), __ldg(Pb + (int64_t)k * d + j), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) dcb_out[w] = acc;
+}
+
 // ---------------------------------------------------------------- plain sgemm
 template <class SA, class SB>
 __global__ void __launch_bounds__(THREADS) sgemm_kernel(SA A, SB Bs, int M, int N, int K, float* __restrict__ C,
@@ -256,9 +287,10 @@ size_t coper_cpg_fc_fwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
   return cpg_fwd_layout(B, dc, F, d).total;
 }
 
-int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb, int B, int dc,
-                     int F, int d, int dcb, float keep_out, const uint64_t* seed_dev, uint64_t salt_out, float* y,
-                     void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
+int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
+                     const float* Pb, int B, int dc, int F, int d, int dcb, float keep_out, const uint64_t* seed_dev,
+                     uint64_t salt_out, float* y, void* workspace, size_t workspace_bytes, int prec,
+                     coper_stream_t stream) {
   COPER_CHECK_ARG(c && f && P && cb && Pb && y && workspace && B > 0 && dc > 0 && F > 0 && d > 0 && dcb > 0);
   COPER_CHECK_ARG(keep_out > 0.f);
   cudaStream_t st = as_stream(stream);
@@ -266,7 +298,7 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const float
   int n_slabs = 0;
   int rc;
   if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3) {
-    if ((rc = umma_cpg_fwd_partials(c, f, P, B, dc, F, d, workspace, workspace_bytes, prec, st, &part, &n_slabs)))
+    if ((rc = umma_cpg_fwd_partials(c, f, P, P_prepared, B, dc, F, d, workspace, workspace_bytes, prec, st, &part, &n_slabs)))
       return rc;
   } else if (prec == COPER_PREC_FP32) {
     CpgLayout L = cpg_fwd_layout(B, dc, F, d);
@@ -291,8 +323,8 @@ size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
   return align_up((size_t)ceil_div(F, BN) * B * dc * sizeof(float), 256);
 }
 
-int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb,
-                     const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
+int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
+                     const float* Pb, const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
                      float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
                      int reuse_fwd_operands, coper_stream_t stream) {
   COPER_CHECK_ARG(c && f && P && cb && Pb && dy && dP && dPb && df && dc_out && dcb_out && workspace);
@@ -301,7 +333,7 @@ int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float
   cudaStream_t st = as_stream(stream);
   int rc;
   if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3) {
-    if ((rc = umma_cpg_bwd(c, f, P, dy, B, dc, F, d, dP, df, dc_out, workspace, workspace_bytes, prec,
+    if ((rc = umma_cpg_bwd(c, f, P, P_prepared, dy, B, dc, F, d, dP, df, dc_out, workspace, workspace_bytes, prec,
                            reuse_fwd_operands, st)))
       return rc;
   } else if (prec == COPER_PREC_FP32) {
@@ -316,8 +348,10 @@ int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float
     return COPER_ERR_UNSUPPORTED;
   }
   // dPb [dcb, d] = cb^T . dy ;  dcb [B, dcb] = dy . Pb^T
-  if ((rc = coper_sgemm(1, 0, dcb, d, B, cb, dcb, dy, d, dPb, d, 0, stream))) return rc;
-  return coper_sgemm(0, 1, B, dcb, d, dy, d, Pb, d, dcb_out, dcb, 0, stream);
+  cpg_dPb_kernel<<<dim3(ceil_div(d, 32), dcb), 256, 0, st>>>(cb, dy, B, d, dcb, dPb);
+  if ((rc = check_launch())) return rc;
+  cpg_dcb_kernel<<<ceil_div((int64_t)B * dcb * 32, 256), 256, 0, st>>>(dy, Pb, B, d, dcb, dcb_out);
+  return check_launch();
 }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 // HBM-bound pieces of the CoPER-ConvE hot path: lookups, batch-norm/relu/dropout, label bit rows,
 // deterministic reductions, global-norm clip and AMSGrad.  All kernels are streaming: coalesced,
 // 128-bit vectorised where the shape allows, grids sized in multiples of the SM count.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace coper {
@@ -240,14 +241,32 @@ __global__ void dense_to_bits_kernel(const float* __restrict__ dense, int B, int
 }
 
 // ------------------------------------------------------------------ deterministic reductions
-__global__ void reduce_partials_kernel(const float* __restrict__ in, int S, int64_t n, float scale, int accumulate,
-                                       float* __restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[i] = scale * sum_s in[s, i]: block = 32 outputs x 8 slab lanes; every thread sums the slabs s = ty, ty+8, ...
+// in fp64, the 8 lane sums are added in a fixed order -> deterministic, and the slab loop is 8x shorter / pipelined
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ in, int S, int64_t n,
+                                                              float scale, int accumulate, float* __restrict__ out) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int64_t i = (int64_t)blockIdx.x * 32 + tx;
   double acc = 0.0;
-  for (int s = 0; s < S; ++s) acc += (double)in[(int64_t)s * n + i];
-  float r = (float)(acc * (double)scale);
-  out[i] = accumulate ? out[i] + r : r;
+  if (i < n) {
+    int s = ty;
+    for (; s + 24 < S; s += 32) {
+      float a0 = __ldg(in + (int64_t)s * n + i), a1 = __ldg(in + (int64_t)(s + 8) * n + i);
+      float a2 = __ldg(in + (int64_t)(s + 16) * n + i), a3 = __ldg(in + (int64_t)(s + 24) * n + i);
+      acc += (double)a0; acc += (double)a1; acc += (double)a2; acc += (double)a3;
+    }
+    for (; s < S; s += 8) acc += (double)__ldg(in + (int64_t)s * n + i);
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && i < n) {
+    double t = red[0][tx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][tx];
+    float r = (float)(t * (double)scale);
+    out[i] = accumulate ? out[i] + r : r;
+  }
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
@@ -321,6 +340,112 @@ __global__ void step_state_advance_kernel(float* st, uint64_t* seed_dev, float l
     st[1] = b1p * b1;                                // amsgrad.py:234-239
     st[2] = b2p * b2;
     if (seed_dev) *seed_dev += 1ull;
+  }
+}
+
+
+// ------------------------------------------------------------------ multi-tensor clip + AMSGrad (one launch each)
+// work list: chunk c = (tensor id, first element); every chunk covers <= COPER_MT_CHUNK elements of one tensor
+__global__ void __launch_bounds__(256) mt_sumsq_kernel(const coper_param_desc* __restrict__ descs,
+                                                       const int32_t* __restrict__ chunks,
+                                                       double* __restrict__ chunk_partials) {
+  __shared__ double sm[32];
+  const int t = chunks[2 * blockIdx.x];
+  const int64_t start = (int64_t)chunks[2 * blockIdx.x + 1] * COPER_MT_CHUNK;
+  const coper_param_desc d = descs[t];
+  const int64_t end = start + COPER_MT_CHUNK < d.n ? start + COPER_MT_CHUNK : d.n;
+  const float* x = d.grad;
+  float p = 0.f;
+  if (((reinterpret_cast<uintptr_t>(x) & 15) == 0) && end - start == COPER_MT_CHUNK) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + start);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < COPER_MT_CHUNK / 4; j += 256) {
+      float4 v = __ldg(x4 + j);
+      p += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (int64_t j = start + threadIdx.x; j < end; j += 256) { float v = x[j]; p += v * v; }
+  }
+  double tsum = block_sum<double>((double)p, sm);
+  if (threadIdx.x == 0) chunk_partials[blockIdx.x] = tsum;
+}
+// tensor_sumsq[t] = sum of the chunk partials of tensor t (fixed order); chunk_offsets [n_tensors + 1]
+__global__ void mt_tensor_sums_kernel(const double* __restrict__ chunk_partials, const int32_t* __restrict__ chunk_offsets,
+                                      int n_tensors, double* __restrict__ tensor_sumsq) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tensors) return;
+  double acc = 0.0;
+  for (int c = chunk_offsets[t]; c < chunk_offsets[t + 1]; ++c) acc += chunk_partials[c];
+  tensor_sumsq[t] = acc;
+}
+__device__ __forceinline__ void amsgrad_elem(float g, float& th, float* m, float* v, float& vh, int64_t i, float lr_t,
+                                             float b1, float b2, float omb1, float omb2, float eps, int bug_compat) {
+  float mt, vt;
+  if (bug_compat) {
+    mt = g * omb1;
+    vt = (g * g) * omb2;
+  } else {
+    mt = m[i] * b1 + g * omb1;
+    vt = v[i] * b2 + (g * g) * omb2;
+    m[i] = mt;
+    v[i] = vt;
+  }
+  vh = fmaxf(vh, vt);
+  th -= lr_t * mt / (sqrtf(vh) + eps);
+}
+__device__ __forceinline__ void emit_prepared(const coper_param_desc& d, int64_t i, float th) {
+  if (d.prepared_prec == COPER_PREC_BF16) {
+    static_cast<__nv_bfloat16*>(d.prepared)[i] = __float2bfloat16_rn(th);
+  } else {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(th));
+    float hf = __uint_as_float(h);
+    static_cast<float*>(d.prepared)[i] = hf;
+    static_cast<float*>(d.prepared)[d.n + i] = th - hf;
+  }
+}
+__global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc* __restrict__ descs,
+                                                         const int32_t* __restrict__ chunks,
+                                                         const float* __restrict__ step_state, float b1, float b2,
+                                                         float eps, const float* __restrict__ clip_scale,
+                                                         int bug_compat) {
+  const int t = chunks[2 * blockIdx.x];
+  const int64_t start = (int64_t)chunks[2 * blockIdx.x + 1] * COPER_MT_CHUNK;
+  const coper_param_desc d = descs[t];
+  const int64_t end = start + COPER_MT_CHUNK < d.n ? start + COPER_MT_CHUNK : d.n;
+  const float lr_t = step_state[0];
+  const float cs = clip_scale ? *clip_scale : 1.0f;
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  const bool vec = end - start == COPER_MT_CHUNK && bug_compat &&
+                   (((reinterpret_cast<uintptr_t>(d.theta) | reinterpret_cast<uintptr_t>(d.grad) |
+                      reinterpret_cast<uintptr_t>(d.vhat)) & 15) == 0);
+  if (vec) {
+    float4* th4 = reinterpret_cast<float4*>(d.theta + start);
+    const float4* g4 = reinterpret_cast<const float4*>(d.grad + start);
+    float4* vh4 = reinterpret_cast<float4*>(d.vhat + start);
+#pragma unroll 2
+    for (int j = threadIdx.x; j < COPER_MT_CHUNK / 4; j += 256) {
+      float4 g = g4[j], th = th4[j], vh = vh4[j];
+      amsgrad_elem(g.x * cs, th.x, nullptr, nullptr, vh.x, 0, lr_t, b1, b2, omb1, omb2, eps, 1);
+      amsgrad_elem(g.y * cs, th.y, nullptr, nullptr, vh.y, 0, lr_t, b1, b2, omb1, omb2, eps, 1);
+      amsgrad_elem(g.z * cs, th.z, nullptr, nullptr, vh.z, 0, lr_t, b1, b2, omb1, omb2, eps, 1);
+      amsgrad_elem(g.w * cs, th.w, nullptr, nullptr, vh.w, 0, lr_t, b1, b2, omb1, omb2, eps, 1);
+      th4[j] = th;
+      vh4[j] = vh;
+      if (d.prepared) {
+        int64_t i = start + 4 * (int64_t)j;
+        emit_prepared(d, i, th.x); emit_prepared(d, i + 1, th.y); emit_prepared(d, i + 2, th.z);
+        emit_prepared(d, i + 3, th.w);
+      }
+    }
+  } else {
+    for (int64_t i = start + threadIdx.x; i < end; i += 256) {
+      float th = d.theta[i], vh = d.vhat[i];
+      amsgrad_elem(d.grad[i] * cs, th, d.m, d.v, vh, i, lr_t, b1, b2, omb1, omb2, eps, bug_compat);
+      d.theta[i] = th;
+      d.vhat[i] = vh;
+      if (d.prepared) emit_prepared(d, i, th);
+    }
   }
 }
 
@@ -477,7 +602,7 @@ int coper_dense_to_bits(const float* dense, int B, int64_t N, uint32_t* bits, co
 int coper_reduce_partials(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
                           coper_stream_t stream) {
   COPER_CHECK_ARG(in && out && S > 0 && n > 0);
-  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate, out);
+  reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate, out);
   return check_launch();
 }
 int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_stream_t stream) {
@@ -488,6 +613,29 @@ int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_str
 int coper_clip_scale(const double* partials, int n_slots, float clip_norm, float* out2, coper_stream_t stream) {
   COPER_CHECK_ARG(partials && out2 && n_slots > 0 && clip_norm > 0.f);
   clip_scale_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, n_slots * COPER_SUMSQ_BLOCKS, clip_norm, out2);
+  return check_launch();
+}
+int coper_clip_scale_n(const double* sums, int n, float clip_norm, float* out2, coper_stream_t stream) {
+  COPER_CHECK_ARG(sums && out2 && n > 0 && clip_norm > 0.f);
+  clip_scale_kernel<<<1, 256, 0, as_stream(stream)>>>(sums, n, clip_norm, out2);
+  return check_launch();
+}
+int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
+                   const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, coper_stream_t stream) {
+  COPER_CHECK_ARG(descs && chunks && chunk_offsets && chunk_partials && tensor_sumsq && n_tensors > 0 && n_chunks > 0);
+  mt_sumsq_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, chunk_partials);
+  int rc = check_launch();
+  if (rc) return rc;
+  mt_tensor_sums_kernel<<<(n_tensors + 63) / 64, 64, 0, as_stream(stream)>>>(chunk_partials, chunk_offsets, n_tensors,
+                                                                            tensor_sumsq);
+  return check_launch();
+}
+int coper_mt_amsgrad(const coper_param_desc* descs, const int32_t* chunks, int n_chunks, const float* step_state,
+                     float beta1, float beta2, float eps, const float* clip_scale, int bug_compat,
+                     coper_stream_t stream) {
+  COPER_CHECK_ARG(descs && chunks && step_state && n_chunks > 0);
+  mt_amsgrad_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, step_state, beta1, beta2, eps, clip_scale,
+                                                            bug_compat);
   return check_launch();
 }
 int coper_step_state_advance(float* step_state, uint64_t* seed_dev, float lr, float beta1, float beta2,

@@ -17,7 +17,8 @@ size_t umma_score1n_workspace_bytes(int B, int64_t Ns, int d, int prec);
 // implemented in umma_bce.cu (tcgen05 path)
 size_t umma_bce_workspace_bytes(int B, int64_t Ns, int d, int prec);
 size_t umma_bce_G_bytes(int B, int64_t Ns, int prec);
-int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const float* bias, const uint32_t* label_bits, int B,
+int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
+                             const uint32_t* label_bits, int B,
                              int64_t Ns, int d, float pos, float neg, float inv_count, double* loss_sum, void* G,
                              int64_t ldG, float* dq, float* dE, float* dbias, void* ws, size_t ws_bytes, int prec,
                              cudaStream_t st);
@@ -238,14 +239,15 @@ size_t coper_score1n_bce_G_bytes(int B, int64_t Ns, int prec) {
   return (size_t)B * ((Ns + 31) / 32 * 32) * sizeof(float);
 }
 
-int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const float* bias, const uint32_t* label_bits, int B,
+int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
+                              const uint32_t* label_bits, int B,
                               int64_t Ns, int d, float pos_target, float neg_target, float inv_count,
                               double* loss_sum, void* Gv, int64_t ldG, float* dq, float* dE, float* dbias,
                               void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
   COPER_CHECK_ARG(q && E && bias && label_bits && loss_sum && Gv && dq && dE && dbias && workspace);
   COPER_CHECK_ARG(B > 0 && Ns > 0 && d > 0 && ldG >= Ns);
   if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3)
-    return umma_score1n_bce_fwd_bwd(q, E, bias, label_bits, B, Ns, d, pos_target, neg_target, inv_count, loss_sum, Gv,
+    return umma_score1n_bce_fwd_bwd(q, E, E_prepared, bias, label_bits, B, Ns, d, pos_target, neg_target, inv_count, loss_sum, Gv,
                                     ldG, dq, dE, dbias, workspace, workspace_bytes, prec, as_stream(stream));
   if (prec != COPER_PREC_FP32) return COPER_ERR_UNSUPPORTED;
   float* G = static_cast<float*>(Gv);

@@ -164,7 +164,8 @@ static int launch_bce(const TcOperand& Q, const TcOperand& E, int B, int64_t Ns,
   return launch_gemm<Cfg, BceEpi<Cfg::PREC>>(Q, E, p, epi, st);
 }
 
-int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const float* bias, const uint32_t* label_bits, int B,
+int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
+                             const uint32_t* label_bits, int B,
                              int64_t Ns, int d, float pos, float neg, float inv_count, double* loss_sum, void* G,
                              int64_t ldG, float* dq, float* dE, float* dbias, void* ws, size_t ws_bytes, int prec,
                              cudaStream_t st) {
@@ -175,13 +176,13 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const float* bias, 
   if (reinterpret_cast<uintptr_t>(ws) & 255) return COPER_ERR_INVALID_ARG;
   char* w = static_cast<char*>(ws);
   void* qp = w + L.off_q;
-  void* Ep = w + L.off_E;
+  const void* Ep = E_prepared ? E_prepared : w + L.off_E;
   float* dq_part = reinterpret_cast<float*>(w + L.off_dq);
   float* dbias_part = reinterpret_cast<float*>(w + L.off_dbias);
   double* loss_part = reinterpret_cast<double*>(w + L.off_loss);
   int rc;
   if ((rc = tc_prepare(q, B, d, d, prec, qp, st))) return rc;
-  if ((rc = tc_prepare(E, Ns, d, d, prec, Ep, st))) return rc;
+  if (!E_prepared && (rc = tc_prepare(E, Ns, d, d, prec, w + L.off_E, st))) return rc;
   TcOperand Qo = tc_operand(qp, B, d, prec), Eo = tc_operand(Ep, Ns, d, prec);
   // ---- pass 1: scores -> loss, G, dbias partials
   int grid = 0;

@@ -176,19 +176,19 @@ size_t umma_cpg_bwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
 }
 
 // Computes the split-K slabs of (c (x) f) . P^ into the workspace; *slabs / *n_slabs describe them.
-int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, int B, int dc, int F, int d, void* ws,
-                          size_t ws_bytes, int prec, cudaStream_t st, float** slabs, int* n_slabs) {
+int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, const void* P_prepared, int B, int dc, int F,
+                          int d, void* ws, size_t ws_bytes, int prec, cudaStream_t st, float** slabs, int* n_slabs) {
   if (F % 32 != 0 || d > 256) return COPER_ERR_UNSUPPORTED;
   CpgFwdPlan L = cpg_fwd_plan(B, dc, F, d, prec);
   if (!ws || ws_bytes < L.total) return COPER_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(ws) & 255) return COPER_ERR_INVALID_ARG;
   char* w = static_cast<char*>(ws);
   void* fp = w + L.off_f;
-  void* Pp = w + L.off_P;
+  const void* Pp = P_prepared ? P_prepared : w + L.off_P;
   float* out = reinterpret_cast<float*>(w + L.off_slabs);
   int rc;
   if ((rc = tc_prepare(f, B, F, F, prec, fp, st))) return rc;
-  if ((rc = tc_prepare(P, (int64_t)dc * F, d, d, prec, Pp, st))) return rc;
+  if (!P_prepared && (rc = tc_prepare(P, (int64_t)dc * F, d, d, prec, w + L.off_P, st))) return rc;
   CpgFwdEpi epi;
   epi.c = c; epi.dc = dc; epi.out = out; epi.ld = d; epi.split_stride = (long long)B * d;
   TcOperand A = tc_operand(fp, B, F, prec), Bo = tc_operand(Pp, (int64_t)dc * F, d, prec);
@@ -201,23 +201,23 @@ int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, int B,
 
 // df, dc_out, dP through the tensor pipe.  reuse_fwd_operands: the workspace still holds the prepared f and P
 // operands written by umma_cpg_fwd_partials for the same (f, P).
-int umma_cpg_bwd(const float* c, const float* f, const float* P, const float* dy, int B, int dc, int F, int d,
-                 float* dP, float* df, float* dc_out, void* ws, size_t ws_bytes, int prec, int reuse_fwd_operands,
-                 cudaStream_t st) {
+int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* dy, int B, int dc,
+                 int F, int d, float* dP, float* df, float* dc_out, void* ws, size_t ws_bytes, int prec,
+                 int reuse_fwd_operands, cudaStream_t st) {
   if (F % 32 != 0 || d > 256) return COPER_ERR_UNSUPPORTED;
   CpgBwdPlan L = cpg_bwd_plan(B, dc, F, d, prec);
   if (!ws || ws_bytes < L.total) return COPER_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(ws) & 255) return COPER_ERR_INVALID_ARG;
   char* w = static_cast<char*>(ws);
   void* fp = w + L.off_f;
-  void* Pp = w + L.off_P;
+  const void* Pp = P_prepared ? P_prepared : w + L.off_P;
   void* dyp = w + L.off_dy;
   void* dycp = w + L.off_dyc;
   float* dc_part = reinterpret_cast<float*>(w + L.off_dcpart);
   int rc;
   if (!reuse_fwd_operands) {
     if ((rc = tc_prepare(f, B, F, F, prec, fp, st))) return rc;
-    if ((rc = tc_prepare(P, (int64_t)dc * F, d, d, prec, Pp, st))) return rc;
+    if (!P_prepared && (rc = tc_prepare(P, (int64_t)dc * F, d, d, prec, w + L.off_P, st))) return rc;
   }
   if ((rc = tc_prepare(dy, B, d, d, prec, dyp, st))) return rc;
   {

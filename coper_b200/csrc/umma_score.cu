@@ -13,29 +13,51 @@ using namespace umma;
 // ------------------------------------------------------------------------------------------ operand preparation
 static inline int64_t prepared_ld(int cols, int prec) { return prec == COPER_PREC_BF16 ? (cols + 7) / 8 * 8 : (cols + 3) / 4 * 4; }
 
-__global__ void prepare_bf16_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src,
-                                    __nv_bfloat16* __restrict__ dst, int64_t ldp) {
-  int64_t n = rows * ldp;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-    int64_t r = e / ldp;
-    int c = (int)(e - r * ldp);
-    dst[e] = __float2bfloat16_rn(c < cols ? src[r * ld_src + c] : 0.f);
-  }
-}
-__global__ void prepare_tf32_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src,
-                                    float* __restrict__ hi, float* __restrict__ lo, int64_t ldp) {
-  int64_t n = rows * ldp;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-    int64_t r = e / ldp;
-    int c = (int)(e - r * ldp);
-    float x = c < cols ? src[r * ld_src + c] : 0.f;
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));   // round-to-nearest tf32, low 13 bits zero
-    float hf = __uint_as_float(h);
-    hi[e] = hf;
-    lo[e] = x - hf;                                      // exact in fp32
+// block = (64 column lanes) x (4 rows); grid-stride over rows; each lane converts VEC consecutive columns per pass
+// (VEC = 8 bf16 / 4 tf32 -> one 16-byte store per plane); no integer division anywhere
+template <int PREC>
+__global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ src, int64_t rows, int cols,
+                                                      int64_t ld_src, void* __restrict__ dst, int64_t ldp) {
+  constexpr int VEC = PREC == COPER_PREC_BF16 ? 8 : 4;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int nvec = (int)(ldp / VEC);
+  const bool vec_src = ((ld_src & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int64_t r = (int64_t)blockIdx.x * 4 + ty; r < rows; r += (int64_t)gridDim.x * 4) {
+    const float* srow = src + r * ld_src;
+    for (int v = tx; v < nvec; v += 64) {
+      const int c0 = v * VEC;
+      float x[VEC];
+      if (vec_src && c0 + VEC <= cols) {
+#pragma unroll
+        for (int k = 0; k < VEC; k += 4) {
+          float4 t = __ldg(reinterpret_cast<const float4*>(srow + c0 + k));
+          x[k] = t.x; x[k + 1] = t.y; x[k + 2] = t.z; x[k + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) x[k] = (c0 + k < cols) ? __ldg(srow + c0 + k) : 0.f;
+      }
+      if (PREC == COPER_PREC_BF16) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(x[4 % VEC], x[5 % VEC]), p3 = __floats2bfloat162_rn(x[6 % VEC], x[7 % VEC]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+        u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(dst) + r * ldp + c0) = u;
+      } else {
+        float h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t hb;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x[k]));   // round-to-nearest tf32, low 13 bits zero
+          h[k] = __uint_as_float(hb);
+          l[k] = x[k] - h[k];                                        // exact in fp32
+        }
+        float* hi = static_cast<float*>(dst) + r * ldp + c0;
+        *reinterpret_cast<float4*>(hi) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(hi + rows * ldp) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+    }
   }
 }
 
@@ -186,14 +208,13 @@ size_t umma_score1n_workspace_bytes(int B, int64_t Ns, int d, int prec) {
 
 static int prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst, cudaStream_t st) {
   int64_t ldp = prepared_ld(cols, prec);
-  int64_t n = rows * ldp;
-  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  int64_t blocks = (rows + 3) / 4;
+  int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
   if (grid < 1) grid = 1;
   if (prec == COPER_PREC_BF16)
-    prepare_bf16_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, static_cast<__nv_bfloat16*>(dst), ldp);
+    prepare_kernel<COPER_PREC_BF16><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ldp);
   else if (prec == COPER_PREC_TF32X3)
-    prepare_tf32_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, static_cast<float*>(dst),
-                                              static_cast<float*>(dst) + n, ldp);
+    prepare_kernel<COPER_PREC_TF32X3><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ldp);
   else
     return COPER_ERR_UNSUPPORTED;
   return check_launch();

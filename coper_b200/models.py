@@ -163,6 +163,7 @@ class ConvE:
         self._bufs = {}
         self._graphs = {}
         self._build_trainables()
+        self.refresh_prepared()
         # device-resident step state: {lr_t, beta1^t, beta2^t, -} and the dropout seed
         self.step_state = torch.tensor([0.0, self.beta1, self.beta2, 0.0], dtype=f32, device=dev)
         self.seed_dev = torch.tensor([seed * 1000003 + 12345], dtype=torch.int64, device=dev)
@@ -190,7 +191,40 @@ class ConvE:
         if not self.bug_compat:
             self.m = {n: torch.zeros_like(p) for n, p, _ in tr}
             self.v = {n: torch.zeros_like(p) for n, p, _ in tr}
-        self.sumsq = torch.zeros(len(tr) * _lib.SUMSQ_BLOCKS, dtype=torch.float64, device=self.dev)
+        # tensor-pipe operand copies of the two big GEMM operands, kept current by the optimizer kernel
+        self.E_prep = self.P_prep = None
+        lib = _lib.load()
+        d = self.ent_emb_size
+        if self.prec != 0 and d % (8 if self.prec == PREC["bf16"] else 4) == 0:
+            Pw = self.fc_weights.projections[-1]
+            self.E_prep = torch.zeros(lib.coper_prepared_bytes(self.shard.rows, d, self.prec), dtype=torch.uint8,
+                                      device=self.dev)
+            self.P_prep = torch.zeros(lib.coper_prepared_bytes(Pw.shape[0] * self.F, d, self.prec), dtype=torch.uint8,
+                                      device=self.dev)
+        # multi-tensor work list (include/coper.h: coper_param_desc, COPER_MT_CHUNK)
+        desc = np.zeros(len(tr), dtype=np.dtype([("theta", "<u8"), ("grad", "<u8"), ("m", "<u8"), ("v", "<u8"),
+                                                 ("vhat", "<u8"), ("prepared", "<u8"), ("n", "<i8"),
+                                                 ("prepared_prec", "<i4"), ("reserved", "<i4")]))
+        chunks, offsets = [], [0]
+        last_w = "fc_weights/CPG/Projection%d" % (len(self.fc_weights.projections) - 1)
+        for i, (n, p, _) in enumerate(tr):
+            desc[i]["theta"], desc[i]["grad"], desc[i]["vhat"] = p.data_ptr(), self.grads[n].data_ptr(), \
+                self.vhat[n].data_ptr()
+            if not self.bug_compat:
+                desc[i]["m"], desc[i]["v"] = self.m[n].data_ptr(), self.v[n].data_ptr()
+            desc[i]["n"] = p.numel()
+            prep = self.E_prep if n == "ent_emb" else self.P_prep if n == last_w else None
+            if prep is not None:
+                desc[i]["prepared"], desc[i]["prepared_prec"] = prep.data_ptr(), self.prec
+            nch = max(1, -(-p.numel() // _lib.MT_CHUNK))
+            chunks += [(i, c) for c in range(nch)]
+            offsets.append(len(chunks))
+        self.mt_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.dev)
+        self.mt_chunks = torch.tensor(chunks, dtype=torch.int32).to(self.dev)
+        self.mt_offsets = torch.tensor(offsets, dtype=torch.int32).to(self.dev)
+        self.mt_nchunks = len(chunks)
+        self.mt_partials = torch.zeros(len(chunks), dtype=torch.float64, device=self.dev)
+        self.sumsq = torch.zeros(len(tr), dtype=torch.float64, device=self.dev)
 
     def _ident(self, C):
         if C not in self._identity:
@@ -216,6 +250,16 @@ class ConvE:
                 self._put_bn(bn, b)
         self._put_bn(self.conv1_bn, params["Conv1BN"])
         self._put_bn(self.fc_bn, params["FCBN"])
+        self.refresh_prepared()
+
+    def refresh_prepared(self):
+        """(Re)build the tensor-pipe operand copies after the variables were written from outside the optimizer."""
+        if self.E_prep is None:
+            return
+        d = self.ent_emb_size
+        Pw = self.fc_weights.projections[-1]
+        call("coper_prepare_operand", ptr(self.ent_emb), self.shard.rows, d, d, self.prec, ptr(self.E_prep))
+        call("coper_prepare_operand", ptr(Pw), Pw.shape[0] * self.F, d, d, self.prec, ptr(self.P_prep))
 
     @staticmethod
     def _put_bn(bn, b):
@@ -240,6 +284,9 @@ class ConvE:
         b.x0, b.r = z(B, d), z(B, dr)
         b.z, b.f = z(B, F), z(B, F)
         b.y, b.q = z(B, d), z(B, d)
+        b.q_prep = None
+        if self.E_prep is not None:
+            b.q_prep = torch.zeros(lib.coper_prepared_bytes(B, d, self.prec), dtype=torch.uint8, device=dev)
         b.dq, b.dy, b.df, b.dz, b.dx0, b.dr = z(B, d), z(B, d), z(B, F), z(B, F), z(B, d), z(B, dr)
         R1 = B * self.OH * self.OW
         nch = max(lib.coper_colstats_chunks(R1), lib.coper_colstats_chunks(B))
@@ -446,7 +493,8 @@ class ConvE:
         cb = self._ctx_forward(self.fc_bias, 1, b, is_train)
         Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
         keep2 = 1.0 - (self.output_dropout if is_train else 0.0)
-        call("coper_cpg_fc_fwd", ptr(cw), ptr(b.f), ptr(Pw), ptr(cb), ptr(Pb), B, Pw.shape[0], F, d, Pb.shape[0],
+        call("coper_cpg_fc_fwd", ptr(cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(cb), ptr(Pb), B, Pw.shape[0], F, d,
+             Pb.shape[0],
              keep2, ptr(self.seed_dev), SALT_OUTPUT, ptr(b.y), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec)
         self._bn_forward(self.fc_bn, b.y, B, d, b, use_batch, is_train, False, True, 1.0, 0, b.q)
         b.cw, b.cb = cw, cb
@@ -463,7 +511,8 @@ class ConvE:
                          + np.float32(1.0 / self.num_ent))                     # models.py:450 in fp32
         neg = np.float32(1.0 / self.num_ent)
         inv_count = 1.0 / (float(B) * float(self.num_ent))                   # mean over B*N (models.py:451)
-        call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), ptr(b.bits), B, Ns, d,
+        call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
+             ptr(b.bits), B, Ns, d,
              float(pos), float(neg), inv_count, ptr(b.loss_sum), ptr(b.SG), b.ld, ptr(b.dq), ptr(g["ent_emb"]),
              ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes, self.prec)
         # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial loss and
@@ -477,7 +526,8 @@ class ConvE:
         g["FCBN/beta"].copy_(self.fc_bn.dbeta)
         Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
         nw, nb = len(self.fc_weights.projections) - 1, len(self.fc_bias.projections) - 1
-        call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(b.cb), ptr(Pb), ptr(b.dy), B, Pw.shape[0], F, d,
+        call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(b.cb), ptr(Pb), ptr(b.dy), B,
+             Pw.shape[0], F, d,
              Pb.shape[0], ptr(g["fc_weights/CPG/Projection%d" % nw]), ptr(g["fc_bias/CPG/Projection%d" % nb]),
              ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec, int(self.prec != 0))
         self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
@@ -501,19 +551,17 @@ class ConvE:
         self._clip_and_apply()
 
     def _clip_and_apply(self):
-        """tf.clip_by_global_norm(5.0) (models.py:199) + AMSGrad apply (amsgrad.py:130-159)."""
-        for i, (n, p, _) in enumerate(self.trainables):
-            call("coper_sumsq", ptr(self.grads[n]), p.numel(), i, ptr(self.sumsq))
+        """tf.clip_by_global_norm(5.0) (models.py:199) + AMSGrad apply (amsgrad.py:130-159): one multi-tensor
+        launch per phase over the whole variable list."""
+        nt = len(self.trainables)
+        call("coper_mt_sumsq", ptr(self.mt_desc), nt, ptr(self.mt_chunks), self.mt_nchunks, ptr(self.mt_offsets),
+             ptr(self.mt_partials), ptr(self.sumsq))
         # trainables 0,1 (ent_emb, pred_bias) are row-sharded: their squared norms add across ranks;
         # every other gradient is replicated (identical on all ranks) and is counted once.
-        sharding.reduce_sharded_sumsq(self.sumsq[:2 * _lib.SUMSQ_BLOCKS], self.world, self.group)
-        call("coper_clip_scale", ptr(self.sumsq), len(self.trainables), CLIP_NORM, ptr(self.clip_out))
-        for n, p, _ in self.trainables:
-            m = None if self.bug_compat else self.m[n]
-            v = None if self.bug_compat else self.v[n]
-            call("coper_amsgrad_step", ptr(p), ptr(self.grads[n]), ptr(m), ptr(v), ptr(self.vhat[n]), p.numel(),
-                 ptr(self.step_state), self.beta1, self.beta2, self.adam_eps, ptr(self.clip_out),
-                 int(self.bug_compat))
+        sharding.reduce_sharded_sumsq(self.sumsq[:2], self.world, self.group)
+        call("coper_clip_scale_n", ptr(self.sumsq), nt, CLIP_NORM, ptr(self.clip_out))
+        call("coper_mt_amsgrad", ptr(self.mt_desc), ptr(self.mt_chunks), self.mt_nchunks, ptr(self.step_state),
+             self.beta1, self.beta2, self.adam_eps, ptr(self.clip_out), int(self.bug_compat))
 
     # ------------------------------------------------------------------------------------------
     def train_step(self, batch: Dict, apply_update: bool = True):
@@ -540,8 +588,14 @@ class ConvE:
         return b.SG[:, :self.shard.rows]
 
     def _score(self, b):
-        call("coper_score1n_fwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), b.B, self.shard.rows,
-             self.ent_emb_size, ptr(b.SG), b.ld, ptr(b.ws), b.ws_bytes, self.prec)
+        d = self.ent_emb_size
+        if self.E_prep is not None:
+            call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
+            call("coper_score1n_fwd_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B,
+                 self.shard.rows, d, ptr(b.SG), b.ld, self.prec)
+        else:
+            call("coper_score1n_fwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), b.B, self.shard.rows, d,
+                 ptr(b.SG), b.ld, ptr(b.ws), b.ws_bytes, self.prec)
 
     def filtered_ranks(self, batch: Dict):
         """Filtered rank of ``e2`` for each query (metrics.py:44-51) computed on device.

@@ -112,18 +112,21 @@ int coper_dropout_apply(float* x, int64_t n, float keep, const uint64_t* seed_de
  *     y[b,:] = f[b,:] . reshape(c[b,:] . P, [F,d]) + cb[b,:] . Pb   ==   (c (x) f) . P^ + cb . Pb
  * c [B,dc] (relation embedding, or last CPG hidden activation), f [B,F], P [dc, F*d] (viewed [dc,F,d]),
  * cb [B,dcb], Pb [dcb,d].  The per-query weights [B,F,d] are never formed.  Output-dropout
- * (models.py:414-415) is applied to y when keep_out < 1.  workspace: coper_cpg_fc_fwd_workspace_bytes. */
+ * (models.py:414-415) is applied to y when keep_out < 1.  workspace: coper_cpg_fc_fwd_workspace_bytes.
+ * P_prepared (optional, tensor-pipe precisions): the operand form of P viewed [dc*F, d] (coper_prepare_operand, or
+ * kept current by coper_mt_amsgrad); NULL = converted from P inside the call. */
 size_t coper_cpg_fc_fwd_workspace_bytes(int B, int dc, int F, int d, int prec);
-int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb, int B,
-                     int dc, int F, int d, int dcb, float keep_out, const uint64_t* seed_dev, uint64_t salt_out,
-                     float* y, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
+int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
+                     const float* Pb, int B, int dc, int F, int d, int dcb, float keep_out, const uint64_t* seed_dev,
+                     uint64_t salt_out, float* y, void* workspace, size_t workspace_bytes, int prec,
+                     coper_stream_t stream);
 /* backward (models.py:198 autodiff of the above): given dy [B,d] (already through the dropout mask)
  *   dP [dc,F*d], dPb [dcb,d], df [B,F], dc_out [B,dc], dcb_out [B,dcb].
  * reuse_fwd_operands != 0 (tensor-pipe precisions only): `workspace` is the buffer the matching
  * coper_cpg_fc_fwd call used and still holds its prepared f and P operands (f, P unchanged since). */
 size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec);
-int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const float* cb, const float* Pb,
-                     const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
+int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
+                     const float* Pb, const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
                      float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
                      int reuse_fwd_operands, coper_stream_t stream);
 
@@ -165,10 +168,12 @@ int coper_tc_gemm(int transA, int transB, int M, int N, int K, const float* A, i
  * dL/dS with row pitch ldG (a multiple of 32, >= Ns): fp32 [B, ldG] (FP32), bf16 [B, ldG] (BF16) or tf32
  * hi/lo planes 2 x fp32 [B, ldG] (TF32X3) - on the tensor-pipe paths G is written by the scorer epilogue
  * directly in operand form and consumed by the dq / dE GEMMs through TMA.  workspace must be 256-byte
- * aligned.  loss_sum is a device double. */
+ * aligned.  loss_sum is a device double.  E_prepared (optional, tensor-pipe precisions): operand form of E
+ * [Ns, d]; NULL = converted from E inside the call. */
 size_t coper_score1n_bce_workspace_bytes(int B, int64_t Ns, int d, int prec);
 size_t coper_score1n_bce_G_bytes(int B, int64_t Ns, int prec);
-int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const float* bias, const uint32_t* label_bits,
+int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
+                              const uint32_t* label_bits,
                               int B, int64_t Ns, int d, float pos_target, float neg_target, float inv_count,
                               double* loss_sum, void* G, int64_t ldG, float* dq, float* dE, float* dbias,
                               void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
@@ -228,6 +233,37 @@ int coper_step_state_advance(float* step_state, uint64_t* seed_dev, float lr, fl
 int coper_amsgrad_step(float* theta, const float* grad, float* m, float* v, float* vhat, int64_t n,
                        const float* step_state, float beta1, float beta2, float eps, const float* clip_scale,
                        int bug_compat, coper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * multi-tensor form of the clip + AMSGrad tail (models.py:199, utils/amsgrad.py:130-159): the whole
+ * variable list is processed by ONE launch per phase instead of one per variable.
+ *   descs         device array [n_tensors] describing every trainable (pointers as in coper_amsgrad_step);
+ *                 `prepared` (optional) is refreshed with the tensor-pipe operand form of the UPDATED variable
+ *                 (bf16 copy, or tf32 hi plane followed by the lo plane; requires row pitch == row length),
+ *                 so the next step's GEMMs need no separate conversion pass.
+ *   chunks        device int32 [n_chunks][2] = (tensor id, chunk index); chunk = COPER_MT_CHUNK elements;
+ *                 sorted by tensor id; chunk_offsets int32 [n_tensors + 1] = first chunk of each tensor.
+ *   coper_mt_sumsq   -> tensor_sumsq[t] = |grad_t|^2 (fp64, fixed order; chunk_partials is scratch [n_chunks])
+ *   coper_clip_scale_n(tensor_sumsq, n_tensors, ...) -> {clip / max(norm, clip), norm}
+ *   coper_mt_amsgrad -> the update of coper_amsgrad_step for every tensor. */
+#define COPER_MT_CHUNK 16384
+typedef struct {
+  float* theta;
+  const float* grad;
+  float* m;
+  float* v;
+  float* vhat;
+  void* prepared;
+  int64_t n;
+  int32_t prepared_prec;
+  int32_t reserved;
+} coper_param_desc;
+int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
+                   const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, coper_stream_t stream);
+int coper_clip_scale_n(const double* sums, int n, float clip_norm, float* out2, coper_stream_t stream);
+int coper_mt_amsgrad(const coper_param_desc* descs, const int32_t* chunks, int n_chunks, const float* step_state,
+                     float beta1, float beta2, float eps, const float* clip_scale, int bug_compat,
+                     coper_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -155,7 +155,7 @@ def test_cpg_fc_fwd_bwd(L, B, dc, F, d, prec):
     c, f, P, cb, Pb = (a.astype(np.float32).astype(np.float64) for a in (c, f, P, cb, Pb))
     tc, tf, tP, tcb, tPb = (dev(a, torch.float32) for a in (c, f, P, cb, Pb))
     y = torch.full((B, d), float("nan"), device="cuda")
-    L.call("coper_cpg_fc_fwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), L.ptr(tcb), L.ptr(tPb), B, dc, F, d, dc, 1.0, None, 0,
+    L.call("coper_cpg_fc_fwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), None, L.ptr(tcb), L.ptr(tPb), B, dc, F, d, dc, 1.0, None, 0,
            L.ptr(y), L.ptr(ws), ws.numel(), p)
     dy = rng.normal(size=(B, d)).astype(np.float32).astype(np.float64)
     if prec == "bf16":
@@ -171,7 +171,7 @@ def test_cpg_fc_fwd_bwd(L, B, dc, F, d, prec):
     df = torch.zeros(B, F, device="cuda")
     dcw = torch.zeros(B, dc, device="cuda")
     dcb = torch.zeros(B, dc, device="cuda")
-    L.call("coper_cpg_fc_bwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), L.ptr(tcb), L.ptr(tPb), L.ptr(dev(dy, torch.float32)),
+    L.call("coper_cpg_fc_bwd", L.ptr(tc), L.ptr(tf), L.ptr(tP), None, L.ptr(tcb), L.ptr(tPb), L.ptr(dev(dy, torch.float32)),
            B, dc, F, d, dc, L.ptr(dP), L.ptr(dPb), L.ptr(df), L.ptr(dcw), L.ptr(dcb), L.ptr(ws), ws.numel(), p,
            int(prec != "fp32"))
     dyr = _bf16r(dy) if prec == "bf16" else dy
@@ -202,7 +202,7 @@ def test_cpg_fc_fb15k_shape_linearity(L):
 
     def run(c, ff):
         y = torch.zeros(B, d, device="cuda")
-        L.call("coper_cpg_fc_fwd", L.ptr(c), L.ptr(ff), L.ptr(P), L.ptr(cb), L.ptr(Pb), B, dc, F, d, dc, 1.0, None, 0,
+        L.call("coper_cpg_fc_fwd", L.ptr(c), L.ptr(ff), L.ptr(P), None, L.ptr(cb), L.ptr(Pb), B, dc, F, d, dc, 1.0, None, 0,
                L.ptr(y), L.ptr(ws), ws.numel(), 0)
         return y
     y1, y2, y12 = run(c1, f), run(c2, f), run((c1 + 2 * c2).contiguous(), f)
@@ -243,7 +243,7 @@ def test_score1n_fwd_and_bce(L, B, N, d):
     loss = torch.zeros(1, dtype=torch.float64, device="cuda")
     dq, dE, db = torch.zeros(B, d, device="cuda"), torch.zeros(N, d, device="cuda"), torch.zeros(N, device="cuda")
     inv = 1.0 / (B * N)
-    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
+    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), None, L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
            inv, L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE), L.ptr(db), L.ptr(ws), ws.numel(), 0)
     el = np.maximum(Sr, 0) - Sr * zs + np.log1p(np.exp(-np.abs(Sr)))
     Gr = (O.sigmoid(Sr) - zs) * inv
@@ -360,3 +360,69 @@ def test_sgemm_all_layouts(L):
             c = torch.zeros(M, N, device="cuda")
             L.call("coper_sgemm", ta, tb, M, N, K, L.ptr(a), a.shape[1], L.ptr(b), b.shape[1], L.ptr(c), N, 0)
             assert relerr(c.cpu().numpy(), ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ multi-tensor clip + AMSGrad
+@pytest.mark.parametrize("bug_compat", [1, 0])
+def test_multi_tensor_optimizer_matches_per_tensor(L, bug_compat):
+    """coper_mt_sumsq / coper_clip_scale_n / coper_mt_amsgrad == the per-variable kernels, bit for bit, and the
+    operand copies they emit == coper_prepare_operand of the updated variable."""
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    shapes = [(40943, 200), (1,), (16384,), (16385,), (8, 4608 * 40), (3, 3, 1, 32), (200,)]
+    th = [torch.randn(*s, device="cuda", generator=g) for s in shapes]
+    gr = [torch.randn(*s, device="cuda", generator=g) * 3 for s in shapes]
+    vh = [torch.rand(*s, device="cuda", generator=g) for s in shapes]
+    m = [torch.randn(*s, device="cuda", generator=g) for s in shapes]
+    v = [torch.rand(*s, device="cuda", generator=g) for s in shapes]
+    th2, vh2, m2, v2 = ([t.clone() for t in x] for x in (th, vh, m, v))
+    prep = {0: (1, torch.zeros(lib.coper_prepared_bytes(40943, 200, 1), dtype=torch.uint8, device="cuda")),
+            4: (2, torch.zeros(lib.coper_prepared_bytes(8 * 4608, 40, 2), dtype=torch.uint8, device="cuda"))}
+    desc = np.zeros(len(shapes), dtype=np.dtype([("theta", "<u8"), ("grad", "<u8"), ("m", "<u8"), ("v", "<u8"),
+                                                 ("vhat", "<u8"), ("prepared", "<u8"), ("n", "<i8"),
+                                                 ("prepared_prec", "<i4"), ("reserved", "<i4")]))
+    chunks, offs = [], [0]
+    for i in range(len(shapes)):
+        desc[i]["theta"], desc[i]["grad"], desc[i]["vhat"] = th[i].data_ptr(), gr[i].data_ptr(), vh[i].data_ptr()
+        desc[i]["m"], desc[i]["v"], desc[i]["n"] = m[i].data_ptr(), v[i].data_ptr(), th[i].numel()
+        if i in prep:
+            desc[i]["prepared"], desc[i]["prepared_prec"] = prep[i][1].data_ptr(), prep[i][0]
+        chunks += [(i, c) for c in range(max(1, -(-th[i].numel() // L.MT_CHUNK)))]
+        offs.append(len(chunks))
+    d_desc = torch.from_numpy(desc.view(np.uint8).copy()).cuda()
+    d_chunks, d_offs = torch.tensor(chunks, dtype=torch.int32).cuda(), torch.tensor(offs, dtype=torch.int32).cuda()
+    part = torch.zeros(len(chunks), dtype=torch.float64, device="cuda")
+    sums = torch.zeros(len(shapes), dtype=torch.float64, device="cuda")
+    state = torch.tensor([0.0, 0.9, 0.999, 0.0], device="cuda")
+    L.call("coper_step_state_advance", L.ptr(state), None, 1e-2, 0.9, 0.999)
+    clip = torch.zeros(2, device="cuda")
+    L.call("coper_mt_sumsq", L.ptr(d_desc), len(shapes), L.ptr(d_chunks), len(chunks), L.ptr(d_offs), L.ptr(part), L.ptr(sums))
+    ref = np.array([float((x.double() ** 2).sum().item()) for x in gr])
+    assert np.allclose(sums.cpu().numpy(), ref, rtol=1e-6)
+    L.call("coper_clip_scale_n", L.ptr(sums), len(shapes), 5.0, L.ptr(clip))
+    norm = np.sqrt(ref.sum())
+    assert abs(clip[1].item() - norm) < 1e-5 * norm and abs(clip[0].item() - 5.0 / max(norm, 5.0)) < 1e-6
+    L.call("coper_mt_amsgrad", L.ptr(d_desc), L.ptr(d_chunks), len(chunks), L.ptr(state), 0.9, 0.999, 1e-8, L.ptr(clip),
+           bug_compat)
+    for i in range(len(shapes)):
+        L.call("coper_amsgrad_step", L.ptr(th2[i]), L.ptr(gr[i]), L.ptr(m2[i]), L.ptr(v2[i]), L.ptr(vh2[i]),
+               th2[i].numel(), L.ptr(state), 0.9, 0.999, 1e-8, L.ptr(clip), bug_compat)
+        assert torch.equal(th[i], th2[i]) and torch.equal(vh[i], vh2[i]), i
+        if not bug_compat:
+            assert torch.equal(m[i], m2[i]) and torch.equal(v[i], v2[i]), i
+    for i, (rows, cols) in ((0, (40943, 200)), (4, (8 * 4608, 40))):
+        pr, buf = prep[i]
+        chk = torch.zeros_like(buf)
+        L.call("coper_prepare_operand", L.ptr(th[i]), rows, cols, cols, pr, L.ptr(chk))
+        n_bytes = rows * cols * (2 if pr == 1 else 8)
+        assert torch.equal(buf[:n_bytes], chk[:n_bytes]), i
+
+
+def test_reduce_partials_fixed_order(L):
+    rng = np.random.default_rng(0)
+    for S, n in ((37, 102400), (512, 288), (1, 5), (16, 40943), (144, 4096)):
+        x = rng.normal(size=(S, n)).astype(np.float32)
+        out = torch.full((n,), 7.0, device="cuda")
+        L.call("coper_reduce_partials", L.ptr(dev(x)), S, n, 0.5, 1, L.ptr(out))
+        ref = 7.0 + 0.5 * x.astype(np.float64).sum(0)
+        assert np.abs(out.cpu().numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())

@@ -116,7 +116,7 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     loss = torch.zeros(1, dtype=torch.float64, device="cuda")
     nan = float("nan")
     dq, dE, db = (torch.full(s, nan, device="cuda") for s in ((B, d), (N, d), (N,)))
-    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
+    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), None, L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
            inv, L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE), L.ptr(db), L.ptr(ws), ws.numel(), p)
     torch.cuda.synchronize()
     if prec == "tf32x3":
@@ -135,6 +135,6 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     # determinism: a second call is bit-identical
     dq2, dE2, db2 = (torch.zeros_like(t) for t in (dq, dE, db))
     loss2 = torch.zeros_like(loss)
-    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
+    L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), None, L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
            inv, L.ptr(loss2), L.ptr(G), ld, L.ptr(dq2), L.ptr(dE2), L.ptr(db2), L.ptr(ws), ws.numel(), p)
     assert torch.equal(dq, dq2) and torch.equal(dE, dE2) and torch.equal(db, db2) and torch.equal(loss, loss2)

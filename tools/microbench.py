@@ -64,7 +64,7 @@ def bce(B, N, d, precs=("fp32", "bf16", "tf32x3")):
         p = L.PREC[name]
         ws = torch.empty(lib.coper_score1n_bce_workspace_bytes(B, N, d, p), dtype=torch.uint8, device="cuda")
         G = torch.empty(lib.coper_score1n_bce_G_bytes(B, N, p), dtype=torch.uint8, device="cuda")
-        t = timeit(lambda: L.call("coper_score1n_bce_fwd_bwd", L.ptr(q), L.ptr(E), L.ptr(bias), L.ptr(bits), B, N, d,
+        t = timeit(lambda: L.call("coper_score1n_bce_fwd_bwd", L.ptr(q), L.ptr(E), None, L.ptr(bias), L.ptr(bits), B, N, d,
                                   0.9, 1.0 / N, 1.0 / (B * N), L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE),
                                   L.ptr(db), L.ptr(ws), ws.numel(), p))
         print("score1n_bce_fwd_bwd B=%d N=%d d=%d %-7s %.3f ms %.1f TF/s" % (B, N, d, name, t, fl / t / 1e9))
@@ -81,9 +81,9 @@ def cpg(B, dc, F, d, precs=("fp32", "bf16", "tf32x3")):
         p = L.PREC[name]
         ws = torch.empty(max(lib.coper_cpg_fc_fwd_workspace_bytes(B, dc, F, d, p),
                              lib.coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, p)), dtype=torch.uint8, device="cuda")
-        t1 = timeit(lambda: L.call("coper_cpg_fc_fwd", L.ptr(c), L.ptr(f), L.ptr(P), L.ptr(c), L.ptr(Pb), B, dc, F, d, dc,
+        t1 = timeit(lambda: L.call("coper_cpg_fc_fwd", L.ptr(c), L.ptr(f), L.ptr(P), None, L.ptr(c), L.ptr(Pb), B, dc, F, d, dc,
                                    1.0, None, 0, L.ptr(y), L.ptr(ws), ws.numel(), p))
-        t2 = timeit(lambda: L.call("coper_cpg_fc_bwd", L.ptr(c), L.ptr(f), L.ptr(P), L.ptr(c), L.ptr(Pb), L.ptr(dy), B, dc,
+        t2 = timeit(lambda: L.call("coper_cpg_fc_bwd", L.ptr(c), L.ptr(f), L.ptr(P), None, L.ptr(c), L.ptr(Pb), L.ptr(dy), B, dc,
                                    F, d, dc, L.ptr(dP), L.ptr(dPb), L.ptr(df), L.ptr(dcw), L.ptr(dcb), L.ptr(ws),
                                    ws.numel(), p, int(p != 0)))
         print("cpg_fc B=%d dc=%d F=%d d=%d %-7s fwd %.3f ms %.1f TF/s | bwd %.3f ms %.1f TF/s" % (
