@@ -181,7 +181,7 @@ def main():
         for i in range(warmup):
             fn(i)
         barrier()
-        k0 = lib.coper_launch_count()
+        k0 = lib.coper_launch_count() + model.graph_kernel_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -193,7 +193,7 @@ def main():
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / steps, (lib.coper_launch_count() - k0)
+        return ms / steps, (lib.coper_launch_count() + model.graph_kernel_launches - k0)
 
     K, W = args.steps, args.warmup
     sampler = ClockSampler(local_rank)
@@ -246,7 +246,8 @@ def main():
                    "entity-sharded 1-N scorer x%d (rows/GPU=%d), replicated front end" % (world, shard.rows),
                    "l2": "no flush: per-step working set ~%d MB > 126 MB L2; %d distinct input batches cycled"
                          % (ws_mb, n_batches),
-                   "dropout": "on (feature-map 0.3, output 0.2)", "batch_norm": "batch statistics (train)"},
+                   "dropout": "on (feature-map 0.3, output 0.2)", "batch_norm": "batch statistics (train)",
+                   "cuda_graph": bool(model.use_graphs and world == 1)},
         "eval": {"value": B / eval_ms * 1e3, "unit": "eval queries/s", "ms_per_batch": eval_ms,
                  "gpu_launches_per_batch": eval_launches / K},
         "e2e": {"value": B / e2e_train_ms * 1e3, "unit": "train rows/s", "h2d_bytes_per_step": h2d,

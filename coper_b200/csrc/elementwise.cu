@@ -372,11 +372,13 @@ __global__ void __launch_bounds__(256) mt_sumsq_kernel(const coper_param_desc* _
 // tensor_sumsq[t] = sum of the chunk partials of tensor t (fixed order); chunk_offsets [n_tensors + 1]
 __global__ void mt_tensor_sums_kernel(const double* __restrict__ chunk_partials, const int32_t* __restrict__ chunk_offsets,
                                       int n_tensors, double* __restrict__ tensor_sumsq) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per tensor: lanes stride over the tensor's chunks, fixed-order shuffle combine
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n_tensors) return;
   double acc = 0.0;
-  for (int c = chunk_offsets[t]; c < chunk_offsets[t + 1]; ++c) acc += chunk_partials[c];
-  tensor_sumsq[t] = acc;
+  for (int c = chunk_offsets[t] + lane; c < chunk_offsets[t + 1]; c += 32) acc += chunk_partials[c];
+  acc = warp_sum_d(acc);
+  if (lane == 0) tensor_sumsq[t] = acc;
 }
 __device__ __forceinline__ void amsgrad_elem(float g, float& th, float* m, float* v, float& vh, int64_t i, float lr_t,
                                              float b1, float b2, float omb1, float omb2, float eps, int bug_compat) {
@@ -434,8 +436,28 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
       vh4[j] = vh;
       if (d.prepared) {
         int64_t i = start + 4 * (int64_t)j;
-        emit_prepared(d, i, th.x); emit_prepared(d, i + 1, th.y); emit_prepared(d, i + 2, th.z);
-        emit_prepared(d, i + 3, th.w);
+        if (d.prepared_prec == COPER_PREC_BF16) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(th.x, th.y), p1 = __floats2bfloat162_rn(th.z, th.w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&p0);
+          u.y = *reinterpret_cast<uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.prepared) + i) = u;
+        } else if ((d.n & 3) == 0) {
+          float h[4] = {th.x, th.y, th.z, th.w}, l[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(h[k]));
+            l[k] = h[k] - __uint_as_float(hb);
+            h[k] = __uint_as_float(hb);
+          }
+          float* hi = static_cast<float*>(d.prepared) + i;
+          *reinterpret_cast<float4*>(hi) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(hi + d.n) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+          emit_prepared(d, i, th.x); emit_prepared(d, i + 1, th.y); emit_prepared(d, i + 2, th.z);
+          emit_prepared(d, i + 3, th.w);
+        }
       }
     }
   } else {
@@ -626,7 +648,7 @@ int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* 
   mt_sumsq_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, chunk_partials);
   int rc = check_launch();
   if (rc) return rc;
-  mt_tensor_sums_kernel<<<(n_tensors + 63) / 64, 64, 0, as_stream(stream)>>>(chunk_partials, chunk_offsets, n_tensors,
+  mt_tensor_sums_kernel<<<(n_tensors * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(chunk_partials, chunk_offsets, n_tensors,
                                                                             tensor_sumsq);
   return check_launch();
 }

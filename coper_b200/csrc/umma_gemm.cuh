@@ -455,7 +455,8 @@ int make_gemm_tmaps(const TcOperand& A, const TcOperand& B, CUtensorMap* tA, CUt
 }
 
 template <class Cfg, class Epi>
-int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, const Epi& epi, cudaStream_t st) {
+int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, const Epi& epi, cudaStream_t st,
+                int grid_override = 0) {
   if (p.groups_inner && !Epi::kAccumulate) return COPER_ERR_INVALID_ARG;
   CUtensorMap tA, tAlo, tB, tBlo;
   int rc = make_gemm_tmaps<Cfg>(A, B, &tA, &tAlo, &tB, &tBlo);
@@ -469,6 +470,7 @@ int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, co
   }
   long long supers = (long long)p.m_tiles * p.n_tiles * p.splits * (p.groups_inner ? 1 : p.groups);
   int grid = (int)(supers < 148 ? supers : 148);
+  if (grid_override > 0 && grid_override < grid) grid = grid_override;
   if (grid < 1) return COPER_ERR_INVALID_ARG;
   umma_gemm_kernel<Cfg, Epi><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tAlo, tB, tBlo, p, epi);
   return check_launch();

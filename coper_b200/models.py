@@ -84,7 +84,7 @@ class ContextualParameterGenerator:
 class ConvE:
     def __init__(self, model_descriptors: Dict, device: Optional[str] = None, seed: int = 0, prec: str = "fp32",
                  shard: Optional[EntityShard] = None, reference_bug_compat: bool = True,
-                 conv_in_height: int = 10, process_group=None):
+                 conv_in_height: int = 10, process_group=None, use_graphs: bool = True):
         md = model_descriptors
         _lib.load()
         if not torch.cuda.is_available():
@@ -130,6 +130,12 @@ class ConvE:
         self.group = process_group
         self.world = self.shard.world
         self.bug_compat = bool(reference_bug_compat)
+        self.fused_rank = True      # tensor-pipe engines: scorer + filtered rank in one kernel (no logits in HBM)
+        # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
+        # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
+        # and replayed with one launch.  Single-GPU only for now (the sharded path issues NCCL between kernels).
+        self.use_graphs = use_graphs
+        self.graph_kernel_launches = 0
         self.beta1, self.beta2, self.adam_eps = 0.9, 0.999, 1e-8    # amsgrad.py:22-24
 
         # ---- variables (models.py:203-336); entity-sharded rows are initialised from the full-table
@@ -311,7 +317,7 @@ class ConvE:
         b.ws_cpg_bytes = ws_cpg
         ws = max(lib.coper_score1n_bce_workspace_bytes(B, Ns, d, self.prec),
                  lib.coper_score1n_workspace_bytes(B, Ns, d, self.prec),
-                 lib.coper_segscatter_workspace_bytes(B))
+                 lib.coper_segscatter_workspace_bytes(B), lib.coper_score1n_rank_workspace_bytes(B, d, self.prec))
         b.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
         b.ws_bytes = ws
         # context nets: activations per hidden layer for the two generators
@@ -564,6 +570,27 @@ class ConvE:
              self.beta1, self.beta2, self.adam_eps, ptr(self.clip_out), int(self.bug_compat))
 
     # ------------------------------------------------------------------------------------------
+    def _run_graphed(self, key, fn):
+        """First call: eager (allocates buffers, sets kernel attributes).  Second call: capture, then replay."""
+        if not self.use_graphs or self.world > 1:
+            fn()
+            return
+        st = self._graphs.get(key)
+        if st is None:
+            fn()
+            self._graphs[key] = "warm"
+            return
+        if st == "warm":
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            lib = _lib.load()
+            k0 = lib.coper_launch_count()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = st = (g, lib.coper_launch_count() - k0)
+        st[0].replay()
+        self.graph_kernel_launches += st[1]      # kernels of this library executed by the replay
+
     def train_step(self, batch: Dict, apply_update: bool = True):
         """One reference training step (run_cpg.py:210-219).  Returns the loss as a 0-d device tensor
         (float64 -> call .item() to read it; that is the step's only device->host transfer)."""
@@ -576,7 +603,7 @@ class ConvE:
             finally:
                 self._clip_and_apply = saved
         else:
-            self._train_device(b)
+            self._run_graphed(("train", b.B), lambda: self._train_device(b))
         self.global_step += 1
         return b.loss_sum[0] / (float(b.B) * float(self.num_ent))
 
@@ -606,14 +633,28 @@ class ConvE:
             if int(e2.min()) < 0 or int(e2.max()) >= self.num_ent:
                 raise ValueError("e2 out of range (train rows carry e2 = -1 in the reference; SURVEY Q17)")
         b = self.stage_batch(batch, need_e2=True)
+        self._run_graphed(("rank", b.B), lambda: self._rank_device(b))
+        return b.n_greater + 1, b.n_equal
+
+    def _rank_device(self, b):
         self._forward_q(b, False)
-        self._score(b)
         s = self.shard
-        call("coper_gold_scores", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold))
-        sharding.reduce_gold(b.gold, self.world, self.group)
+        d = self.ent_emb_size
         b.n_greater.zero_()
         b.n_equal.zero_()
-        call("coper_filtered_rank", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits),
-             ptr(b.n_greater), ptr(b.n_equal))
+        if self.E_prep is not None and self.fused_rank:
+            # tensor-pipe engines: rank counts straight from the scorer's accumulators, logits never written
+            call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
+            call("coper_score1n_gold_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B, s.rows, d,
+                 ptr(b.e2), s.lo, ptr(b.gold), ptr(b.ws), b.ws_bytes, self.prec)
+            sharding.reduce_gold(b.gold, self.world, self.group)
+            call("coper_score1n_rank_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B, s.rows, d,
+                 ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits), ptr(b.n_greater), ptr(b.n_equal), self.prec)
+        else:
+            self._score(b)
+            call("coper_gold_scores", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold))
+            sharding.reduce_gold(b.gold, self.world, self.group)
+            call("coper_filtered_rank", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits),
+                 ptr(b.n_greater), ptr(b.n_equal))
         sharding.reduce_counts(b.n_greater, b.n_equal, self.world, self.group)
         return b.n_greater + 1, b.n_equal

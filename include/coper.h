@@ -198,6 +198,20 @@ int coper_filtered_rank(const float* scores, int64_t ld, int B, int64_t Ns, cons
                         const float* gold, const uint32_t* filter_bits, int32_t* n_greater, int32_t* n_equal,
                         coper_stream_t stream);
 
+/* a7 + a11 fused (tensor-pipe precisions): filtered-rank counts taken straight from the scorer's TMEM
+ * accumulators - the [B, Ns] logits are never written.  Operands in prepared form (coper_prepare_operand).
+ *   coper_score1n_gold_prepared: gold[b] = q[b].E[e2[b]-ent_lo] + bias[...] if this shard owns e2[b], else 0;
+ *       computed by the same tcgen05 instruction sequence as the ranking pass, so it is bit-identical to the
+ *       logit that pass sees (sum gold over shards before ranking).  workspace: coper_score1n_rank_workspace_bytes.
+ *   coper_score1n_rank_prepared: counts ACCUMULATED into n_greater / n_equal exactly as coper_filtered_rank does. */
+size_t coper_score1n_rank_workspace_bytes(int B, int d, int prec);
+int coper_score1n_gold_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
+                                const int64_t* e2, int64_t ent_lo, float* gold, void* workspace,
+                                size_t workspace_bytes, int prec, coper_stream_t stream);
+int coper_score1n_rank_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
+                                const int64_t* e2, int64_t ent_lo, const float* gold, const uint32_t* filter_bits,
+                                int32_t* n_greater, int32_t* n_equal, int prec, coper_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a10 scatter / K8(3) — gradient of the embedding gathers (IndexedSlices -> dense, models.py:198):
  *   dst[idx[i] - row_lo, :] += src[i, :] for row_lo <= idx[i] < row_hi; one writer per destination row

@@ -138,3 +138,67 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), None, L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
            inv, L.ptr(loss2), L.ptr(G), ld, L.ptr(dq2), L.ptr(dE2), L.ptr(db2), L.ptr(ws), ws.numel(), p)
     assert torch.equal(dq, dq2) and torch.equal(dE, dE2) and torch.equal(db, db2) and torch.equal(loss, loss2)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("B,N,d,lo", [(512, 40943, 200, 0), (7, 97, 40, 0), (130, 1003, 200, 0), (33, 5000, 256, 0),
+                                      (64, 70001, 256, 123456), (300, 33, 64, 0)])
+def test_fused_score_rank_equals_two_pass(prec, B, N, d, lo):
+    """scorer + filtered rank fused (logits stay in TMEM) == scoring into HBM + coper_filtered_rank, bit for bit:
+    the gold logits from the gather+diagonal pass equal the stored logits, and the integer counts agree — including
+    exact ties (duplicated entity rows), filtered entities, and gold entities owned by another shard (ent_lo > 0)."""
+    from coper_b200 import _lib as L
+    from oracle import conve_oracle as O
+    lib = L.load()
+    p = PREC[prec]
+    rng = np.random.default_rng(B + N + d)
+    q = np.maximum(rng.normal(size=(B, d)), 0).astype(np.float32)
+    E = rng.uniform(-0.05, 0.05, size=(N, d)).astype(np.float32)
+    if N > 64:
+        E[N // 2:N // 2 + N // 8] = E[:N // 8]                  # duplicated entities -> exact score ties
+    bias = (rng.normal(size=N) * 0.1).astype(np.float32)
+    if N > 64:
+        bias[N // 2:N // 2 + N // 8] = bias[:N // 8]
+    e2 = rng.integers(lo, lo + N, B)
+    if lo:
+        e2[::3] = rng.integers(0, lo, len(e2[::3]))             # gold owned by another shard
+    filt = rng.random((B, N)) < 0.05
+    own = (e2 >= lo) & (e2 < lo + N)
+    filt[np.arange(B)[own], (e2 - lo)[own]] = True
+    words, ld = -(-N // 32), -(-N // 32) * 32
+    packed = np.zeros((B, words * 32), bool)
+    packed[:, :N] = filt
+    bits = np.packbits(packed.reshape(B, words, 32), axis=2, bitorder="little").view(np.uint32).reshape(B, words)
+    tq, tE, tb = torch.as_tensor(q).cuda(), torch.as_tensor(E).cuda(), torch.as_tensor(bias).cuda()
+    te2, tbits = torch.as_tensor(e2).cuda(), torch.as_tensor(bits.view(np.int32)).cuda()
+    qp = torch.empty(lib.coper_prepared_bytes(B, d, p), dtype=torch.uint8, device="cuda")
+    Ep = torch.empty(lib.coper_prepared_bytes(N, d, p), dtype=torch.uint8, device="cuda")
+    L.call("coper_prepare_operand", L.ptr(tq), B, d, d, p, L.ptr(qp))
+    L.call("coper_prepare_operand", L.ptr(tE), N, d, d, p, L.ptr(Ep))
+    # two-pass
+    S = torch.zeros(B, ld, device="cuda")
+    L.call("coper_score1n_fwd_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(tb), B, N, d, L.ptr(S), ld, p)
+    gold2 = torch.zeros(B, device="cuda")
+    L.call("coper_gold_scores", L.ptr(S), ld, B, N, L.ptr(te2), lo, L.ptr(gold2))
+    ng2, ne2 = torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
+    L.call("coper_filtered_rank", L.ptr(S), ld, B, N, L.ptr(te2), lo, L.ptr(gold2), L.ptr(tbits), L.ptr(ng2), L.ptr(ne2))
+    # fused
+    ws = torch.empty(max(256, lib.coper_score1n_rank_workspace_bytes(B, d, p)), dtype=torch.uint8, device="cuda")
+    gold = torch.full((B,), float("nan"), device="cuda")
+    L.call("coper_score1n_gold_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(tb), B, N, d, L.ptr(te2), lo, L.ptr(gold),
+           L.ptr(ws), ws.numel(), p)
+    assert torch.equal(gold, gold2)                             # bit-identical gold logits
+    if lo:
+        gold = gold + torch.as_tensor((~own).astype(np.float32) * 0.0123).cuda()   # "other shard's" gold logit
+        ng2.zero_(); ne2.zero_()
+        L.call("coper_filtered_rank", L.ptr(S), ld, B, N, L.ptr(te2), lo, L.ptr(gold), L.ptr(tbits), L.ptr(ng2), L.ptr(ne2))
+    ng, ne = torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
+    L.call("coper_score1n_rank_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(tb), B, N, d, L.ptr(te2), lo, L.ptr(gold),
+           L.ptr(tbits), L.ptr(ng), L.ptr(ne), p)
+    assert torch.equal(ng, ng2) and torch.equal(ne, ne2)
+    if N > 64:
+        assert int(ne.sum().item()) > 0                         # the tie path was exercised
+    # and against the oracle's counting rank on the stored logits
+    if not lo:
+        cnt, eq = O.rank_count(S[:, :N].cpu().numpy(), e2, filt.astype(np.float32))
+        assert np.array_equal(ng.cpu().numpy() + 1, cnt) and np.array_equal(ne.cpu().numpy(), eq)
