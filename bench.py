@@ -167,7 +167,8 @@ def main():
     lib = _lib.load()
     md = synthetic.descriptors(args.shape, dropout=True)
     shard = EntityShard(s["num_ent"], rank, world)
-    model = ConvE(md, seed=0, prec=args.prec, shard=shard, conv_in_height=s["H"])
+    model = ConvE(md, seed=0, prec=args.prec, shard=shard, conv_in_height=s["H"],
+                  init_fast=s["num_ent"] > 1_000_000)
     n_batches = 8
     host = synthetic.make_batches(s["num_ent"], s["num_rel"], B, n_batches, seed=1)
     devb = [{k: torch.as_tensor(v).cuda() for k, v in hb.items()} for hb in host]
@@ -293,11 +294,12 @@ def kernel_breakdown(model, batch, peaks, prec, reps=10):
                                     b.ws_cpg_bytes, model.prec, 0), 4.0 * B * dc * F * d, "tensor"),
         "score1n_bce_fwd_bwd": (lambda: call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(model.ent_emb), ptr(model.E_prep),
                                              ptr(model.pred_bias), ptr(b.bits), B, Ns, d, pos, neg,
-                                             1.0 / (B * model.num_ent), ptr(b.loss_sum), ptr(b.SG), b.ld, ptr(b.dq),
+                                             1.0 / (B * model.num_ent), ptr(b.loss_sum), ptr(model._grad_buf(b)), b.ld, ptr(b.dq),
                                              ptr(g["ent_emb"]), ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes,
                                              model.prec), 6.0 * B * d * Ns, "tensor"),
         "score1n_fwd": (lambda: model._score(b), 2.0 * B * d * Ns, "tensor"),
-        "filtered_rank": (lambda: call("coper_filtered_rank", ptr(b.SG), b.ld, B, Ns, ptr(b.e2), model.shard.lo,
+        "score1n_rank_fused": (lambda: model._rank_device(b), 2.0 * B * d * Ns, "tensor"),
+        "filtered_rank": (lambda: call("coper_filtered_rank", ptr(model._scores_buf(b)), b.ld, B, Ns, ptr(b.e2), model.shard.lo,
                                        ptr(b.gold), ptr(b.bits), ptr(b.n_greater), ptr(b.n_equal)),
                           B * (4.0 * Ns + Ns / 8.0), "hbm"),
         "clip_and_amsgrad": (lambda: model._clip_and_apply(),

@@ -57,7 +57,10 @@ SIGNATURES = {
     "coper_filtered_rank": (i32, [vp, i64, i32, i64, vp, i64, vp, vp, vp, vp, vp]),
     "coper_score1n_rank_workspace_bytes": (sz, [i32, i32, i32]),
     "coper_score1n_gold_prepared": (i32, [vp, vp, vp, i32, i64, i32, vp, i64, vp, vp, sz, i32, vp]),
-    "coper_score1n_rank_prepared": (i32, [vp, vp, vp, i32, i64, i32, vp, i64, vp, vp, vp, vp, i32, vp]),
+    "coper_score1n_rank_prepared": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, vp, vp, i32, vp]),
+    "coper_csr_to_bits_t": (i32, [vp, vp, i32, i64, i64, vp, vp]),
+    "coper_dense_to_bits_t": (i32, [vp, i32, i64, i64, vp, vp]),
+    "coper_bits_t_set": (i32, [vp, i32, i64, i64, vp, vp]),
     "coper_segscatter_workspace_bytes": (sz, [i32]),
     "coper_segscatter_add": (i32, [vp, i32, vp, i32, vp, i64, i64, vp, sz, vp]),
     "coper_reduce_partials": (i32, [vp, i32, i64, f32, i32, vp, vp]),

@@ -240,6 +240,38 @@ __global__ void dense_to_bits_kernel(const float* __restrict__ dense, int B, int
   if (lane == 0) bits[gw] = m;
 }
 
+// entity-major bit matrix bitsT [Ns, wordsB]: bit (b & 31) of word (n, b >> 5) = entity n is a positive of query b
+__global__ void csr_to_bits_t_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int B,
+                                     int64_t lo, int64_t hi, int wordsB, uint32_t* bitsT) {
+  int b = blockIdx.x;
+  if (b >= B) return;
+  int s = rowptr[b], e = rowptr[b + 1];
+  for (int i = s + threadIdx.x; i < e; i += blockDim.x) {
+    int64_t n = col[i];
+    if (n >= lo && n < hi) atomicOr(bitsT + (n - lo) * wordsB + (b >> 5), 1u << (b & 31));
+  }
+}
+__global__ void bits_t_set_kernel(const int64_t* __restrict__ ent, int B, int64_t lo, int64_t hi, int wordsB,
+                                  uint32_t* bitsT) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int64_t n = ent[b];
+  if (n >= lo && n < hi) atomicOr(bitsT + (n - lo) * wordsB + (b >> 5), 1u << (b & 31));
+}
+__global__ void dense_to_bits_t_kernel(const float* __restrict__ dense, int B, int64_t N, int64_t ld, int wordsB,
+                                       uint32_t* __restrict__ bitsT) {
+  // one warp per output word (n, w): lane l tests query w*32 + l
+  int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (gw >= N * wordsB) return;
+  int64_t n = gw / wordsB;
+  int w = (int)(gw - n * wordsB);
+  int b = w * 32 + lane;
+  bool on = b < B && dense[(int64_t)b * ld + n] == 1.0f;
+  uint32_t m = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) bitsT[gw] = m;
+}
+
 // ------------------------------------------------------------------ deterministic reductions
 // out[i] = scale * sum_s in[s, i]: block = 32 outputs x 8 slab lanes; every thread sums the slabs s = ty, ty+8, ...
 // in fp64, the 8 lane sums are added in a fixed order -> deterministic, and the slab loop is 8x shorter / pipelined
@@ -618,6 +650,29 @@ int coper_dense_to_bits(const float* dense, int B, int64_t N, uint32_t* bits, co
   int64_t words = (N + 31) / 32;
   int64_t threads = (int64_t)B * words * 32;
   dense_to_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(dense, B, N, words, bits);
+  return check_launch();
+}
+
+int coper_csr_to_bits_t(const int32_t* rowptr, const int32_t* col, int B, int64_t ent_lo, int64_t ent_hi,
+                        uint32_t* bits_t, coper_stream_t stream) {
+  COPER_CHECK_ARG(rowptr && col && bits_t && B > 0 && ent_hi > ent_lo);
+  int wordsB = (B + 31) / 32;
+  int rc = check_cuda(cudaMemsetAsync(bits_t, 0, (size_t)(ent_hi - ent_lo) * wordsB * sizeof(uint32_t), as_stream(stream)));
+  if (rc) return rc;
+  csr_to_bits_t_kernel<<<B, 128, 0, as_stream(stream)>>>(rowptr, col, B, ent_lo, ent_hi, wordsB, bits_t);
+  return check_launch();
+}
+int coper_bits_t_set(const int64_t* ent, int B, int64_t ent_lo, int64_t ent_hi, uint32_t* bits_t, coper_stream_t stream) {
+  COPER_CHECK_ARG(ent && bits_t && B > 0 && ent_hi > ent_lo);
+  bits_t_set_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(ent, B, ent_lo, ent_hi, (B + 31) / 32, bits_t);
+  return check_launch();
+}
+int coper_dense_to_bits_t(const float* dense, int B, int64_t N, int64_t ld_dense, uint32_t* bits_t, coper_stream_t stream) {
+  COPER_CHECK_ARG(dense && bits_t && B > 0 && N > 0 && ld_dense >= N);
+  int wordsB = (B + 31) / 32;
+  int64_t threads = N * wordsB * 32;
+  dense_to_bits_t_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(dense, B, N, ld_dense, wordsB,
+                                                                                           bits_t);
   return check_launch();
 }
 

@@ -25,10 +25,24 @@ static int dispatch_layout(bool a_mn, bool b_mn, const TcOperand& A, const TcOpe
   return launch_gemm<StoreCfg<PREC, true, true>>(A, B, p, epi, st);
 }
 
+// dE-shaped problems (M = entities >> N = d, K = batch <= 512, bf16): the [K, N] operand (q) is kept RESIDENT in shared
+// memory per 128-column block, only the A tiles (G) stream -> L2->SM traffic per output tile drops from A + B to A.
+using ResBCfg = GemmCfg<PREC_BF16, 128, 4, 8, false, true, 0, 8>;
+int tc_gemm_store_resident_b(const TcOperand& A, const TcOperand& B, GemmProblem p, const StoreEpi& epi, cudaStream_t st) {
+  plan_gemm<ResBCfg>(p, false);
+  return launch_gemm<ResBCfg>(A, B, p, epi, st);
+}
+bool tc_resident_b_ok(int prec, bool a_mn, bool b_mn, const GemmProblem& p) {
+  return prec == COPER_PREC_BF16 && !a_mn && b_mn && p.groups == 1 && p.K <= ResBCfg::RES_KB * ResBCfg::BLOCK_K &&
+         p.M >= 16 * BLOCK_M;
+}
+
 // p: M, N, K, groups, groups_inner and group offsets filled by the caller; tiling is planned here.
 // With split == true the caller must size `epi.out` for plan_splits() partial slabs.
 int tc_gemm_store(int prec, bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, const GemmProblem& p,
                   bool split, const StoreEpi& epi, cudaStream_t st) {
+  // (the resident-B variant measured slower than the streaming one for dE - the output stores dominate - and is kept
+  // for reference only)
   if (prec == COPER_PREC_BF16) return dispatch_layout<PREC_BF16>(a_mn, b_mn, A, B, p, split, epi, st);
   if (prec == COPER_PREC_TF32X3) return dispatch_layout<PREC_TF32X3>(a_mn, b_mn, A, B, p, split, epi, st);
   return COPER_ERR_UNSUPPORTED;

@@ -22,9 +22,15 @@ constexpr int NUM_NON_EPI_THREADS = 128;
 // PROMOTE_KB > 0: the tensor core accumulates in fp32 with truncation, so a long chain of MMAs drifts (~2^-25 per
 // accumulate, linear in chain length).  Chains are therefore cut every PROMOTE_KB k-blocks; each partial chain is
 // read back from TMEM and added in fp32 registers (round-to-nearest) by the epilogue warps ("promotion").
-template <int PREC_, int BLOCK_N_, int STAGES_, int EPI_WARPS_, bool A_MN_, bool B_MN_, int PROMOTE_KB_ = 0>
+// RES_KB > 0 ("resident B"): the whole K extent (<= RES_KB k-blocks) of the B tile is loaded ONCE per n-block into
+// a dedicated shared-memory region and reused by every tile of the CTA that shares the n-block; only A tiles stream
+// through the stage ring.  For the entity-major scorers (B = the query block) this cuts the L2->SM traffic per tile
+// from (A + B) to A, which is what bounds a 128 x 128 x 256 bf16 tile on B200 (~42 B/clk/SM of TMA throughput).
+template <int PREC_, int BLOCK_N_, int STAGES_, int EPI_WARPS_, bool A_MN_, bool B_MN_, int PROMOTE_KB_ = 0,
+          int RES_KB_ = 0>
 struct GemmCfg {
   static constexpr int PROMOTE_KB = PROMOTE_KB_;
+  static constexpr int RES_KB = RES_KB_;
   static constexpr int PREC = PREC_, BLOCK_N = BLOCK_N_, STAGES = STAGES_, EPI_WARPS = EPI_WARPS_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   static constexpr int ELEM = (PREC == PREC_BF16) ? 2 : 4;
@@ -34,11 +40,13 @@ struct GemmCfg {
   static constexpr int TERMS = (PREC == PREC_TF32X3) ? 2 : 1;   // operand planes (hi, lo)
   static constexpr int A_BYTES = BLOCK_M * 128;     // one plane of the A tile (BLOCK_M x BLOCK_K or BLOCK_K x BLOCK_M)
   static constexpr int B_BYTES = BLOCK_N * 128;
-  static constexpr int STAGE_BYTES = TERMS * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = RES_KB_ > 0 ? TERMS * A_BYTES : TERMS * (A_BYTES + B_BYTES);
+  static constexpr int RES_BYTES = RES_KB_ * TERMS * B_BYTES;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int THREADS = NUM_NON_EPI_THREADS + EPI_WARPS * 32;
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
   static constexpr uint32_t FMT = (PREC == PREC_BF16) ? FMT_BF16 : FMT_TF32;
   // MN-major smem layout: 16-bit types use the plain 128B swizzle (8-row k atoms); tf32 must use the
   // 128B swizzle with 32-byte atoms (4-row k atoms)
@@ -59,20 +67,27 @@ struct SmemLayout {
   uint64_t* empty;      // [STAGES]
   uint64_t* tfull;      // [2]
   uint64_t* tempty;     // [2]
+  uint64_t* bfull;      // [1] resident B loaded
   uint32_t* tmem_ptr;
+  uint8_t* res;         // resident B region: [RES_KB][TERMS][B_BYTES]
   __device__ __forceinline__ explicit SmemLayout(uint8_t* raw) {
     base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+    res = base + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res + Cfg::RES_BYTES);
     full = bars;
     empty = bars + Cfg::STAGES;
     tfull = bars + 2 * Cfg::STAGES;
     tempty = tfull + 2;
-    tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    bfull = tempty + 2;
+    tmem_ptr = reinterpret_cast<uint32_t*>(bfull + 1);
+  }
+  __device__ __forceinline__ uint8_t* res_plane(int kb, int term) const {
+    return res + ((size_t)kb * Cfg::TERMS + term) * Cfg::B_BYTES;
   }
   __device__ __forceinline__ uint8_t* a_plane(int stage, int term) const {
     return base + (size_t)stage * Cfg::STAGE_BYTES + term * Cfg::A_BYTES;
   }
-  __device__ __forceinline__ uint8_t* b_plane(int stage, int term) const {
+  __device__ __forceinline__ uint8_t* b_plane(int stage, int term) const {   // streaming-B configurations only
     return base + (size_t)stage * Cfg::STAGE_BYTES + Cfg::TERMS * Cfg::A_BYTES + term * Cfg::B_BYTES;
   }
 };
@@ -84,6 +99,7 @@ __device__ __forceinline__ uint32_t cta_setup(const SmemLayout<Cfg>& sm) {
   if (warp == 1 && (threadIdx.x & 31) == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tfull[i], 1); mbar_init(&sm.tempty[i], Cfg::EPI_WARPS); }
+    mbar_init(sm.bfull, 1);
     fence_barrier_init();
   } else if (warp == 2) {
     tmem_alloc(sm.tmem_ptr, Cfg::TMEM_COLS);
@@ -124,7 +140,9 @@ __device__ __forceinline__ void produce_stage(const SmemLayout<Cfg>& sm, int sta
       for (int c = 0; c < BLOCK_M / Cfg::CHUNK; ++c)
         tma_load_2d(sm.a_plane(stage, t) + c * (Cfg::BLOCK_K * 128), ma, bar, a_mn0 + c * Cfg::CHUNK, a_k0);
     }
-    if (!Cfg::B_MN) {
+    if (Cfg::RES_KB > 0) {
+      // B is resident: nothing to stream
+    } else if (!Cfg::B_MN) {
       tma_load_2d(sm.b_plane(stage, t), mb, bar, b_k0, b_mn0);
     } else {
 #pragma unroll
@@ -172,13 +190,13 @@ __device__ __forceinline__ void issue_stage(const SmemLayout<Cfg>& sm, int stage
 // same as issue_stage but with a run-time instruction descriptor (N of the last tile may be < BLOCK_N)
 template <class Cfg>
 __device__ __forceinline__ void issue_stage_rt(const SmemLayout<Cfg>& sm, int stage, uint32_t tmem_d, int kvalid,
-                                               bool first, uint32_t idesc) {
+                                               bool first, uint32_t idesc, int kb_res = 0) {
   int nk = (kvalid + Cfg::UMMA_K - 1) / Cfg::UMMA_K;
   uint32_t a_addr[2], b_addr[2];
 #pragma unroll
   for (int t = 0; t < Cfg::TERMS; ++t) {
     a_addr[t] = smem_u32(sm.a_plane(stage, t));
-    b_addr[t] = smem_u32(sm.b_plane(stage, t));
+    b_addr[t] = smem_u32(Cfg::RES_KB > 0 ? sm.res_plane(kb_res, t) : sm.b_plane(stage, t));
   }
   for (int k = 0; k < nk; ++k) {
     uint32_t a_off = Cfg::A_MN ? k * Cfg::UMMA_K * 128 : k * 32;
@@ -237,6 +255,7 @@ struct TileCoord {
 struct EpiBase {
   static constexpr bool kAccumulate = false;
   __device__ __forceinline__ void tile_begin(const GemmProblem&, const TileCoord&, int, int) {}
+  __device__ __forceinline__ void tile_prefetch(const GemmProblem&, const TileCoord&, int, int) {}
   __device__ __forceinline__ float group_scale(const GemmProblem&, const TileCoord&, int) const { return 1.0f; }
   __device__ __forceinline__ void group_vals(const GemmProblem&, const TileCoord&, int, int, const uint32_t (&)[16],
                                              int) {}
@@ -265,6 +284,8 @@ __device__ __forceinline__ TileCoord gemm_decode(const GemmProblem& p, long long
 //                                       group_scale(row, group) * partial tile, accumulated in fp32 registers
 //   void tile_begin(p, t, row, col0)    before waiting for the accumulators (issue global prefetches here);
 //                                       col0 = first N index of this warp's column range
+//   void tile_prefetch(p, t_next, row_next, col0_next)   right after tile_begin, with the coordinates of the tile
+//                                       this CTA processes next (issue its global loads here)
 //   float group_scale(p, t, row)        kAccumulate: multiplier of this group's partial tile for this row
 //   void group_vals(p, t, row, col, const uint32_t (&v)[16], int half_idx)   kAccumulate: raw partial values
 //   void group_done(p, t, row, col_group, col_groups)                         kAccumulate: after each group
@@ -290,11 +311,36 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
       tma_prefetch_desc(&tA);
       tma_prefetch_desc(&tB);
       PipeState ps;
+      int res_nblk = -1;
       for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
         for (int g = 0; g < g_loop; ++g) {
           TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
           int a_mn0 = t.m_blk * BLOCK_M + t.group * p.a_group_mn;
           int b_mn0 = t.n_blk * Cfg::BLOCK_N + t.group * p.b_group_mn;
+          if (Cfg::RES_KB > 0 && t.n_blk != res_nblk) {
+            // new n-block: wait until every MMA that reads the old resident B has completed (all stages drained),
+            // then load the whole K extent of the new B tile
+            PipeState q = ps;
+            for (int i = 0; i < Cfg::STAGES; ++i) {
+              mbar_wait(&sm.empty[q.stage], q.phase ^ 1);
+              q.template advance<Cfg::STAGES>();
+            }
+            const int kbn = t.kb1 - t.kb0;
+            mbar_expect_tx(sm.bfull, (uint32_t)(kbn * Cfg::TERMS * Cfg::B_BYTES));
+            for (int kb = t.kb0; kb < t.kb1; ++kb)
+#pragma unroll
+              for (int tm = 0; tm < Cfg::TERMS; ++tm) {
+                if (!Cfg::B_MN) {
+                  tma_load_2d(sm.res_plane(kb - t.kb0, tm), tm ? &tBlo : &tB, sm.bfull, kb * Cfg::BLOCK_K, b_mn0);
+                } else {
+#pragma unroll
+                  for (int c = 0; c < Cfg::BLOCK_N / Cfg::CHUNK; ++c)
+                    tma_load_2d(sm.res_plane(kb - t.kb0, tm) + c * (Cfg::BLOCK_K * 128), tm ? &tBlo : &tB, sm.bfull,
+                                b_mn0 + c * Cfg::CHUNK, kb * Cfg::BLOCK_K);
+                }
+              }
+            res_nblk = t.n_blk;
+          }
           for (int kb = t.kb0; kb < t.kb1; ++kb) {
             mbar_wait(&sm.empty[ps.stage], ps.phase ^ 1);
             produce_stage<Cfg>(sm, ps.stage, &tA, &tAlo, &tB, &tBlo, a_mn0, b_mn0,
@@ -309,9 +355,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
       PipeState ps;
       int as = 0;
       uint32_t aphase = 0;
+      int res_nblk = -1;
+      uint32_t bphase = 0;
       for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
         for (int g = 0; g < g_loop; ++g) {
           TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
+          if (Cfg::RES_KB > 0 && t.n_blk != res_nblk) {
+            mbar_wait(sm.bfull, bphase);
+            bphase ^= 1;
+            res_nblk = t.n_blk;
+          }
           int n_rem = p.N - t.n_blk * Cfg::BLOCK_N;
           int n_eff = min(Cfg::BLOCK_N, (n_rem + 15) & ~15);
           uint32_t idesc = make_idesc(Cfg::FMT, BLOCK_M, (uint32_t)n_eff, Cfg::A_MN ? 1u : 0u, Cfg::B_MN ? 1u : 0u);
@@ -324,7 +377,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
               mbar_wait(&sm.full[ps.stage], ps.phase);
               tc_fence_after();
               int kvalid = min(Cfg::BLOCK_K, p.K - kb * Cfg::BLOCK_K);
-              issue_stage_rt<Cfg>(sm, ps.stage, tmem_base + as * Cfg::BLOCK_N, kvalid, kb == kc, idesc);
+              issue_stage_rt<Cfg>(sm, ps.stage, tmem_base + as * Cfg::BLOCK_N, kvalid, kb == kc, idesc, kb - t.kb0);
               mma_commit(&sm.empty[ps.stage]);
               ps.template advance<Cfg::STAGES>();
             }
@@ -350,6 +403,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
       const int row = t.m_blk * BLOCK_M + quarter * 32 + lane;
       const int col0 = t.n_blk * Cfg::BLOCK_N + group_c * COLS;
       epi.tile_begin(p, t, row, col0);
+      if (s + gridDim.x < supers) {      // per-row data of the NEXT tile is fetched while this one is processed
+        const TileCoord t2 = gemm_decode(p, s + gridDim.x, 0, Cfg::BLOCK_K);
+        epi.tile_prefetch(p, t2, t2.m_blk * BLOCK_M + quarter * 32 + lane, t2.n_blk * Cfg::BLOCK_N + group_c * COLS);
+      }
       if constexpr (Cfg::PROMOTE_KB == 0 && !Epi::kAccumulate) {
         // one accumulation chain per tile: TMEM -> registers -> epi.chunk
         mbar_wait(&sm.tfull[as], aphase);
@@ -458,6 +515,8 @@ template <class Cfg, class Epi>
 int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, const Epi& epi, cudaStream_t st,
                 int grid_override = 0) {
   if (p.groups_inner && !Epi::kAccumulate) return COPER_ERR_INVALID_ARG;
+  if (Cfg::RES_KB > 0 && (p.splits != 1 || p.groups != 1 || (p.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K > Cfg::RES_KB))
+    return COPER_ERR_UNSUPPORTED;
   CUtensorMap tA, tAlo, tB, tBlo;
   int rc = make_gemm_tmaps<Cfg>(A, B, &tA, &tAlo, &tB, &tBlo);
   if (rc) return rc;
@@ -492,6 +551,34 @@ inline void plan_gemm(GemmProblem& p, bool allow_split, int target_ctas = 148) {
   p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
 }
 
+// Warp-cooperative store of a [32 rows x 32 fp32] block held one row per lane.  Writing it straight from the
+// registers makes every store instruction touch 32 different rows with 16 bytes each: half-written 32-byte sectors
+// that L2 completes with DRAM fill reads (measured: ~1-2 TB/s and +60 % DRAM reads).  Instead the block is staged
+// through a 4 KB XOR-swizzled shared-memory tile (conflict-free 16-byte accesses both ways) and written out with
+// 8 lanes per row: each instruction stores 4 rows x 128 contiguous bytes.
+//   st: this warp's 256-float4 staging tile; out0: address of (row_base, col); rows_valid / cols_valid (multiple of 4)
+__device__ __forceinline__ void staged_store_f32(float4* st, const float (&v)[32], float* out0, long long ld,
+                                                 int rows_valid, int cols_valid) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    st[lane * 8 + (g ^ (lane & 7))] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  __syncwarp();
+  const int g = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int rr = 4 * k + (lane >> 3);
+    const float4 x = st[rr * 8 + (g ^ (rr & 7))];
+    if (rr < rows_valid && 4 * g < cols_valid) *reinterpret_cast<float4*>(out0 + (long long)rr * ld + 4 * g) = x;
+  }
+  __syncwarp();
+}
+constexpr int kStageWarps = 8;
+__device__ __forceinline__ float4* stage_tile() {
+  __shared__ float4 stage_s[kStageWarps][256];
+  return stage_s[((threadIdx.x >> 5) - 4) & (kStageWarps - 1)];
+}
+
 // Plain store epilogue: out[(group, split)][row, col] = acc * row_scale[row, group] (+ col_bias[col])
 struct StoreEpi : EpiBase {
   float* out;
@@ -503,18 +590,24 @@ struct StoreEpi : EpiBase {
   float* extra_out;
   __device__ __forceinline__ void chunk(const GemmProblem& p, const TileCoord& t, int row, int col,
                                         const uint32_t (&r)[32], int) const {
+    const int lane = threadIdx.x & 31;
+    const int n_out = extra_col >= 0 ? min(p.N, extra_col) : p.N;
+    float* base = out + t.group * group_stride + t.split * split_stride;
+    float* o0 = base + (long long)(row - lane) * ld + col;          // (first row of this warp, col)
+    // warp-uniform: whole float4 granules, 16-byte aligned rows
+    const bool vec = !col_bias && !row_scale && extra_col < 0 && ((ld & 3) == 0) && ((n_out & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(o0) & 15) == 0);
+    if (vec) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      staged_store_f32(stage_tile(), v, o0, ld, p.M - (row - lane), n_out - col);
+      return;
+    }
     if (row >= p.M) return;
     float sc = row_scale ? __ldg(row_scale + (long long)row * row_scale_ld + t.group) : 1.0f;
-    float* o = out + t.group * group_stride + t.split * split_stride + (long long)row * ld + col;
-    int n_out = extra_col >= 0 ? min(p.N, extra_col) : p.N;
-    bool vec = (col + 31 < n_out) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && !col_bias;
-    if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) =
-            make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc, __uint_as_float(r[j + 2]) * sc,
-                        __uint_as_float(r[j + 3]) * sc);
-    } else {
+    float* o = base + (long long)row * ld + col;
+    {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         int cj = col + j;

@@ -61,140 +61,9 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------------------------------ scorer kernel
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
-umma_score_fwd_kernel(const __grid_constant__ CUtensorMap tQ, const __grid_constant__ CUtensorMap tQlo,
-                      const __grid_constant__ CUtensorMap tE, const __grid_constant__ CUtensorMap tElo, int B,
-                      int64_t Ns, int K, const float* __restrict__ bias, float* __restrict__ out, int64_t ld) {
-  extern __shared__ uint8_t smem_raw[];
-  SmemLayout<Cfg> sm(smem_raw);
-  uint32_t tmem_base = cta_setup<Cfg>(sm);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (B + BLOCK_M - 1) / BLOCK_M;
-  const int64_t n_tiles = (Ns + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
-  const int64_t total = n_tiles * m_tiles;
-  const int kb_count = (K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tQ);
-      tma_prefetch_desc(&tE);
-      PipeState ps;
-      for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        int m_blk = (int)(tile % m_tiles);
-        int n_blk = (int)(tile / m_tiles);
-        for (int kb = 0; kb < kb_count; ++kb) {
-          mbar_wait(&sm.empty[ps.stage], ps.phase ^ 1);
-          produce_stage<Cfg>(sm, ps.stage, &tQ, &tQlo, &tE, &tElo, m_blk * BLOCK_M, n_blk * Cfg::BLOCK_N,
-                             kb * Cfg::BLOCK_K, kb * Cfg::BLOCK_K);
-          ps.template advance<Cfg::STAGES>();
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      PipeState ps;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        mbar_wait(&sm.tempty[as], aphase ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < kb_count; ++kb) {
-          mbar_wait(&sm.full[ps.stage], ps.phase);
-          tc_fence_after();
-          int kvalid = min(Cfg::BLOCK_K, K - kb * Cfg::BLOCK_K);
-          issue_stage<Cfg>(sm, ps.stage, tmem_base + as * Cfg::BLOCK_N, kvalid, kb == 0);
-          mma_commit(&sm.empty[ps.stage]);
-          ps.template advance<Cfg::STAGES>();
-        }
-        mma_commit(&sm.tfull[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
-      }
-    }
-  } else if (warp >= 4) {
-    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-    const int group = (warp - 4) >> 2;             // column group
-    constexpr int GROUPS = Cfg::EPI_WARPS / 4;
-    constexpr int COLS = Cfg::BLOCK_N / GROUPS;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      int m_blk = (int)(tile % m_tiles);
-      int64_t n_blk = tile / m_tiles;
-      mbar_wait(&sm.tfull[as], aphase);
-      tc_fence_after();
-      int row = m_blk * BLOCK_M + quarter * 32 + lane;
-      for (int c = group * COLS; c < (group + 1) * COLS; c += 32) {
-        int64_t n0 = n_blk * Cfg::BLOCK_N + c;
-        if (n0 >= Ns) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + as * Cfg::BLOCK_N + c + ((uint32_t)(quarter * 32) << 16), r);
-        tmem_ld_wait();
-        if (row < B) {
-          float* o = out + (int64_t)row * ld + n0;       // ld is a multiple of 32 >= Ns: the padded tail is writable
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = __uint_as_float(r[j]) + ((n0 + j < Ns) ? __ldg(bias + n0 + j) : 0.f);
-            v.y = __uint_as_float(r[j + 1]) + ((n0 + j + 1 < Ns) ? __ldg(bias + n0 + j + 1) : 0.f);
-            v.z = __uint_as_float(r[j + 2]) + ((n0 + j + 2 < Ns) ? __ldg(bias + n0 + j + 2) : 0.f);
-            v.w = __uint_as_float(r[j + 3]) + ((n0 + j + 3 < Ns) ? __ldg(bias + n0 + j + 3) : 0.f);
-            *reinterpret_cast<float4*>(o + j) = v;
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.tempty[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
-    }
-  }
-  cta_teardown<Cfg>(tmem_base);
-}
-
-template <class Cfg>
-static int launch_score_fwd(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
-                            float* scores, int64_t ld, cudaStream_t st) {
-  constexpr bool bf16 = Cfg::PREC == PREC_BF16;
-  int64_t ldp = prepared_ld(d, Cfg::PREC);
-  CUtensorMap tQ, tQlo, tE, tElo;
-  int rc;
-  if ((rc = make_tmap_2d(&tQ, q_prep, Cfg::ELEM, bf16, B, d, ldp, Cfg::CHUNK, BLOCK_M))) return rc;
-  if ((rc = make_tmap_2d(&tE, E_prep, Cfg::ELEM, bf16, Ns, d, ldp, Cfg::CHUNK, Cfg::BLOCK_N))) return rc;
-  tQlo = tQ;
-  tElo = tE;
-  if (!bf16) {
-    const float* qlo = static_cast<const float*>(q_prep) + (int64_t)B * ldp;
-    const float* Elo = static_cast<const float*>(E_prep) + Ns * ldp;
-    if ((rc = make_tmap_2d(&tQlo, qlo, 4, false, B, d, ldp, Cfg::CHUNK, BLOCK_M))) return rc;
-    if ((rc = make_tmap_2d(&tElo, Elo, 4, false, Ns, d, ldp, Cfg::CHUNK, Cfg::BLOCK_N))) return rc;
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    rc = check_cuda(cudaFuncSetAttribute(umma_score_fwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM_BYTES));
-    if (rc) return rc;
-    attr_done = true;
-  }
-  int64_t total = ((Ns + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N) * ((B + BLOCK_M - 1) / BLOCK_M);
-  int grid = (int)(total < 148 ? total : 148);
-  umma_score_fwd_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tQ, tQlo, tE, tElo, B, Ns, d, bias, scores, ld);
-  return check_launch();
-}
-
-using ScoreCfgBf16 = GemmCfg<PREC_BF16, 256, 4, 8, false, false>;
-using ScoreCfgTf32 = GemmCfg<PREC_TF32X3, 128, 3, 4, false, false>;
-
+// entity-major scorer kernels: umma_entity.cu
 int umma_score1n_fwd_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
-                              float* scores, int64_t ld, int prec, cudaStream_t st) {
-  if (ld % 32 != 0 || ld < Ns) return COPER_ERR_INVALID_ARG;
-  if (prec == COPER_PREC_BF16) return launch_score_fwd<ScoreCfgBf16>(q_prep, E_prep, bias, B, Ns, d, scores, ld, st);
-  if (prec == COPER_PREC_TF32X3) return launch_score_fwd<ScoreCfgTf32>(q_prep, E_prep, bias, B, Ns, d, scores, ld, st);
-  return COPER_ERR_UNSUPPORTED;
-}
+                              float* scores, int64_t ld, int prec, cudaStream_t st);
 
 static size_t prepared_bytes(int64_t rows, int cols, int prec) {
   int64_t ldp = prepared_ld(cols, prec);

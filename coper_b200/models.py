@@ -84,7 +84,8 @@ class ContextualParameterGenerator:
 class ConvE:
     def __init__(self, model_descriptors: Dict, device: Optional[str] = None, seed: int = 0, prec: str = "fp32",
                  shard: Optional[EntityShard] = None, reference_bug_compat: bool = True,
-                 conv_in_height: int = 10, process_group=None, use_graphs: bool = True):
+                 conv_in_height: int = 10, process_group=None, use_graphs: bool = True,
+                 init_fast: bool = False):
         md = model_descriptors
         _lib.load()
         if not torch.cuda.is_available():
@@ -130,7 +131,6 @@ class ConvE:
         self.group = process_group
         self.world = self.shard.world
         self.bug_compat = bool(reference_bug_compat)
-        self.fused_rank = True      # tensor-pipe engines: scorer + filtered rank in one kernel (no logits in HBM)
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
         # and replayed with one launch.  Single-GPU only for now (the sharded path issues NCCL between kernels).
@@ -143,10 +143,21 @@ class ConvE:
         gen = torch.Generator().manual_seed(seed)
         dev, f32 = self.dev, torch.float32
         d, dr = self.ent_emb_size, self.rel_emb_size
-        ent = torch.empty(self.num_ent, d, dtype=f32)
-        _xavier_(ent, gen)
-        self.ent_emb = ent[self.shard.lo:self.shard.hi].contiguous().to(dev)
-        del ent
+        # the table is drawn as ONE stream in row chunks (a P-way sharded model then holds exactly the rows of the
+        # unsharded one) but only this rank's rows are kept: no [N, d] host copy at 10 M entities
+        lim = math.sqrt(6.0 / (self.num_ent + d))
+        self.ent_emb = torch.empty(self.shard.rows, d, dtype=f32, device=dev)
+        step = 1 << 18
+        for r0 in range(0, self.num_ent, step):
+            r1 = min(self.num_ent, r0 + step)
+            if r0 >= self.shard.hi and init_fast:
+                break
+            blk = (torch.rand(r1 - r0, d, generator=gen, dtype=f32) * 2 - 1) * lim
+            lo, hi = max(r0, self.shard.lo), min(r1, self.shard.hi)
+            if lo < hi:
+                self.ent_emb[lo - self.shard.lo:hi - self.shard.lo].copy_(blk[lo - r0:hi - r0])
+        if init_fast:                                  # later draws need not line up with the full stream
+            gen = torch.Generator().manual_seed(seed + 7919)
         self.rel_emb = torch.empty(self.num_rel, dr, dtype=f32)
         _xavier_(self.rel_emb, gen)
         self.rel_emb = self.rel_emb.to(dev)
@@ -201,7 +212,9 @@ class ConvE:
         self.E_prep = self.P_prep = None
         lib = _lib.load()
         d = self.ent_emb_size
-        if self.prec != 0 and d % (8 if self.prec == PREC["bf16"] else 4) == 0:
+        # emission from inside the optimizer kernel needs operand pitch == row length; otherwise re-convert per step
+        self._emit_prepared = d % (8 if self.prec == PREC["bf16"] else 4) == 0
+        if self.prec != 0:
             Pw = self.fc_weights.projections[-1]
             self.E_prep = torch.zeros(lib.coper_prepared_bytes(self.shard.rows, d, self.prec), dtype=torch.uint8,
                                       device=self.dev)
@@ -220,7 +233,7 @@ class ConvE:
                 desc[i]["m"], desc[i]["v"] = self.m[n].data_ptr(), self.v[n].data_ptr()
             desc[i]["n"] = p.numel()
             prep = self.E_prep if n == "ent_emb" else self.P_prep if n == last_w else None
-            if prep is not None:
+            if prep is not None and self._emit_prepared:
                 desc[i]["prepared"], desc[i]["prepared_prec"] = prep.data_ptr(), self.prec
             nch = max(1, -(-p.numel() // _lib.MT_CHUNK))
             chunks += [(i, c) for c in range(nch)]
@@ -299,11 +312,13 @@ class ConvE:
         maxC = max([C, d] + self.fc_weights.hidden)
         b.stat = z(nch * maxC * 2)
         b.stat1 = z(maxC * 2)
-        # logits (eval, fp32 [B, ld]) / dL/dS in the scorer's operand form (train); never read by the host
-        sg_bytes = max(B * ld * 4, lib.coper_score1n_bce_G_bytes(B, Ns, self.prec))
-        b.SG_store = z(-(-sg_bytes // 4))
-        b.SG = b.SG_store[:B * ld].view(B, ld)
-        b.bits = z(B, words, dt=torch.int32)
+        # allocated on first use (each exactly once, so captured graphs keep valid pointers):
+        #   b.S  logits fp32 [B, ld] (predict_all / the two-pass ranking of the fp32 engine)
+        #   b.G  dL/dS in the scorer's operand form (train); never read by the host
+        b.S = b.G = None
+        # label / filter bits: query-major rows for the fp32 engine, the entity-major matrix for the tensor pipe
+        b.bits = z(B, words, dt=torch.int32) if self.prec == 0 else None
+        b.bitsT = z(max(Ns, 1), -(-B // 32), dt=torch.int32) if self.prec != 0 else None
         b.loss_sum = z(1, dt=torch.float64)
         b.gold = z(B)
         b.n_greater, b.n_equal = z(B, dt=torch.int32), z(B, dt=torch.int32)
@@ -337,6 +352,17 @@ class ConvE:
         b.h2d_event = None
         self._bufs[B] = b
         return b
+
+    def _scores_buf(self, b):
+        if b.S is None:
+            b.S = torch.zeros(b.B, b.ld, dtype=torch.float32, device=self.dev)
+        return b.S
+
+    def _grad_buf(self, b):
+        if b.G is None:
+            nbytes = _lib.load().coper_score1n_bce_G_bytes(b.B, self.shard.rows, self.prec)
+            b.G = torch.zeros(-(-nbytes // 4), dtype=torch.float32, device=self.dev)
+        return b.G
 
     def _ensure_csr(self, b, nnz):
         if b.csr_cap < nnz:
@@ -383,7 +409,10 @@ class ConvE:
                 b.h_col[:nnz].copy_(torch.as_tensor(np.asarray(col), dtype=torch.int32))
                 b.rowptr.copy_(b.h_rowptr, non_blocking=True)
                 b.col[:nnz].copy_(b.h_col[:nnz], non_blocking=True)
-            call("coper_csr_to_bits", ptr(b.rowptr), ptr(b.col), B, s.lo, s.hi, ptr(b.bits))
+            if self.prec == 0:
+                call("coper_csr_to_bits", ptr(b.rowptr), ptr(b.col), B, s.lo, s.hi, ptr(b.bits))
+            else:
+                call("coper_csr_to_bits_t", ptr(b.rowptr), ptr(b.col), B, s.lo, s.hi, ptr(b.bitsT))
         elif "e2_multi" in batch and batch["e2_multi"] is not None:
             dense = batch["e2_multi"]
             if not (isinstance(dense, torch.Tensor) and dense.is_cuda):
@@ -391,7 +420,10 @@ class ConvE:
             if s.world > 1:
                 dense = dense[:, s.lo:s.hi].contiguous()
             dense = dense.contiguous()
-            call("coper_dense_to_bits", ptr(dense), B, s.rows, ptr(b.bits))
+            if self.prec == 0:
+                call("coper_dense_to_bits", ptr(dense), B, s.rows, ptr(b.bits))
+            else:
+                call("coper_dense_to_bits_t", ptr(dense), B, s.rows, s.rows, ptr(b.bitsT))
         if b.h2d_event is None:
             b.h2d_event = torch.cuda.Event()
         b.h2d_event.record()
@@ -518,8 +550,9 @@ class ConvE:
         neg = np.float32(1.0 / self.num_ent)
         inv_count = 1.0 / (float(B) * float(self.num_ent))                   # mean over B*N (models.py:451)
         call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
-             ptr(b.bits), B, Ns, d,
-             float(pos), float(neg), inv_count, ptr(b.loss_sum), ptr(b.SG), b.ld, ptr(b.dq), ptr(g["ent_emb"]),
+             ptr(b.bits if self.prec == 0 else b.bitsT), B, Ns, d,
+             float(pos), float(neg), inv_count, ptr(b.loss_sum), ptr(self._grad_buf(b)), b.ld, ptr(b.dq),
+             ptr(g["ent_emb"]),
              ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes, self.prec)
         # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial loss and
         # the partial dq = G_shard . E_shard; dE / dbias stay local.
@@ -568,6 +601,8 @@ class ConvE:
         call("coper_clip_scale_n", ptr(self.sumsq), nt, CLIP_NORM, ptr(self.clip_out))
         call("coper_mt_amsgrad", ptr(self.mt_desc), ptr(self.mt_chunks), self.mt_nchunks, ptr(self.step_state),
              self.beta1, self.beta2, self.adam_eps, ptr(self.clip_out), int(self.bug_compat))
+        if not self._emit_prepared:
+            self.refresh_prepared()
 
     # ------------------------------------------------------------------------------------------
     def _run_graphed(self, key, fn):
@@ -612,17 +647,17 @@ class ConvE:
         b = self.stage_batch(batch)
         self._forward_q(b, False)
         self._score(b)
-        return b.SG[:, :self.shard.rows]
+        return b.S[:, :self.shard.rows]
 
     def _score(self, b):
         d = self.ent_emb_size
         if self.E_prep is not None:
             call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
             call("coper_score1n_fwd_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B,
-                 self.shard.rows, d, ptr(b.SG), b.ld, self.prec)
+                 self.shard.rows, d, ptr(self._scores_buf(b)), b.ld, self.prec)
         else:
             call("coper_score1n_fwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), b.B, self.shard.rows, d,
-                 ptr(b.SG), b.ld, ptr(b.ws), b.ws_bytes, self.prec)
+                 ptr(self._scores_buf(b)), b.ld, ptr(b.ws), b.ws_bytes, self.prec)
 
     def filtered_ranks(self, batch: Dict):
         """Filtered rank of ``e2`` for each query (metrics.py:44-51) computed on device.
@@ -633,6 +668,8 @@ class ConvE:
             if int(e2.min()) < 0 or int(e2.max()) >= self.num_ent:
                 raise ValueError("e2 out of range (train rows carry e2 = -1 in the reference; SURVEY Q17)")
         b = self.stage_batch(batch, need_e2=True)
+        if self.prec != 0:          # the gold entity joins the filter set (metrics.py:44-46 never compares it)
+            call("coper_bits_t_set", ptr(b.e2), b.B, self.shard.lo, self.shard.hi, ptr(b.bitsT))
         self._run_graphed(("rank", b.B), lambda: self._rank_device(b))
         return b.n_greater + 1, b.n_equal
 
@@ -642,19 +679,19 @@ class ConvE:
         d = self.ent_emb_size
         b.n_greater.zero_()
         b.n_equal.zero_()
-        if self.E_prep is not None and self.fused_rank:
+        if self.E_prep is not None:
             # tensor-pipe engines: rank counts straight from the scorer's accumulators, logits never written
             call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
             call("coper_score1n_gold_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B, s.rows, d,
                  ptr(b.e2), s.lo, ptr(b.gold), ptr(b.ws), b.ws_bytes, self.prec)
             sharding.reduce_gold(b.gold, self.world, self.group)
             call("coper_score1n_rank_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B, s.rows, d,
-                 ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits), ptr(b.n_greater), ptr(b.n_equal), self.prec)
+                 ptr(b.gold), ptr(b.bitsT), ptr(b.n_greater), ptr(b.n_equal), self.prec)
         else:
             self._score(b)
-            call("coper_gold_scores", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold))
+            call("coper_gold_scores", ptr(b.S), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold))
             sharding.reduce_gold(b.gold, self.world, self.group)
-            call("coper_filtered_rank", ptr(b.SG), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits),
+            call("coper_filtered_rank", ptr(b.S), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits),
                  ptr(b.n_greater), ptr(b.n_equal))
         sharding.reduce_counts(b.n_greater, b.n_equal, self.world, self.group)
         return b.n_greater + 1, b.n_equal

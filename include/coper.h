@@ -163,7 +163,8 @@ int coper_tc_gemm(int transA, int transB, int M, int N, int K, const float* A, i
  *   loss_sum = sum_{b,n} max(s,0) - s z' + log1p(exp(-|s|))   (caller divides by B*N_total)
  *   G[b,n]   = (sigmoid(s) - z') * inv_count                    (inv_count = 1/(B*N_total))
  *   dq = G.E, dE = G^T.q, dbias = sum_b G.
- * label_bits [B, words] (words = ceil(Ns/32), bit n of row b = 1 iff entity n is a positive of query b);
+ * label_bits: FP32 engine - query-major rows [B, ceil(Ns/32)] (coper_csr_to_bits: bit n of row b = 1 iff entity n
+ * is a positive of query b); tensor-pipe engines - the ENTITY-MAJOR matrix [Ns, ceil(B/32)] (coper_csr_to_bits_t);
  * G is caller-provided scratch of coper_score1n_bce_G_bytes (never read by the host; 128-byte aligned) holding
  * dL/dS with row pitch ldG (a multiple of 32, >= Ns): fp32 [B, ldG] (FP32), bf16 [B, ldG] (BF16) or tf32
  * hi/lo planes 2 x fp32 [B, ldG] (TF32X3) - on the tensor-pipe paths G is written by the scorer epilogue
@@ -184,6 +185,16 @@ int coper_csr_to_bits(const int32_t* rowptr, const int32_t* col, int B, int64_t 
                       uint32_t* bits, coper_stream_t stream);
 /* dense fp32 multi-hot [B, N] (the reference batch schema, models.py:144) -> bits (value == 1.0f) */
 int coper_dense_to_bits(const float* dense, int B, int64_t N, uint32_t* bits, coper_stream_t stream);
+/* ENTITY-MAJOR bit matrix used by the tensor-pipe scorers (one entity per epilogue thread):
+ *   bits_t [ent_hi - ent_lo, ceil(B/32)]: bit (b & 31) of word (n, b >> 5) = 1 iff entity ent_lo + n is a positive /
+ *   filtered tail of query b.  coper_bits_t_set ORs in the bits (ent[b], b) - used to add the gold entity to the
+ *   filter set so the fused ranking kernel needs no per-element identity test. */
+int coper_csr_to_bits_t(const int32_t* rowptr, const int32_t* col, int B, int64_t ent_lo, int64_t ent_hi,
+                        uint32_t* bits_t, coper_stream_t stream);
+int coper_dense_to_bits_t(const float* dense, int B, int64_t N, int64_t ld_dense, uint32_t* bits_t,
+                          coper_stream_t stream);
+int coper_bits_t_set(const int64_t* ent, int B, int64_t ent_lo, int64_t ent_hi, uint32_t* bits_t,
+                     coper_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a11 / K10 — filtered rank (metrics.py:44-51): for each query b over this shard's scores [B, ld]
@@ -203,14 +214,16 @@ int coper_filtered_rank(const float* scores, int64_t ld, int B, int64_t Ns, cons
  *   coper_score1n_gold_prepared: gold[b] = q[b].E[e2[b]-ent_lo] + bias[...] if this shard owns e2[b], else 0;
  *       computed by the same tcgen05 instruction sequence as the ranking pass, so it is bit-identical to the
  *       logit that pass sees (sum gold over shards before ranking).  workspace: coper_score1n_rank_workspace_bytes.
- *   coper_score1n_rank_prepared: counts ACCUMULATED into n_greater / n_equal exactly as coper_filtered_rank does. */
+ *   coper_score1n_rank_prepared: counts ACCUMULATED into n_greater / n_equal exactly as coper_filtered_rank does;
+ *       filter_bits_t is the entity-major matrix (coper_csr_to_bits_t) and must contain the gold entity of every
+ *       query (coper_bits_t_set) - metrics.py:44-46 excludes it from the comparison. */
 size_t coper_score1n_rank_workspace_bytes(int B, int d, int prec);
 int coper_score1n_gold_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
                                 const int64_t* e2, int64_t ent_lo, float* gold, void* workspace,
                                 size_t workspace_bytes, int prec, coper_stream_t stream);
 int coper_score1n_rank_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
-                                const int64_t* e2, int64_t ent_lo, const float* gold, const uint32_t* filter_bits,
-                                int32_t* n_greater, int32_t* n_equal, int prec, coper_stream_t stream);
+                                const float* gold, const uint32_t* filter_bits_t, int32_t* n_greater,
+                                int32_t* n_equal, int prec, coper_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a10 scatter / K8(3) — gradient of the embedding gathers (IndexedSlices -> dense, models.py:198):

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "coper.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(coper_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(coper_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_builds_and_loads():

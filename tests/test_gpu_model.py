@@ -145,7 +145,7 @@ def test_train_step_parity(name):
     assert relerr(b.f.cpu().numpy(), out["f"]) < 1e-5
     assert relerr(b.q.cpu().numpy(), out["q"]) < 1e-5
     assert abs(loss - out["loss"]) < 1e-6 * abs(out["loss"])
-    assert relerr(b.SG[:, :cfg.num_ent].cpu().numpy(), g["_G"]) < 1e-5
+    assert relerr(b.G[:B * b.ld].view(B, b.ld)[:, :cfg.num_ent].cpu().numpy(), g["_G"]) < 1e-5
     assert relerr(b.dq.cpu().numpy(), g["_dq"]) < 1e-4
     assert relerr(b.dy.cpu().numpy(), g["_dy"]) < 1e-4
     assert relerr(b.df.cpu().numpy(), g["_df"]) < 1e-4

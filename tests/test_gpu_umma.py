@@ -103,9 +103,9 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     cfg = O.OracleConfig(num_ent=N, num_rel=2, ent_emb_size=d, rel_emb_size=2, conv_in_height=d // 4 if d % 10 else 10)
     _, _, _, rowptr, col = O.synthetic_batch(cfg, B, seed=9, mean_pos=4.0)
     words, ld = -(-N // 32), -(-N // 32) * 32
-    bits = torch.zeros(B, words, dtype=torch.int32, device="cuda")
+    bits = torch.full((N, -(-B // 32)), -1, dtype=torch.int32, device="cuda")     # entity-major label bits
     trp, tcol = torch.as_tensor(rowptr.astype(np.int32)).cuda(), torch.as_tensor(col.astype(np.int32)).cuda()
-    L.call("coper_csr_to_bits", L.ptr(trp), L.ptr(tcol), B, 0, N, L.ptr(bits))
+    L.call("coper_csr_to_bits_t", L.ptr(trp), L.ptr(tcol), B, 0, N, L.ptr(bits))
     z = O.csr_to_dense(rowptr, col, N, np.float64)
     pos, neg = np.float32(np.float32(0.9) + np.float32(1.0 / N)), np.float32(1.0 / N)
     zs = np.where(z > 0, np.float64(pos), np.float64(neg))
@@ -171,6 +171,26 @@ def test_fused_score_rank_equals_two_pass(prec, B, N, d, lo):
     bits = np.packbits(packed.reshape(B, words, 32), axis=2, bitorder="little").view(np.uint32).reshape(B, words)
     tq, tE, tb = torch.as_tensor(q).cuda(), torch.as_tensor(E).cuda(), torch.as_tensor(bias).cuda()
     te2, tbits = torch.as_tensor(e2).cuda(), torch.as_tensor(bits.view(np.int32)).cuda()
+    wordsB = -(-B // 32)
+    packedT = np.zeros((N, wordsB * 32), bool)
+    packedT[:, :B] = filt.T
+    bitsT = np.packbits(packedT.reshape(N, wordsB, 32), axis=2, bitorder="little").view(np.uint32).reshape(N, wordsB)
+    tbitsT = torch.as_tensor(bitsT.view(np.int32)).cuda()
+    # the library's own builders give the same matrix
+    nz = [np.flatnonzero(filt[b]) + lo for b in range(B)]
+    rp = np.zeros(B + 1, np.int32); rp[1:] = np.cumsum([len(x) for x in nz])
+    cl = np.concatenate(nz).astype(np.int32) if rp[-1] else np.zeros(0, np.int32)
+    chk = torch.full((N, wordsB), -1, dtype=torch.int32, device="cuda")
+    trp = torch.as_tensor(rp).cuda()                      # keep references: the calls are asynchronous
+    tcl = torch.as_tensor(cl).cuda() if len(cl) else torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("coper_csr_to_bits_t", L.ptr(trp), L.ptr(tcl), B, lo, lo + N, L.ptr(chk))
+    torch.cuda.synchronize()
+    assert torch.equal(chk, tbitsT)
+    chk2 = torch.zeros((N, wordsB), dtype=torch.int32, device="cuda")
+    tdense = torch.as_tensor(filt.astype(np.float32)).cuda()
+    L.call("coper_dense_to_bits_t", L.ptr(tdense), B, N, N, L.ptr(chk2))
+    torch.cuda.synchronize()
+    assert torch.equal(chk2, tbitsT)
     qp = torch.empty(lib.coper_prepared_bytes(B, d, p), dtype=torch.uint8, device="cuda")
     Ep = torch.empty(lib.coper_prepared_bytes(N, d, p), dtype=torch.uint8, device="cuda")
     L.call("coper_prepare_operand", L.ptr(tq), B, d, d, p, L.ptr(qp))
@@ -193,8 +213,8 @@ def test_fused_score_rank_equals_two_pass(prec, B, N, d, lo):
         ng2.zero_(); ne2.zero_()
         L.call("coper_filtered_rank", L.ptr(S), ld, B, N, L.ptr(te2), lo, L.ptr(gold), L.ptr(tbits), L.ptr(ng2), L.ptr(ne2))
     ng, ne = torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
-    L.call("coper_score1n_rank_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(tb), B, N, d, L.ptr(te2), lo, L.ptr(gold),
-           L.ptr(tbits), L.ptr(ng), L.ptr(ne), p)
+    L.call("coper_score1n_rank_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(tb), B, N, d, L.ptr(gold), L.ptr(tbitsT),
+           L.ptr(ng), L.ptr(ne), p)
     assert torch.equal(ng, ng2) and torch.equal(ne, ne2)
     if N > 64:
         assert int(ne.sum().item()) > 0                         # the tie path was exercised

@@ -55,8 +55,10 @@ def bce(B, N, d, precs=("fp32", "bf16", "tf32x3")):
     E = (torch.rand(N, d, device="cuda") - 0.5) * 0.1
     bias = torch.zeros(N, device="cuda")
     ld = -(-N // 32) * 32
-    bits = torch.zeros(B, ld // 32, dtype=torch.int32, device="cuda")
-    bits[:, ::97] = 5
+    bits_q = torch.zeros(B, ld // 32, dtype=torch.int32, device="cuda")
+    bits_q[:, ::97] = 5
+    bits_t = torch.zeros(N, -(-B // 32), dtype=torch.int32, device="cuda")
+    bits_t[::97] = 5
     loss = torch.zeros(1, dtype=torch.float64, device="cuda")
     dq, dE, db = torch.zeros(B, d, device="cuda"), torch.zeros(N, d, device="cuda"), torch.zeros(N, device="cuda")
     fl = 6.0 * B * N * d
@@ -64,10 +66,35 @@ def bce(B, N, d, precs=("fp32", "bf16", "tf32x3")):
         p = L.PREC[name]
         ws = torch.empty(lib.coper_score1n_bce_workspace_bytes(B, N, d, p), dtype=torch.uint8, device="cuda")
         G = torch.empty(lib.coper_score1n_bce_G_bytes(B, N, p), dtype=torch.uint8, device="cuda")
+        bits = bits_q if p == 0 else bits_t
         t = timeit(lambda: L.call("coper_score1n_bce_fwd_bwd", L.ptr(q), L.ptr(E), None, L.ptr(bias), L.ptr(bits), B, N, d,
                                   0.9, 1.0 / N, 1.0 / (B * N), L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE),
                                   L.ptr(db), L.ptr(ws), ws.numel(), p))
         print("score1n_bce_fwd_bwd B=%d N=%d d=%d %-7s %.3f ms %.1f TF/s" % (B, N, d, name, t, fl / t / 1e9))
+
+
+def rankf(B, N, d, precs=("bf16", "tf32x3")):
+    q = torch.randn(B, d, device="cuda").clamp_(min=0)
+    E = (torch.rand(N, d, device="cuda") - 0.5) * 0.1
+    bias = torch.zeros(N, device="cuda")
+    ld = -(-N // 32) * 32
+    bits = torch.zeros(N, -(-B // 32), dtype=torch.int32, device="cuda")
+    e2 = torch.randint(0, N, (B,), device="cuda")
+    gold = torch.zeros(B, device="cuda")
+    ng, ne = torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
+    fl = 2.0 * B * N * d
+    for name in precs:
+        p = L.PREC[name]
+        qp = torch.empty(lib.coper_prepared_bytes(B, d, p), dtype=torch.uint8, device="cuda")
+        Ep = torch.empty(lib.coper_prepared_bytes(N, d, p), dtype=torch.uint8, device="cuda")
+        ws = torch.empty(max(256, lib.coper_score1n_rank_workspace_bytes(B, d, p)), dtype=torch.uint8, device="cuda")
+        L.call("coper_prepare_operand", L.ptr(E), N, d, d, p, L.ptr(Ep))
+        L.call("coper_prepare_operand", L.ptr(q), B, d, d, p, L.ptr(qp))
+        t0 = timeit(lambda: L.call("coper_score1n_gold_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(bias), B, N, d, L.ptr(e2), 0,
+                                   L.ptr(gold), L.ptr(ws), ws.numel(), p))
+        t = timeit(lambda: L.call("coper_score1n_rank_prepared", L.ptr(qp), L.ptr(Ep), L.ptr(bias), B, N, d,
+                                  L.ptr(gold), L.ptr(bits), L.ptr(ng), L.ptr(ne), p))
+        print("score1n_rank_fused B=%d N=%d d=%d %-7s gold %.3f ms, rank %.3f ms %.1f TF/s" % (B, N, d, name, t0, t, fl / t / 1e9))
 
 
 def cpg(B, dc, F, d, precs=("fp32", "bf16", "tf32x3")):
@@ -98,6 +125,14 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prof":
         bce(512, 40943, 200, precs=(sys.argv[2],))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rank":
+        precs = tuple(sys.argv[2:]) or ("bf16", "tf32x3")
+        rankf(512, 40943, 200, precs)
+        rankf(512, 1000000, 256, precs)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "bcebig":
+        bce(512, 1250000, 256, precs=(sys.argv[2],))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "bce":
         bce(512, 40943, 200)
