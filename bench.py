@@ -129,6 +129,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--graph-multi", action="store_true",
+                    help="N > 1: capture the step including its NCCL collectives in a CUDA graph (experimental: hung on "
+                         "the 2-GPU box in round 1, off by default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -168,7 +171,7 @@ def main():
     md = synthetic.descriptors(args.shape, dropout=True)
     shard = EntityShard(s["num_ent"], rank, world)
     model = ConvE(md, seed=0, prec=args.prec, shard=shard, conv_in_height=s["H"],
-                  init_fast=s["num_ent"] > 1_000_000)
+                  init_fast=s["num_ent"] > 1_000_000, graphs_multi_gpu=args.graph_multi)
     n_batches = 8
     host = synthetic.make_batches(s["num_ent"], s["num_rel"], B, n_batches, seed=1)
     devb = [{k: torch.as_tensor(v).cuda() for k, v in hb.items()} for hb in host]
@@ -248,7 +251,7 @@ def main():
                    "l2": "no flush: per-step working set ~%d MB > 126 MB L2; %d distinct input batches cycled"
                          % (ws_mb, n_batches),
                    "dropout": "on (feature-map 0.3, output 0.2)", "batch_norm": "batch statistics (train)",
-                   "cuda_graph": bool(model.use_graphs and world == 1)},
+                   "cuda_graph": bool(model.use_graphs and (world == 1 or model.graphs_multi_gpu))},
         "eval": {"value": B / eval_ms * 1e3, "unit": "eval queries/s", "ms_per_batch": eval_ms,
                  "gpu_launches_per_batch": eval_launches / K},
         "e2e": {"value": B / e2e_train_ms * 1e3, "unit": "train rows/s", "h2d_bytes_per_step": h2d,
@@ -284,6 +287,10 @@ def kernel_breakdown(model, batch, peaks, prec, reps=10):
     Pw, Pb = model.fc_weights.projections[-1], model.fc_bias.projections[-1]
     dc = Pw.shape[0]
     pos, neg = 0.9 + 1.0 / model.num_ent, 1.0 / model.num_ent
+    bits_q = b.bits                      # query-major filter rows for the standalone (two-pass) rank kernel
+    if bits_q is None:
+        bits_q = torch.zeros(B, b.words, dtype=torch.int32, device=model.dev)
+        call("coper_csr_to_bits", ptr(b.rowptr), ptr(b.col), B, model.shard.lo, model.shard.hi, ptr(bits_q))
     stages = {
         "cpg_fc_fwd": (lambda: call("coper_cpg_fc_fwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(model.P_prep), ptr(b.cb), ptr(Pb), B, dc, F, d,
                                     Pb.shape[0], 1.0, None, 0, ptr(b.y), ptr(b.ws_cpg), b.ws_cpg_bytes, model.prec),
@@ -293,14 +300,14 @@ def kernel_breakdown(model, batch, peaks, prec, reps=10):
                                     ptr(g["fc_bias/CPG/Projection0"]), ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg),
                                     b.ws_cpg_bytes, model.prec, 0), 4.0 * B * dc * F * d, "tensor"),
         "score1n_bce_fwd_bwd": (lambda: call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(model.ent_emb), ptr(model.E_prep),
-                                             ptr(model.pred_bias), ptr(b.bits), B, Ns, d, pos, neg,
+                                             ptr(model.pred_bias), ptr(b.bits if model.prec == 0 else b.bitsT), B, Ns, d, pos, neg,
                                              1.0 / (B * model.num_ent), ptr(b.loss_sum), ptr(model._grad_buf(b)), b.ld, ptr(b.dq),
                                              ptr(g["ent_emb"]), ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes,
                                              model.prec), 6.0 * B * d * Ns, "tensor"),
         "score1n_fwd": (lambda: model._score(b), 2.0 * B * d * Ns, "tensor"),
         "score1n_rank_fused": (lambda: model._rank_device(b), 2.0 * B * d * Ns, "tensor"),
         "filtered_rank": (lambda: call("coper_filtered_rank", ptr(model._scores_buf(b)), b.ld, B, Ns, ptr(b.e2), model.shard.lo,
-                                       ptr(b.gold), ptr(b.bits), ptr(b.n_greater), ptr(b.n_equal)),
+                                       ptr(b.gold), ptr(bits_q), ptr(b.n_greater), ptr(b.n_equal)),
                           B * (4.0 * Ns + Ns / 8.0), "hbm"),
         "clip_and_amsgrad": (lambda: model._clip_and_apply(),
                              sum(p.numel() for _, p, _ in model.trainables) * 4.0 * 5, "hbm"),

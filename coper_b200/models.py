@@ -85,7 +85,7 @@ class ConvE:
     def __init__(self, model_descriptors: Dict, device: Optional[str] = None, seed: int = 0, prec: str = "fp32",
                  shard: Optional[EntityShard] = None, reference_bug_compat: bool = True,
                  conv_in_height: int = 10, process_group=None, use_graphs: bool = True,
-                 init_fast: bool = False):
+                 init_fast: bool = False, graphs_multi_gpu: bool = False):
         md = model_descriptors
         _lib.load()
         if not torch.cuda.is_available():
@@ -133,8 +133,10 @@ class ConvE:
         self.bug_compat = bool(reference_bug_compat)
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
-        # and replayed with one launch.  Single-GPU only for now (the sharded path issues NCCL between kernels).
+        # and replayed with one launch.  The sharded path captures its NCCL collectives into the same graph
+        # (graphs_multi_gpu; all ranks replay the same sequence).
         self.use_graphs = use_graphs
+        self.graphs_multi_gpu = graphs_multi_gpu
         self.graph_kernel_launches = 0
         self.beta1, self.beta2, self.adam_eps = 0.9, 0.999, 1e-8    # amsgrad.py:22-24
 
@@ -607,7 +609,7 @@ class ConvE:
     # ------------------------------------------------------------------------------------------
     def _run_graphed(self, key, fn):
         """First call: eager (allocates buffers, sets kernel attributes).  Second call: capture, then replay."""
-        if not self.use_graphs or self.world > 1:
+        if not self.use_graphs or (self.world > 1 and not self.graphs_multi_gpu):
             fn()
             return
         st = self._graphs.get(key)

@@ -32,7 +32,7 @@ def _descr(cfg):
             "do_parameter_lookup": False}
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, prec):
     import torch.distributed as dist
     from coper_b200.models import ConvE
     from coper_b200.sharding import EntityShard
@@ -48,10 +48,10 @@ def _worker(rank, world, port, out_dir):
         e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5, mean_pos=5.0)
         batch = {"e1": e1, "rel": rel, "e2": e2, "e2_multi_rowptr": rowptr, "e2_multi_col": col}
         sh = EntityShard(cfg.num_ent, rank, world)
-        m = ConvE(_descr(cfg), device="cuda:%d" % rank, seed=0, shard=sh)
+        m = ConvE(_descr(cfg), device="cuda:%d" % rank, seed=0, shard=sh, prec=prec)
         m.load_variables(params)
         ranks, n_equal = m.filtered_ranks(batch)
-        S_local = m._bufs[B].SG[:, :sh.rows].cpu().numpy().copy()
+        S_local = m.predict_all(batch).cpu().numpy().copy()
         loss = float(m.train_step(batch).item())
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), ranks=ranks.cpu().numpy(), n_equal=n_equal.cpu().numpy(),
@@ -62,23 +62,26 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "bf16"])
 @pytest.mark.parametrize("world", [2])
-def test_entity_sharded_matches_single_gpu(world, tmp_path):
+def test_entity_sharded_matches_single_gpu(world, prec, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    _worker_single(str(tmp_path))
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), prec), nprocs=world, join=True)
+    _worker_single(str(tmp_path), prec)
     ref = np.load(os.path.join(str(tmp_path), "single.npz"))
     outs = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
     S = np.concatenate([o["S"] for o in outs], axis=1)
     assert np.array_equal(S, ref["S"])                               # same kernels, same rows -> bit-identical logits
     for o in outs:
         assert np.array_equal(o["ranks"], ref["ranks"]) and np.array_equal(o["n_equal"], ref["n_equal"])
-        assert abs(o["loss"] - float(ref["loss"])) < 1e-6 * abs(float(ref["loss"]))
+        assert abs(o["loss"] - float(ref["loss"])) < 2e-6 * abs(float(ref["loss"]))
         assert abs(o["norm"] - float(ref["norm"])) < 1e-5 * float(ref["norm"])
         lo, hi = int(o["lo"]), int(o["hi"])
-        assert np.abs(o["dE"] - ref["dE"][lo:hi]).max() < 1e-5 * np.abs(ref["dE"]).max()
+        assert np.abs(o["dE"] - ref["dE"][lo:hi]).max() < (1e-5 if prec != "bf16" else 1e-3) * np.abs(ref["dE"]).max()
+        if prec == "bf16":      # bf16 dL/dS: the update direction is compared by the single-GPU bf16 tests
+            continue
         # updated variables: AMSGrad as written steps by ~ g / sqrt(g^2), which amplifies fp32 summation-order noise
         # on near-zero gradient entries -> compare at 5e-4 (the gradients themselves are compared at 1e-5 above)
         assert np.abs(o["ent"] - ref["ent"][lo:hi]).max() < 5e-4 * np.abs(ref["ent"]).max()
@@ -88,7 +91,7 @@ def test_entity_sharded_matches_single_gpu(world, tmp_path):
     assert np.array_equal(outs[0]["P"], outs[1]["P"]) and np.array_equal(outs[0]["rel_emb"], outs[1]["rel_emb"])
 
 
-def _worker_single(out_dir):
+def _worker_single(out_dir, prec):
     from coper_b200.models import ConvE
     cfg = O.OracleConfig(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[],
                          batch_norm_train_stats=True, batch_norm_momentum=0.1, hidden_dropout=0.3, output_dropout=0.2)
@@ -96,10 +99,10 @@ def _worker_single(out_dir):
     B = 130
     e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5, mean_pos=5.0)
     batch = {"e1": e1, "rel": rel, "e2": e2, "e2_multi_rowptr": rowptr, "e2_multi_col": col}
-    m = ConvE(_descr(cfg), device="cuda:0", seed=0)
+    m = ConvE(_descr(cfg), device="cuda:0", seed=0, prec=prec)
     m.load_variables(params)
     ranks, n_equal = m.filtered_ranks(batch)
-    S = m._bufs[B].SG[:, :cfg.num_ent].cpu().numpy().copy()
+    S = m.predict_all(batch).cpu().numpy().copy()
     loss = float(m.train_step(batch).item())
     np.savez(os.path.join(out_dir, "single.npz"), ranks=ranks.cpu().numpy(), n_equal=n_equal.cpu().numpy(), S=S,
              loss=loss, dE=m.grads["ent_emb"].cpu().numpy(), ent=m.ent_emb.cpu().numpy(),
