@@ -165,6 +165,11 @@ def main():
     from coper_b200 import _lib
     from coper_b200.models import ConvE, EntityShard
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly ONE JSON line: everything libraries print while we run (e.g. NCCL's version banner)
+    # is diverted to stderr at the file-descriptor level
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
@@ -262,7 +267,9 @@ def main():
         "clocks": clocks, "roofline": roofline, "kernel_ms": breakdown, "cpu_baseline": cpu,
         "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "_source")},
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
