@@ -24,6 +24,7 @@ SIGNATURES = {
     "coper_device_is_sm100": (i32, []),
     "coper_gather_rows": (i32, [vp, i64, i64, i32, vp, i32, vp, vp]),
     "coper_conv_fwd": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
+    "coper_conv_bwd_slabs": (i32, [i32, i32, i32, i32, i32, i32, i32]),
     "coper_conv_bwd": (i32, [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "coper_colstats_chunks": (i32, [i64]),
     "coper_colstats": (i32, [vp, i64, i32, vp, vp]),

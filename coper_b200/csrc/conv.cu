@@ -93,6 +93,132 @@ __global__ void __launch_bounds__(kConvThreads) conv_bwd_kernel(const float* __r
     dbc_part[(int64_t)b * C + c] = acc;
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path for the configuration every shipped config uses: 3x3 filters, 32 channels, shared filters.
+// Thread (c = lane, hs = warp): output row h is produced by sliding a 3x3 register window along w, so an output costs
+// 3 shared-memory loads + 9 FMAs and no integer division; for a fixed (h, w) the 32 lanes write 32 consecutive
+// channels (128 B).  IMG images per CTA amortise the filter load and cut the number of gradient partial slabs.
+constexpr int kFastC = 32;
+template <int IMG>
+__global__ void __launch_bounds__(256) conv3x3_fwd_kernel(const float* __restrict__ x0, int B, int H, int W,
+                                                          const float* __restrict__ wc, const float* __restrict__ bc,
+                                                          float* __restrict__ z) {
+  extern __shared__ float sm[];                    // IMG * H * W
+  const int c = threadIdx.x & 31, hs = threadIdx.x >> 5;
+  const int OH = H - 2, OW = W - 2, HW = H * W;
+  const int b0 = blockIdx.x * IMG;
+  for (int i = threadIdx.x; i < IMG * HW; i += 256) {
+    int b = b0 + i / HW;
+    sm[i] = b < B ? x0[(int64_t)b0 * HW + i] : 0.f;
+  }
+  float wr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wr[k] = __ldg(wc + k * kFastC + c);
+  const float bias = __ldg(bc + c);
+  __syncthreads();
+  for (int q = 0; q < IMG; ++q) {
+    const int b = b0 + q;
+    if (b >= B) break;
+    const float* img = sm + q * HW;
+    float* zo = z + (int64_t)b * OH * OW * kFastC + c;
+    for (int h = hs; h < OH; h += 8) {
+      const float* r0 = img + h * W;
+      float a0 = r0[0], a1 = r0[1], b0_ = r0[W], b1 = r0[W + 1], c0 = r0[2 * W], c1 = r0[2 * W + 1];
+      for (int w = 0; w < OW; ++w) {
+        const float a2 = r0[w + 2], b2 = r0[W + w + 2], c2 = r0[2 * W + w + 2];
+        float acc = bias;
+        acc = fmaf(a0, wr[0], acc); acc = fmaf(a1, wr[1], acc); acc = fmaf(a2, wr[2], acc);
+        acc = fmaf(b0_, wr[3], acc); acc = fmaf(b1, wr[4], acc); acc = fmaf(b2, wr[5], acc);
+        acc = fmaf(c0, wr[6], acc); acc = fmaf(c1, wr[7], acc); acc = fmaf(c2, wr[8], acc);
+        zo[(h * OW + w) * kFastC] = acc;
+        a0 = a1; a1 = a2; b0_ = b1; b1 = b2; c0 = c1; c1 = c2;
+      }
+    }
+  }
+}
+
+// backward fast path.  Per image: dz staged in shared memory; phase 1 (thread = (c, h-slice)) accumulates the 9 filter
+// taps + bias gradient in registers with the same sliding window; phase 2 (warp per pixel, lanes = channels) forms dx.
+// The per-CTA filter / bias partials (IMG images, 8 h-slices) are combined in shared memory in a fixed order:
+// dwc_part / dbc_part get ONE slab per CTA.
+template <int IMG>
+__global__ void __launch_bounds__(256) conv3x3_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x0,
+                                                          int B, int H, int W, const float* __restrict__ wc,
+                                                          float* __restrict__ dx0, float* __restrict__ dwc_part,
+                                                          float* __restrict__ dbc_part) {
+  extern __shared__ float sm[];
+  const int c = threadIdx.x & 31, hs = threadIdx.x >> 5, lane = c;
+  const int OH = H - 2, OW = W - 2, HW = H * W, total = OH * OW * kFastC;
+  float* img = sm;                  // HW
+  float* dzs = img + HW;            // total
+  float* red = dzs + total;         // 8 * 10 * 32
+  const int b0 = blockIdx.x * IMG;
+  float wr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wr[k] = __ldg(wc + k * kFastC + c);
+  float g[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) g[k] = 0.f;
+  for (int q = 0; q < IMG; ++q) {
+    const int b = b0 + q;
+    if (b >= B) break;
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += 256) img[i] = x0[(int64_t)b * HW + i];
+    {
+      const float4* src = reinterpret_cast<const float4*>(dz + (int64_t)b * total);
+      float4* dst = reinterpret_cast<float4*>(dzs);
+      for (int i = threadIdx.x; i < total / 4; i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    // phase 1: filter / bias gradient, thread (c, h = hs, hs + 8, ...)
+    for (int h = hs; h < OH; h += 8) {
+      const float* r0 = img + h * W;
+      float a0 = r0[0], a1 = r0[1], b0_ = r0[W], b1 = r0[W + 1], c0 = r0[2 * W], c1 = r0[2 * W + 1];
+      for (int w = 0; w < OW; ++w) {
+        const float a2 = r0[w + 2], b2 = r0[W + w + 2], c2 = r0[2 * W + w + 2];
+        const float d = dzs[(h * OW + w) * kFastC + c];
+        g[0] = fmaf(a0, d, g[0]); g[1] = fmaf(a1, d, g[1]); g[2] = fmaf(a2, d, g[2]);
+        g[3] = fmaf(b0_, d, g[3]); g[4] = fmaf(b1, d, g[4]); g[5] = fmaf(b2, d, g[5]);
+        g[6] = fmaf(c0, d, g[6]); g[7] = fmaf(c1, d, g[7]); g[8] = fmaf(c2, d, g[8]);
+        g[9] += d;
+        a0 = a1; a1 = a2; b0_ = b1; b1 = b2; c0 = c1; c1 = c2;
+      }
+    }
+    // phase 2: dx, one warp per pixel, lanes over channels, fixed-order shuffle reduction
+    for (int y = 0; y < H; ++y) {
+      for (int x = hs; x < W; x += 8) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int h = y - i;
+          if (h < 0 || h >= OH) continue;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int w = x - j;
+            if (w < 0 || w >= OW) continue;
+            acc = fmaf(dzs[(h * OW + w) * kFastC + lane], wr[i * 3 + j], acc);
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) dx0[(int64_t)b * HW + y * W + x] = acc;
+      }
+    }
+  }
+  // combine the 8 h-slices (fixed order) -> one slab per CTA: dwc [9][32], dbc [32]
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 10; ++k) red[(hs * 10 + k) * kFastC + c] = g[k];
+  __syncthreads();
+  for (int o = threadIdx.x; o < 10 * kFastC; o += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int s8 = 0; s8 < 8; ++s8) t += red[s8 * 10 * kFastC + o];
+    if (o < 9 * kFastC) dwc_part[(int64_t)blockIdx.x * 9 * kFastC + o] = t;
+    else dbc_part[(int64_t)blockIdx.x * kFastC + (o - 9 * kFastC)] = t;
+  }
+}
+constexpr int kConvImgPerCta = 4;
 }  // namespace coper
 
 using namespace coper;
@@ -103,9 +229,24 @@ int coper_conv_fwd(const float* x0, int B, int H, int W, const float* wc, const 
                    int per_query, float* z, coper_stream_t stream) {
   COPER_CHECK_ARG(x0 && wc && bc && z && B > 0 && H >= KH && W >= KW && KH > 0 && KW > 0 && C > 0);
   if (H * W > kMaxImg || KH * KW * C > kMaxFilt) return COPER_ERR_UNSUPPORTED;
+  if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3) {
+    size_t sm_fast = (size_t)kConvImgPerCta * H * W * sizeof(float);
+    conv3x3_fwd_kernel<kConvImgPerCta><<<(B + kConvImgPerCta - 1) / kConvImgPerCta, 256, sm_fast, as_stream(stream)>>>(
+        x0, B, H, W, wc, bc, z);
+    return check_launch();
+  }
   size_t smem = (size_t)(H * W + KH * KW * C + C) * sizeof(float);
   conv_fwd_kernel<<<B, kConvThreads, smem, as_stream(stream)>>>(x0, H, W, wc, bc, KH, KW, C, per_query, z);
   return check_launch();
+}
+
+int coper_conv_bwd_slabs(int B, int H, int W, int KH, int KW, int C, int per_query) {
+  int OH = H - KH + 1, OW = W - KW + 1;
+  size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
+  if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3 && sm_fast <= 48 * 1024 &&
+      (OH * OW * C) % 4 == 0)
+    return (B + kConvImgPerCta - 1) / kConvImgPerCta;
+  return B;
 }
 
 int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const float* wc, int KH, int KW, int C,
@@ -114,6 +255,14 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
   int OH = H - KH + 1, OW = W - KW + 1;
   size_t smem = (size_t)(H * W + KH * KW * C + OH * OW * C) * sizeof(float);
   if (H * W > kMaxImg || KH * KW * C > kMaxFilt || smem > 200 * 1024) return COPER_ERR_UNSUPPORTED;
+  if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3) {
+    size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
+    if (sm_fast <= 48 * 1024 && (OH * OW * C) % 4 == 0) {
+      conv3x3_bwd_kernel<kConvImgPerCta><<<(B + kConvImgPerCta - 1) / kConvImgPerCta, 256, sm_fast, as_stream(stream)>>>(
+          dz, x0, B, H, W, wc, dx0, dwc_part, dbc_part);
+      return check_launch();
+    }
+  }
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

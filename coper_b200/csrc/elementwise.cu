@@ -31,7 +31,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, int64_t row_
 
 // ------------------------------------------------------------------ column statistics
 // mode 0: (x, x^2); mode 1: backward (g1, g1*xhat) with g1 = dout * drop_post * relu'(a x + b)
-constexpr int kStatRows = 512;  // rows per chunk
+// rows per chunk: enough chunks to fill the machine (R = B*OH*OW = 73,728 -> 576 CTAs; R = B = 512 -> 8 per column slab)
+__host__ __device__ __forceinline__ int stat_rows(int64_t R) { return R >= 32768 ? 128 : 64; }
 struct StatBwdArgs {
   const float* dout;
   const float* a;
@@ -51,6 +52,7 @@ __global__ void colstats_kernel(const float* __restrict__ x, int64_t R, int C, f
   // block (32, 8): x = column in slab, y = row lane
   __shared__ float s1[8][33], s2[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
+  const int kStatRows = stat_rows(R);
   int64_t r0 = (int64_t)blockIdx.y * kStatRows;
   int64_t r1 = r0 + kStatRows < R ? r0 + kStatRows : R;
   float v1 = 0.f, v2 = 0.f;
@@ -91,21 +93,26 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchun
                                    float* moving_mean, float* moving_var, float momentum, float eps,
                                    int use_batch, int update_moving, int bessel, float* a, float* b, float* mean,
                                    float* invstd) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel: lanes stride over the chunk partials, fixed-order shuffle combine
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float mu, var;
   if (use_batch) {
     double s = 0.0, ss = 0.0;
-    for (int k = 0; k < nchunk; ++k) {
-      s += (double)partials[((int64_t)k * C + c) * 2];
-      ss += (double)partials[((int64_t)k * C + c) * 2 + 1];
+    for (int k = lane; k < nchunk; k += 32) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partials) + (int64_t)k * C + c);
+      s += (double)v.x;
+      ss += (double)v.y;
     }
+    s = warp_sum_d(s);
+    ss = warp_sum_d(ss);
     double m = s / (double)R;
     double v = ss / (double)R - m * m;
     if (v < 0.0) v = 0.0;
     mu = (float)m;
     var = (float)v;
-    if (update_moving) {
+    if (update_moving && lane == 0) {
       double vm = bessel ? v * ((double)R / (double)(R > 1 ? R - 1 : 1)) : v;
       moving_mean[c] = moving_mean[c] * momentum + mu * (1.0f - momentum);
       moving_var[c] = moving_var[c] * momentum + (float)vm * (1.0f - momentum);
@@ -114,6 +121,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchun
     mu = moving_mean[c];
     var = moving_var[c];
   }
+  if (lane != 0) return;
   float inv = 1.0f / sqrtf(var + eps);
   float ac = gamma[c] * inv;
   a[c] = ac;
@@ -161,13 +169,18 @@ __global__ void bn_act_fwd_kernel4(const float4* __restrict__ x, int64_t n4, int
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C,
                                        int use_batch, float* dgamma, float* dbeta, float* c1, float* c2) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, ss = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    s += (double)partials[((int64_t)k * C + c) * 2];
-    ss += (double)partials[((int64_t)k * C + c) * 2 + 1];
+  for (int k = lane; k < nchunk; k += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(partials) + (int64_t)k * C + c);
+    s += (double)v.x;
+    ss += (double)v.y;
   }
+  s = warp_sum_d(s);
+  ss = warp_sum_d(ss);
+  if (lane != 0) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)ss;
   c1[c] = use_batch ? (float)(s / (double)R) : 0.f;
@@ -544,7 +557,7 @@ int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int wi
   return check_launch();
 }
 
-int coper_colstats_chunks(int64_t R) { return R <= 0 ? 0 : (int)((R + kStatRows - 1) / kStatRows); }
+int coper_colstats_chunks(int64_t R) { return R <= 0 ? 0 : (int)((R + stat_rows(R) - 1) / stat_rows(R)); }
 
 int coper_colstats(const float* x, int64_t R, int C, float* partials, coper_stream_t stream) {
   COPER_CHECK_ARG(x && partials && R > 0 && C > 0);
@@ -560,7 +573,7 @@ int coper_bn_finalize(const float* partials, int nchunk, int64_t R, int C, const
                       coper_stream_t stream) {
   COPER_CHECK_ARG(gamma && beta && moving_mean && moving_var && a && b && mean && invstd && C > 0);
   COPER_CHECK_ARG(!use_batch_stats || (partials && nchunk > 0 && R > 0));
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nchunk, R, C, gamma, beta, moving_mean,
+  bn_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, gamma, beta, moving_mean,
                                                                      moving_var, momentum, eps, use_batch_stats,
                                                                      update_moving, bessel, a, b, mean, invstd);
   return check_launch();
@@ -600,7 +613,7 @@ int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, 
 int coper_bn_act_bwd_finalize(const float* partials, int nchunk, int64_t R, int C, int use_batch_stats,
                               float* dgamma, float* dbeta, float* c1, float* c2, coper_stream_t stream) {
   COPER_CHECK_ARG(partials && dgamma && dbeta && c1 && c2 && nchunk > 0 && R > 0 && C > 0);
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(partials, nchunk, R, C, use_batch_stats,
+  bn_bwd_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, use_batch_stats,
                                                                          dgamma, dbeta, c1, c2);
   return check_launch();
 }

@@ -581,8 +581,10 @@ class ConvE:
         call("coper_conv_bwd", ptr(b.dz), ptr(b.x0), B, self.H, self.W, ptr(self.conv1_weights),
              self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.dx0), ptr(b.dwc_part), ptr(b.dbc_part))
         KK = self.conv_filter_height * self.conv_filter_width * C
-        call("coper_reduce_partials", ptr(b.dwc_part), B, KK, 1.0, 0, ptr(g["conv1_weights"]))
-        call("coper_reduce_partials", ptr(b.dbc_part), B, C, 1.0, 0, ptr(g["conv1_bias"]))
+        slabs = _lib.load().coper_conv_bwd_slabs(B, self.H, self.W, self.conv_filter_height, self.conv_filter_width,
+                                                 C, 0)
+        call("coper_reduce_partials", ptr(b.dwc_part), slabs, KK, 1.0, 0, ptr(g["conv1_weights"]))
+        call("coper_reduce_partials", ptr(b.dbc_part), slabs, C, 1.0, 0, ptr(g["conv1_bias"]))
         # gradients of the two embedding gathers (models.py:176-178): deterministic segmented scatter
         call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(b.ws),
              b.ws_bytes)

@@ -67,8 +67,10 @@ int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int wi
 int coper_conv_fwd(const float* x0, int B, int H, int W, const float* wc, const float* bc, int KH, int KW,
                    int C, int per_query, float* z, coper_stream_t stream);
 /* backward of the above: dz [B,OH*OW*C] -> dx0 [B,H*W]; shared filters: per-sample partials
- * dwc_part [B, KH*KW*C], dbc_part [B, C] (reduce over B with coper_reduce_partials);
- * per_query: the same buffers ARE the per-query gradients. */
+ * dwc_part [S, KH*KW*C], dbc_part [S, C] with S = coper_conv_bwd_slabs(...) <= B slabs (reduce over S with
+ * coper_reduce_partials; the 3x3 x 32-channel fast path emits one slab per 4 images);
+ * per_query: S = B and the same buffers ARE the per-query gradients. */
+int coper_conv_bwd_slabs(int B, int H, int W, int KH, int KW, int C, int per_query);
 int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const float* wc, int KH, int KW,
                    int C, int per_query, float* dx0, float* dwc_part, float* dbc_part, coper_stream_t stream);
 

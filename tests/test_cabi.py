@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_workspace_queries_run_without_gpu():
     lib = _lib.load()
-    assert lib.coper_colstats_chunks(1000) == 2
+    assert lib.coper_colstats_chunks(1000) == 16
     assert lib.coper_cpg_fc_fwd_workspace_bytes(512, 8, 4608, 200, 0) > 0
     assert lib.coper_score1n_bce_workspace_bytes(512, 40943, 200, 0) > 0
 

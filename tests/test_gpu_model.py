@@ -247,9 +247,11 @@ def test_multi_step_training_matches_oracle_amsgrad():
         opt.apply({k: (th[k], c) for k, c in zip(flat.keys(), clipped)})
         for nm in ("Conv1BN", "FCBN"):
             p64[nm]["moving_mean"], p64[nm]["moving_var"] = out["moving"][nm]
-    assert relerr(model.ent_emb.cpu().numpy(), p64["ent_emb"]) < 5e-4
-    assert relerr(model.fc_weights.projections[0].cpu().numpy(), p64["fc_weights_proj"][0]) < 5e-4
-    assert relerr(model.rel_emb.cpu().numpy(), p64["rel_emb"]) < 5e-4
+    # 5 steps of the sign-like AMSGrad-as-written rule at lr = 1e-2: entries whose gradient is ~0 move by +-lr per step
+    # on fp32 summation-order noise, so the drift bar is 1e-3 of max (single-step gradients are held to 2e-4 above)
+    assert relerr(model.ent_emb.cpu().numpy(), p64["ent_emb"]) < 1e-3
+    assert relerr(model.fc_weights.projections[0].cpu().numpy(), p64["fc_weights_proj"][0]) < 1e-3
+    assert relerr(model.rel_emb.cpu().numpy(), p64["rel_emb"]) < 1e-3
 
 
 def test_train_step_is_deterministic():
