@@ -273,6 +273,46 @@ class ConvE:
         self._put_bn(self.fc_bn, params["FCBN"])
         self.refresh_prepared()
 
+    # checkpoint = every variable + BN moving statistics + optimizer slots + step state (tf.train.Saver over all
+    # global variables, run_cpg.py:189,252); entity-sharded models save / load their own rows (one file per rank)
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = {"var/" + n: p for n, p, _ in self.trainables}
+        sd.update({"vhat/" + n: v for n, v in self.vhat.items()})
+        if not self.bug_compat:
+            sd.update({"m/" + n: v for n, v in self.m.items()})
+            sd.update({"v/" + n: v for n, v in self.v.items()})
+        bns = [("Conv1BN", self.conv1_bn), ("FCBN", self.fc_bn)]
+        for cpg in (self.fc_weights, self.fc_bias):
+            bns += [("%s/CPG/Projection%d/BatchNorm" % (cpg.name, i), bn) for i, bn in enumerate(cpg.bns)]
+        for nm, bn in bns:
+            sd["bn/%s/moving_mean" % nm], sd["bn/%s/moving_var" % nm] = bn.moving_mean, bn.moving_var
+            if not any(nm + "/gamma" == n for n, _, _ in self.trainables):      # BN without trainable scale/shift
+                sd["bn/%s/gamma" % nm], sd["bn/%s/beta" % nm] = bn.gamma, bn.beta
+        sd["step_state"], sd["seed_dev"] = self.step_state, self.seed_dev
+        return sd
+
+    def save_checkpoint(self, path: str):
+        if self.world > 1:
+            path = "%s.rank%d" % (path, self.shard.rank)
+        torch.save({"state": {k: v.detach().cpu() for k, v in self.state_dict().items()},
+                    "global_step": self.global_step, "shard": (self.shard.lo, self.shard.hi, self.num_ent)}, path)
+
+    def load_checkpoint(self, path: str):
+        if self.world > 1:
+            path = "%s.rank%d" % (path, self.shard.rank)
+        ck = torch.load(path, map_location="cpu")
+        if tuple(ck["shard"]) != (self.shard.lo, self.shard.hi, self.num_ent):
+            raise ValueError("checkpoint was written for entity rows %s, this model owns %s" % (
+                ck["shard"], (self.shard.lo, self.shard.hi, self.num_ent)))
+        own = self.state_dict()
+        missing = set(own) - set(ck["state"])
+        if missing:
+            raise KeyError("checkpoint lacks %s" % sorted(missing))
+        for k, dst in own.items():
+            dst.copy_(ck["state"][k].to(dst.dtype))
+        self.global_step = int(ck["global_step"])
+        self.refresh_prepared()
+
     def refresh_prepared(self):
         """(Re)build the tensor-pipe operand copies after the variables were written from outside the optimizer."""
         if self.E_prep is None:

@@ -6,6 +6,8 @@ Tolerances (fp32 path, ``prec='fp32'``):
   * gradients: <= 2e-4 * max|grad| (fp32 accumulation over B*N / B*F*dc products vs the fp64 oracle)
   * filtered ranks, MR/MRR/Hits: bit-exact against the oracle ranking of the SAME device logits.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -332,3 +334,47 @@ def test_eval_scores_and_ranks_tensor_pipe(name, prec):
     if prec == "tf32x3" and ne.sum() == 0:
         ref_rank = O.rank_literal(out["scores"].astype(np.float32), e2, dense)
         assert (rank.cpu().numpy() == ref_rank).mean() > 0.98  # fp32-class logits: ranks agree except near-ties
+
+
+# ------------------------------------------------------------------------------------------ entry point / checkpoint
+def test_run_cpg_entry_point_synthetic(tmp_path):
+    """python -m coper_b200.run_cpg on a synthetic toy KG: step loop, periodic eval, best-dev checkpoint + embeddings
+    pickle, config dump (run_cpg.py:87-105,209-256) and --model-load-path = restore + test eval + exit (:205-208)."""
+    import glob
+    import pickle
+    from coper_b200 import run_cpg
+    wd = str(tmp_path)
+    assert run_cpg.main(["--synthetic", "toy", "--max-steps", "12", "--working-dir", wd, "--eval-batches", "2",
+                         "--prec", "tf32x3"]) == 0
+    ck = glob.glob(os.path.join(wd, "checkpoints", "*", "model_weights.ckpt", "model_weights.ckpt"))
+    assert len(ck) == 1
+    emb = glob.glob(os.path.join(wd, "evaluation", "*", "best_embeddings.ckpt"))
+    rel_emb, ent_emb = pickle.load(open(emb[0], "rb"))
+    assert ent_emb.shape == (997, 40) and rel_emb.shape == (6, 5)
+    assert glob.glob(os.path.join(wd, "configs", "*", "config.yml"))
+    assert run_cpg.main(["--synthetic", "toy", "--working-dir", wd, "--eval-batches", "2", "--prec", "tf32x3",
+                         "--model-load-path", ck[0]]) == 0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_checkpoint_roundtrip(prec, tmp_path):
+    kw, B = CASES["ragged_mid"]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5)
+    batch = batch_of(e1, rel, e2, rowptr, col)
+    m = make(cfg, params, prec=prec)
+    for _ in range(3):
+        m.train_step(batch)
+    path = os.path.join(str(tmp_path), "ck.pt")
+    m.save_checkpoint(path)
+    S = m.predict_all(batch).clone()
+    r1, _ = m.filtered_ranks(batch)
+    m2 = make(cfg, O.init_params(cfg, seed=99), prec=prec)
+    m2.load_checkpoint(path)
+    assert torch.equal(m2.predict_all(batch), S)
+    r2, _ = m2.filtered_ranks(batch)
+    assert torch.equal(r1, r2)
+    # training continues identically (optimizer slots, step state and dropout seed were restored)
+    l1, l2 = m.train_step(batch).item(), m2.train_step(batch).item()
+    assert l1 == l2
