@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra bf16-engine measurement")
     ap.add_argument("--graph-multi", action="store_true",
                     help="N > 1: capture the step including its NCCL collectives in a CUDA graph (experimental: hung on "
                          "the 2-GPU box in round 1, off by default)")
@@ -229,8 +230,19 @@ def main():
     roofline, breakdown = None, None
     peaks = load_peaks()
     if not args.no_breakdown and rank == 0 and world == 1:
-        breakdown, roofline = kernel_breakdown(model, devb[0], peaks, args.prec)
+        breakdown, roofline = kernel_breakdown(model, devb[0], peaks, args.prec, args.shape)
 
+    # the same workload on the bf16 tensor-pipe engine (north_star's throughput path), reported beside the headline
+    alt = None
+    if world == 1 and args.prec != "bf16" and not args.no_alt:
+        del model
+        torch.cuda.empty_cache()
+        m16 = ConvE(md, seed=0, prec="bf16", shard=shard, conv_in_height=s["H"], init_fast=s["num_ent"] > 1_000_000)
+        model = m16                                   # timed() reads model.graph_kernel_launches
+        t_ms, _ = timed(lambda i: m16.train_step(devb[i % n_batches]), K, W)
+        e_ms, _ = timed(lambda i: m16.filtered_ranks(devb[i % n_batches]), K, W)
+        alt = {"precision": "bf16 (tcgen05 kind::f16, fp32 accumulate)", "value": B / t_ms * 1e3, "unit": "train rows/s",
+               "ms_per_step": t_ms, "eval_value": B / e_ms * 1e3, "eval_unit": "eval queries/s", "eval_ms_per_batch": e_ms}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -264,7 +276,7 @@ def main():
                 "eval_value": B / e2e_eval_ms * 1e3, "eval_unit": "eval queries/s", "eval_ms_per_batch": e2e_eval_ms,
                 "eval_d2h_bytes_per_batch": B * 4},
         "gpu_launches": int(train_launches), "gpu_launches_per_step": train_launches / K,
-        "clocks": clocks, "roofline": roofline, "kernel_ms": breakdown, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "kernel_ms": breakdown, "bf16": alt, "cpu_baseline": cpu,
         "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "_source")},
     }
     sys.stdout.flush()
@@ -281,7 +293,7 @@ def working_set_mb(s, B):
     return int((3 * N * d * 4 + 3 * dr * F * d * 4 + B * N * 4 + 4 * B * F * 4) / 1e6)
 
 
-def kernel_breakdown(model, batch, peaks, prec, reps=10):
+def kernel_breakdown(model, batch, peaks, prec, shape="wn18rr", reps=10):
     """CUDA-event time of each C-ABI stage in isolation (same stream, warm) and the roofline of the dominant one."""
     import torch
     from coper_b200._lib import call, ptr
@@ -343,10 +355,19 @@ def kernel_breakdown(model, batch, peaks, prec, reps=10):
         peak = peaks["hbm_gbs"]
         achieved = work / (ms * 1e-3) / 1e9
         unit = "GB/s"
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tj.get(shape, {}).get(prec, {}).get(name)
+    except Exception:
+        pass
     roof = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-            "traffic": None, "ms": ms, "algorithmic_work": work,
+            "traffic": traffic, "ms": ms, "algorithmic_work": work,
             "peak_source": peaks["_source"] + (", bf16 dense burst" if bound == "tensor" else ", copy bandwidth"),
-            "note": "isolated launches, CUDA events on the launching stream; prec=%s" % prec}
+            "note": "isolated launches of the C-ABI stage (its tcgen05 kernels + reductions), CUDA events on the launching "
+                    "stream; prec=%s%s; traffic = DRAM bytes of the stage from the committed ncu capture" % (
+                        prec, " (3 tf32 MMAs per product: tensor-pipe time = 6x the bf16-equivalent of the algorithmic "
+                              "FLOPs)" if prec == "tf32x3" else "")}
     return out, roof
 
 

@@ -398,8 +398,14 @@ template <>
 struct BceSel<PREC_TF32X3, false> { using Cfg = GemmCfg<PREC_TF32X3, 128, 3, kBceEpiWarps, false, false, 0, 0>; };
 template <class Cfg>
 constexpr int ent_nch() { return Cfg::BLOCK_N / (Cfg::EPI_WARPS / 4) / 32; }
-static inline bool ent_resident(int d, int prec) { return prec == COPER_PREC_BF16 && d <= 256; }
-static inline int ent_block_n(int d, int prec) { return ent_resident(d, prec) ? 256 : 128; }
+// the resident-query-block configuration pays a 128 KB fill per CTA: worth it once a CTA processes >= 8 tiles
+// (WN18RR: 640 tiles / 148 CTAs -> streaming configuration; 1 M entities: 106 tiles per CTA -> resident)
+static inline bool ent_resident(int d, int prec, int64_t Ns, int B) {
+  if (prec != COPER_PREC_BF16 || d > 256) return false;
+  const int64_t tiles = ((Ns + BLOCK_M - 1) / BLOCK_M) * ((B + 255) / 256);
+  return tiles >= 8 * 148;
+}
+static inline int ent_block_n(int d, int prec, int64_t Ns, int B) { return ent_resident(d, prec, Ns, B) ? 256 : 128; }
 
 static GemmProblem ent_problem(int B, int64_t Ns, int d, int block_n) {
   GemmProblem p{};
@@ -430,7 +436,7 @@ static int score_t_impl(const TcOperand& E, const TcOperand& Q, const float* bia
 // dispatch over (precision, resident query block)
 #define ENT_DISPATCH(FN, ...)                                                                              \
   do {                                                                                                     \
-    if (prec == COPER_PREC_BF16 && ent_resident(d, prec)) return FN<EntSel<PREC_BF16, true>::Cfg>(__VA_ARGS__);  \
+    if (prec == COPER_PREC_BF16 && ent_resident(d, prec, Ns, B)) return FN<EntSel<PREC_BF16, true>::Cfg>(__VA_ARGS__);  \
     if (prec == COPER_PREC_BF16) return FN<EntSel<PREC_BF16, false>::Cfg>(__VA_ARGS__);                   \
     if (prec == COPER_PREC_TF32X3) return FN<EntSel<PREC_TF32X3, false>::Cfg>(__VA_ARGS__);               \
     return COPER_ERR_UNSUPPORTED;                                                                          \
@@ -504,7 +510,7 @@ static BceTcLayout bce_tc_layout(int B, int64_t Ns, int d, int prec) {
   GemmProblem p{};
   p.M = B; p.N = d; p.K = (int)Ns; p.groups = 1;
   L.splits = tc_plan_splits(prec, p, true);
-  int bn = ent_block_n(d, prec);
+  int bn = ent_block_n(d, prec, Ns, B);
   L.dbias_slabs = ((B + bn - 1) / bn) * (kBceEpiWarps / 4);
   size_t o = 0;
   L.off_q = o; o = align_up(o + tc_prepared_bytes(B, d, prec), 256);
@@ -563,7 +569,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
   // ---- pass 1: scores -> loss, G, dbias partials
   int grid = 0;
   auto run_bce = [&]() -> int {
-    if (prec == COPER_PREC_BF16 && ent_resident(d, prec))
+    if (prec == COPER_PREC_BF16 && ent_resident(d, prec, Ns, B))
       return bce_impl<BceSel<PREC_BF16, true>::Cfg>(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT,
                                                     dbias_part, loss_part, st, &grid);
     if (prec == COPER_PREC_BF16)
