@@ -341,7 +341,16 @@ class ConvE:
         lib = _lib.load()
         b = type("Buf", (), {})()
         b.B, b.ld, b.words = B, ld, words
-        b.e1, b.rel, b.e2 = z(B, dt=torch.int64), z(B, dt=torch.int64), z(B, dt=torch.int64)
+        # query ids + CSR row pointers live in ONE device block so that a host batch needs one H2D copy for them:
+        # [e1 | rel | e2] int64 [3, B] followed by rowptr int32 [B + 1]
+        head_words = 6 * B + (B + 2)
+        b.d_head = z(head_words, dt=torch.int32)
+        b.h_head = torch.zeros(head_words, dtype=torch.int32).pin_memory()
+        idx64 = b.d_head[:6 * B].view(torch.int64).view(3, B)
+        b.e1, b.rel, b.e2 = idx64[0], idx64[1], idx64[2]
+        b.h_head_np = b.h_head.numpy()
+        b.h_idx_np = b.h_head_np[:6 * B].view(np.int64).reshape(3, B)
+        b.h_rowptr_np = b.h_head_np[6 * B:6 * B + B + 1]
         b.x0, b.r = z(B, d), z(B, dr)
         b.z, b.f = z(B, F), z(B, F)
         b.y, b.q = z(B, d), z(B, d)
@@ -385,10 +394,8 @@ class ConvE:
         b.dcw, b.dcb = z(B, dcw), z(B, dcb)
         b.dr2 = z(B, dr)
         # pinned staging for host batches
-        b.h_idx = torch.zeros(3, B, dtype=torch.int64).pin_memory()
         b.csr_cap = 0
-        b.rowptr = z(B + 1, dt=torch.int32)
-        b.h_rowptr = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        b.rowptr = b.d_head[6 * B:6 * B + B + 1]
         b.col = None
         b.h_col = None
         b.h2d_event = None
@@ -411,6 +418,7 @@ class ConvE:
             cap = max(1024, int(nnz * 1.5))
             b.col = torch.zeros(cap, dtype=torch.int32, device=self.dev)
             b.h_col = torch.zeros(cap, dtype=torch.int32).pin_memory()
+            b.h_col_np = b.h_col.numpy()
             b.csr_cap = cap
 
     # ------------------------------------------------------------------------------------------
@@ -424,37 +432,44 @@ class ConvE:
         b = self._buffers(B)
         if b.h2d_event is not None:
             b.h2d_event.synchronize()          # previous async copies out of the pinned staging are done
-        if isinstance(e1, torch.Tensor) and e1.is_cuda:
+        s = self.shard
+        on_device = isinstance(e1, torch.Tensor) and e1.is_cuda
+        has_csr = "e2_multi_rowptr" in batch
+        if on_device:
             b.e1.copy_(e1)
             b.rel.copy_(batch["rel"])
             if need_e2:
                 b.e2.copy_(batch["e2"])
         else:
-            b.h_idx[0].copy_(torch.as_tensor(np.asarray(e1), dtype=torch.int64))
-            b.h_idx[1].copy_(torch.as_tensor(np.asarray(batch["rel"]), dtype=torch.int64))
+            b.h_idx_np[0] = e1
+            b.h_idx_np[1] = batch["rel"]
             if need_e2:
-                b.h_idx[2].copy_(torch.as_tensor(np.asarray(batch["e2"]), dtype=torch.int64))
-            b.e1.copy_(b.h_idx[0], non_blocking=True)
-            b.rel.copy_(b.h_idx[1], non_blocking=True)
-            if need_e2:
-                b.e2.copy_(b.h_idx[2], non_blocking=True)
-        s = self.shard
-        if "e2_multi_rowptr" in batch:
+                b.h_idx_np[2] = batch["e2"]
+        if has_csr:
             rp, col = batch["e2_multi_rowptr"], batch["e2_multi_col"]
             nnz = int(col.shape[0])
             self._ensure_csr(b, nnz)
             if isinstance(rp, torch.Tensor) and rp.is_cuda:
                 b.rowptr.copy_(rp)
                 b.col[:nnz].copy_(col)
+                if not on_device:
+                    b.d_head[:6 * B].copy_(b.h_head[:6 * B], non_blocking=True)
             else:
-                b.h_rowptr.copy_(torch.as_tensor(np.asarray(rp), dtype=torch.int32))
-                b.h_col[:nnz].copy_(torch.as_tensor(np.asarray(col), dtype=torch.int32))
-                b.rowptr.copy_(b.h_rowptr, non_blocking=True)
+                b.h_rowptr_np[:] = rp
+                b.h_col_np[:nnz] = col
+                if on_device:
+                    b.rowptr.copy_(b.h_head[6 * B:6 * B + B + 1], non_blocking=True)
+                else:
+                    b.d_head.copy_(b.h_head, non_blocking=True)          # ids + row pointers: one copy
                 b.col[:nnz].copy_(b.h_col[:nnz], non_blocking=True)
             if self.prec == 0:
                 call("coper_csr_to_bits", ptr(b.rowptr), ptr(b.col), B, s.lo, s.hi, ptr(b.bits))
             else:
                 call("coper_csr_to_bits_t", ptr(b.rowptr), ptr(b.col), B, s.lo, s.hi, ptr(b.bitsT))
+        elif not on_device:
+            b.d_head[:6 * B].copy_(b.h_head[:6 * B], non_blocking=True)
+        if has_csr:
+            pass
         elif "e2_multi" in batch and batch["e2_multi"] is not None:
             dense = batch["e2_multi"]
             if not (isinstance(dense, torch.Tensor) and dense.is_cuda):
