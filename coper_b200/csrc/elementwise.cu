@@ -401,7 +401,10 @@ __global__ void __launch_bounds__(256) mt_sumsq_kernel(const coper_param_desc* _
   const int64_t end = start + COPER_MT_CHUNK < d.n ? start + COPER_MT_CHUNK : d.n;
   const float* x = d.grad;
   float p = 0.f;
-  if (((reinterpret_cast<uintptr_t>(x) & 15) == 0) && end - start == COPER_MT_CHUNK) {
+  if (d.mode == COPER_GRAD_INDEXED_SLICES) {
+    // IndexedSlices: norm over the slice values = sum of the per-row sums of squared slices
+    for (int64_t j = start + threadIdx.x; j < end; j += 256) p += d.grad_sq[j];
+  } else if (((reinterpret_cast<uintptr_t>(x) & 15) == 0) && end - start == COPER_MT_CHUNK) {
     const float4* x4 = reinterpret_cast<const float4*>(x + start);
 #pragma unroll 4
     for (int j = threadIdx.x; j < COPER_MT_CHUNK / 4; j += 256) {
@@ -463,6 +466,21 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
   const float lr_t = step_state[0];
   const float cs = clip_scale ? *clip_scale : 1.0f;
   const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  if (d.mode == COPER_GRAD_INDEXED_SLICES) {                 // utils/amsgrad.py:161-189 (slots accumulate)
+    for (int64_t i = start + threadIdx.x; i < end; i += 256) {
+      const float g1 = d.grad[i] * cs, g2 = d.grad_sq[i] * cs * cs;
+      const float mt = d.m[i] * b1 + g1 * omb1;
+      const float vt = d.v[i] * b2 + g2 * omb2;
+      d.m[i] = mt;
+      d.v[i] = vt;
+      const float vh = fmaxf(d.vhat[i], vt);
+      d.vhat[i] = vh;
+      const float th = d.theta[i] - lr_t * mt / (sqrtf(vh) + eps);
+      d.theta[i] = th;
+      if (d.prepared) emit_prepared(d, i, th);
+    }
+    return;
+  }
   const bool vec = end - start == COPER_MT_CHUNK && bug_compat &&
                    (((reinterpret_cast<uintptr_t>(d.theta) | reinterpret_cast<uintptr_t>(d.grad) |
                       reinterpret_cast<uintptr_t>(d.vhat)) & 15) == 0);

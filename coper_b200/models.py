@@ -207,9 +207,16 @@ class ConvE:
         self.trainables = tr
         self.grads = {n: torch.zeros_like(p) for n, p, _ in tr}
         self.vhat = {n: torch.zeros_like(p) for n, p, _ in tr}
+        # variables read only through embedding_lookup get an IndexedSlices gradient in TF -> sparse AMSGrad rule
+        # (slots accumulate) and a slice-wise contribution to the global norm (include/coper.h, coper_param_desc)
+        self.sparse_vars = {"rel_emb"}
+        self.grad_sq = {n: torch.zeros_like(p) for n, p, _ in tr if n in self.sparse_vars}
         if not self.bug_compat:
             self.m = {n: torch.zeros_like(p) for n, p, _ in tr}
             self.v = {n: torch.zeros_like(p) for n, p, _ in tr}
+        else:
+            self.m = {n: torch.zeros_like(p) for n, p, _ in tr if n in self.sparse_vars}
+            self.v = {n: torch.zeros_like(p) for n, p, _ in tr if n in self.sparse_vars}
         # tensor-pipe operand copies of the two big GEMM operands, kept current by the optimizer kernel
         self.E_prep = self.P_prep = None
         lib = _lib.load()
@@ -224,15 +231,17 @@ class ConvE:
                                       device=self.dev)
         # multi-tensor work list (include/coper.h: coper_param_desc, COPER_MT_CHUNK)
         desc = np.zeros(len(tr), dtype=np.dtype([("theta", "<u8"), ("grad", "<u8"), ("m", "<u8"), ("v", "<u8"),
-                                                 ("vhat", "<u8"), ("prepared", "<u8"), ("n", "<i8"),
-                                                 ("prepared_prec", "<i4"), ("reserved", "<i4")]))
+                                                 ("vhat", "<u8"), ("prepared", "<u8"), ("grad_sq", "<u8"),
+                                                 ("n", "<i8"), ("prepared_prec", "<i4"), ("mode", "<i4")]))
         chunks, offsets = [], [0]
         last_w = "fc_weights/CPG/Projection%d" % (len(self.fc_weights.projections) - 1)
         for i, (n, p, _) in enumerate(tr):
             desc[i]["theta"], desc[i]["grad"], desc[i]["vhat"] = p.data_ptr(), self.grads[n].data_ptr(), \
                 self.vhat[n].data_ptr()
-            if not self.bug_compat:
+            if n in self.m:
                 desc[i]["m"], desc[i]["v"] = self.m[n].data_ptr(), self.v[n].data_ptr()
+            if n in self.sparse_vars:
+                desc[i]["grad_sq"], desc[i]["mode"] = self.grad_sq[n].data_ptr(), 1
             desc[i]["n"] = p.numel()
             prep = self.E_prep if n == "ent_emb" else self.P_prep if n == last_w else None
             if prep is not None and self._emit_prepared:
@@ -278,9 +287,8 @@ class ConvE:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         sd = {"var/" + n: p for n, p, _ in self.trainables}
         sd.update({"vhat/" + n: v for n, v in self.vhat.items()})
-        if not self.bug_compat:
-            sd.update({"m/" + n: v for n, v in self.m.items()})
-            sd.update({"v/" + n: v for n, v in self.v.items()})
+        sd.update({"m/" + n: v for n, v in self.m.items()})
+        sd.update({"v/" + n: v for n, v in self.v.items()})
         bns = [("Conv1BN", self.conv1_bn), ("FCBN", self.fc_bn)]
         for cpg in (self.fc_weights, self.fc_bias):
             bns += [("%s/CPG/Projection%d/BatchNorm" % (cpg.name, i), bn) for i, bn in enumerate(cpg.bns)]
@@ -393,6 +401,7 @@ class ConvE:
                                "dact": [z(B, n) for n in cpg.hidden], "dpre": [z(B, n) for n in cpg.hidden]}
         b.dcw, b.dcb = z(B, dcw), z(B, dcb)
         b.dr2 = z(B, dr)
+        b.dr_sq = z(B, dr)
         # pinned staging for host batches
         b.csr_cap = 0
         b.rowptr = b.d_head[6 * B:6 * B + B + 1]
@@ -646,6 +655,11 @@ class ConvE:
         g["rel_emb"].zero_()
         call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]), 0, self.num_rel, ptr(b.ws),
              b.ws_bytes)
+        # IndexedSlices bookkeeping for rel_emb: per-row sums of the SQUARED slices (global norm + sparse AMSGrad)
+        torch.mul(b.dr, b.dr, out=b.dr_sq)
+        self.grad_sq["rel_emb"].zero_()
+        call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0, self.num_rel,
+             ptr(b.ws), b.ws_bytes)
         self._clip_and_apply()
 
     def _clip_and_apply(self):

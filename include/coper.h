@@ -270,12 +270,21 @@ int coper_amsgrad_step(float* theta, const float* grad, float* m, float* v, floa
  *                 `prepared` (optional) is refreshed with the tensor-pipe operand form of the UPDATED variable
  *                 (bf16 copy, or tf32 hi plane followed by the lo plane; requires row pitch == row length),
  *                 so the next step's GEMMs need no separate conversion pass.
+ *                 mode = COPER_GRAD_DENSE: the dense rule of coper_amsgrad_step.  mode = COPER_GRAD_INDEXED_SLICES: the
+ *                 variable is read only through tf.nn.embedding_lookup (rel_emb, models.py:178), TF hands the
+ *                 optimizer an IndexedSlices and runs _apply_sparse_shared (utils/amsgrad.py:161-189), where the
+ *                 slots DO accumulate: `grad` = sum of the slices per row, `grad_sq` = sum of the SQUARED slices
+ *                 per row (each slice squared on its own); m <- b1 m + (1-b1) c grad; v <- b2 v + (1-b2) c^2 grad_sq;
+ *                 vhat <- max(vhat, v); theta -= lr_t m / (sqrt(vhat) + eps) on the whole variable (c = clip scale;
+ *                 m, v required).  The squared norm such a variable contributes to tf.clip_by_global_norm is
+ *                 sum(grad_sq) - slices sharing an index are not summed first (clip_ops.global_norm on .values).
  *   chunks        device int32 [n_chunks][2] = (tensor id, chunk index); chunk = COPER_MT_CHUNK elements;
  *                 sorted by tensor id; chunk_offsets int32 [n_tensors + 1] = first chunk of each tensor.
  *   coper_mt_sumsq   -> tensor_sumsq[t] = |grad_t|^2 (fp64, fixed order; chunk_partials is scratch [n_chunks])
  *   coper_clip_scale_n(tensor_sumsq, n_tensors, ...) -> {clip / max(norm, clip), norm}
  *   coper_mt_amsgrad -> the update of coper_amsgrad_step for every tensor. */
 #define COPER_MT_CHUNK 16384
+enum { COPER_GRAD_DENSE = 0, COPER_GRAD_INDEXED_SLICES = 1 };
 typedef struct {
   float* theta;
   const float* grad;
@@ -283,9 +292,10 @@ typedef struct {
   float* v;
   float* vhat;
   void* prepared;
+  const float* grad_sq;
   int64_t n;
   int32_t prepared_prec;
-  int32_t reserved;
+  int32_t mode;
 } coper_param_desc;
 int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
                    const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, coper_stream_t stream);

@@ -426,11 +426,21 @@ def flatten_grads(g) -> List[np.ndarray]:
     return outl
 
 
-def clip_by_global_norm(grads: List[np.ndarray], clip_norm: float = 5.0):
-    """tf.clip_by_global_norm (models.py:199): scale = clip / max(norm, clip)."""
-    norm = math.sqrt(sum(float((x.astype(np.float64) ** 2).sum()) for x in grads))
+def clip_by_global_norm(grads: List[np.ndarray], clip_norm: float = 5.0, sparse_values: Sequence[np.ndarray] = ()):
+    """tf.clip_by_global_norm (models.py:199): scale = clip / max(norm, clip).
+
+    ``sparse_values``: the ``values`` of gradients TF represents as ``tf.IndexedSlices`` (a variable read only through
+    ``tf.nn.embedding_lookup`` — ``rel_emb`` on this path, models.py:178).  ``clip_ops.global_norm`` takes
+    ``l2_loss(t.values)`` for those, i.e. slices that share an index are NOT summed before squaring.  Returns
+    (clipped dense grads, norm) or, when sparse values are given, (clipped dense, clipped sparse values, norm)."""
+    sq = sum(float((x.astype(np.float64) ** 2).sum()) for x in grads)
+    sq += sum(float((x.astype(np.float64) ** 2).sum()) for x in sparse_values)
+    norm = math.sqrt(sq)
     scale = clip_norm / max(norm, clip_norm)
-    return [x * x.dtype.type(scale) for x in grads], norm
+    dense = [x * x.dtype.type(scale) for x in grads]
+    if len(sparse_values):
+        return dense, [x * x.dtype.type(scale) for x in sparse_values], norm
+    return dense, norm
 
 
 # --------------------------------------------------------------------------------------
@@ -455,9 +465,23 @@ class AMSGradOracle:
     def lr_t(self):
         return self.lr * math.sqrt(1 - self.b2p) / (1 - self.b1p)   # amsgrad.py:137
 
-    def apply(self, named):
-        """named: dict name -> (theta, grad) ndarrays; updates theta in place."""
+    def apply(self, named, sparse=None):
+        """named: dict name -> (theta, grad) ndarrays, dense rule; sparse: dict name -> (theta, values [M, ...],
+        indices [M]) for IndexedSlices gradients, which TF routes to ``_apply_sparse_shared`` (amsgrad.py:161-189):
+        there the slots ARE accumulated (``scatter_add`` mutates them): m <- b1 m; m[idx] += (1-b1) g_i (duplicates
+        add); v <- b2 v; v[idx] += (1-b2) g_i^2 (each slice squared on its own); v_hat <- max(v_hat, v);
+        theta <- theta - lr_t m / (sqrt(v_hat) + eps) over the WHOLE variable.  Updates theta in place."""
         lr_t = self.lr_t()
+        for k, (th, vals, idx) in (sparse or {}).items():
+            st = self.state.setdefault(k, {"m": np.zeros_like(th), "v": np.zeros_like(th),
+                                           "vhat": np.zeros_like(th)})
+            dt = th.dtype.type
+            st["m"] *= dt(self.b1)
+            np.add.at(st["m"], idx, vals * dt(1 - self.b1))
+            st["v"] *= dt(self.b2)
+            np.add.at(st["v"], idx, vals * vals * dt(1 - self.b2))
+            st["vhat"] = np.maximum(st["vhat"], st["v"])
+            th -= dt(lr_t) * st["m"] / (np.sqrt(st["vhat"]) + dt(self.eps))
         for k, (th, g) in named.items():
             st = self.state.setdefault(k, {"m": np.zeros_like(th), "v": np.zeros_like(th),
                                            "vhat": np.zeros_like(th)})

@@ -41,6 +41,8 @@ class _State:
         self.rng = _np.random.default_rng(0)
         self.scope = []
         self.last_gradients = None
+        self.gather_tape = []          # embedding_lookup records of trainable variables (for IndexedSlices grads)
+        self.block_gather = False      # backward of embedding_lookup returns no gradient (usage probing)
 
 
 state = _State()
@@ -274,17 +276,66 @@ def map_fn(fn, elems):
     return tuple(_torch.stack([o[j] for o in outs]) for j in range(len(outs[0])))
 
 
+class IndexedSlices:
+    """tf.IndexedSlices: what TF-1.14 returns as the gradient of a variable that is only read through
+    tf.nn.embedding_lookup / tf.gather (ResourceGather's gradient).  A variable that ALSO has a dense gradient
+    gets the sum as a dense tensor (gradients_util._AggregateIndexedSlicesGradients: "if any gradient is a Tensor,
+    add_n them")."""
+
+    def __init__(self, values, indices, dense_shape=None):
+        self.values, self.indices, self.dense_shape = values, indices, dense_shape
+
+    def to_dense(self):
+        out = _torch.zeros(self.dense_shape, dtype=self.values.dtype)
+        return out.index_add_(0, self.indices, self.values)
+
+
 def clip_by_global_norm(t_list, clip_norm):
-    """tf.clip_by_global_norm: t * clip_norm / max(global_norm, clip_norm); None entries pass through."""
-    norm = _torch.sqrt(sum((_u(t) ** 2).sum() for t in t_list if t is not None))
+    """tf.clip_by_global_norm: t * clip_norm / max(global_norm, clip_norm); None entries pass through.
+    For an IndexedSlices the norm is taken over its `values` (clip_ops.global_norm uses l2_loss(t.values)):
+    slices that share an index are NOT summed first."""
+    def vals(t):
+        return t.values if isinstance(t, IndexedSlices) else _u(t)
+    norm = _torch.sqrt(sum((vals(t) ** 2).sum() for t in t_list if t is not None))
     scale = clip_norm / _torch.maximum(norm, _torch.tensor(float(clip_norm), dtype=norm.dtype))
-    return [None if t is None else _u(t) * scale for t in t_list], norm
+    out = []
+    for t in t_list:
+        if t is None:
+            out.append(None)
+        elif isinstance(t, IndexedSlices):
+            out.append(IndexedSlices(t.values * scale, t.indices, t.dense_shape))
+        else:
+            out.append(_u(t) * scale)
+    return out, norm
+
+
+class _GatherFn(_torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, ids, rec):
+        ctx.rec, ctx.shape = rec, params.shape
+        ctx.save_for_backward(ids)
+        return params[ids]
+
+    @staticmethod
+    def backward(ctx, go):
+        (ids,) = ctx.saved_tensors
+        flat = go.reshape(-1, *ctx.shape[1:])
+        ctx.rec["values"] = flat.detach().clone()
+        if state.block_gather:
+            return None, None, None
+        dense = _torch.zeros(ctx.shape, dtype=go.dtype).index_add_(0, ids.reshape(-1), flat)
+        return dense, None, None
 
 
 class nn:
     @staticmethod
     def embedding_lookup(params, ids, name=None):
-        return _u(params)[_u(ids).long()]
+        ids = _u(ids).long()
+        if isinstance(params, Variable) and params.trainable:
+            rec = {"var": params, "ids": ids.reshape(-1)}
+            state.gather_tape.append(rec)
+            return _GatherFn.apply(params.t, ids, rec)
+        return _u(params)[ids]
 
     @staticmethod
     def relu(x):

@@ -1,2 +1,9 @@
+"""resource_variable_ops subset: scatter-add into a shim Variable (duplicate indices accumulate)."""
+import torch as _torch
+import tensorflow as _tf
+
+
 def resource_scatter_add(handle, indices, updates):
-    raise NotImplementedError("sparse path is not on the 1-N hot path")
+    with _torch.no_grad():
+        handle.t.index_add_(0, _tf._u(indices).long(), _tf._u(updates))
+    return handle

@@ -14,4 +14,6 @@ def assign_sub(ref, value, use_locking=None):
 
 
 def scatter_add(ref, indices, updates, use_locking=None):
-    raise NotImplementedError("sparse path is not on the 1-N hot path")
+    with _torch.no_grad():
+        ref.t.index_add_(0, _tf._u(indices).long(), _tf._u(updates))
+    return ref

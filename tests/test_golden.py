@@ -149,11 +149,15 @@ def test_oracle_multi_step_training_matches_reference(name):
         dense = O.csr_to_dense(z[pre + "rowptr"], z[pre + "col"], cfg.num_ent)
         out = O.forward(p, cfg, z[pre + "e1"], z[pre + "rel"], True, masks_of(z, step, case), dense, np.float64)
         assert abs(out["loss"] - float(z[pre + "loss"])) < 1e-4 * abs(out["loss"]), step
-        g = named_grads(O.backward(out, cfg), case)
-        names = list(g)
-        clipped, _ = O.clip_by_global_norm([g[k] for k in names], 5.0)
+        raw = O.backward(out, cfg)
+        g = named_grads(raw, case)
+        # rel_emb is read only through tf.nn.embedding_lookup (models.py:178): TF hands the optimizer an IndexedSlices
+        # (values = per-query rows dr, indices = rel) -> slice-wise global norm and the sparse AMSGrad rule
+        names = [k for k in g if k != "rel_emb"]
+        clipped, (dr_c,), _ = O.clip_by_global_norm([g[k] for k in names], 5.0, sparse_values=[raw["_dr"]])
         th = named_params(p, case)
-        opt.apply({k: (th[k], c.reshape(th[k].shape)) for k, c in zip(names, clipped)})
+        opt.apply({k: (th[k], c.reshape(th[k].shape)) for k, c in zip(names, clipped)},
+                  sparse={"rel_emb": (th["rel_emb"], dr_c, np.asarray(z[pre + "rel"]))})
         for nm in ("Conv1BN", "FCBN"):
             p[nm]["moving_mean"], p[nm]["moving_var"] = out["moving"][nm]
         for which, key in (("fc_weights", "ctx_w"), ("fc_bias", "ctx_b")):
@@ -171,6 +175,10 @@ def test_oracle_multi_step_training_matches_reference(name):
         # the reference's dense AMSGrad never accumulates m / v (amsgrad.py:142-151)
         assert np.abs(z[pre + "after/ent_emb/AMSGrad/m"]).max() == 0.0
         assert np.abs(z[pre + "after/ent_emb/AMSGrad/v"]).max() == 0.0
+        # ... while the sparse path (rel_emb) does (amsgrad.py:175-181)
+        assert np.abs(z[pre + "after/rel_emb/AMSGrad/m"]).max() > 0.0
+        assert relerr(opt.state["rel_emb"]["m"], z[pre + "after/rel_emb/AMSGrad/m"]) < 1e-4
+        assert relerr(opt.state["rel_emb"]["v"], z[pre + "after/rel_emb/AMSGrad/v"]) < 1e-4
 
 
 def test_dropout_hash_restatement_is_uniform():
@@ -237,6 +245,9 @@ def test_cuda_training_matches_reference_model(name):
     assert relerr(m.conv1_bn.moving_var.cpu().numpy(), z["step2/after/Conv1BN/moving_variance"]) < 1e-4
     assert relerr(m.fc_bn.moving_mean.cpu().numpy(), z["step2/after/FCBN/moving_mean"]) < 1e-4
     assert relerr(m.vhat["ent_emb"].cpu().numpy(), z["step2/after/ent_emb/AMSGrad/v_hat"]) < 1e-3
+    # rel_emb took the IndexedSlices route (utils/amsgrad.py:161-189): its m / v slots accumulate in the reference
+    assert relerr(m.m["rel_emb"].cpu().numpy(), z["step2/after/rel_emb/AMSGrad/m"]) < 1e-3
+    assert relerr(m.v["rel_emb"].cpu().numpy(), z["step2/after/rel_emb/AMSGrad/v"]) < 1e-3
 
 
 @pytest.mark.gpu

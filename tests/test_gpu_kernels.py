@@ -369,7 +369,8 @@ def test_multi_tensor_optimizer_matches_per_tensor(L, bug_compat):
     operand copies they emit == coper_prepare_operand of the updated variable."""
     lib = L.load()
     g = torch.Generator(device="cuda").manual_seed(1)
-    shapes = [(40943, 200), (1,), (16384,), (16385,), (8, 4608 * 40), (3, 3, 1, 32), (200,)]
+    shapes = [(40943, 200), (1,), (16384,), (16385,), (8, 4608 * 40), (3, 3, 1, 32), (200,), (22, 8)]
+    SPARSE = 7                                   # the last tensor plays rel_emb: IndexedSlices rule
     th = [torch.randn(*s, device="cuda", generator=g) for s in shapes]
     gr = [torch.randn(*s, device="cuda", generator=g) * 3 for s in shapes]
     vh = [torch.rand(*s, device="cuda", generator=g) for s in shapes]
@@ -379,14 +380,17 @@ def test_multi_tensor_optimizer_matches_per_tensor(L, bug_compat):
     prep = {0: (1, torch.zeros(lib.coper_prepared_bytes(40943, 200, 1), dtype=torch.uint8, device="cuda")),
             4: (2, torch.zeros(lib.coper_prepared_bytes(8 * 4608, 40, 2), dtype=torch.uint8, device="cuda"))}
     desc = np.zeros(len(shapes), dtype=np.dtype([("theta", "<u8"), ("grad", "<u8"), ("m", "<u8"), ("v", "<u8"),
-                                                 ("vhat", "<u8"), ("prepared", "<u8"), ("n", "<i8"),
-                                                 ("prepared_prec", "<i4"), ("reserved", "<i4")]))
+                                                 ("vhat", "<u8"), ("prepared", "<u8"), ("grad_sq", "<u8"),
+                                                 ("n", "<i8"), ("prepared_prec", "<i4"), ("mode", "<i4")]))
     chunks, offs = [], [0]
     for i in range(len(shapes)):
         desc[i]["theta"], desc[i]["grad"], desc[i]["vhat"] = th[i].data_ptr(), gr[i].data_ptr(), vh[i].data_ptr()
         desc[i]["m"], desc[i]["v"], desc[i]["n"] = m[i].data_ptr(), v[i].data_ptr(), th[i].numel()
         if i in prep:
             desc[i]["prepared"], desc[i]["prepared_prec"] = prep[i][1].data_ptr(), prep[i][0]
+        if i == SPARSE:
+            gsq = torch.rand(*shapes[i], device="cuda", generator=g) * 9
+            desc[i]["grad_sq"], desc[i]["mode"] = gsq.data_ptr(), 1
         chunks += [(i, c) for c in range(max(1, -(-th[i].numel() // L.MT_CHUNK)))]
         offs.append(len(chunks))
     d_desc = torch.from_numpy(desc.view(np.uint8).copy()).cuda()
@@ -398,13 +402,22 @@ def test_multi_tensor_optimizer_matches_per_tensor(L, bug_compat):
     clip = torch.zeros(2, device="cuda")
     L.call("coper_mt_sumsq", L.ptr(d_desc), len(shapes), L.ptr(d_chunks), len(chunks), L.ptr(d_offs), L.ptr(part), L.ptr(sums))
     ref = np.array([float((x.double() ** 2).sum().item()) for x in gr])
+    ref[SPARSE] = float(gsq.double().sum().item())            # slice-wise norm of an IndexedSlices gradient
     assert np.allclose(sums.cpu().numpy(), ref, rtol=1e-6)
     L.call("coper_clip_scale_n", L.ptr(sums), len(shapes), 5.0, L.ptr(clip))
     norm = np.sqrt(ref.sum())
     assert abs(clip[1].item() - norm) < 1e-5 * norm and abs(clip[0].item() - 5.0 / max(norm, 5.0)) < 1e-6
     L.call("coper_mt_amsgrad", L.ptr(d_desc), L.ptr(d_chunks), len(chunks), L.ptr(state), 0.9, 0.999, 1e-8, L.ptr(clip),
            bug_compat)
-    for i in range(len(shapes)):
+    # IndexedSlices rule (utils/amsgrad.py:161-189) against a torch restatement
+    cs, lr_t = clip[0].item(), state[0].item()
+    m_ref = m2[SPARSE] * 0.9 + gr[SPARSE] * cs * 0.1
+    v_ref = v2[SPARSE] * 0.999 + gsq * cs * cs * 0.001
+    vh_ref = torch.maximum(vh2[SPARSE], v_ref)
+    th_ref = th2[SPARSE] - lr_t * m_ref / (vh_ref.sqrt() + 1e-8)
+    assert torch.allclose(m[SPARSE], m_ref, rtol=1e-6, atol=1e-7) and torch.allclose(v[SPARSE], v_ref, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(vh[SPARSE], vh_ref, rtol=1e-6, atol=1e-7) and torch.allclose(th[SPARSE], th_ref, rtol=1e-6, atol=1e-6)
+    for i in range(len(shapes) - 1):
         L.call("coper_amsgrad_step", L.ptr(th2[i]), L.ptr(gr[i]), L.ptr(m2[i]), L.ptr(v2[i]), L.ptr(vh2[i]),
                th2[i].numel(), L.ptr(state), 0.9, 0.999, 1e-8, L.ptr(clip), bug_compat)
         assert torch.equal(th[i], th2[i]) and torch.equal(vh[i], vh2[i]), i

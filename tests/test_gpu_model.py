@@ -236,17 +236,19 @@ def test_multi_step_training_matches_oracle_amsgrad():
         out = O.forward(p64, cfg, e1, rel, True, None, dense, np.float64)
         g = O.backward(out, cfg)
         assert abs(loss - out["loss"]) < 2e-5 * abs(out["loss"]), step
-        flat = {"ent_emb": g["ent_emb"], "rel_emb": g["rel_emb"], "conv1_weights": g["conv1_weights"],
+        flat = {"ent_emb": g["ent_emb"], "conv1_weights": g["conv1_weights"],
                 "conv1_bias": g["conv1_bias"], "pred_bias": g["pred_bias"], "fcw": g["fc_weights_proj"][0],
                 "fcb": g["fc_bias_proj"][0], "bn1g": g["Conv1BN"]["gamma"], "bn1b": g["Conv1BN"]["beta"],
                 "bn2g": g["FCBN"]["gamma"], "bn2b": g["FCBN"]["beta"]}
-        clipped, norm = O.clip_by_global_norm(list(flat.values()), 5.0)
+        # rel_emb: IndexedSlices gradient (slice-wise norm, sparse AMSGrad rule)
+        clipped, (dr_c,), norm = O.clip_by_global_norm(list(flat.values()), 5.0, sparse_values=[g["_dr"]])
         assert abs(float(model.clip_out[1].item()) - norm) < 1e-4 * norm
-        th = {"ent_emb": p64["ent_emb"], "rel_emb": p64["rel_emb"], "conv1_weights": p64["conv1_weights"],
+        th = {"ent_emb": p64["ent_emb"], "conv1_weights": p64["conv1_weights"],
               "conv1_bias": p64["conv1_bias"], "pred_bias": p64["pred_bias"], "fcw": p64["fc_weights_proj"][0],
               "fcb": p64["fc_bias_proj"][0], "bn1g": p64["Conv1BN"]["gamma"], "bn1b": p64["Conv1BN"]["beta"],
               "bn2g": p64["FCBN"]["gamma"], "bn2b": p64["FCBN"]["beta"]}
-        opt.apply({k: (th[k], c) for k, c in zip(flat.keys(), clipped)})
+        opt.apply({k: (th[k], c) for k, c in zip(flat.keys(), clipped)},
+                  sparse={"rel_emb": (p64["rel_emb"], dr_c, rel)})
         for nm in ("Conv1BN", "FCBN"):
             p64[nm]["moving_mean"], p64[nm]["moving_var"] = out["moving"][nm]
     # 5 steps of the sign-like AMSGrad-as-written rule at lr = 1e-2: entries whose gradient is ~0 move by +-lr per step
