@@ -130,6 +130,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra bf16-engine measurement")
+    ap.add_argument("--num-labels", type=int, default=1000,
+                    help="also time the sampled-label training step (SURVEY §8f-2) with this many labels; 0 = skip")
     ap.add_argument("--graph-multi", action="store_true",
                     help="N > 1: capture the step including its NCCL collectives in a CUDA graph (experimental: hung on "
                          "the 2-GPU box in round 1, off by default)")
@@ -243,6 +245,24 @@ def main():
         e_ms, _ = timed(lambda i: m16.filtered_ranks(devb[i % n_batches]), K, W)
         alt = {"precision": "bf16 (tcgen05 kind::f16, fp32 accumulate)", "value": B / t_ms * 1e3, "unit": "train rows/s",
                "ms_per_step": t_ms, "eval_value": B / e_ms * 1e3, "eval_unit": "eval queries/s", "eval_ms_per_batch": e_ms}
+    # the sampled-label training step the shipped big-dataset configs use (num_labels = 1000)
+    sampled = None
+    if world == 1 and args.num_labels > 0:
+        import copy
+        md_s = copy.deepcopy(md)
+        md_s["use_negative_sampling"] = True
+        del model
+        torch.cuda.empty_cache()
+        ms = ConvE(md_s, seed=0, prec=args.prec, shard=shard, conv_in_height=s["H"])
+        model = ms
+        sb_host = [synthetic.to_sampled(hb, s["num_ent"], args.num_labels, seed=7 + i) for i, hb in enumerate(host)]
+        sb_dev = [{k: torch.as_tensor(v).cuda() for k, v in hb.items()} for hb in sb_host]
+        t_ms, n_l = timed(lambda i: ms.train_step(sb_dev[i % n_batches]), K, W)
+        e2e_ms, _ = timed(lambda i: float(ms.train_step(sb_host[i % n_batches]).item()), K, W)
+        sampled = {"num_labels": args.num_labels, "value": B / t_ms * 1e3, "unit": "train rows/s", "ms_per_step": t_ms,
+                   "e2e_value": B / e2e_ms * 1e3, "e2e_ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(B * 16 + B * args.num_labels * 8), "gpu_launches_per_step": n_l / K,
+                   "gather_bytes_per_step": int(B * args.num_labels * s["ent_emb_size"] * 4)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -276,7 +296,7 @@ def main():
                 "eval_value": B / e2e_eval_ms * 1e3, "eval_unit": "eval queries/s", "eval_ms_per_batch": e2e_eval_ms,
                 "eval_d2h_bytes_per_batch": B * 4},
         "gpu_launches": int(train_launches), "gpu_launches_per_step": train_launches / K,
-        "clocks": clocks, "roofline": roofline, "kernel_ms": breakdown, "bf16": alt, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "kernel_ms": breakdown, "bf16": alt, "sampled_labels": sampled, "cpu_baseline": cpu,
         "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "_source")},
     }
     sys.stdout.flush()

@@ -52,6 +52,9 @@ SIGNATURES = {
     "coper_score1n_bce_G_bytes": (sz, [i32, i64, i32]),
     "coper_score1n_bce_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
                                         sz, i32, vp]),
+    "coper_score_sampled_workspace_bytes": (sz, [i32, i32]),
+    "coper_score_sampled_bce_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, f32, f32, vp, vp, vp, vp, vp,
+                                              vp, vp, vp, vp, sz, vp]),
     "coper_csr_to_bits": (i32, [vp, vp, i32, i64, i64, vp, vp]),
     "coper_dense_to_bits": (i32, [vp, i32, i64, vp, vp]),
     "coper_gold_scores": (i32, [vp, i64, i32, i64, vp, i64, vp, vp]),

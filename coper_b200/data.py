@@ -20,8 +20,13 @@ pipeline underneath:
 * nothing is downloaded: there is no network here, so missing files raise ``FileNotFoundError`` naming the URL the
   reference would fetch (``data.py:58-72``).
 
-Only full 1-N labels (``num_labels=None``) are produced; the sampled-label pipelines
-(``_sample_negatives`` / ``_create_negative_sampling_dataset``, ``data.py:228-312``) are SURVEY §8f-2.
+Training labels: full 1-N (``num_labels=None``, ``_add_lookup_values``, ``data.py:314-330``) or the two sampled-label
+pipelines the shipped configs use — ``_sample_negatives`` (``data.py:228-277``) and, with
+``one_positive_label_per_sample``, ``_create_negative_sampling_dataset`` (``data.py:279-312``) — restated in NumPy: the
+same index/label construction and the same distributions (TF's RNG streams cannot be reproduced; the "prefix / window
+of a random permutation of all entities" the reference takes as negatives is drawn directly as a uniformly random
+ordered set of distinct entities).  Sampled batches carry ``lookup_values`` int32 ``[B, L]`` and ``e2_multi`` fp32
+``[B, L]`` exactly as ``models.py:135-152,165`` expects them.
 """
 from __future__ import annotations
 
@@ -240,10 +245,12 @@ class _DataLoader(Loader):
                       dense=False) -> Iterator[Dict[str, np.ndarray]]:
         """Endless iterator of training batches (``data.py:89-166``: repeat -> labels -> shuffle -> batch).
         The reference shuffles with a 1000-element buffer; here every epoch is a seeded full permutation."""
-        if num_labels is not None:
-            raise NotImplementedError("sampled-label training pipelines (num_labels != null, data.py:228-312) are "
-                                      "SURVEY §8f-2; pass num_labels=None for full 1-N labels")
         c = self.load_and_preprocess(directory, buffer_size)
+        if num_labels is not None:
+            if num_labels > self.num_ent:                         # data.py:149
+                raise ValueError("Parameter `num_labels` needs to be at most the total number of entities.")
+            return self._sampled_train_dataset(c, batch_size, include_inv_relations, prop_negatives, int(num_labels),
+                                               one_positive_label_per_sample, seed, prefetch_buffer_size)
         sel = np.arange(len(c["train_e1"]))
         if not include_inv_relations:
             sel = sel[~c["train_inv"]]
@@ -258,6 +265,89 @@ class _DataLoader(Loader):
                     yield self._make_batch(split.e1[idx], split.rel[idx], np.full(len(idx), -1, np.int64),
                                            idx, split.rowptr, split.col, dense)
         return gen()
+
+    # ------------------------------------------------------------------------------------------ sampled labels
+    @staticmethod
+    def _distinct_random(rng, num_ent, rows, k):
+        """[rows, k] uniformly random DISTINCT entity ids per row, in random order (== the first k entries of an
+        independent random permutation per row, data.py:238,270-272), by vectorised rejection of repeats."""
+        x = rng.integers(0, num_ent, (rows, k), dtype=np.int64)
+        if k <= 1:
+            return x
+        while True:
+            order = np.argsort(x, axis=1, kind="stable")
+            xs = np.take_along_axis(x, order, axis=1)
+            dup_sorted = np.zeros(x.shape, bool)
+            dup_sorted[:, 1:] = xs[:, 1:] == xs[:, :-1]
+            n = int(dup_sorted.sum())
+            if n == 0:
+                return x
+            dup = np.zeros(x.shape, bool)
+            np.put_along_axis(dup, order, dup_sorted, axis=1)
+            x[dup] = rng.integers(0, num_ent, n, dtype=np.int64)
+
+    def _sampled_train_dataset(self, c, batch_size, include_inv, prop_negatives, num_labels, one_pos, seed, prefetch):
+        e1a, rela, rowptr, col, inv = (c["train_" + k] for k in ("e1", "rel", "rowptr", "col", "inv"))
+        sel = np.arange(len(e1a))
+        if not include_inv:
+            sel = sel[~inv]
+        sel = sel[(rowptr[sel + 1] - rowptr[sel]) > 0]              # a query without positives yields no sampled row
+        N = self.num_ent
+        rng = np.random.default_rng(seed)
+        n_pos_needed = int(1.0 / (1.0 + prop_negatives) * num_labels)     # data.py:244
+
+        def labels_of(rows, lookup):
+            """label 1 where the looked-up entity is a positive of its query (tf.gather(e2s_dense, indexes))."""
+            out = np.zeros(lookup.shape, np.float32)
+            for i, r in enumerate(rows):
+                out[i] = np.isin(lookup[i], col[rowptr[r]:rowptr[r + 1]])
+            return out
+
+        def batch_sample_negatives(rows):                            # data.py:228-277
+            B = len(rows)
+            lookup = np.empty((B, num_labels), np.int64)
+            wrong = self._distinct_random(rng, N, B, num_labels)     # prefix of a random permutation of all entities
+            for i, r in enumerate(rows):
+                pos = rng.permutation(col[rowptr[r]:rowptr[r + 1]])
+                if len(pos) <= n_pos_needed:
+                    n_pos = len(pos)
+                else:
+                    n_pos = num_labels - min(N, num_labels - n_pos_needed)
+                lookup[i, :n_pos] = pos[:n_pos]
+                lookup[i, n_pos:] = wrong[i, :num_labels - n_pos]
+            return rows, lookup
+
+        def gen_rows_one_positive(order):                            # data.py:279-312: one row per positive
+            for r in order:
+                pos = col[rowptr[r]:rowptr[r + 1]]
+                for p in pos:
+                    yield r, p
+
+        def gen():
+            while True:
+                order = rng.permutation(sel)
+                if not one_pos:
+                    for s0 in range(0, len(order), batch_size):
+                        rows, lookup = batch_sample_negatives(order[s0:s0 + batch_size])
+                        yield self._sampled_batch(e1a, rela, rows, lookup, labels_of(rows, lookup))
+                else:
+                    buf_r, buf_p = [], []
+                    for r, p in gen_rows_one_positive(order):
+                        buf_r.append(r)
+                        buf_p.append(p)
+                        if len(buf_r) == batch_size:
+                            rows = np.array(buf_r)
+                            lookup = np.concatenate([np.array(buf_p, np.int64)[:, None],
+                                                     self._distinct_random(rng, N, len(rows), num_labels - 1)], axis=1)
+                            yield self._sampled_batch(e1a, rela, rows, lookup, labels_of(rows, lookup))
+                            buf_r, buf_p = [], []
+        return _prefetch(gen(), prefetch)
+
+    @staticmethod
+    def _sampled_batch(e1a, rela, rows, lookup, labels):
+        return {"e1": e1a[rows].astype(np.int64), "rel": rela[rows].astype(np.int64),
+                "e2": np.full(len(rows), -1, np.int64), "e2_multi": labels.astype(np.float32),
+                "lookup_values": lookup.astype(np.int32)}
 
     def eval_dataset(self, directory, dataset_type, batch_size, include_inv_relations=True, buffer_size=1024 * 1024,
                      prefetch_buffer_size=10, dense=False) -> Iterator[Dict[str, np.ndarray]]:
@@ -291,6 +381,31 @@ class _DataLoader(Loader):
         else:
             batch["e2_multi_rowptr"], batch["e2_multi_col"] = out_ptr, out_col
         return batch
+
+
+def _prefetch(iterator, depth):
+    """tf.data's .prefetch(n): a daemon thread keeps up to n batches ready while the device works."""
+    if not depth or depth <= 0:
+        return iterator
+    import queue
+    import threading
+    q = queue.Queue(maxsize=int(depth))
+
+    def worker():
+        try:
+            for item in iterator:
+                q.put(item)
+        except BaseException as exc:          # surface producer errors in the consumer
+            q.put(exc)
+    threading.Thread(target=worker, daemon=True).start()
+
+    def consume():
+        while True:
+            item = q.get()
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    return consume()
 
 
 class _ConvEDataLoader(_DataLoader):

@@ -16,8 +16,10 @@ CPU / PyTorch fallback: without the CUDA library or a GPU this raises.
 
 Supported configuration = the one every shipped ``*_cpg.yaml`` uses: ``context_rel_conv: null``
 (shared conv filters), ``context_rel_out: [...]`` (g_linear ``[]`` or g_MLP ``[n, ...]``),
-``concat_rel: False``, full 1-N scoring (``num_labels: null``).  Anything else raises
-NotImplementedError (SURVEY §8f rows 2 and 4).
+``concat_rel: False``; training with full 1-N labels (``num_labels: null``, entity-sharded across GPUs) or with
+sampled labels (``use_negative_sampling``, ``models.py:438-443``: ``batch['lookup_values']`` [B, L], single GPU).
+Evaluation is always 1-N.  ``do_parameter_lookup``, CPG-generated conv filters and ``concat_rel`` raise
+NotImplementedError (SURVEY §8f row 4).
 """
 from __future__ import annotations
 
@@ -112,8 +114,6 @@ class ConvE:
         self.batch_norm_momentum = float(md.get("batch_norm_momentum", 0.1))
         self.batch_norm_train_stats = bool(md.get("batch_norm_train_stats", False))
         self.learning_rate = float(md.get("learning_rate", 1e-3))
-        if self.use_negative_sampling:
-            raise NotImplementedError("sampled-label training (num_labels != null) is SURVEY §8f-2, not built yet")
         if self.is_parameter_lookup or self.context_rel_conv is not None or self.context_rel_out is None \
                 or self.concat_rel:
             raise NotImplementedError("only the CPG-FC configuration (context_rel_conv=null, context_rel_out=[...], "
@@ -130,6 +130,8 @@ class ConvE:
         self.shard = shard or EntityShard(self.num_ent)
         self.group = process_group
         self.world = self.shard.world
+        if self.use_negative_sampling and self.world > 1:
+            raise NotImplementedError("sampled-label training is single-GPU (the 1-N path is the entity-sharded one)")
         self.bug_compat = bool(reference_bug_compat)
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
@@ -210,6 +212,9 @@ class ConvE:
         # variables read only through embedding_lookup get an IndexedSlices gradient in TF -> sparse AMSGrad rule
         # (slots accumulate) and a slice-wise contribution to the global norm (include/coper.h, coper_param_desc)
         self.sparse_vars = {"rel_emb"}
+        if self.use_negative_sampling:
+            # sampled labels (models.py:438-443): ent_emb / pred_bias are read only through gathers as well
+            self.sparse_vars |= {"ent_emb", "pred_bias"}
         self.grad_sq = {n: torch.zeros_like(p) for n, p, _ in tr if n in self.sparse_vars}
         if not self.bug_compat:
             self.m = {n: torch.zeros_like(p) for n, p, _ in tr}
@@ -401,6 +406,8 @@ class ConvE:
                                "dact": [z(B, n) for n in cpg.hidden], "dpre": [z(B, n) for n in cpg.hidden]}
         b.dcw, b.dcb = z(B, dcw), z(B, dcb)
         b.dr2 = z(B, dr)
+        b.dx0_sq = z(B, d) if self.use_negative_sampling else None
+        b.samp = {}                                  # per-L buffers of the sampled-label path
         b.dr_sq = z(B, dr)
         # pinned staging for host batches
         b.csr_cap = 0
@@ -615,11 +622,13 @@ class ConvE:
                          + np.float32(1.0 / self.num_ent))                     # models.py:450 in fp32
         neg = np.float32(1.0 / self.num_ent)
         inv_count = 1.0 / (float(B) * float(self.num_ent))                   # mean over B*N (models.py:451)
-        call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
-             ptr(b.bits if self.prec == 0 else b.bitsT), B, Ns, d,
-             float(pos), float(neg), inv_count, ptr(b.loss_sum), ptr(self._grad_buf(b)), b.ld, ptr(b.dq),
-             ptr(g["ent_emb"]),
-             ptr(g["pred_bias"]), ptr(b.ws), b.ws_bytes, self.prec)
+        if self.use_negative_sampling:
+            self._sampled_scorer(b)
+        else:
+            call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
+                 ptr(b.bits if self.prec == 0 else b.bitsT), B, Ns, d, float(pos), float(neg), inv_count,
+                 ptr(b.loss_sum), ptr(self._grad_buf(b)), b.ld, ptr(b.dq), ptr(g["ent_emb"]), ptr(g["pred_bias"]),
+                 ptr(b.ws), b.ws_bytes, self.prec)
         # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial loss and
         # the partial dq = G_shard . E_shard; dE / dbias stay local.
         sharding.reduce_scorer_partials(b.loss_sum, b.dq, self.world, self.group)
@@ -652,6 +661,10 @@ class ConvE:
         # gradients of the two embedding gathers (models.py:176-178): deterministic segmented scatter
         call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(b.ws),
              b.ws_bytes)
+        if self.use_negative_sampling:      # the e1-gather slices also enter the slice-wise norm / sparse AMSGrad
+            torch.mul(b.dx0, b.dx0, out=b.dx0_sq)
+            call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0_sq), d, ptr(self.grad_sq["ent_emb"]), s.lo, s.hi,
+                 ptr(b.ws), b.ws_bytes)
         g["rel_emb"].zero_()
         call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]), 0, self.num_rel, ptr(b.ws),
              b.ws_bytes)
@@ -661,6 +674,31 @@ class ConvE:
         call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0, self.num_rel,
              ptr(b.ws), b.ws_bytes)
         self._clip_and_apply()
+
+    def _sampled_buffers(self, b, L):
+        if L not in b.samp:
+            f = dict(dtype=torch.float32, device=self.dev)
+            sb = type("Samp", (), {})()
+            sb.L = L
+            sb.lookup = torch.zeros(b.B, L, dtype=torch.int32, device=self.dev)
+            sb.labels, sb.scores, sb.g = (torch.zeros(b.B, L, **f) for _ in range(3))
+            sb.h_lookup = torch.zeros(b.B, L, dtype=torch.int32).pin_memory()
+            sb.h_labels = torch.zeros(b.B, L, dtype=torch.float32).pin_memory()
+            nbytes = _lib.load().coper_score_sampled_workspace_bytes(b.B, L)
+            sb.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            b.samp[L] = sb
+        return b.samp[L]
+
+    def _sampled_scorer(self, b):
+        """models.py:438-443 + 448-453 on the staged [B, L] lookup ids / labels (b.cur_samp)."""
+        sb, g, gsq = b.cur_samp, self.grads, self.grad_sq
+        for t in (g["ent_emb"], gsq["ent_emb"], g["pred_bias"], gsq["pred_bias"]):
+            t.zero_()
+        call("coper_score_sampled_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), ptr(sb.lookup),
+             ptr(sb.labels), b.B, sb.L, self.num_ent, self.ent_emb_size, 1.0 - self.label_smoothing_epsilon,
+             1.0 / self.num_ent, 1.0 / (float(b.B) * float(sb.L)), ptr(b.loss_sum), ptr(sb.scores), ptr(sb.g),
+             ptr(b.dq), ptr(g["ent_emb"]), ptr(gsq["ent_emb"]), ptr(g["pred_bias"]), ptr(gsq["pred_bias"]),
+             ptr(sb.ws), sb.ws.numel())
 
     def _clip_and_apply(self):
         """tf.clip_by_global_norm(5.0) (models.py:199) + AMSGrad apply (amsgrad.py:130-159): one multi-tensor
@@ -702,6 +740,8 @@ class ConvE:
     def train_step(self, batch: Dict, apply_update: bool = True):
         """One reference training step (run_cpg.py:210-219).  Returns the loss as a 0-d device tensor
         (float64 -> call .item() to read it; that is the step's only device->host transfer)."""
+        if self.use_negative_sampling:
+            return self._train_step_sampled(batch, apply_update)
         b = self.stage_batch(batch)
         if not apply_update:
             saved = self._clip_and_apply
@@ -714,6 +754,35 @@ class ConvE:
             self._run_graphed(("train", b.B), lambda: self._train_device(b))
         self.global_step += 1
         return b.loss_sum[0] / (float(b.B) * float(self.num_ent))
+
+    def _train_step_sampled(self, batch: Dict, apply_update: bool):
+        """Sampled-label step: ``batch['lookup_values']`` int32 [B, L] entity ids and ``batch['e2_multi']`` fp32 [B, L]
+        their labels (data.py:228-312 produce them; models.py:165,438-443 consume them)."""
+        lookup, labels = batch["lookup_values"], batch["e2_multi"]
+        if lookup is None or len(lookup.shape) != 2 or lookup.shape[1] == 0 or tuple(labels.shape) != tuple(lookup.shape):
+            raise ValueError("sampled-label training needs lookup_values [B, L] and e2_multi [B, L] (L = num_labels)")
+        b = self.stage_batch({k: batch[k] for k in ("e1", "rel", "e2") if k in batch})
+        sb = self._sampled_buffers(b, int(lookup.shape[1]))
+        for src, dev_t, host_t, dt in ((lookup, sb.lookup, sb.h_lookup, torch.int32),
+                                      (labels, sb.labels, sb.h_labels, torch.float32)):
+            if isinstance(src, torch.Tensor) and src.is_cuda:
+                dev_t.copy_(src)
+            else:
+                host_t.copy_(torch.as_tensor(np.asarray(src), dtype=dt))
+                dev_t.copy_(host_t, non_blocking=True)
+        b.h2d_event.record()
+        b.cur_samp = sb
+        if not apply_update:
+            saved = self._clip_and_apply
+            self._clip_and_apply = lambda: None
+            try:
+                self._train_device(b)
+            finally:
+                self._clip_and_apply = saved
+        else:
+            self._run_graphed(("train_sampled", b.B, sb.L), lambda: self._train_device(b))
+        self.global_step += 1
+        return b.loss_sum[0] / (float(b.B) * float(sb.L))
 
     def predict_all(self, batch: Dict):
         """Logits of every query against this rank's entity rows: [B, rows] view (metrics.py:40-42)."""

@@ -53,3 +53,20 @@ def make_batches(num_ent: int, num_rel: int, B: int, n_batches: int, seed: int =
         e2 = col[rowptr[:-1]].astype(np.int64)
         out.append({"e1": e1, "rel": rel, "e2": e2, "e2_multi_rowptr": rowptr, "e2_multi_col": col})
     return out
+
+
+def to_sampled(batch, num_ent: int, num_labels: int, seed: int = 0, prop_negatives: float = 10.0):
+    """Sampled-label form of a 1-N batch (data.py:228-277): [B, L] lookup ids = the query's positives (at most
+    L / (1 + prop_negatives) of them) followed by random entities, and their labels."""
+    rng = np.random.default_rng(seed)
+    B = len(batch["e1"])
+    rp, col = batch["e2_multi_rowptr"], batch["e2_multi_col"]
+    lookup = rng.integers(0, num_ent, (B, num_labels), dtype=np.int64)
+    labels = np.zeros((B, num_labels), np.float32)
+    n_pos_needed = max(1, int(1.0 / (1.0 + prop_negatives) * num_labels))
+    for i in range(B):
+        pos = col[rp[i]:rp[i + 1]][:n_pos_needed]
+        lookup[i, :len(pos)] = pos
+        labels[i] = np.isin(lookup[i], col[rp[i]:rp[i + 1]])
+    return {"e1": batch["e1"], "rel": batch["rel"], "e2": batch["e2"], "e2_multi": labels,
+            "lookup_values": lookup.astype(np.int32)}

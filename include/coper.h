@@ -181,6 +181,24 @@ int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prep
                               double* loss_sum, void* G, int64_t ldG, float* dq, float* dE, float* dbias,
                               void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
 
+/* a8 / SURVEY §8f-2 — SAMPLED-label scorer (models.py:438-443), loss (:448-453) and gradients: what the shipped
+ * big-dataset configs train with (training.num_labels = 100 / 1000).  lookup int32 [B, L] entity ids
+ * (batch['lookup_values'], models.py:165), labels fp32 [B, L] (batch['e2_multi'] in sampled mode):
+ *   s[b,l] = q[b].E[lookup[b,l]] + bias[lookup[b,l]]        (scores [B, L], optional output)
+ *   z'     = one_minus_eps * label + inv_num_ent             (models.py:450: + 1/num_ent, also in sampled mode)
+ *   loss_sum = sum BCE(s, z');  g[b,l] = (sigmoid(s) - z') * inv_count   (inv_count = 1/(B*L))
+ *   dq[b]  = sum_l g[b,l] E[lookup[b,l]]
+ * TF's gradient of the two gathers is an IndexedSlices (values g[b,l]*q[b] / g[b,l] at row lookup[b,l]); the sparse
+ * AMSGrad rule and the slice-wise global norm need per entity row the SUM of its slices and the sum of their SQUARES:
+ *   dE_sum, dE_sq [N, d], dbias_sum, dbias_sq [N] are ACCUMULATED (zero them first; the e1-gather slices are added on
+ *   top with coper_segscatter_add).  Exact fp32 (gather-bound, no tensor-pipe variant); deterministic. */
+size_t coper_score_sampled_workspace_bytes(int B, int L);
+int coper_score_sampled_bce_fwd_bwd(const float* q, const float* E, const float* bias, const int32_t* lookup,
+                                    const float* labels, int B, int L, int64_t N, int d, float one_minus_eps,
+                                    float inv_num_ent, float inv_count, double* loss_sum, float* scores, float* g,
+                                    float* dq, float* dE_sum, float* dE_sq, float* dbias_sum, float* dbias_sq,
+                                    void* workspace, size_t workspace_bytes, coper_stream_t stream);
+
 /* labels / filters: CSR positives (rowptr int32 [B+1], col int32 [nnz], global entity ids) -> bit rows for
  * the shard [ent_lo, ent_hi); replaces the dense fp32 multi-hot of data.py:182-186,318-322. */
 int coper_csr_to_bits(const int32_t* rowptr, const int32_t* col, int B, int64_t ent_lo, int64_t ent_hi,

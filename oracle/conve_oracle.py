@@ -262,13 +262,15 @@ def _cpg_context_backward(dh, caches, use_bn):
 # forward / backward
 # --------------------------------------------------------------------------------------
 def forward(params, cfg: OracleConfig, e1, rel, is_train=False, masks=None, labels=None,
-            dtype=np.float64, want_scores=True):
+            dtype=np.float64, want_scores=True, lookup=None):
     """Restates models.py:176-192 for the CPG (``context_rel_out`` not None,
     ``context_rel_conv`` None) configuration every shipped ``*_cpg.yaml`` uses.
 
     masks: optional dict of Bernoulli keep-masks (bool/0-1 arrays) with keys
       'feature_map' [B,OH,OW,C], 'output' [B,d], 'ctx_w'/'ctx_b' lists per hidden layer.
     labels: dense multi-hot [B,N] (e2_multi) or None.
+    lookup: sampled-label mode (models.py:438-443; ``use_negative_sampling``): int [B,L] entity ids, ``labels`` is then
+      the [B,L] label matrix of those ids; the loss is the mean over B*L (same ``+ 1/num_ent`` smoothing, :450).
     Returns a dict of tensors (and caches for :func:`backward`).
     """
     dt = np.dtype(dtype).type
@@ -319,6 +321,20 @@ def forward(params, cfg: OracleConfig, e1, rel, is_train=False, masks=None, labe
            "moving": {"Conv1BN": (mm1, mv1), "FCBN": (mm2, mv2), "ctx_w": cw_upd, "ctx_b": cb_upd},
            "_cache": dict(e1=e1, rel=rel, X=X, bn1=bn1c, relu1=relu1, m1=m1, keep1=keep1, m2=m2, keep2=keep2,
                           bn2=bn2c, relu2=relu2, cw_caches=cw_caches, cb_caches=cb_caches, p=p, B=B)}
+    if lookup is not None:
+        lk = np.asarray(lookup, np.int64)
+        Eg = p["ent_emb"][lk]                                  # tf.gather -> [B, L, d]   (models.py:438)
+        SL = np.einsum("bd,bld->bl", q, Eg) + p["pred_bias"][lk]   # models.py:439-442
+        out["scores_lookup"] = SL
+        if want_scores:
+            out["scores"] = q @ p["ent_emb"].T + p["pred_bias"]
+        z = np.asarray(labels).astype(dtype)
+        zs = dt(1.0 - cfg.label_smoothing_epsilon) * z + dt(1.0 / cfg.num_ent)       # models.py:450
+        el = np.maximum(SL, 0) - SL * zs + np.log1p(np.exp(-np.abs(SL)))
+        out["loss"] = el.mean()                                # mean over B*L
+        out["_cache"]["zs"] = zs
+        out["_cache"]["lookup"] = lk
+        return out
     if want_scores or labels is not None:
         S = q @ p["ent_emb"].T + p["pred_bias"]              # models.py:434-437
         out["scores"] = S
@@ -342,7 +358,7 @@ def backward(out, cfg: OracleConfig):
     """
     c = out["_cache"]
     p, B = c["p"], c["B"]
-    S, q, f = out["scores"], out["q"], out["f"]
+    q, f = out["q"], out["f"]
     N, d = p["ent_emb"].shape
     C = cfg.conv_num_channels
     F = cfg.fc_input_size
@@ -350,10 +366,28 @@ def backward(out, cfg: OracleConfig):
     KH, KW = cfg.conv_filter_height, cfg.conv_filter_width
     g: Dict[str, object] = {}
 
-    G = (sigmoid(S) - c["zs"]) / S.dtype.type(B * N)           # dL/dS
-    g["pred_bias"] = G.sum(axis=0)
-    dE = G.T @ q
-    dq = G @ p["ent_emb"]
+    if "lookup" in c:
+        # sampled labels (models.py:438-443): the gradients of the two tf.gather calls are IndexedSlices; the dense
+        # sums are returned under the usual names, the slices under "_sparse" (values [M, ...], indices [M]) in the
+        # form tf.clip_by_global_norm / the sparse AMSGrad rule consume them.
+        lk = c["lookup"]
+        L = lk.shape[1]
+        SL = out["scores_lookup"]
+        G = (sigmoid(SL) - c["zs"]) / SL.dtype.type(B * L)
+        dq = np.einsum("bl,bld->bd", G, p["ent_emb"][lk])
+        dE = np.zeros_like(p["ent_emb"])
+        sl_vals = (G[:, :, None] * q[:, None, :]).reshape(B * L, d)
+        np.add.at(dE, lk.reshape(-1), sl_vals)
+        db = np.zeros_like(p["pred_bias"])
+        np.add.at(db, lk.reshape(-1), G.reshape(-1))
+        g["pred_bias"] = db
+        g["_sparse"] = {"ent_emb": [(sl_vals, lk.reshape(-1))], "pred_bias": [(G.reshape(-1), lk.reshape(-1))]}
+    else:
+        S = out["scores"]
+        G = (sigmoid(S) - c["zs"]) / S.dtype.type(B * N)       # dL/dS
+        g["pred_bias"] = G.sum(axis=0)
+        dE = G.T @ q
+        dq = G @ p["ent_emb"]
     # FC block backward: relu -> FCBN -> output dropout
     dybn = dq * c["relu2"]
     dyd, dg2, db2 = _bn_backward(dybn, c["bn2"])
@@ -405,6 +439,9 @@ def backward(out, cfg: OracleConfig):
     np.add.at(dRel, c["rel"], dr)
     g["rel_emb"] = dRel
     g["_dq"], g["_dy"], g["_df"], g["_dr"], g["_dx0"], g["_G"] = dq, dy, df, dr, dx0, G
+    if "_sparse" in g:
+        g["_sparse"]["ent_emb"].append((dx0, c["e1"]))         # the e1 gather (models.py:176)
+    g.setdefault("_sparse", {})["rel_emb"] = [(dr, c["rel"])]  # models.py:178: always an IndexedSlices
     return g
 
 

@@ -94,6 +94,10 @@ CASES = {
                                       d=30, C=8),
     "gmlp_train": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9, d=30, C=8),
     "gmlp_eval": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, B=9, d=30, C=8),
+    # sampled labels (use_negative_sampling, models.py:438-443): L = 12 ids per query, positives + random entities,
+    # with repeats inside a row and across rows (the reference's samplers allow both, data.py:236-238)
+    "glinear_train_sampled": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9, d=30,
+                                  C=8, sampled=12),
 }
 
 
@@ -145,10 +149,20 @@ def gen_model(tf, models, name, case, n_steps=1):
         st.init_values = init
         st.is_train = case["is_train"]
         st.batch = {"e1": e1, "e2": e2, "rel": rel, "e2_multi": dense, "lookup_values": np.zeros((B, 0), np.int32)}
+        L = case.get("sampled")
+        if L:
+            rng = np.random.default_rng(500 + step)
+            lookup = rng.integers(0, cfg.num_ent, (B, L)).astype(np.int32)
+            for i in range(B):                                   # up to 3 positives first, then random entities
+                pos = col[rowptr[i]:rowptr[i + 1]][:3]
+                lookup[i, :len(pos)] = pos
+            lookup[:, -1] = lookup[:, 0]                         # a repeated id inside every row
+            labels = dense[np.arange(B)[:, None], lookup].astype(np.float32)
+            st.batch["e2_multi"], st.batch["lookup_values"] = labels, lookup
         st.dropout_masks = [m_fm] + m_cw + m_cb + [m_out]
         st.dropout_calls = 0
         model = models.ConvE(model_descriptors={
-            "use_negative_sampling": False, "label_smoothing_epsilon": 0.1, "num_ent": cfg.num_ent,
+            "use_negative_sampling": bool(case.get("sampled")), "label_smoothing_epsilon": 0.1, "num_ent": cfg.num_ent,
             "num_rel": cfg.num_rel, "ent_emb_size": d, "rel_emb_size": 5, "concat_rel": False,
             "conv_num_channels": C,
             "context_rel_conv": None, "context_rel_out": ctx, "context_rel_dropout": case["drop"][2],
@@ -162,6 +176,9 @@ def gen_model(tf, models, name, case, n_steps=1):
         save[pre + "mask_fm"], save[pre + "mask_out"] = m_fm, m_out
         for i, (a, b) in enumerate(zip(m_cw, m_cb)):
             save[pre + "mask_cw%d" % i], save[pre + "mask_cb%d" % i] = a, b
+        if L:
+            save[pre + "lookup"], save[pre + "labels"] = lookup, labels
+            save[pre + "predictions_lookup"] = model.predictions_lookup.detach().numpy()
         save[pre + "loss"] = float(model.loss.detach())
         save[pre + "predictions_all"] = model.predictions_all.detach().numpy()
         save[pre + "predicted_e2_emb"] = model.predicted_e2_emb.detach().numpy()

@@ -248,7 +248,7 @@ def concat(values, axis):
 
 
 def gather(params, indices):
-    return _u(params)[_u(indices).long()]
+    return nn.embedding_lookup(params, indices)        # same ResourceGather op / IndexedSlices gradient in TF
 
 
 def shape(x):

@@ -24,6 +24,8 @@ CASE_CFG = {
                                       d=30, C=8),
     "gmlp_train": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, d=30, C=8),
     "gmlp_eval": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, d=30, C=8),
+    "glinear_train_sampled": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, d=30, C=8,
+                                  sampled=12),
 }
 LR = 1e-2
 
@@ -129,7 +131,12 @@ def test_oracle_forward_backward_matches_reference_model(name):
     p = params_of(z, "init/", case)
     e1, rel = z["step0/e1"], z["step0/rel"]
     dense = O.csr_to_dense(z["step0/rowptr"], z["step0/col"], cfg.num_ent)
-    out = O.forward(p, cfg, e1, rel, case["is_train"], masks_of(z, 0, case), dense, np.float64)
+    if case.get("sampled"):
+        out = O.forward(p, cfg, e1, rel, True, masks_of(z, 0, case), z["step0/labels"], np.float64,
+                        lookup=z["step0/lookup"])
+        assert relerr(out["scores_lookup"], z["step0/predictions_lookup"]) < 1e-5
+    else:
+        out = O.forward(p, cfg, e1, rel, case["is_train"], masks_of(z, 0, case), dense, np.float64)
     assert relerr(out["scores"], z["step0/predictions_all"]) < 1e-5
     assert relerr(out["q"], z["step0/predicted_e2_emb"]) < 1e-5
     assert abs(out["loss"] - float(z["step0/loss"])) < 2e-6 * abs(out["loss"])
@@ -147,17 +154,26 @@ def test_oracle_multi_step_training_matches_reference(name):
     for step in range(3):
         pre = "step%d/" % step
         dense = O.csr_to_dense(z[pre + "rowptr"], z[pre + "col"], cfg.num_ent)
-        out = O.forward(p, cfg, z[pre + "e1"], z[pre + "rel"], True, masks_of(z, step, case), dense, np.float64)
+        if case.get("sampled"):
+            out = O.forward(p, cfg, z[pre + "e1"], z[pre + "rel"], True, masks_of(z, step, case), z[pre + "labels"],
+                            np.float64, lookup=z[pre + "lookup"])
+        else:
+            out = O.forward(p, cfg, z[pre + "e1"], z[pre + "rel"], True, masks_of(z, step, case), dense, np.float64)
         assert abs(out["loss"] - float(z[pre + "loss"])) < 1e-4 * abs(out["loss"]), step
         raw = O.backward(out, cfg)
         g = named_grads(raw, case)
-        # rel_emb is read only through tf.nn.embedding_lookup (models.py:178): TF hands the optimizer an IndexedSlices
-        # (values = per-query rows dr, indices = rel) -> slice-wise global norm and the sparse AMSGrad rule
-        names = [k for k in g if k != "rel_emb"]
-        clipped, (dr_c,), _ = O.clip_by_global_norm([g[k] for k in names], 5.0, sparse_values=[raw["_dr"]])
+        # variables read only through tf.nn.embedding_lookup / tf.gather (rel_emb always, models.py:178; ent_emb and
+        # pred_bias too with sampled labels, :438-441): TF hands the optimizer IndexedSlices -> slice-wise global norm
+        # and the sparse AMSGrad rule
+        sp = raw["_sparse"]
+        names = [k for k in g if k not in sp]
+        sp_names = sorted(sp)
+        sp_vals = [np.concatenate([v for v, _ in sp[k]]) for k in sp_names]
+        sp_idx = [np.concatenate([np.asarray(i) for _, i in sp[k]]) for k in sp_names]
+        clipped, sp_clipped, _ = O.clip_by_global_norm([g[k] for k in names], 5.0, sparse_values=sp_vals)
         th = named_params(p, case)
         opt.apply({k: (th[k], c.reshape(th[k].shape)) for k, c in zip(names, clipped)},
-                  sparse={"rel_emb": (th["rel_emb"], dr_c, np.asarray(z[pre + "rel"]))})
+                  sparse={k: (th[k], v, i) for k, v, i in zip(sp_names, sp_clipped, sp_idx)})
         for nm in ("Conv1BN", "FCBN"):
             p[nm]["moving_mean"], p[nm]["moving_var"] = out["moving"][nm]
         for which, key in (("fc_weights", "ctx_w"), ("fc_bias", "ctx_b")):
@@ -173,8 +189,12 @@ def test_oracle_multi_step_training_matches_reference(name):
         assert relerr(p["Conv1BN"]["moving_var"], after["Conv1BN"]["moving_var"]) < 1e-5
         assert relerr(p["FCBN"]["moving_mean"], after["FCBN"]["moving_mean"]) < 1e-5
         # the reference's dense AMSGrad never accumulates m / v (amsgrad.py:142-151)
-        assert np.abs(z[pre + "after/ent_emb/AMSGrad/m"]).max() == 0.0
-        assert np.abs(z[pre + "after/ent_emb/AMSGrad/v"]).max() == 0.0
+        dense_var = "conv1_weights" if case.get("sampled") else "ent_emb"
+        assert np.abs(z[pre + "after/%s/AMSGrad/m" % dense_var]).max() == 0.0
+        assert np.abs(z[pre + "after/%s/AMSGrad/v" % dense_var]).max() == 0.0
+        if case.get("sampled"):
+            assert relerr(opt.state["ent_emb"]["v"], z[pre + "after/ent_emb/AMSGrad/v"]) < 1e-4
+            assert relerr(opt.state["pred_bias"]["m"], z[pre + "after/pred_bias/AMSGrad/m"]) < 1e-4
         # ... while the sparse path (rel_emb) does (amsgrad.py:175-181)
         assert np.abs(z[pre + "after/rel_emb/AMSGrad/m"]).max() > 0.0
         assert relerr(opt.state["rel_emb"]["m"], z[pre + "after/rel_emb/AMSGrad/m"]) < 1e-4
@@ -191,7 +211,8 @@ def test_dropout_hash_restatement_is_uniform():
 # ================================================================================================ GPU: CUDA vs goldens
 def _model(case, p, lr=LR):
     from coper_b200.models import ConvE
-    md = {"use_negative_sampling": False, "label_smoothing_epsilon": 0.1, "num_ent": 97, "num_rel": 6,
+    md = {"use_negative_sampling": bool(case.get("sampled")), "label_smoothing_epsilon": 0.1, "num_ent": 97,
+          "num_rel": 6,
           "ent_emb_size": case["d"], "rel_emb_size": 5, "concat_rel": False, "conv_num_channels": case["C"],
           "context_rel_conv": None, "context_rel_out": case["ctx"], "context_rel_dropout": case["drop"][2],
           "context_rel_use_batch_norm": case["usebn"], "input_dropout": 0.2, "hidden_dropout": case["drop"][0],
@@ -205,6 +226,9 @@ def _model(case, p, lr=LR):
 
 def _batch(z, step):
     pre = "step%d/" % step
+    if pre + "lookup" in z.files:            # sampled labels: the reference's batch schema (models.py:135-152,165)
+        return {"e1": z[pre + "e1"], "rel": z[pre + "rel"], "e2": z[pre + "e2"], "e2_multi": z[pre + "labels"],
+                "lookup_values": z[pre + "lookup"]}
     return {"e1": z[pre + "e1"], "rel": z[pre + "rel"], "e2": z[pre + "e2"], "e2_multi_rowptr": z[pre + "rowptr"],
             "e2_multi_col": z[pre + "col"]}
 
@@ -245,6 +269,14 @@ def test_cuda_training_matches_reference_model(name):
     assert relerr(m.conv1_bn.moving_var.cpu().numpy(), z["step2/after/Conv1BN/moving_variance"]) < 1e-4
     assert relerr(m.fc_bn.moving_mean.cpu().numpy(), z["step2/after/FCBN/moving_mean"]) < 1e-4
     assert relerr(m.vhat["ent_emb"].cpu().numpy(), z["step2/after/ent_emb/AMSGrad/v_hat"]) < 1e-3
+    if case.get("sampled"):
+        assert relerr(m.m["ent_emb"].cpu().numpy(), z["step2/after/ent_emb/AMSGrad/m"]) < 1e-3
+        assert relerr(m.v["pred_bias"].cpu().numpy(), z["step2/after/pred_bias/AMSGrad/v"]) < 1e-3
+        sb = m._bufs[len(z["step0/e1"])].samp[12]
+        m2 = _model(case, p0)
+        m2.train_step(_batch(z, 0), apply_update=False)
+        sc = m2._bufs[len(z["step0/e1"])].samp[12].scores.cpu().numpy()
+        assert relerr(sc, z["step0/predictions_lookup"]) < 1e-5
     # rel_emb took the IndexedSlices route (utils/amsgrad.py:161-189): its m / v slots accumulate in the reference
     assert relerr(m.m["rel_emb"].cpu().numpy(), z["step2/after/rel_emb/AMSGrad/m"]) < 1e-3
     assert relerr(m.v["rel_emb"].cpu().numpy(), z["step2/after/rel_emb/AMSGrad/v"]) < 1e-3

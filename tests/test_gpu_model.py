@@ -380,3 +380,75 @@ def test_checkpoint_roundtrip(prec, tmp_path):
     # training continues identically (optimizer slots, step state and dropout seed were restored)
     l1, l2 = m.train_step(batch).item(), m2.train_step(batch).item()
     assert l1 == l2
+
+
+# ------------------------------------------------------------------------------------------ sampled labels (§8f-2)
+@pytest.mark.parametrize("L", [12, 100])
+def test_sampled_label_step_parity(L):
+    """use_negative_sampling (models.py:438-443): scores of the [B, L] lookup ids, loss, dq, the aggregated
+    IndexedSlices of ent_emb / pred_bias (sum and sum of squares per row) vs the oracle; then three steps with the
+    sparse AMSGrad rule + slice-wise global norm against the oracle's restatement."""
+    kw, B = CASES["ragged_mid"]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5)
+    e1[B // 2:] = e1[: B - B // 2]
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    rng = np.random.default_rng(1)
+    lookup = rng.integers(0, cfg.num_ent, (B, L)).astype(np.int32)
+    for i in range(B):
+        pos = col[rowptr[i]:rowptr[i + 1]][:3]
+        lookup[i, :len(pos)] = pos
+    lookup[:, -1] = lookup[:, 0]
+    labels = dense[np.arange(B)[:, None], lookup].astype(np.float32)
+    md = descriptors(cfg, lr=1e-2)
+    md["use_negative_sampling"] = True
+    from coper_b200.models import ConvE
+    model = ConvE(md, conv_in_height=cfg.conv_in_height)
+    model.load_variables(params)
+    batch = {"e1": e1, "rel": rel, "e2": e2, "e2_multi": labels, "lookup_values": lookup}
+    loss = float(model.train_step(batch, apply_update=False).item())
+    masks = export_masks(model, cfg, B)
+    out = O.forward(params, cfg, e1, rel, True, masks, labels, np.float64, lookup=lookup)
+    g = O.backward(out, cfg)
+    b = model._bufs[B]
+    assert relerr(b.samp[L].scores.cpu().numpy(), out["scores_lookup"]) < 1e-5
+    assert abs(loss - out["loss"]) < 1e-6 * abs(out["loss"])
+    assert relerr(b.dq.cpu().numpy(), g["_dq"]) < 1e-4
+    assert relerr(model.grads["ent_emb"].cpu().numpy(), g["ent_emb"]) < 2e-4
+    assert relerr(model.grads["pred_bias"].cpu().numpy(), g["pred_bias"]) < 2e-4
+    sq = np.zeros_like(g["ent_emb"])
+    for vals, idx in g["_sparse"]["ent_emb"]:
+        np.add.at(sq, np.asarray(idx), vals * vals)
+    assert relerr(model.grad_sq["ent_emb"].cpu().numpy(), sq) < 2e-4
+    compare_grads(model, g, cfg)
+    # multi-step: optimizer semantics (IndexedSlices for ent_emb, pred_bias, rel_emb)
+    model = ConvE(md, conv_in_height=cfg.conv_in_height)
+    model.load_variables(params)
+    p64 = O.cast_params(params, np.float64)
+    opt = O.AMSGradOracle(1e-2)
+    for step in range(3):
+        loss = model.train_step(batch).item()
+        masks = export_masks(model, cfg, B)
+        out = O.forward(p64, cfg, e1, rel, True, masks, labels, np.float64, lookup=lookup)
+        g = O.backward(out, cfg)
+        assert abs(loss - out["loss"]) < 2e-5 * abs(out["loss"]), step
+        sp = g["_sparse"]
+        dense_g = {"conv1_weights": g["conv1_weights"], "conv1_bias": g["conv1_bias"], "fcw": g["fc_weights_proj"][0],
+                   "fcb": g["fc_bias_proj"][0], "bn1g": g["Conv1BN"]["gamma"], "bn1b": g["Conv1BN"]["beta"],
+                   "bn2g": g["FCBN"]["gamma"], "bn2b": g["FCBN"]["beta"]}
+        names = sorted(sp)
+        vals = [np.concatenate([v for v, _ in sp[k]]) for k in names]
+        idxs = [np.concatenate([np.asarray(i) for _, i in sp[k]]) for k in names]
+        clipped, sp_c, norm = O.clip_by_global_norm(list(dense_g.values()), 5.0, sparse_values=vals)
+        assert abs(float(model.clip_out[1].item()) - norm) < 1e-4 * norm
+        th = {"conv1_weights": p64["conv1_weights"], "conv1_bias": p64["conv1_bias"], "fcw": p64["fc_weights_proj"][0],
+              "fcb": p64["fc_bias_proj"][0], "bn1g": p64["Conv1BN"]["gamma"], "bn1b": p64["Conv1BN"]["beta"],
+              "bn2g": p64["FCBN"]["gamma"], "bn2b": p64["FCBN"]["beta"]}
+        opt.apply({k: (th[k], c) for k, c in zip(dense_g.keys(), clipped)},
+                  sparse={k: (p64[k], v, i) for k, v, i in zip(names, sp_c, idxs)})
+        for nm in ("Conv1BN", "FCBN"):
+            p64[nm]["moving_mean"], p64[nm]["moving_var"] = out["moving"][nm]
+    assert relerr(model.ent_emb.cpu().numpy(), p64["ent_emb"]) < 1e-3
+    assert relerr(model.pred_bias.cpu().numpy(), p64["pred_bias"]) < 1e-3
+    assert relerr(model.rel_emb.cpu().numpy(), p64["rel_emb"]) < 1e-3

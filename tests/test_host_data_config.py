@@ -104,10 +104,44 @@ def test_test_set_cleaning(tmp_path):
     assert len(t["e1"]) == 1                                            # unseen entity / relation questions dropped
 
 
-def test_sampled_labels_are_flagged_as_next(tmp_path):
-    _write(str(tmp_path))
-    with pytest.raises(NotImplementedError):
-        _loader().train_dataset(str(tmp_path), batch_size=4, num_labels=100)
+def _big_graph(tmp_path, n_ent=60, n_trip=400, seed=0):
+    rng = np.random.default_rng(seed)
+    rows = {("e%d" % rng.integers(n_ent), "r%d" % rng.integers(3), "e%d" % rng.integers(n_ent)) for _ in range(n_trip)}
+    rows = sorted(rows)
+    for fn, part in (("train.txt", rows[:-20]), ("dev.txt", rows[-20:-10]), ("test.txt", rows[-10:])):
+        with open(os.path.join(tmp_path, fn), "w") as fh:
+            for r in part:
+                fh.write("\t".join(r) + "\n")
+
+
+@pytest.mark.parametrize("one_pos", [False, True])
+def test_sampled_label_pipelines(tmp_path, one_pos):
+    """data.py:228-312: [B, L] lookup ids + labels; negatives are distinct entities, labels are 1 exactly where the
+    looked-up id is a positive of the query, positives come first."""
+    _big_graph(str(tmp_path))
+    ld = _loader()
+    L, B = 16, 8
+    it = ld.train_dataset(str(tmp_path), batch_size=B, num_labels=L, prop_negatives=3.0,
+                          one_positive_label_per_sample=one_pos, prefetch_buffer_size=2)
+    c = ld.load_and_preprocess(str(tmp_path))
+    key = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(c["train_e1"], c["train_rel"]))}
+    for _ in range(5):
+        b = next(it)
+        assert b["lookup_values"].shape == (B, L) and b["lookup_values"].dtype == np.int32
+        assert b["e2_multi"].shape == (B, L) and b["e2_multi"].dtype == np.float32 and (b["e2"] == -1).all()
+        for i in range(B):
+            r = key[(int(b["e1"][i]), int(b["rel"][i]))]
+            pos = set(c["train_col"][c["train_rowptr"][r]:c["train_rowptr"][r + 1]].tolist())
+            lk, lab = b["lookup_values"][i], b["e2_multi"][i]
+            assert np.array_equal(lab, np.isin(lk, list(pos)).astype(np.float32))
+            if one_pos:
+                assert int(lk[0]) in pos and len(set(lk[1:].tolist())) == L - 1          # 1 positive + distinct negatives
+            else:
+                n_needed = int(1.0 / (1.0 + 3.0) * L)
+                n_pos = len(pos) if len(pos) <= n_needed else L - min(ld.num_ent, L - n_needed)
+                assert set(lk[:n_pos].tolist()) <= pos and len(set(lk[n_pos:].tolist())) == L - n_pos
+    with pytest.raises(ValueError):
+        ld.train_dataset(str(tmp_path), batch_size=4, num_labels=10 ** 6)
 
 
 def test_nell995_fixture_format_if_present():
