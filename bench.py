@@ -132,9 +132,8 @@ def main():
     ap.add_argument("--no-alt", action="store_true", help="skip the extra bf16-engine measurement")
     ap.add_argument("--num-labels", type=int, default=1000,
                     help="also time the sampled-label training step (SURVEY §8f-2) with this many labels; 0 = skip")
-    ap.add_argument("--graph-multi", action="store_true",
-                    help="N > 1: capture the step including its NCCL collectives in a CUDA graph (experimental: hung on "
-                         "the 2-GPU box in round 1, off by default)")
+    ap.add_argument("--no-graph-multi", action="store_true",
+                    help="N > 1: do not capture the step (with its NCCL collectives) in a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -179,7 +178,7 @@ def main():
     md = synthetic.descriptors(args.shape, dropout=True)
     shard = EntityShard(s["num_ent"], rank, world)
     model = ConvE(md, seed=0, prec=args.prec, shard=shard, conv_in_height=s["H"],
-                  init_fast=s["num_ent"] > 1_000_000, graphs_multi_gpu=args.graph_multi)
+                  init_fast=s["num_ent"] > 1_000_000, graphs_multi_gpu=not args.no_graph_multi)
     n_batches = 8
     host = synthetic.make_batches(s["num_ent"], s["num_rel"], B, n_batches, seed=1)
     devb = [{k: torch.as_tensor(v).cuda() for k, v in hb.items()} for hb in host]
@@ -273,8 +272,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, torch, dist)
         return
     ws_mb = working_set_mb(s, B)
     line = {
@@ -302,8 +300,17 @@ def main():
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
+    _finish(world, torch, dist)
+
+
+def _finish(world, torch, dist):
+    """N > 1: leave without tearing NCCL down — destroy_process_group() blocks forever once collectives have been
+    captured into CUDA graphs (observed on the 2-GPU box); everything is flushed and synchronised first."""
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def working_set_mb(s, B):

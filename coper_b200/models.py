@@ -731,7 +731,9 @@ class ConvE:
             torch.cuda.synchronize()
             lib = _lib.load()
             k0 = lib.coper_launch_count()
-            with torch.cuda.graph(g):
+            # thread_local capture mode: other threads (e.g. the NCCL watchdog polling events) must not invalidate
+            # or block the capture when the step contains collectives
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 fn()
             self._graphs[key] = st = (g, lib.coper_launch_count() - k0)
         st[0].replay()
