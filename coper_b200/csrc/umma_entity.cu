@@ -25,7 +25,7 @@ int tc_gemm_store(int prec, bool a_mn, bool b_mn, const TcOperand& A, const TcOp
                   bool split, const StoreEpi& epi, cudaStream_t st);
 int tc_plan_splits(int prec, GemmProblem p, bool split);
 
-constexpr int kEntEpiWarps = 8;
+constexpr int kEntEpiWarps = 16;
 constexpr int kBceEpiWarps = 16;   // the BCE epilogue is MUFU / latency bound: 4 warps per scheduler
 
 // ------------------------------------------------------------------------------------------ shared per-row state
@@ -414,13 +414,16 @@ static GemmProblem ent_problem(int B, int64_t Ns, int d, int block_n) {
   p.n_tiles = (B + block_n - 1) / block_n;
   p.splits = 1;
   p.kb_per_split = 1 << 28;   // clamped to the real block count by gemm_decode
+  p.n_fastest = 1;            // see GemmProblem: one query block per CTA, entity tiles shared through L2
   return p;
 }
 // every CTA keeps ONE query block for as long as possible: tiles are enumerated entity-tile fastest, so with
 // grid <= m_tiles a CTA changes its query block at most n_tiles - 1 times
 static int ent_grid(const GemmProblem& p) {
   long long supers = (long long)p.m_tiles * p.n_tiles;
-  return (int)(supers < 148 ? supers : 148);
+  int grid = (int)(supers < 148 ? supers : 148);
+  if (p.n_tiles <= grid) grid = grid / p.n_tiles * p.n_tiles;    // multiple of n_tiles: fixed n-block per CTA
+  return grid;
 }
 
 // ------------------------------------------------------------------------------------------ logits

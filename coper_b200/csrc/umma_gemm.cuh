@@ -247,6 +247,10 @@ struct GemmProblem {
                                 //    (m_blk, n_blk, split) consecutively (epilogue may accumulate across groups)
   int a_group_mn, a_group_k;    // per-group coordinate offsets into the operand tensor maps
   int b_group_mn, b_group_k;
+  int n_fastest;                // 0: tiles enumerated m-block fastest (default); 1: n-block fastest - with a grid that
+                                //    is a multiple of n_tiles every CTA keeps ONE n-block (resident B is loaded once)
+                                //    and neighbouring CTAs work on the same m-block at the same time, so the A tile
+                                //    is fetched from HBM once and served from L2 to the other n-blocks
 };
 struct TileCoord {
   int group, split, m_blk, n_blk, kb0, kb1;
@@ -269,8 +273,13 @@ __device__ __forceinline__ long long gemm_supers(const GemmProblem& p) {
 }
 __device__ __forceinline__ TileCoord gemm_decode(const GemmProblem& p, long long s, int g_inner, int block_k) {
   TileCoord t;
-  t.m_blk = (int)(s % p.m_tiles); s /= p.m_tiles;
-  t.n_blk = (int)(s % p.n_tiles); s /= p.n_tiles;
+  if (p.n_fastest) {
+    t.n_blk = (int)(s % p.n_tiles); s /= p.n_tiles;
+    t.m_blk = (int)(s % p.m_tiles); s /= p.m_tiles;
+  } else {
+    t.m_blk = (int)(s % p.m_tiles); s /= p.m_tiles;
+    t.n_blk = (int)(s % p.n_tiles); s /= p.n_tiles;
+  }
   t.split = (int)(s % p.splits);  s /= p.splits;
   t.group = p.groups_inner ? g_inner : (int)s;
   int kb_total = (p.K + block_k - 1) / block_k;
