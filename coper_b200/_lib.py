@@ -66,6 +66,7 @@ SIGNATURES = {
     "coper_dense_to_bits_t": (i32, [vp, i32, i64, i64, vp, vp]),
     "coper_bits_t_set": (i32, [vp, i32, i64, i64, vp, vp]),
     "coper_segscatter_workspace_bytes": (sz, [i32]),
+    "coper_segscatter_add_sq": (i32, [vp, i32, vp, i32, vp, vp, i64, i64, vp]),
     "coper_segscatter_add": (i32, [vp, i32, vp, i32, vp, i64, i64, vp, sz, vp]),
     "coper_reduce_partials": (i32, [vp, i32, i64, f32, i32, vp, vp]),
     "coper_sumsq": (i32, [vp, i64, i32, vp, vp]),

@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_kernel(const float* __restric
     else dbc_part[(int64_t)blockIdx.x * kFastC + (o - 9 * kFastC)] = t;
   }
 }
-constexpr int kConvImgPerCta = 4;
+constexpr int kConvImgPerCta = 2;      // forward: 256 CTAs at B = 512
+constexpr int kConvImgPerCtaBwd = 1;   // backward: every image its own CTA (3-4 resident per SM), one partial slab each
 }  // namespace coper
 
 using namespace coper;
@@ -245,7 +246,7 @@ int coper_conv_bwd_slabs(int B, int H, int W, int KH, int KW, int C, int per_que
   size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
   if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3 && sm_fast <= 48 * 1024 &&
       (OH * OW * C) % 4 == 0)
-    return (B + kConvImgPerCta - 1) / kConvImgPerCta;
+    return (B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd;
   return B;
 }
 
@@ -258,7 +259,7 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
   if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3) {
     size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
     if (sm_fast <= 48 * 1024 && (OH * OW * C) % 4 == 0) {
-      conv3x3_bwd_kernel<kConvImgPerCta><<<(B + kConvImgPerCta - 1) / kConvImgPerCta, 256, sm_fast, as_stream(stream)>>>(
+      conv3x3_bwd_kernel<kConvImgPerCtaBwd><<<(B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd, 256, sm_fast, as_stream(stream)>>>(
           dz, x0, B, H, W, wc, dx0, dwc_part, dbc_part);
       return check_launch();
     }

@@ -34,6 +34,58 @@ __global__ void segscatter_kernel(const int64_t* __restrict__ keys, const int32_
   }
 }
 
+// Small-M path (M <= kSegSmallM: the e1 / rel gathers of one batch): no sort at all.  One warp per position i; the
+// warp scans the index array (M/32 coalesced steps) to see whether an earlier position holds the same row - then it is
+// not a segment head and exits - and otherwise sums every later member of its row in INDEX order (the order a stable
+// sort would give): same result bit for bit as the sorted path, one launch, no workspace.
+// dst_sq (optional): sum of the SQUARED source rows per destination row (the IndexedSlices bookkeeping).
+constexpr int kSegSmallM = 4096;
+__global__ void segscatter_small_kernel(const int64_t* __restrict__ idx, int M, const float* __restrict__ src, int width,
+                                        float* __restrict__ dst, float* __restrict__ dst_sq, int64_t row_lo,
+                                        int64_t row_hi) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const int64_t key = idx[i];
+  if (key < row_lo || key >= row_hi) return;
+  bool dup = false;
+  for (int j0 = 0; j0 < i; j0 += 32) {
+    const int j = j0 + lane;
+    dup |= (j < i) && (__ldg(idx + j) == key);
+  }
+  if (__any_sync(0xffffffffu, dup)) return;          // an earlier position owns this row
+  float* drow = dst + (key - row_lo) * (int64_t)width;
+  float* qrow = dst_sq ? dst_sq + (key - row_lo) * (int64_t)width : nullptr;
+  for (int c0 = 0; c0 < width; c0 += 32 * 4) {       // 4 columns per lane per pass
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j0 = (i / 32) * 32; j0 < M; j0 += 32) {
+      const int j = j0 + lane;
+      uint32_t m = __ballot_sync(0xffffffffu, j >= i && j < M && __ldg(idx + j) == key);
+      while (m) {
+        const int jj = j0 + __ffs(m) - 1;
+        m &= m - 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + lane + 32 * k;
+          if (c < width) {
+            const float v = __ldg(src + (int64_t)jj * width + c);
+            a[k] += v;
+            q[k] = fmaf(v, v, q[k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + lane + 32 * k;
+      if (c < width) {
+        drow[c] += a[k];
+        if (qrow) qrow[c] += q[k];
+      }
+    }
+  }
+}
+
 struct SegLayout {
   size_t off_keys_out, off_pos_in, off_pos_out, off_cub, cub_bytes, total;
 };
@@ -59,10 +111,20 @@ extern "C" {
 
 size_t coper_segscatter_workspace_bytes(int M) { return M <= 0 ? 256 : seg_layout(M).total; }
 
+int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int width, float* dst, float* dst_sq,
+                            int64_t row_lo, int64_t row_hi, coper_stream_t stream) {
+  COPER_CHECK_ARG(idx && src && dst && M >= 0 && width > 0 && row_hi >= row_lo);
+  if (M > kSegSmallM) return COPER_ERR_UNSUPPORTED;
+  if (M == 0) return COPER_OK;
+  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(idx, M, src, width, dst, dst_sq, row_lo, row_hi);
+  return check_launch();
+}
+
 int coper_segscatter_add(const int64_t* idx, int M, const float* src, int width, float* dst, int64_t row_lo,
                          int64_t row_hi, void* workspace, size_t workspace_bytes, coper_stream_t stream) {
   COPER_CHECK_ARG(idx && src && dst && workspace && M >= 0 && width > 0 && row_hi >= row_lo);
   if (M == 0) return COPER_OK;
+  if (M <= kSegSmallM) return coper_segscatter_add_sq(idx, M, src, width, dst, nullptr, row_lo, row_hi, stream);
   SegLayout L = seg_layout(M);
   if (workspace_bytes < L.total) return COPER_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);

@@ -659,20 +659,30 @@ class ConvE:
         call("coper_reduce_partials", ptr(b.dwc_part), slabs, KK, 1.0, 0, ptr(g["conv1_weights"]))
         call("coper_reduce_partials", ptr(b.dbc_part), slabs, C, 1.0, 0, ptr(g["conv1_bias"]))
         # gradients of the two embedding gathers (models.py:176-178): deterministic segmented scatter
-        call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(b.ws),
-             b.ws_bytes)
-        if self.use_negative_sampling:      # the e1-gather slices also enter the slice-wise norm / sparse AMSGrad
-            torch.mul(b.dx0, b.dx0, out=b.dx0_sq)
-            call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0_sq), d, ptr(self.grad_sq["ent_emb"]), s.lo, s.hi,
-                 ptr(b.ws), b.ws_bytes)
+        # IndexedSlices bookkeeping (rel_emb always; ent_emb with sampled labels): the same pass also accumulates the
+        # per-row sums of the SQUARED slices (slice-wise global norm + sparse AMSGrad rule)
+        small = B <= 4096
+        gsq_e = self.grad_sq["ent_emb"] if self.use_negative_sampling else None
+        if small:
+            call("coper_segscatter_add_sq", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi)
+        else:
+            call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(b.ws),
+                 b.ws_bytes)
+            if gsq_e is not None:
+                torch.mul(b.dx0, b.dx0, out=b.dx0_sq)
+                call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0_sq), d, ptr(gsq_e), s.lo, s.hi, ptr(b.ws),
+                     b.ws_bytes)
         g["rel_emb"].zero_()
-        call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]), 0, self.num_rel, ptr(b.ws),
-             b.ws_bytes)
-        # IndexedSlices bookkeeping for rel_emb: per-row sums of the SQUARED slices (global norm + sparse AMSGrad)
-        torch.mul(b.dr, b.dr, out=b.dr_sq)
         self.grad_sq["rel_emb"].zero_()
-        call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0, self.num_rel,
-             ptr(b.ws), b.ws_bytes)
+        if small:
+            call("coper_segscatter_add_sq", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]),
+                 ptr(self.grad_sq["rel_emb"]), 0, self.num_rel)
+        else:
+            call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]), 0, self.num_rel, ptr(b.ws),
+                 b.ws_bytes)
+            torch.mul(b.dr, b.dr, out=b.dr_sq)
+            call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0,
+                 self.num_rel, ptr(b.ws), b.ws_bytes)
         self._clip_and_apply()
 
     def _sampled_buffers(self, b, L):

@@ -250,6 +250,11 @@ int coper_score1n_rank_prepared(const void* q_prep, const void* E_prep, const fl
  *   dst[idx[i] - row_lo, :] += src[i, :] for row_lo <= idx[i] < row_hi; one writer per destination row
  *   (sort by key, warp per segment, fixed summation order) -> deterministic. */
 size_t coper_segscatter_workspace_bytes(int M);
+/* M <= 4096 (one batch of gathers): sort-free variant that can also accumulate the per-row sums of the SQUARED source
+ * rows into dst_sq (NULL = skip) - the IndexedSlices bookkeeping of the sparse AMSGrad rule / slice-wise global norm.
+ * Same summation order (index order) as coper_segscatter_add, which uses this path for small M. */
+int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int width, float* dst, float* dst_sq,
+                            int64_t row_lo, int64_t row_hi, coper_stream_t stream);
 int coper_segscatter_add(const int64_t* idx, int M, const float* src, int width, float* dst, int64_t row_lo,
                          int64_t row_hi, void* workspace, size_t workspace_bytes, coper_stream_t stream);
 

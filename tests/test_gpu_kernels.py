@@ -63,8 +63,10 @@ def test_gather_rows_full_and_sharded(L):
     assert np.array_equal(out.cpu().numpy(), exp)
 
 
-@pytest.mark.parametrize("M,rows,w", [(512, 97, 200), (1, 5, 8), (4096, 11, 37), (300, 100000, 256)])
+@pytest.mark.parametrize("M,rows,w", [(512, 97, 200), (1, 5, 8), (4096, 11, 37), (300, 100000, 256),
+                                      (20000, 5000, 64), (4097, 3, 200)])
 def test_segscatter_deterministic_and_exact(L, M, rows, w):
+    """M <= 4096 takes the sort-free path, larger M the radix-sort path; both sum in index order."""
     rng = np.random.default_rng(1)
     idx = rng.integers(0, rows, M)
     idx[: M // 3] = idx[0]                                         # a hub row
@@ -87,6 +89,14 @@ def test_segscatter_deterministic_and_exact(L, M, rows, w):
     L.call("coper_segscatter_add", L.ptr(dev(idx, torch.int64)), M, L.ptr(dev(src)), w, L.ptr(dst), lo, hi,
            L.ptr(ws), ws.numel())
     assert np.abs(dst.cpu().numpy() - exp[lo:hi]).max() < 1e-4 * max(1.0, np.abs(exp).max())
+    if M <= 4096:      # sum + sum of squares in one pass (IndexedSlices bookkeeping)
+        d1, d2 = dev(base), torch.zeros(rows, w, device="cuda")
+        L.call("coper_segscatter_add_sq", L.ptr(dev(idx, torch.int64)), M, L.ptr(dev(src)), w, L.ptr(d1), L.ptr(d2),
+               0, rows)
+        assert np.array_equal(d1.cpu().numpy(), outs[0])
+        sq = np.zeros((rows, w))
+        np.add.at(sq, idx, src.astype(np.float64) ** 2)
+        assert np.abs(d2.cpu().numpy() - sq).max() < 1e-4 * max(1.0, np.abs(sq).max())
 
 
 # ------------------------------------------------------------------------------------------ conv
