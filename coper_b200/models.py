@@ -87,7 +87,7 @@ class ConvE:
     def __init__(self, model_descriptors: Dict, device: Optional[str] = None, seed: int = 0, prec: str = "fp32",
                  shard: Optional[EntityShard] = None, reference_bug_compat: bool = True,
                  conv_in_height: int = 10, process_group=None, use_graphs: bool = True,
-                 init_fast: bool = False, graphs_multi_gpu: bool = False):
+                 init_fast: bool = False, graphs_multi_gpu: bool = False, data_parallel: bool = False):
         md = model_descriptors
         _lib.load()
         if not torch.cuda.is_available():
@@ -132,6 +132,10 @@ class ConvE:
         self.world = self.shard.world
         if self.use_negative_sampling and self.world > 1:
             raise NotImplementedError("sampled-label training is single-GPU (the 1-N path is the entity-sharded one)")
+        # data-parallel front end: every rank receives the GLOBAL batch [Bg], runs lookups' conv / CPG /
+        # FC on its own Bg/P rows (batch-norm statistics synchronised), all-gathers q and scores all Bg queries
+        # against its entity rows; replicated-parameter gradients are all-reduced in one flat bucket.
+        self.dp = bool(data_parallel) and self.world > 1
         self.bug_compat = bool(reference_bug_compat)
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
@@ -187,7 +191,9 @@ class ConvE:
         self.refresh_prepared()
         # device-resident step state: {lr_t, beta1^t, beta2^t, -} and the dropout seed
         self.step_state = torch.tensor([0.0, self.beta1, self.beta2, 0.0], dtype=f32, device=dev)
-        self.seed_dev = torch.tensor([seed * 1000003 + 12345], dtype=torch.int64, device=dev)
+        # (data-parallel ranks draw different masks for their different rows: rank offset in the high bits)
+        self.seed_dev = torch.tensor([seed * 1000003 + 12345 + ((self.shard.rank << 32) if self.dp else 0)],
+                                     dtype=torch.int64, device=dev)
         self.clip_out = torch.zeros(2, dtype=f32, device=dev)       # {scale, norm}
         self.global_step = 0
 
@@ -208,6 +214,19 @@ class ConvE:
             tr.append((nm + "/beta", bn.beta, False))
         self.trainables = tr
         self.grads = {n: torch.zeros_like(p) for n, p, _ in tr}
+        if getattr(self, "dp", False):
+            # gradients that every rank only holds a partial sum of (its own rows of the batch) live in ONE flat
+            # buffer -> a single all-reduce; BN gamma / beta gradients come out of the synchronised statistics and
+            # the entity-table gradients are row-sharded: neither is in the bucket
+            names = [n for n, _, sh in tr if not sh and not n.endswith("/gamma") and not n.endswith("/beta")]
+            sizes = [-(-self.grads[n].numel() // 64) * 64 for n in names]
+            extra = -(-self.rel_emb.numel() // 64) * 64                      # sum of squared rel_emb slices
+            self.flat_grads = torch.zeros(sum(sizes) + extra, dtype=torch.float32, device=self.dev)
+            off = 0
+            for n, sz in zip(names, sizes):
+                self.grads[n] = self.flat_grads[off:off + self.grads[n].numel()].view(self.grads[n].shape)
+                off += sz
+            self._flat_gsq_rel = self.flat_grads[off:off + self.rel_emb.numel()].view(self.rel_emb.shape)
         self.vhat = {n: torch.zeros_like(p) for n, p, _ in tr}
         # variables read only through embedding_lookup get an IndexedSlices gradient in TF -> sparse AMSGrad rule
         # (slots accumulate) and a slice-wise contribution to the global norm (include/coper.h, coper_param_desc)
@@ -216,6 +235,8 @@ class ConvE:
             # sampled labels (models.py:438-443): ent_emb / pred_bias are read only through gathers as well
             self.sparse_vars |= {"ent_emb", "pred_bias"}
         self.grad_sq = {n: torch.zeros_like(p) for n, p, _ in tr if n in self.sparse_vars}
+        if getattr(self, "dp", False):
+            self.grad_sq["rel_emb"] = self._flat_gsq_rel
         if not self.bug_compat:
             self.m = {n: torch.zeros_like(p) for n, p, _ in tr}
             self.v = {n: torch.zeros_like(p) for n, p, _ in tr}
@@ -341,10 +362,11 @@ class ConvE:
             getattr(bn, k).copy_(torch.as_tensor(np.asarray(b[k]), dtype=torch.float32))
 
     # ------------------------------------------------------------------------------------------
-    def _buffers(self, B: int):
+    def _buffers(self, B: int, key=None):
         """Static per-batch-size device buffers (pointer-stable -> CUDA-graph friendly)."""
-        if B in self._bufs:
-            return self._bufs[B]
+        key = B if key is None else key
+        if key in self._bufs:
+            return self._bufs[key]
         dev, f32 = self.dev, torch.float32
         d, dr, F, C = self.ent_emb_size, self.rel_emb_size, self.F, self.C
         Ns = self.shard.rows
@@ -415,8 +437,18 @@ class ConvE:
         b.col = None
         b.h_col = None
         b.h2d_event = None
-        self._bufs[B] = b
+        self._bufs[key] = b
         return b
+
+    def _local_buffers(self, bg):
+        """Data-parallel front end: buffer set of this rank's Bg/P rows; its query ids alias the global batch."""
+        P, r = self.world, self.shard.rank
+        if bg.B % P:
+            raise ValueError("data-parallel batch %d is not a multiple of the world size %d" % (bg.B, P))
+        Bl = bg.B // P
+        bl = self._buffers(Bl, key=("dp", bg.B))
+        bl.e1, bl.rel, bl.e2 = (t[r * Bl:(r + 1) * Bl] for t in (bg.e1, bg.rel, bg.e2))
+        return bl
 
     def _scores_buf(self, b):
         if b.S is None:
@@ -506,10 +538,13 @@ class ConvE:
     def _bn_forward(self, bn: _BatchNorm, x, R, C, b, use_batch, is_train, bessel, relu, keep_post, salt, out):
         lib = _lib.load()
         nch = 0
+        stat, Rt = b.stat, R
         if use_batch:
             nch = lib.coper_colstats_chunks(R)
             call("coper_colstats", ptr(x), R, C, ptr(b.stat))
-        call("coper_bn_finalize", ptr(b.stat), nch, R, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
+            if self.dp:          # synchronised batch statistics: every rank finalises over all ranks' chunk partials
+                stat, nch, Rt = self._gather_stats(b, nch * C * 2), nch * self.world, R * self.world
+        call("coper_bn_finalize", ptr(stat), nch, Rt, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
              ptr(bn.moving_var), self.batch_norm_momentum, BN_EPS, int(use_batch), int(use_batch and is_train),
              int(bessel), ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd))
         call("coper_bn_act_fwd", ptr(x), R, C, ptr(bn.a), ptr(bn.b), int(relu), keep_post, ptr(self.seed_dev), salt,
@@ -521,10 +556,21 @@ class ConvE:
         nch = lib.coper_colstats_chunks(R)
         call("coper_bn_act_bwd_stats", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
              int(relu), keep_post, ptr(self.seed_dev), salt_post, ptr(b.stat))
-        call("coper_bn_act_bwd_finalize", ptr(b.stat), nch, R, C, int(use_batch), ptr(bn.dgamma), ptr(bn.dbeta),
+        stat, Rt = b.stat, R
+        if self.dp:              # gradient statistics over the global batch (also makes dgamma / dbeta global)
+            stat, nch, Rt = self._gather_stats(b, nch * C * 2), nch * self.world, R * self.world
+        call("coper_bn_act_bwd_finalize", ptr(stat), nch, Rt, C, int(use_batch), ptr(bn.dgamma), ptr(bn.dbeta),
              ptr(bn.c1), ptr(bn.c2))
         call("coper_bn_act_bwd_apply", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
              ptr(bn.c1), ptr(bn.c2), int(relu), keep_post, ptr(self.seed_dev), salt_post, keep_pre, salt_pre, ptr(dx))
+
+    def _gather_stats(self, b, n):
+        import torch.distributed as dist
+        if getattr(b, "stat_all", None) is None:
+            b.stat_all = torch.zeros(self.world * b.stat.numel(), dtype=torch.float32, device=self.dev)
+        out = b.stat_all[:self.world * n]
+        dist.all_gather_into_tensor(out, b.stat[:n], group=self.group)
+        return out
 
     def _ctx_forward(self, cpg: ContextualParameterGenerator, net_id, b, is_train):
         """Hidden layers of CPG.generate (models.py:59-68): matmul -> [BN] -> relu -> dropout."""
@@ -589,10 +635,15 @@ class ConvE:
     # ------------------------------------------------------------------------------------------
     def _forward_q(self, b, is_train: bool):
         """Lookups -> conv block -> fused CPG-FC -> FC block; leaves q in b.q (models.py:176-183, 354-426)."""
-        B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
+        B, d = b.B, self.ent_emb_size
         s = self.shard
         call("coper_gather_rows", ptr(self.ent_emb), s.lo, s.hi, d, ptr(b.e1), B, ptr(b.x0))
         sharding.exchange_rows(b.x0, self.world, self.group)
+        self._front_end(b, is_train)
+
+    def _front_end(self, b, is_train: bool):
+        """b.x0, b.rel -> b.q for the rows of buffer set b (conv block, fused CPG-FC, FC block)."""
+        B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
         call("coper_gather_rows", ptr(self.rel_emb), 0, self.num_rel, dr, ptr(b.rel), B, ptr(b.r))
         call("coper_conv_fwd", ptr(b.x0), B, self.H, self.W, ptr(self.conv1_weights), ptr(self.conv1_bias),
              self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.z))
@@ -610,28 +661,57 @@ class ConvE:
         self._bn_forward(self.fc_bn, b.y, B, d, b, use_batch, is_train, False, True, 1.0, 0, b.q)
         b.cw, b.cb = cw, cb
 
+    def _forward_q_dp(self, bg, bl, is_train: bool):
+        """Data-parallel forward: masked gather of all Bg head rows -> reduce-scatter (each rank receives ITS rows,
+        summed over the owning shards) -> front end on Bg/P rows -> all-gather q."""
+        import torch.distributed as dist
+        s, d = self.shard, self.ent_emb_size
+        call("coper_gather_rows", ptr(self.ent_emb), s.lo, s.hi, d, ptr(bg.e1), bg.B, ptr(bg.x0))
+        dist.reduce_scatter_tensor(bl.x0, bg.x0, group=self.group)
+        self._front_end(bl, is_train)
+        dist.all_gather_into_tensor(bg.q, bl.q, group=self.group)
+
     def _train_device(self, b):
         """fwd + bwd + clip + AMSGrad on staged buffers; everything is enqueued, nothing syncs."""
+        if self.dp:
+            return self._train_device_dp(b)
+        self._train_device_impl(b, b)
+
+    def _train_device_dp(self, bg):
+        self._train_device_impl(bg, self._local_buffers(bg))
+
+    def _train_device_impl(self, bg, b):
+        """bg: buffers of the batch the scorer sees; b: buffers of the rows this rank's front end owns
+        (b is bg unless the front end is data-parallel)."""
+        import torch.distributed as dist
+        dp = b is not bg
         B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
         s, g = self.shard, self.grads
         Ns = s.rows
         call("coper_step_state_advance", ptr(self.step_state), ptr(self.seed_dev), self.learning_rate, self.beta1,
              self.beta2)
-        self._forward_q(b, True)
+        if dp:
+            self._forward_q_dp(bg, b, True)
+        else:
+            self._forward_q(b, True)
         pos = np.float32(np.float32(1.0 - self.label_smoothing_epsilon) * np.float32(1.0)
                          + np.float32(1.0 / self.num_ent))                     # models.py:450 in fp32
         neg = np.float32(1.0 / self.num_ent)
-        inv_count = 1.0 / (float(B) * float(self.num_ent))                   # mean over B*N (models.py:451)
+        inv_count = 1.0 / (float(bg.B) * float(self.num_ent))                # mean over B*N (models.py:451)
         if self.use_negative_sampling:
             self._sampled_scorer(b)
         else:
-            call("coper_score1n_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
-                 ptr(b.bits if self.prec == 0 else b.bitsT), B, Ns, d, float(pos), float(neg), inv_count,
-                 ptr(b.loss_sum), ptr(self._grad_buf(b)), b.ld, ptr(b.dq), ptr(g["ent_emb"]), ptr(g["pred_bias"]),
-                 ptr(b.ws), b.ws_bytes, self.prec)
+            call("coper_score1n_bce_fwd_bwd", ptr(bg.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
+                 ptr(bg.bits if self.prec == 0 else bg.bitsT), bg.B, Ns, d, float(pos), float(neg), inv_count,
+                 ptr(bg.loss_sum), ptr(self._grad_buf(bg)), bg.ld, ptr(bg.dq), ptr(g["ent_emb"]),
+                 ptr(g["pred_bias"]), ptr(bg.ws), bg.ws_bytes, self.prec)
         # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial loss and
         # the partial dq = G_shard . E_shard (SURVEY §8e step 4); dE / dbias stay local.
-        sharding.reduce_scorer_partials(b.loss_sum, b.dq, self.world, self.group)
+        if dp:      # each rank only needs the summed dq of its own rows
+            dist.all_reduce(bg.loss_sum, group=self.group)
+            dist.reduce_scatter_tensor(b.dq, bg.dq, group=self.group)
+        else:
+            sharding.reduce_scorer_partials(b.loss_sum, b.dq, self.world, self.group)
         use_batch = self.batch_norm_train_stats
         keep1, keep2 = 1.0 - self.hidden_dropout, 1.0 - self.output_dropout
         # FC block backward: relu -> FCBN -> output dropout (models.py:414-419)
@@ -663,11 +743,13 @@ class ConvE:
         # per-row sums of the SQUARED slices (slice-wise global norm + sparse AMSGrad rule)
         small = B <= 4096
         gsq_e = self.grad_sq["ent_emb"] if self.use_negative_sampling else None
-        if small:
-            call("coper_segscatter_add_sq", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi)
+        if dp:      # every shard needs dx0 of ALL queries whose head entity it owns
+            dist.all_gather_into_tensor(bg.dx0, b.dx0, group=self.group)
+        if bg.B <= 4096:
+            call("coper_segscatter_add_sq", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi)
         else:
-            call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(b.ws),
-                 b.ws_bytes)
+            call("coper_segscatter_add", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(bg.ws),
+                 bg.ws_bytes)
             if gsq_e is not None:
                 torch.mul(b.dx0, b.dx0, out=b.dx0_sq)
                 call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0_sq), d, ptr(gsq_e), s.lo, s.hi, ptr(b.ws),
@@ -683,6 +765,8 @@ class ConvE:
             torch.mul(b.dr, b.dr, out=b.dr_sq)
             call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0,
                  self.num_rel, ptr(b.ws), b.ws_bytes)
+        if dp:      # partial sums over this rank's rows -> one all-reduce of the flat bucket
+            dist.all_reduce(self.flat_grads, group=self.group)
         self._clip_and_apply()
 
     def _sampled_buffers(self, b, L):
@@ -799,7 +883,10 @@ class ConvE:
     def predict_all(self, batch: Dict):
         """Logits of every query against this rank's entity rows: [B, rows] view (metrics.py:40-42)."""
         b = self.stage_batch(batch)
-        self._forward_q(b, False)
+        if self.dp:
+            self._forward_q_dp(b, self._local_buffers(b), False)
+        else:
+            self._forward_q(b, False)
         self._score(b)
         return b.S[:, :self.shard.rows]
 
@@ -828,7 +915,10 @@ class ConvE:
         return b.n_greater + 1, b.n_equal
 
     def _rank_device(self, b):
-        self._forward_q(b, False)
+        if self.dp:
+            self._forward_q_dp(b, self._local_buffers(b), False)
+        else:
+            self._forward_q(b, False)
         s = self.shard
         d = self.ent_emb_size
         b.n_greater.zero_()

@@ -14,11 +14,20 @@ pytestmark = pytest.mark.gpu
 
 
 def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+    """A port below the ephemeral range (so no outgoing connection grabs it between the probe and the rendezvous)."""
+    import random
+    rng = random.Random(os.getpid() ^ int.from_bytes(os.urandom(4), "little"))
+    for _ in range(64):
+        p = rng.randrange(15000, 30000)
+        s = socket.socket()
+        try:
+            s.bind(("127.0.0.1", p))
+            return p
+        except OSError:
+            continue
+        finally:
+            s.close()
+    raise RuntimeError("no free rendezvous port")
 
 
 def _descr(cfg):
@@ -108,3 +117,110 @@ def _worker_single(out_dir, prec):
              loss=loss, dE=m.grads["ent_emb"].cpu().numpy(), ent=m.ent_emb.cpu().numpy(),
              rel_emb=m.rel_emb.cpu().numpy(), P=m.fc_weights.projections[0].cpu().numpy(),
              norm=float(m.clip_out[1].item()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Data-parallel front end (weak scaling): every rank runs conv / CPG / FC on its own slice of the GLOBAL batch with
+# synchronised batch-norm statistics, the scorer stays entity-sharded.  One step on P ranks over Bg queries must be
+# the oracle's step over the same Bg queries (masks: each rank's own dropout draw, assembled in batch order).
+DP_CFG = dict(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[12],
+              context_rel_use_batch_norm=True, context_rel_dropout=0.1, batch_norm_train_stats=True,
+              batch_norm_momentum=0.1, hidden_dropout=0.3, output_dropout=0.2)
+DP_B = 132
+
+
+def _dp_worker(rank, world, port, out_dir, prec):
+    import torch.distributed as dist
+    from coper_b200.models import ConvE
+    from coper_b200.sharding import EntityShard
+    from test_gpu_model import descriptors, export_masks
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg = O.OracleConfig(**DP_CFG)
+        params = O.init_params(cfg, seed=3, bias_noise=0.05)
+        e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, DP_B, seed=5, mean_pos=5.0)
+        e1[DP_B // 2:] = e1[:DP_B - DP_B // 2]           # heads shared ACROSS the two ranks' slices
+        batch = {"e1": e1, "rel": rel, "e2": e2, "e2_multi_rowptr": rowptr, "e2_multi_col": col}
+        sh = EntityShard(cfg.num_ent, rank, world)
+        m = ConvE(descriptors(cfg, 1e-2), device="cuda:%d" % rank, seed=0, shard=sh, prec=prec, data_parallel=True)
+        m.load_variables(params)
+        ranks, n_equal = m.filtered_ranks(batch)
+        loss = float(m.train_step(batch, apply_update=False).item())
+        Bl = DP_B // world
+        masks = export_masks(m, cfg, Bl)
+        g = {k.replace("/", "__"): v.cpu().numpy() for k, v in m.grads.items()}
+        bl = m._bufs[("dp", DP_B)]
+        q1, dx01, mm1 = bl.q.cpu().numpy(), bl.dx0.cpu().numpy(), m.conv1_bn.moving_mean.cpu().numpy()
+        extra = {"mask_" + k: (np.stack(v) if isinstance(v, list) else v) for k, v in masks.items()}
+        m._clip_and_apply()
+        loss2 = float(m.train_step(batch).item())          # second step through the full (update) path
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, "dp%d.npz" % rank), ranks=ranks.cpu().numpy(), n_equal=n_equal.cpu().numpy(),
+                 loss=loss, loss2=loss2, q=q1, dx0=dx01, lo=sh.lo, hi=sh.hi,
+                 norm=float(m.clip_out[1].item()), rel_emb_new=m.rel_emb.cpu().numpy(),
+                 P_new=m.fc_weights.projections[-1].cpu().numpy(), conv_mm=mm1,
+                 **g, **extra)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_data_parallel_front_end_matches_oracle(prec, tmp_path):
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path), prec), nprocs=world, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), "dp%d.npz" % r)) for r in range(world)]
+    cfg = O.OracleConfig(**DP_CFG)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, DP_B, seed=5, mean_pos=5.0)
+    e1[DP_B // 2:] = e1[:DP_B - DP_B // 2]
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    masks = {"feature_map": np.concatenate([o["mask_feature_map"] for o in outs], 0),
+             "output": np.concatenate([o["mask_output"] for o in outs], 0)}
+    for key in ("ctx_w", "ctx_b"):
+        masks[key] = list(np.concatenate([o["mask_" + key] for o in outs], 1))      # [layers, B, n]
+    out = O.forward(params, cfg, e1, rel, True, masks, dense, np.float64)
+    g = O.backward(out, cfg)
+
+    def rel_err(a, b, floor=0.0):
+        return np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-30)
+    q = np.concatenate([o["q"] for o in outs], 0)
+    assert rel_err(q, out["q"]) < 1e-5
+    assert rel_err(np.concatenate([o["dx0"] for o in outs], 0), g["_dx0"]) < 2e-4
+    scale = max(np.abs(g[k]).max() for k in ("ent_emb", "rel_emb", "conv1_weights"))
+    nw = len(g["fc_weights_proj"])
+    for o in outs:
+        lo, hi = int(o["lo"]), int(o["hi"])
+        assert abs(float(o["loss"]) - out["loss"]) < 1e-6 * abs(out["loss"])
+        assert rel_err(o["ent_emb"], g["ent_emb"][lo:hi]) < 2e-4
+        assert rel_err(o["pred_bias"], g["pred_bias"][lo:hi]) < 2e-4
+        assert rel_err(o["rel_emb"].reshape(g["rel_emb"].shape), g["rel_emb"]) < 2e-4
+        assert rel_err(o["conv1_weights"].reshape(g["conv1_weights"].shape), g["conv1_weights"]) < 2e-4
+        for nm in ("FCBN", "Conv1BN"):
+            for k in ("gamma", "beta"):
+                assert rel_err(o["%s__%s" % (nm, k)], g[nm][k], 1e-4 * scale) < 2e-4, (nm, k)
+        for i in range(nw):
+            assert rel_err(o["fc_weights__CPG__Projection%d" % i].reshape(g["fc_weights_proj"][i].shape),
+                           g["fc_weights_proj"][i], 1e-4 * scale) < 2e-4
+            assert rel_err(o["fc_bias__CPG__Projection%d" % i].reshape(g["fc_bias_proj"][i].shape),
+                           g["fc_bias_proj"][i], 1e-4 * scale) < 2e-4
+        for i in range(nw - 1):
+            assert rel_err(o["fc_weights__CPG__Projection%d__BatchNorm__gamma" % i], g["fc_weights_bn"][i]["gamma"],
+                           1e-4 * scale) < 2e-4
+        mm, _ = out["moving"]["Conv1BN"]
+        assert rel_err(o["conv_mm"], mm) < 1e-5
+        assert np.isfinite(float(o["loss2"])) and float(o["loss2"]) < float(o["loss"]) * 1.5
+    # evaluation: every rank holds the global ranks; the oracle ranks its own fp64 logits -> compare where no
+    # near-ties exist (|score gap| checks live in the single-GPU tests); here: ranks agree between the two ranks and
+    # with the oracle on >= 95 % of queries (rounding can flip near-tied neighbours)
+    assert np.array_equal(outs[0]["ranks"], outs[1]["ranks"]) and np.array_equal(outs[0]["n_equal"], outs[1]["n_equal"])
+    ev = O.forward(params, cfg, e1, rel, False, None, None, np.float64)
+    cnt, _ = O.rank_count(ev["scores"], e2, dense)
+    assert (outs[0]["ranks"] == cnt).mean() >= 0.95
+    # replicated variables identical on both ranks after the bucketed all-reduce + update
+    assert np.array_equal(outs[0]["rel_emb_new"], outs[1]["rel_emb_new"])
+    assert np.array_equal(outs[0]["P_new"], outs[1]["P_new"])
