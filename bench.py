@@ -139,6 +139,9 @@ def main():
                     help="N > 1: data-parallel = every rank owns B rows of a global batch of N*B (weak scaling, "
                          "synchronised batch norm, bucketed gradient all-reduce); replicated = all ranks run the "
                          "front end of the same B rows, only the scorer is sharded (strong scaling)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="data-parallel: all-reduce the whole gradient bucket at the end of the backward pass instead "
+                         "of overlapping the generator-weight gradient with the conv backward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -185,7 +188,8 @@ def main():
     md = synthetic.descriptors(args.shape, dropout=True)
     shard = EntityShard(s["num_ent"], rank, world)
     model = ConvE(md, seed=0, prec=args.prec, shard=shard, conv_in_height=s["H"],
-                  init_fast=s["num_ent"] > 1_000_000, graphs_multi_gpu=not args.no_graph_multi, data_parallel=dp)
+                  init_fast=s["num_ent"] > 1_000_000, graphs_multi_gpu=not args.no_graph_multi, data_parallel=dp,
+                  overlap_grad_allreduce=not args.no_overlap)
     n_batches = 8
     host = synthetic.make_batches(s["num_ent"], s["num_rel"], B, n_batches, seed=1)
     devb = [{k: torch.as_tensor(v).cuda() for k, v in hb.items()} for hb in host]

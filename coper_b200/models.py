@@ -87,7 +87,8 @@ class ConvE:
     def __init__(self, model_descriptors: Dict, device: Optional[str] = None, seed: int = 0, prec: str = "fp32",
                  shard: Optional[EntityShard] = None, reference_bug_compat: bool = True,
                  conv_in_height: int = 10, process_group=None, use_graphs: bool = True,
-                 init_fast: bool = False, graphs_multi_gpu: bool = False, data_parallel: bool = False):
+                 init_fast: bool = False, graphs_multi_gpu: bool = False, data_parallel: bool = False,
+                 overlap_grad_allreduce: bool = True):
         md = model_descriptors
         _lib.load()
         if not torch.cuda.is_available():
@@ -136,6 +137,11 @@ class ConvE:
         # FC on its own Bg/P rows (batch-norm statistics synchronised), all-gathers q and scores all Bg queries
         # against its entity rows; replicated-parameter gradients are all-reduced in one flat bucket.
         self.dp = bool(data_parallel) and self.world > 1
+        self.group_big = None
+        if self.dp and overlap_grad_allreduce:
+            import torch.distributed as dist
+            ranks = dist.get_process_group_ranks(process_group) if process_group is not None else None
+            self.group_big = dist.new_group(ranks=ranks)          # collective: every rank builds its model here
         self.bug_compat = bool(reference_bug_compat)
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
@@ -216,9 +222,13 @@ class ConvE:
         self.grads = {n: torch.zeros_like(p) for n, p, _ in tr}
         if getattr(self, "dp", False):
             # gradients that every rank only holds a partial sum of (its own rows of the batch) live in ONE flat
-            # buffer -> a single all-reduce; BN gamma / beta gradients come out of the synchronised statistics and
-            # the entity-table gradients are row-sharded: neither is in the bucket
+            # buffer; BN gamma / beta gradients come out of the synchronised statistics and the entity-table
+            # gradients are row-sharded: neither is in the bucket.  The generator's last projection (dc*F*d floats,
+            # 66 MB at the WN18RR shape) sits at the front: its all-reduce is issued as soon as the CPG backward has
+            # written it, on a second communicator, and overlaps the rest of the backward pass.
+            last_w = "fc_weights/CPG/Projection%d" % (len(self.fc_weights.projections) - 1)
             names = [n for n, _, sh in tr if not sh and not n.endswith("/gamma") and not n.endswith("/beta")]
+            names = [last_w] + [n for n in names if n != last_w]
             sizes = [-(-self.grads[n].numel() // 64) * 64 for n in names]
             extra = -(-self.rel_emb.numel() // 64) * 64                      # sum of squared rel_emb slices
             self.flat_grads = torch.zeros(sum(sizes) + extra, dtype=torch.float32, device=self.dev)
@@ -227,6 +237,7 @@ class ConvE:
                 self.grads[n] = self.flat_grads[off:off + self.grads[n].numel()].view(self.grads[n].shape)
                 off += sz
             self._flat_gsq_rel = self.flat_grads[off:off + self.rel_emb.numel()].view(self.rel_emb.shape)
+            self.flat_big, self.flat_small = self.flat_grads[:sizes[0]], self.flat_grads[sizes[0]:]
         self.vhat = {n: torch.zeros_like(p) for n, p, _ in tr}
         # variables read only through embedding_lookup get an IndexedSlices gradient in TF -> sparse AMSGrad rule
         # (slots accumulate) and a slice-wise contribution to the global norm (include/coper.h, coper_param_desc)
@@ -724,6 +735,9 @@ class ConvE:
              Pw.shape[0], F, d,
              Pb.shape[0], ptr(g["fc_weights/CPG/Projection%d" % nw]), ptr(g["fc_bias/CPG/Projection%d" % nb]),
              ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec, int(self.prec != 0))
+        big_work = None
+        if dp and self.group_big is not None:
+            big_work = dist.all_reduce(self.flat_big, group=self.group_big, async_op=True)
         self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
         self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
         # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)
@@ -765,8 +779,12 @@ class ConvE:
             torch.mul(b.dr, b.dr, out=b.dr_sq)
             call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0,
                  self.num_rel, ptr(b.ws), b.ws_bytes)
-        if dp:      # partial sums over this rank's rows -> one all-reduce of the flat bucket
-            dist.all_reduce(self.flat_grads, group=self.group)
+        if dp:      # partial sums over this rank's rows -> all-reduce of the flat bucket
+            if big_work is not None:
+                dist.all_reduce(self.flat_small, group=self.group)
+                big_work.wait()
+            else:
+                dist.all_reduce(self.flat_grads, group=self.group)
         self._clip_and_apply()
 
     def _sampled_buffers(self, b, L):

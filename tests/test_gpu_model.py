@@ -122,6 +122,8 @@ CASES = {
     "ragged_mid": (dict(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[],
                         batch_norm_train_stats=True, batch_norm_momentum=0.1, hidden_dropout=0.3,
                         output_dropout=0.2), 130),
+    "big_batch": (dict(num_ent=2047, num_rel=11, ent_emb_size=40, rel_emb_size=4, context_rel_out=[],
+                       batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 4096),
     "d256_16x16": (dict(num_ent=515, num_rel=10, ent_emb_size=256, rel_emb_size=4, context_rel_out=[],
                         conv_in_height=16, batch_norm_train_stats=True), 40),
 }
