@@ -576,12 +576,9 @@ class ConvE:
              ptr(bn.c1), ptr(bn.c2), int(relu), keep_post, ptr(self.seed_dev), salt_post, keep_pre, salt_pre, ptr(dx))
 
     def _gather_stats(self, b, n):
-        import torch.distributed as dist
         if getattr(b, "stat_all", None) is None:
             b.stat_all = torch.zeros(self.world * b.stat.numel(), dtype=torch.float32, device=self.dev)
-        out = b.stat_all[:self.world * n]
-        dist.all_gather_into_tensor(out, b.stat[:n], group=self.group)
-        return out
+        return sharding.gather_stat_partials(b.stat_all[:self.world * n], b.stat[:n], self.world, self.group)
 
     def _ctx_forward(self, cpg: ContextualParameterGenerator, net_id, b, is_train):
         """Hidden layers of CPG.generate (models.py:59-68): matmul -> [BN] -> relu -> dropout."""
@@ -675,12 +672,11 @@ class ConvE:
     def _forward_q_dp(self, bg, bl, is_train: bool):
         """Data-parallel forward: masked gather of all Bg head rows -> reduce-scatter (each rank receives ITS rows,
         summed over the owning shards) -> front end on Bg/P rows -> all-gather q."""
-        import torch.distributed as dist
         s, d = self.shard, self.ent_emb_size
         call("coper_gather_rows", ptr(self.ent_emb), s.lo, s.hi, d, ptr(bg.e1), bg.B, ptr(bg.x0))
-        dist.reduce_scatter_tensor(bl.x0, bg.x0, group=self.group)
+        sharding.scatter_rows(bg.x0, bl.x0, self.world, self.group)
         self._front_end(bl, is_train)
-        dist.all_gather_into_tensor(bg.q, bl.q, group=self.group)
+        sharding.gather_batch(bg.q, bl.q, self.world, self.group)
 
     def _train_device(self, b):
         """fwd + bwd + clip + AMSGrad on staged buffers; everything is enqueued, nothing syncs."""
@@ -694,7 +690,6 @@ class ConvE:
     def _train_device_impl(self, bg, b):
         """bg: buffers of the batch the scorer sees; b: buffers of the rows this rank's front end owns
         (b is bg unless the front end is data-parallel)."""
-        import torch.distributed as dist
         dp = b is not bg
         B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
         s, g = self.shard, self.grads
@@ -719,8 +714,7 @@ class ConvE:
         # entity-sharded scorer: every rank scored all B queries against its rows -> sum the partial loss and
         # the partial dq = G_shard . E_shard; dE / dbias stay local.
         if dp:      # each rank only needs the summed dq of its own rows
-            dist.all_reduce(bg.loss_sum, group=self.group)
-            dist.reduce_scatter_tensor(b.dq, bg.dq, group=self.group)
+            sharding.scatter_dq(bg.dq, b.dq, bg.loss_sum, self.world, self.group)
         else:
             sharding.reduce_scorer_partials(b.loss_sum, b.dq, self.world, self.group)
         use_batch = self.batch_norm_train_stats
@@ -737,7 +731,7 @@ class ConvE:
              ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec, int(self.prec != 0))
         big_work = None
         if dp and self.group_big is not None:
-            big_work = dist.all_reduce(self.flat_big, group=self.group_big, async_op=True)
+            big_work = sharding.reduce_replicated_grads(self.flat_big, self.world, self.group_big, async_op=True)
         self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
         self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
         # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)
@@ -758,7 +752,7 @@ class ConvE:
         small = B <= 4096
         gsq_e = self.grad_sq["ent_emb"] if self.use_negative_sampling else None
         if dp:      # every shard needs dx0 of ALL queries whose head entity it owns
-            dist.all_gather_into_tensor(bg.dx0, b.dx0, group=self.group)
+            sharding.gather_batch(bg.dx0, b.dx0, self.world, self.group)
         if bg.B <= 4096:
             call("coper_segscatter_add_sq", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi)
         else:
@@ -781,10 +775,10 @@ class ConvE:
                  self.num_rel, ptr(b.ws), b.ws_bytes)
         if dp:      # partial sums over this rank's rows -> all-reduce of the flat bucket
             if big_work is not None:
-                dist.all_reduce(self.flat_small, group=self.group)
+                sharding.reduce_replicated_grads(self.flat_small, self.world, self.group)
                 big_work.wait()
             else:
-                dist.all_reduce(self.flat_grads, group=self.group)
+                sharding.reduce_replicated_grads(self.flat_grads, self.world, self.group)
         self._clip_and_apply()
 
     def _sampled_buffers(self, b, L):

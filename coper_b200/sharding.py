@@ -12,6 +12,17 @@ collective on a tiny tensor; dE / dbias / optimizer state of the table never lea
   reduce_sharded_sumsq   all-reduce(sum) of the squared-norm partials of the sharded gradients (global-norm clip)
   reduce_gold_and_counts all-reduce(sum) of the owner-provided gold logits, then of the integer rank counts
 
+"Data-parallel front end" (weak scaling: the global batch grows with the number of GPUs): every rank receives the
+global batch [Bg] but runs the front end only on ITS Bg/P rows; the scorer still sees all Bg queries against the
+rank's entity rows.  Additional exchange steps:
+
+  scatter_rows           reduce-scatter of the zero-masked [Bg, d] gather -> each rank has E[e1] of its own rows
+  gather_batch           all-gather of per-rank [Bl, w] rows (q forward, dx0 backward) into batch order [Bg, w]
+  gather_stat_partials   all-gather of the per-chunk batch-norm partial sums -> every rank finalises the statistics of
+                         the GLOBAL batch (synchronised batch norm, forward and backward)
+  scatter_dq             reduce-scatter of the per-shard partial dq [Bg, d] -> each rank has the summed dq of its rows
+  reduce_replicated_grads all-reduce(sum) of the flat bucket of replicated-parameter gradients
+
 All functions work on tensors of any device (NCCL on GPU; gloo on CPU in the unit tests).
 """
 from __future__ import annotations
@@ -82,3 +93,50 @@ def reduce_counts(n_greater: torch.Tensor, n_equal: torch.Tensor, world: int, gr
         dist.all_reduce(n_greater, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(n_equal, op=dist.ReduceOp.SUM, group=group)
     return n_greater, n_equal
+
+
+# ---- data-parallel front end -------------------------------------------------------------------------------------
+def scatter_rows(x_masked_global: torch.Tensor, x_local: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """x_masked_global [Bg, d] as in exchange_rows; rank r receives rows [r*Bl, (r+1)*Bl) summed over the owners
+    (bit-exact: one owner, zeros elsewhere)."""
+    if _active(world, group):
+        dist.reduce_scatter_tensor(x_local, x_masked_global, op=dist.ReduceOp.SUM, group=group)
+    else:
+        x_local.copy_(x_masked_global)
+    return x_local
+
+
+def gather_batch(x_global: torch.Tensor, x_local: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """Per-rank rows [Bl, w] -> [Bg, w] in batch order on every rank."""
+    if _active(world, group):
+        dist.all_gather_into_tensor(x_global, x_local, group=group)
+    else:
+        x_global.copy_(x_local)
+    return x_global
+
+
+def gather_stat_partials(all_partials: torch.Tensor, partials: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """partials [nchunk, C, 2] (per-chunk sums the stats kernels write) -> [P*nchunk, C, 2]; the finalise kernels
+    then run with nchunk*P chunks and R*P rows: the statistics of the global batch, identical on every rank."""
+    if _active(world, group):
+        dist.all_gather_into_tensor(all_partials, partials, group=group)
+    else:
+        all_partials.copy_(partials)
+    return all_partials
+
+
+def scatter_dq(dq_partial_global: torch.Tensor, dq_local: torch.Tensor, loss_sum: torch.Tensor, world: int, group=None):
+    """Entity-sharded scorer over all Bg queries: partial dq [Bg, d] sums over shards; each rank keeps its rows."""
+    if _active(world, group):
+        dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)
+        dist.reduce_scatter_tensor(dq_local, dq_partial_global, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dq_local.copy_(dq_partial_global)
+    return dq_local
+
+
+def reduce_replicated_grads(flat: torch.Tensor, world: int, group=None, async_op: bool = False):
+    """Gradients of replicated parameters are partial sums over the rank's rows of the batch."""
+    if _active(world, group):
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return None
