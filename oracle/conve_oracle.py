@@ -76,6 +76,12 @@ class OracleConfig:
     context_rel_use_batch_norm: bool = False
     batch_norm_momentum: float = 0.1
     batch_norm_train_stats: bool = False
+    # "cpg"          context_rel_out = [...] (every *_cpg.yaml): FC weights / bias generated from the relation embedding
+    # "plain"        context_rel_out = context_rel_conv = None (*_plain.yaml): the relation embedding is reshaped and
+    #                stacked under the entity image (models.py:360-362), shared FC weights (models.py:334-340, 410)
+    # "param_lookup" do_parameter_lookup (*_param_lookup.yaml): FC weights / bias are rows of per-relation tables
+    #                (ParameterLookup, models.py:79-94, 279-287); there is no relation embedding (models.py:210, 180)
+    variant: str = "cpg"
 
     @property
     def conv_in_width(self) -> int:
@@ -83,8 +89,15 @@ class OracleConfig:
         return self.ent_emb_size // self.conv_in_height
 
     @property
+    def conv_total_height(self) -> int:  # models.py:261-265: plain ConvE convolves the stacked [e1; rel] image
+        if self.variant == "plain":
+            assert self.rel_emb_size == self.ent_emb_size, "tf.concat(axis=1) needs equal image widths (models.py:361)"
+            return 2 * self.conv_in_height
+        return self.conv_in_height
+
+    @property
     def conv_out_hw(self):
-        return (self.conv_in_height - self.conv_filter_height + 1,
+        return (self.conv_total_height - self.conv_filter_height + 1,
                 self.conv_in_width - self.conv_filter_width + 1)
 
     @property
@@ -94,6 +107,10 @@ class OracleConfig:
 
     @property
     def context_sizes(self) -> List[int]:  # models.py:294: [rel_emb_size] + context_rel_out
+        if self.variant == "plain":          # shared weights == a generator with the constant context [1]
+            return [1]
+        if self.variant == "param_lookup":   # table rows == a linear generator applied to one-hot(rel)
+            return [self.num_rel]
         return [self.rel_emb_size] + list(self.context_rel_out or [])
 
 
@@ -126,13 +143,18 @@ def init_params(cfg: OracleConfig, seed: int = 0, bias_noise: float = 0.0) -> Di
     ctx = cfg.context_sizes
     p: Dict[str, object] = {}
     p["ent_emb"] = xavier_uniform(rng, (cfg.num_ent, d))
-    p["rel_emb"] = xavier_uniform(rng, (cfg.num_rel, cfg.rel_emb_size))
+    if cfg.variant != "param_lookup":                                   # models.py:210
+        p["rel_emb"] = xavier_uniform(rng, (cfg.num_rel, cfg.rel_emb_size))
     p["conv1_weights"] = xavier_uniform(rng, (KH, KW, 1, C))
     p["conv1_bias"] = np.zeros(C, np.float32)
     sizes_w = ctx + [F * d]
     sizes_b = ctx + [d]
     p["fc_weights_proj"] = [xavier_uniform(rng, (sizes_w[i], sizes_w[i + 1])) for i in range(len(sizes_w) - 1)]
     p["fc_bias_proj"] = [np.zeros((sizes_b[i], sizes_b[i + 1]), np.float32) for i in range(len(sizes_b) - 1)]
+    if cfg.variant == "plain":          # the variable is [F, d] (models.py:334-337): Xavier limits of THAT shape
+        p["fc_weights_proj"] = [xavier_uniform(rng, (F, d)).reshape(1, F * d)]
+    if cfg.variant == "param_lookup":   # ParameterLookup initialises BOTH tables Xavier (models.py:86-89)
+        p["fc_bias_proj"] = [xavier_uniform(rng, (cfg.num_rel, d))]
     p["fc_weights_bn"] = [_bn_init(n) for n in ctx[1:]]
     p["fc_bias_bn"] = [_bn_init(n) for n in ctx[1:]]
     p["Conv1BN"] = _bn_init(C)
@@ -284,9 +306,12 @@ def forward(params, cfg: OracleConfig, e1, rel, is_train=False, masks=None, labe
     OH, OW = cfg.conv_out_hw
     F, d = cfg.fc_input_size, cfg.ent_emb_size
 
+    variant = cfg.variant
     x0 = p["ent_emb"][e1]                                     # models.py:176
-    r = p["rel_emb"][rel]                                     # models.py:178
+    r = p["rel_emb"][rel] if variant != "param_lookup" else None   # models.py:178 / 180
     X = x0.reshape(B, H, W)                                   # models.py:355
+    if variant == "plain":                                    # models.py:360-362: [e1 image; rel image] along height
+        X = np.concatenate([X, r.reshape(B, H, W)], axis=1)
     Z = _conv_valid(X, p["conv1_weights"][:, :, 0, :]) + p["conv1_bias"]     # models.py:382-385
     use_batch = bool(cfg.batch_norm_train_stats and is_train)  # models.py:358
     Zbn, bn1c, mm1, mv1 = _bn_forward(Z.reshape(-1, C), p["Conv1BN"], use_batch, True, cfg.batch_norm_momentum)
@@ -299,10 +324,21 @@ def forward(params, cfg: OracleConfig, e1, rel, is_train=False, masks=None, labe
     f = A1.reshape(B, F)                                      # models.py:404  (h,w,c) order
 
     # CPG (models.py:338-352, 56-76): weights and bias generators own separate hidden nets.
-    cw, cw_caches, cw_upd = cpg_context(r, p["fc_weights_proj"], p["fc_weights_bn"], cfg, is_train,
-                                        masks.get("ctx_w"), dt)
-    cb, cb_caches, cb_upd = cpg_context(r, p["fc_bias_proj"], p["fc_bias_bn"], cfg, is_train,
-                                        masks.get("ctx_b"), dt)
+    if variant == "cpg":
+        cw, cw_caches, cw_upd = cpg_context(r, p["fc_weights_proj"], p["fc_weights_bn"], cfg, is_train,
+                                            masks.get("ctx_w"), dt)
+        cb, cb_caches, cb_upd = cpg_context(r, p["fc_bias_proj"], p["fc_bias_bn"], cfg, is_train,
+                                            masks.get("ctx_b"), dt)
+    else:
+        # plain: y = f.W + b (models.py:410) == the contraction below with the constant context [1];
+        # param_lookup: y_b = f_b . table[rel_b] + bias_table[rel_b] (models.py:90-94, 412) == the same contraction
+        # with the one-hot context (adding exact zeros)
+        if variant == "plain":
+            cw = np.ones((B, 1), dtype)
+        else:
+            cw = np.zeros((B, cfg.num_rel), dtype)
+            cw[np.arange(B), rel] = 1
+        cb, cw_caches, cb_caches, cw_upd, cb_upd = cw, [], [], [], []
     Pw = p["fc_weights_proj"][-1]                             # [dc, F*d]
     Pb = p["fc_bias_proj"][-1]                                # [dc, d]
     dc = Pw.shape[0]
@@ -407,13 +443,17 @@ def backward(out, cfg: OracleConfig):
     dcw = np.einsum("bi,bki->bk", f, T)
     dcb = dy @ Pb.T
     use_bn = cfg.context_rel_use_batch_norm
-    dr_w, dPs_w, dbn_w = _cpg_context_backward(dcw, c["cw_caches"], use_bn)
-    dr_b, dPs_b, dbn_b = _cpg_context_backward(dcb, c["cb_caches"], use_bn)
+    variant = cfg.variant
+    if variant == "cpg":
+        dr_w, dPs_w, dbn_w = _cpg_context_backward(dcw, c["cw_caches"], use_bn)
+        dr_b, dPs_b, dbn_b = _cpg_context_backward(dcb, c["cb_caches"], use_bn)
+        dr = dr_w + dr_b
+    else:                                                       # constant / one-hot context: nothing flows into it
+        dPs_w, dPs_b, dbn_w, dbn_b, dr = [], [], [], [], None
     g["fc_weights_proj"] = dPs_w + [dPw]
     g["fc_bias_proj"] = dPs_b + [dPb]
     g["fc_weights_bn"] = [None if t is None else {"gamma": t[0], "beta": t[1]} for t in dbn_w]
     g["fc_bias_bn"] = [None if t is None else {"gamma": t[0], "beta": t[1]} for t in dbn_b]
-    dr = dr_w + dr_b
     # conv block backward: feature-map dropout -> relu -> Conv1BN -> bias -> conv
     dA1 = df.reshape(-1, C)
     if c["m1"] is not None:
@@ -432,15 +472,26 @@ def backward(out, cfg: OracleConfig):
             dWc[i, j] = np.einsum("bhw,bhwc->c", X[:, i:i + OH, j:j + OW], dZ)
             dX[:, i:i + OH, j:j + OW] += dZ @ Wc[i, j]
     g["conv1_weights"] = dWc[:, :, None, :]
-    dx0 = dX.reshape(B, d)
+    H = cfg.conv_in_height
+    if variant == "plain":                                     # tf.concat backward: the two halves of the image
+        dx0, dr = dX[:, :H].reshape(B, d), dX[:, H:].reshape(B, d)
+    else:
+        dx0 = dX.reshape(B, d)
     np.add.at(dE, c["e1"], dx0)                               # gather gradient (IndexedSlices -> dense)
     g["ent_emb"] = dE
-    dRel = np.zeros_like(p["rel_emb"])
-    np.add.at(dRel, c["rel"], dr)
-    g["rel_emb"] = dRel
     g["_dq"], g["_dy"], g["_df"], g["_dr"], g["_dx0"], g["_G"] = dq, dy, df, dr, dx0, G
     if "_sparse" in g:
         g["_sparse"]["ent_emb"].append((dx0, c["e1"]))         # the e1 gather (models.py:176)
+    if variant == "param_lookup":
+        # ParameterLookup.generate is an embedding_lookup of the tables (models.py:91): their gradients are
+        # IndexedSlices with one [F*d] / [d] slice per query
+        sp = g.setdefault("_sparse", {})
+        sp["fc_weights"] = [((f[:, :, None] * dy[:, None, :]).reshape(B, F * d), c["rel"])]
+        sp["fc_bias"] = [(dy, c["rel"])]
+        return g
+    dRel = np.zeros_like(p["rel_emb"])
+    np.add.at(dRel, c["rel"], dr)
+    g["rel_emb"] = dRel
     g.setdefault("_sparse", {})["rel_emb"] = [(dr, c["rel"])]  # models.py:178: always an IndexedSlices
     return g
 

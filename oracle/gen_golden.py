@@ -98,6 +98,16 @@ CASES = {
     # with repeats inside a row and across rows (the reference's samplers allow both, data.py:236-238)
     "glinear_train_sampled": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9, d=30,
                                   C=8, sampled=12),
+    # the other two shipped model types: plain ConvE (*_plain.yaml: relation image stacked under the entity image,
+    # shared FC weights; rel_emb_size == ent_emb_size) and per-relation parameter tables (*_param_lookup.yaml)
+    "plain_train": dict(ctx=None, bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9, d=30, C=8,
+                        variant="plain"),
+    "plain_eval": dict(ctx=None, bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, B=7, d=30, C=8,
+                       variant="plain"),
+    "lookup_train": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9, d=30, C=8,
+                         variant="param_lookup"),
+    "lookup_eval": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, B=7, d=30, C=8,
+                        variant="param_lookup"),
 }
 
 
@@ -106,15 +116,26 @@ def gen_model(tf, models, name, case, n_steps=1):
     import torch
     ctx, B = case["ctx"], case["B"]
     d, C = case["d"], case["C"]
-    cfg = O.OracleConfig(num_ent=97, num_rel=6, ent_emb_size=d, rel_emb_size=5, context_rel_out=ctx,
+    variant = case.get("variant", "cpg")
+    dr = d if variant == "plain" else 5
+    cfg = O.OracleConfig(num_ent=97, num_rel=6, ent_emb_size=d, rel_emb_size=dr, context_rel_out=ctx, variant=variant,
                          conv_num_channels=C, hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
                          context_rel_dropout=case["drop"][2], context_rel_use_batch_norm=case["usebn"],
                          batch_norm_train_stats=case["bn_train"], batch_norm_momentum=0.9)
     p = O.init_params(cfg, seed=11, bias_noise=0.1)
     save = {}
-    init = {"ent_emb": p["ent_emb"], "rel_emb": p["rel_emb"], "conv1_weights": p["conv1_weights"],
+    init = {"ent_emb": p["ent_emb"], "conv1_weights": p["conv1_weights"],
             "conv1_bias": p["conv1_bias"], "pred_bias": p["pred_bias"]}
+    if variant != "param_lookup":
+        init["rel_emb"] = p["rel_emb"]
+    F = cfg.fc_input_size
     for which in ("fc_weights", "fc_bias"):
+        if variant == "plain":            # plain tf variables fc_weights [F, d], fc_bias [d] (models.py:334-340)
+            init[which] = p[which + "_proj"][0].reshape((F, d) if which == "fc_weights" else (d,))
+            continue
+        if variant == "param_lookup":     # ParameterLookup tables, named after the generator (models.py:86)
+            init[which] = p[which + "_proj"][0]
+            continue
         for i, a in enumerate(p[which + "_proj"]):
             init["%s/CPG/Projection%d" % (which, i)] = a
         for i, bn in enumerate(p[which + "_bn"]):
@@ -137,9 +158,9 @@ def gen_model(tf, models, name, case, n_steps=1):
         m_fm = DH.keep_mask(B * OH * OW * C, 1 - case["drop"][0], sd, DH.SALT_FEATURE_MAP).reshape(B, OH, OW, C)
         m_out = DH.keep_mask(B * d, 1 - case["drop"][1], sd, DH.SALT_OUTPUT).reshape(B, d)
         m_cw = [DH.keep_mask(B * n, 1 - case["drop"][2], sd, DH.ctx_salt(0, i)).reshape(B, n)
-                for i, n in enumerate(ctx)]
+                for i, n in enumerate(ctx or [])]
         m_cb = [DH.keep_mask(B * n, 1 - case["drop"][2], sd, DH.ctx_salt(1, i)).reshape(B, n)
-                for i, n in enumerate(ctx)]
+                for i, n in enumerate(ctx or [])]
         # tf.nn.dropout call order in models.py: conv1 (:390), fc_weights CPG hidden, fc_bias CPG hidden, fc (:414)
         tf.state.reset() if step == 0 else None
         st = tf.state
@@ -163,13 +184,13 @@ def gen_model(tf, models, name, case, n_steps=1):
         st.dropout_calls = 0
         model = models.ConvE(model_descriptors={
             "use_negative_sampling": bool(case.get("sampled")), "label_smoothing_epsilon": 0.1, "num_ent": cfg.num_ent,
-            "num_rel": cfg.num_rel, "ent_emb_size": d, "rel_emb_size": 5, "concat_rel": False,
+            "num_rel": cfg.num_rel, "ent_emb_size": d, "rel_emb_size": dr, "concat_rel": False,
             "conv_num_channels": C,
             "context_rel_conv": None, "context_rel_out": ctx, "context_rel_dropout": case["drop"][2],
             "context_rel_use_batch_norm": case["usebn"], "input_dropout": 0.2, "hidden_dropout": case["drop"][0],
             "output_dropout": case["drop"][1], "learning_rate": 1e-2, "batch_size": B, "add_loss_summaries": False,
             "add_variable_summaries": False, "add_tensor_summaries": False, "batch_norm_momentum": 0.9,
-            "batch_norm_train_stats": case["bn_train"], "do_parameter_lookup": False})
+            "batch_norm_train_stats": case["bn_train"], "do_parameter_lookup": variant == "param_lookup"})
         pre = "step%d/" % step
         save[pre + "e1"], save[pre + "rel"], save[pre + "e2"] = e1, rel, e2
         save[pre + "rowptr"], save[pre + "col"] = rowptr, col
