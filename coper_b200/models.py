@@ -115,15 +115,34 @@ class ConvE:
         self.batch_norm_momentum = float(md.get("batch_norm_momentum", 0.1))
         self.batch_norm_train_stats = bool(md.get("batch_norm_train_stats", False))
         self.learning_rate = float(md.get("learning_rate", 1e-3))
-        if self.is_parameter_lookup or self.context_rel_conv is not None or self.context_rel_out is None \
-                or self.concat_rel:
-            raise NotImplementedError("only the CPG-FC configuration (context_rel_conv=null, context_rel_out=[...], "
-                                      "concat_rel=False) of the shipped *_cpg.yaml files is built (SURVEY §8f-4)")
-        self.H = int(conv_in_height)                                # models.py:261 hard-codes 10
-        if self.ent_emb_size % self.H:
+        # the three model types the reference ships configurations for (configs/config_*_{cpg,plain,param_lookup}.yaml)
+        #   cpg           context_rel_out = [...]: FC weights / bias generated from the relation embedding
+        #   plain         context_rel_out = context_rel_conv = null: the relation embedding, reshaped, is stacked under
+        #                 the entity image (models.py:360-362); ONE shared FC weight [F, d] (models.py:334-340, 410)
+        #   param_lookup  do_parameter_lookup: FC weights / bias are rows of per-relation tables (models.py:79-94,
+        #                 279-287), no relation embedding (models.py:210, 180)
+        # Both of the latter run on the SAME fused generate-and-apply kernels: shared weights are a linear generator
+        # applied to the constant context [1], table rows one applied to one-hot(rel) (adding exact zeros).
+        if self.context_rel_conv is not None or self.concat_rel:
+            raise NotImplementedError("per-query conv filters (context_rel_conv) and concat_rel are not built: no "
+                                      "shipped configuration uses them (SURVEY §8f-4)")
+        if self.is_parameter_lookup:
+            if self.context_rel_out is None:
+                raise NotImplementedError("do_parameter_lookup needs context_rel_out: [] (config_*_param_lookup.yaml)")
+            self.variant = "param_lookup"
+        else:
+            self.variant = "plain" if self.context_rel_out is None else "cpg"
+        H_ent = int(conv_in_height)                                 # models.py:261 hard-codes 10
+        if self.ent_emb_size % H_ent:
             raise ValueError("entity_embedding_size %d is not a multiple of the conv image height %d "
-                             "(models.py:355 would fail the same way)" % (self.ent_emb_size, self.H))
-        self.W = self.ent_emb_size // self.H
+                             "(models.py:355 would fail the same way)" % (self.ent_emb_size, H_ent))
+        self.W = self.ent_emb_size // H_ent
+        self.H = H_ent                                              # height of the image the conv sees
+        if self.variant == "plain":
+            if self.rel_emb_size != self.ent_emb_size:
+                raise ValueError("plain ConvE stacks the relation image under the entity image: "
+                                 "relation_embedding_size must equal entity_embedding_size (models.py:361-362)")
+            self.H = 2 * H_ent                                      # models.py:264-265
         self.OH, self.OW = self.H - self.conv_filter_height + 1, self.W - self.conv_filter_width + 1
         self.C = self.conv_num_channels
         self.F = self.OH * self.OW * self.C                          # models.py:268
@@ -137,6 +156,9 @@ class ConvE:
         # FC on its own Bg/P rows (batch-norm statistics synchronised), all-gathers q and scores all Bg queries
         # against its entity rows; replicated-parameter gradients are all-reduced in one flat bucket.
         self.dp = bool(data_parallel) and self.world > 1
+        if self.dp and self.variant == "param_lookup":
+            raise NotImplementedError("data-parallel front end: the per-relation tables' IndexedSlices bookkeeping is "
+                                      "single-process; use the replicated front end")
         self.group_big = None
         if self.dp and overlap_grad_allreduce:
             import torch.distributed as dist
@@ -172,24 +194,38 @@ class ConvE:
                 self.ent_emb[lo - self.shard.lo:hi - self.shard.lo].copy_(blk[lo - r0:hi - r0])
         if init_fast:                                  # later draws need not line up with the full stream
             gen = torch.Generator().manual_seed(seed + 7919)
-        self.rel_emb = torch.empty(self.num_rel, dr, dtype=f32)
-        _xavier_(self.rel_emb, gen)
-        self.rel_emb = self.rel_emb.to(dev)
+        self.rel_emb = None
+        if self.variant != "param_lookup":
+            self.rel_emb = torch.empty(self.num_rel, dr, dtype=f32)
+            _xavier_(self.rel_emb, gen)
+            self.rel_emb = self.rel_emb.to(dev)
         w = torch.empty(self.conv_filter_height, self.conv_filter_width, 1, self.C, dtype=f32)
         _xavier_(w, gen)
         self.conv1_weights = w.to(dev)
         self.conv1_bias = torch.zeros(self.C, dtype=f32, device=dev)
-        ctx = [dr] + list(self.context_rel_out)
+        if self.variant == "cpg":
+            ctx = [dr] + list(self.context_rel_out)
+        else:                      # constant context [1] (shared weights) / one-hot(rel) (table rows)
+            ctx = [1] if self.variant == "plain" else [self.num_rel]
         self.fc_weights = ContextualParameterGenerator(ctx, "fc_weights", [self.F, d], False,
                                                        self.context_rel_use_batch_norm, dev, gen)
-        self.fc_bias = ContextualParameterGenerator(ctx, "fc_bias", [d], True,
+        self.fc_bias = ContextualParameterGenerator(ctx, "fc_bias", [d], self.variant != "param_lookup",
                                                     self.context_rel_use_batch_norm, dev, gen)
+        if self.variant == "plain":                                  # Xavier limits of the [F, d] variable
+            w = torch.empty(self.F, d, dtype=f32)
+            _xavier_(w, gen)
+            self.fc_weights.projections[0].copy_(w.view(1, -1))
         self.conv1_bn = _BatchNorm(self.C, dev)
         self.fc_bn = _BatchNorm(d, dev)
         self.pred_bias = torch.zeros(self.shard.rows, dtype=f32, device=dev)
-        self.variables = {"ent_emb": self.ent_emb, "rel_emb": self.rel_emb, "conv1_weights": self.conv1_weights,
+        self.variables = {"ent_emb": self.ent_emb, "conv1_weights": self.conv1_weights,
                           "conv1_bias": self.conv1_bias, "fc_weights": self.fc_weights, "fc_bias": self.fc_bias,
                           "pred_bias": self.pred_bias}
+        if self.rel_emb is not None:
+            self.variables["rel_emb"] = self.rel_emb                 # models.py:326-327
+        if self.variant == "plain":                                  # plain tf variables (models.py:334-340)
+            self.variables["fc_weights"] = self.fc_weights.projections[0].view(self.F, d)
+            self.variables["fc_bias"] = self.fc_bias.projections[0].view(d)
         self._identity = {}
         self._bufs = {}
         self._graphs = {}
@@ -206,9 +242,18 @@ class ConvE:
     # ------------------------------------------------------------------------------------------
     def _build_trainables(self):
         """(name, param, sharded?) for everything optimizer.compute_gradients would return (models.py:198)."""
-        tr = [("ent_emb", self.ent_emb, True), ("pred_bias", self.pred_bias, True), ("rel_emb", self.rel_emb, False),
-              ("conv1_weights", self.conv1_weights, False), ("conv1_bias", self.conv1_bias, False)]
+        tr = [("ent_emb", self.ent_emb, True), ("pred_bias", self.pred_bias, True)]
+        if self.rel_emb is not None:
+            tr.append(("rel_emb", self.rel_emb, False))
+        tr += [("conv1_weights", self.conv1_weights, False), ("conv1_bias", self.conv1_bias, False)]
+        self._last_w_name = "fc_weights/CPG/Projection%d" % (len(self.fc_weights.projections) - 1)
+        self._last_b_name = "fc_bias/CPG/Projection%d" % (len(self.fc_bias.projections) - 1)
+        if self.variant != "cpg":        # tf variable names: 'fc_weights' / 'fc_bias' (models.py:334-340, 86)
+            self._last_w_name, self._last_b_name = "fc_weights", "fc_bias"
         for cpg in (self.fc_weights, self.fc_bias):
+            if self.variant != "cpg":
+                tr.append((cpg.name, cpg.projections[0], False))
+                continue
             for i, p in enumerate(cpg.projections):
                 tr.append(("%s/CPG/Projection%d" % (cpg.name, i), p, False))
             if cpg.use_batch_norm:
@@ -226,7 +271,7 @@ class ConvE:
             # gradients are row-sharded: neither is in the bucket.  The generator's last projection (dc*F*d floats,
             # 66 MB at the WN18RR shape) sits at the front: its all-reduce is issued as soon as the CPG backward has
             # written it, on a second communicator, and overlaps the rest of the backward pass.
-            last_w = "fc_weights/CPG/Projection%d" % (len(self.fc_weights.projections) - 1)
+            last_w = self._last_w_name
             names = [n for n, _, sh in tr if not sh and not n.endswith("/gamma") and not n.endswith("/beta")]
             names = [last_w] + [n for n in names if n != last_w]
             sizes = [-(-self.grads[n].numel() // 64) * 64 for n in names]
@@ -241,7 +286,7 @@ class ConvE:
         self.vhat = {n: torch.zeros_like(p) for n, p, _ in tr}
         # variables read only through embedding_lookup get an IndexedSlices gradient in TF -> sparse AMSGrad rule
         # (slots accumulate) and a slice-wise contribution to the global norm (include/coper.h, coper_param_desc)
-        self.sparse_vars = {"rel_emb"}
+        self.sparse_vars = {"rel_emb"} if self.variant != "param_lookup" else {"fc_weights", "fc_bias"}
         if self.use_negative_sampling:
             # sampled labels (models.py:438-443): ent_emb / pred_bias are read only through gathers as well
             self.sparse_vars |= {"ent_emb", "pred_bias"}
@@ -271,7 +316,7 @@ class ConvE:
                                                  ("vhat", "<u8"), ("prepared", "<u8"), ("grad_sq", "<u8"),
                                                  ("n", "<i8"), ("prepared_prec", "<i4"), ("mode", "<i4")]))
         chunks, offsets = [], [0]
-        last_w = "fc_weights/CPG/Projection%d" % (len(self.fc_weights.projections) - 1)
+        last_w = self._last_w_name
         for i, (n, p, _) in enumerate(tr):
             desc[i]["theta"], desc[i]["grad"], desc[i]["vhat"] = p.data_ptr(), self.grads[n].data_ptr(), \
                 self.vhat[n].data_ptr()
@@ -307,7 +352,8 @@ class ConvE:
         s = self.shard
         put(self.ent_emb, params["ent_emb"][s.lo:s.hi])
         put(self.pred_bias, params["pred_bias"][s.lo:s.hi])
-        put(self.rel_emb, params["rel_emb"])
+        if self.rel_emb is not None:
+            put(self.rel_emb, params["rel_emb"])
         put(self.conv1_weights, params["conv1_weights"])
         put(self.conv1_bias, params["conv1_bias"])
         for cpg, key in ((self.fc_weights, "fc_weights"), (self.fc_bias, "fc_bias")):
@@ -438,6 +484,12 @@ class ConvE:
             b.ctx[cpg.name] = {"pre": [z(B, n) for n in cpg.hidden], "act": [z(B, n) for n in cpg.hidden],
                                "dact": [z(B, n) for n in cpg.hidden], "dpre": [z(B, n) for n in cpg.hidden]}
         b.dcw, b.dcb = z(B, dcw), z(B, dcb)
+        if self.variant == "plain":          # the stacked [entity image; relation image] and its gradient
+            b.xc, b.dxc = z(B, d + dr), z(B, d + dr)
+            b.cconst = torch.ones(B, 1, dtype=f32, device=dev)
+        if self.variant == "param_lookup":   # one-hot(rel) context; squared operands of the slice-wise bookkeeping
+            b.cconst = z(B, self.num_rel)
+            b.f_sq, b.dy_sq, b.df_scratch = z(B, F), z(B, d), z(B, F)
         b.dr2 = z(B, dr)
         b.dx0_sq = z(B, d) if self.use_negative_sampling else None
         b.samp = {}                                  # per-L buffers of the sampled-label path
@@ -652,15 +704,27 @@ class ConvE:
     def _front_end(self, b, is_train: bool):
         """b.x0, b.rel -> b.q for the rows of buffer set b (conv block, fused CPG-FC, FC block)."""
         B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
-        call("coper_gather_rows", ptr(self.rel_emb), 0, self.num_rel, dr, ptr(b.rel), B, ptr(b.r))
-        call("coper_conv_fwd", ptr(b.x0), B, self.H, self.W, ptr(self.conv1_weights), ptr(self.conv1_bias),
+        x_img = b.x0
+        if self.rel_emb is not None:
+            call("coper_gather_rows", ptr(self.rel_emb), 0, self.num_rel, dr, ptr(b.rel), B, ptr(b.r))
+        if self.variant == "plain":          # models.py:360-362: rows 0..H/2 = entity image, the rest = relation image
+            b.xc[:, :d].copy_(b.x0)
+            b.xc[:, d:].copy_(b.r)
+            x_img = b.xc
+        elif self.variant == "param_lookup":
+            b.cconst.zero_()
+            b.cconst.scatter_(1, b.rel.view(-1, 1), 1.0)
+        call("coper_conv_fwd", ptr(x_img), B, self.H, self.W, ptr(self.conv1_weights), ptr(self.conv1_bias),
              self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.z))
         use_batch = self.batch_norm_train_stats and is_train
         keep1 = 1.0 - (self.hidden_dropout if is_train else 0.0)
         self._bn_forward(self.conv1_bn, b.z, B * self.OH * self.OW, C, b, use_batch, is_train, True, True, keep1,
                          SALT_FEATURE_MAP, b.f)
-        cw = self._ctx_forward(self.fc_weights, 0, b, is_train)
-        cb = self._ctx_forward(self.fc_bias, 1, b, is_train)
+        if self.variant == "cpg":
+            cw = self._ctx_forward(self.fc_weights, 0, b, is_train)
+            cb = self._ctx_forward(self.fc_bias, 1, b, is_train)
+        else:
+            cw = cb = b.cconst
         Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
         keep2 = 1.0 - (self.output_dropout if is_train else 0.0)
         call("coper_cpg_fc_fwd", ptr(cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(cb), ptr(Pb), B, Pw.shape[0], F, d,
@@ -727,20 +791,36 @@ class ConvE:
         nw, nb = len(self.fc_weights.projections) - 1, len(self.fc_bias.projections) - 1
         call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(b.cb), ptr(Pb), ptr(b.dy), B,
              Pw.shape[0], F, d,
-             Pb.shape[0], ptr(g["fc_weights/CPG/Projection%d" % nw]), ptr(g["fc_bias/CPG/Projection%d" % nb]),
+             Pb.shape[0], ptr(g[self._last_w_name]), ptr(g[self._last_b_name]),
              ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec, int(self.prec != 0))
+        if self.variant == "param_lookup":
+            # the tables are read through embedding_lookup (models.py:91): IndexedSlices gradients, one [F*d] / [d]
+            # slice per query.  The slice-wise norm and the sparse AMSGrad rule need, per table row, the sum of the
+            # SQUARED slices = onehot^T . (f^2 (x) dy^2): the same contraction on the squared operands.
+            torch.mul(b.f, b.f, out=b.f_sq)
+            torch.mul(b.dy, b.dy, out=b.dy_sq)
+            call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f_sq), ptr(Pw), ptr(self.P_prep), ptr(b.cb), ptr(Pb),
+                 ptr(b.dy_sq), B, Pw.shape[0], F, d, Pb.shape[0], ptr(self.grad_sq["fc_weights"]),
+                 ptr(self.grad_sq["fc_bias"]), ptr(b.df_scratch), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg),
+                 b.ws_cpg_bytes, self.prec, 0)
         big_work = None
         if dp and self.group_big is not None:
             big_work = sharding.reduce_replicated_grads(self.flat_big, self.world, self.group_big, async_op=True)
-        self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
-        self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
+        if self.variant == "cpg":
+            self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
+            self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
         # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)
         R1 = B * self.OH * self.OW
         self._bn_backward(self.conv1_bn, b.df, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz)
         g["Conv1BN/gamma"].copy_(self.conv1_bn.dgamma)
         g["Conv1BN/beta"].copy_(self.conv1_bn.dbeta)
-        call("coper_conv_bwd", ptr(b.dz), ptr(b.x0), B, self.H, self.W, ptr(self.conv1_weights),
-             self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.dx0), ptr(b.dwc_part), ptr(b.dbc_part))
+        plain = self.variant == "plain"
+        call("coper_conv_bwd", ptr(b.dz), ptr(b.xc if plain else b.x0), B, self.H, self.W, ptr(self.conv1_weights),
+             self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.dxc if plain else b.dx0), ptr(b.dwc_part),
+             ptr(b.dbc_part))
+        if plain:                            # tf.concat backward: the two halves of the stacked image
+            b.dx0.copy_(b.dxc[:, :d])
+            b.dr.copy_(b.dxc[:, d:])
         KK = self.conv_filter_height * self.conv_filter_width * C
         slabs = _lib.load().coper_conv_bwd_slabs(B, self.H, self.W, self.conv_filter_height, self.conv_filter_width,
                                                  C, 0)
@@ -762,6 +842,10 @@ class ConvE:
                 torch.mul(b.dx0, b.dx0, out=b.dx0_sq)
                 call("coper_segscatter_add", ptr(b.e1), B, ptr(b.dx0_sq), d, ptr(gsq_e), s.lo, s.hi, ptr(b.ws),
                      b.ws_bytes)
+        if self.rel_emb is None:
+            if dp:
+                raise NotImplementedError
+            return self._clip_and_apply()
         g["rel_emb"].zero_()
         self.grad_sq["rel_emb"].zero_()
         if small:
