@@ -92,6 +92,8 @@ def main(argv=None):
     if args.synthetic:
         s = synthetic.SHAPES[args.synthetic]
         cfg.model.entity_embedding_size, cfg.model.relation_embedding_size = s["ent_emb_size"], s["rel_emb_size"]
+        if args.model_type == "plain":      # the relation image is stacked under the entity image (models.py:361)
+            cfg.model.relation_embedding_size = s["ent_emb_size"]
         cfg.training.batch_size = s["batch"]
         num_ent, num_rel, conv_h = s["num_ent"], s["num_rel"], s["H"]
         dataset_name = "synthetic-" + args.synthetic

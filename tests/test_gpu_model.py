@@ -388,6 +388,23 @@ def test_run_cpg_entry_point_synthetic(tmp_path):
                          "--model-load-path", ck[0]]) == 0
 
 
+@pytest.mark.parametrize("model_type", ["plain", "param_lookup"])
+def test_run_cpg_entry_point_other_model_types(model_type, tmp_path):
+    """config_*_plain.yaml / config_*_param_lookup.yaml through the same entry point (run_cpg.py:49-60, 83)."""
+    import glob
+    import pickle
+    from coper_b200 import run_cpg
+    wd = str(tmp_path)
+    assert run_cpg.main(["--synthetic", "toy", "--dataset", "kinship", "--model-type", model_type, "--max-steps", "8",
+                         "--working-dir", wd, "--eval-batches", "2", "--prec", "tf32x3"]) == 0
+    emb = glob.glob(os.path.join(wd, "evaluation", "*", "best_embeddings.ckpt"))
+    obj = pickle.load(open(emb[0], "rb"))
+    if model_type == "param_lookup":         # run_cpg.py:245-248: no relation embedding to save
+        assert obj.shape == (997, 40)
+    else:
+        assert obj[1].shape == (997, 40) and obj[0].shape == (6, 40)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_checkpoint_roundtrip(prec, tmp_path):
     kw, B = CASES["ragged_mid"]
