@@ -65,6 +65,9 @@ class OracleConfig:
     ent_emb_size: int
     rel_emb_size: int
     context_rel_out: Optional[List[int]] = field(default_factory=list)  # [] = g_linear, [64] = g_MLP
+    # not None: the conv filter [KH,KW,1,C] and bias [C] are generated per query as well (models.py:216-241) and the
+    # convolution runs per example (tf.map_fn, models.py:375-380); restated for the cpg model type only
+    context_rel_conv: Optional[List[int]] = None
     conv_in_height: int = 10           # models.py:261 hard-codes 10; parametrised for d=256 (16x16)
     conv_filter_height: int = 3
     conv_filter_width: int = 3
@@ -147,6 +150,15 @@ def init_params(cfg: OracleConfig, seed: int = 0, bias_noise: float = 0.0) -> Di
         p["rel_emb"] = xavier_uniform(rng, (cfg.num_rel, cfg.rel_emb_size))
     p["conv1_weights"] = xavier_uniform(rng, (KH, KW, 1, C))
     p["conv1_bias"] = np.zeros(C, np.float32)
+    if cfg.context_rel_conv is not None:                                # models.py:216-241
+        assert cfg.variant == "cpg"
+        cs = [cfg.rel_emb_size] + list(cfg.context_rel_conv)
+        sw, sb = cs + [KH * KW * C], cs + [C]
+        p["conv1_weights_proj"] = [xavier_uniform(rng, (sw[i], sw[i + 1])) for i in range(len(sw) - 1)]
+        p["conv1_bias_proj"] = [np.zeros((sb[i], sb[i + 1]), np.float32) for i in range(len(sb) - 1)]
+        p["conv1_weights_bn"] = [_bn_init(n) for n in cs[1:]]
+        p["conv1_bias_bn"] = [_bn_init(n) for n in cs[1:]]
+        del p["conv1_weights"], p["conv1_bias"]
     sizes_w = ctx + [F * d]
     sizes_b = ctx + [d]
     p["fc_weights_proj"] = [xavier_uniform(rng, (sizes_w[i], sizes_w[i + 1])) for i in range(len(sizes_w) - 1)]
@@ -164,9 +176,13 @@ def init_params(cfg: OracleConfig, seed: int = 0, bias_noise: float = 0.0) -> Di
         def noise(a, scale=bias_noise):
             return (a + rng.normal(0, scale, a.shape)).astype(np.float32)
         p["pred_bias"] = noise(p["pred_bias"])
-        p["conv1_bias"] = noise(p["conv1_bias"])
+        if "conv1_bias" in p:
+            p["conv1_bias"] = noise(p["conv1_bias"])
         p["fc_bias_proj"] = [noise(a) for a in p["fc_bias_proj"]]
-        for bn in [p["Conv1BN"], p["FCBN"]] + p["fc_weights_bn"] + p["fc_bias_bn"]:
+        if "conv1_bias_proj" in p:
+            p["conv1_bias_proj"] = [noise(a) for a in p["conv1_bias_proj"]]
+        for bn in [p["Conv1BN"], p["FCBN"]] + p["fc_weights_bn"] + p["fc_bias_bn"] + p.get("conv1_weights_bn", []) \
+                + p.get("conv1_bias_bn", []):
             bn["gamma"] = noise(bn["gamma"])
             bn["beta"] = noise(bn["beta"])
             bn["moving_mean"] = noise(bn["moving_mean"])
@@ -229,6 +245,18 @@ def _conv_valid(X, Wc):
     for i in range(KH):
         for j in range(KW):
             Z += X[:, i:i + OH, j:j + OW, None] * Wc[i, j][None, None, None, :]
+    return Z
+
+
+def _conv_valid_per_query(X, Wq):
+    """X: [B,H,W], Wq: [B,KH,KW,C] -> [B,OH,OW,C]: one filter per example (tf.map_fn of conv2d, models.py:375-380)."""
+    B, H, W = X.shape
+    _, KH, KW, C = Wq.shape
+    OH, OW = H - KH + 1, W - KW + 1
+    Z = np.zeros((B, OH, OW, C), X.dtype)
+    for i in range(KH):
+        for j in range(KW):
+            Z += X[:, i:i + OH, j:j + OW, None] * Wq[:, i, j][:, None, None, :]
     return Z
 
 
@@ -312,7 +340,19 @@ def forward(params, cfg: OracleConfig, e1, rel, is_train=False, masks=None, labe
     X = x0.reshape(B, H, W)                                   # models.py:355
     if variant == "plain":                                    # models.py:360-362: [e1 image; rel image] along height
         X = np.concatenate([X, r.reshape(B, H, W)], axis=1)
-    Z = _conv_valid(X, p["conv1_weights"][:, :, 0, :]) + p["conv1_bias"]     # models.py:382-385
+    conv_cpg = cfg.context_rel_conv is not None
+    if conv_cpg:
+        # models.py:367 (_get_conv_params) generates weights then bias: their hidden-layer dropouts are drawn first
+        KH, KW = cfg.conv_filter_height, cfg.conv_filter_width
+        ccw, ccw_caches, ccw_upd = cpg_context(r, p["conv1_weights_proj"], p["conv1_weights_bn"], cfg, is_train,
+                                               masks.get("ctx_cw"), dt)
+        ccb, ccb_caches, ccb_upd = cpg_context(r, p["conv1_bias_proj"], p["conv1_bias_bn"], cfg, is_train,
+                                               masks.get("ctx_cb"), dt)
+        Wq = (ccw @ p["conv1_weights_proj"][-1]).reshape(B, KH, KW, C)       # [-1] + [KH, KW, 1, C]
+        bq = ccb @ p["conv1_bias_proj"][-1]                                  # [B, C]
+        Z = _conv_valid_per_query(X, Wq) + bq[:, None, None, :]               # models.py:375-381
+    else:
+        Z = _conv_valid(X, p["conv1_weights"][:, :, 0, :]) + p["conv1_bias"]     # models.py:382-385
     use_batch = bool(cfg.batch_norm_train_stats and is_train)  # models.py:358
     Zbn, bn1c, mm1, mv1 = _bn_forward(Z.reshape(-1, C), p["Conv1BN"], use_batch, True, cfg.batch_norm_momentum)
     A1 = np.maximum(Zbn, 0)                                   # models.py:389
@@ -357,6 +397,10 @@ def forward(params, cfg: OracleConfig, e1, rel, is_train=False, masks=None, labe
            "moving": {"Conv1BN": (mm1, mv1), "FCBN": (mm2, mv2), "ctx_w": cw_upd, "ctx_b": cb_upd},
            "_cache": dict(e1=e1, rel=rel, X=X, bn1=bn1c, relu1=relu1, m1=m1, keep1=keep1, m2=m2, keep2=keep2,
                           bn2=bn2c, relu2=relu2, cw_caches=cw_caches, cb_caches=cb_caches, p=p, B=B)}
+    if conv_cpg:
+        out["ccw"], out["ccb"] = ccw, ccb
+        out["moving"]["ctx_cw"], out["moving"]["ctx_cb"] = ccw_upd, ccb_upd
+        out["_cache"].update(Wq=Wq, ccw_caches=ccw_caches, ccb_caches=ccb_caches)
     if lookup is not None:
         lk = np.asarray(lookup, np.int64)
         Eg = p["ent_emb"][lk]                                  # tf.gather -> [B, L, d]   (models.py:438)
@@ -462,16 +506,34 @@ def backward(out, cfg: OracleConfig):
     dZ2, dg1, db1 = _bn_backward(dZbn, c["bn1"])
     g["Conv1BN"] = {"gamma": dg1, "beta": db1}
     dZ = dZ2.reshape(B, OH, OW, C)
-    g["conv1_bias"] = dZ.sum(axis=(0, 1, 2))
     X = c["X"]
-    Wc = p["conv1_weights"][:, :, 0, :]
-    dWc = np.zeros_like(Wc)
     dX = np.zeros_like(X)
-    for i in range(KH):
-        for j in range(KW):
-            dWc[i, j] = np.einsum("bhw,bhwc->c", X[:, i:i + OH, j:j + OW], dZ)
-            dX[:, i:i + OH, j:j + OW] += dZ @ Wc[i, j]
-    g["conv1_weights"] = dWc[:, :, None, :]
+    if "Wq" in c:                                              # per-query filters: back through the two generators
+        Wq = c["Wq"]
+        dWq = np.zeros_like(Wq)
+        for i in range(KH):
+            for j in range(KW):
+                dWq[:, i, j] = np.einsum("bhw,bhwc->bc", X[:, i:i + OH, j:j + OW], dZ)
+                dX[:, i:i + OH, j:j + OW] += np.einsum("bhwc,bc->bhw", dZ, Wq[:, i, j])
+        dbq = dZ.sum(axis=(1, 2))
+        Pc, Pcb = p["conv1_weights_proj"][-1], p["conv1_bias_proj"][-1]
+        dWq2 = dWq.reshape(B, -1)
+        dr_cw, dPs_cw, dbn_cw = _cpg_context_backward(dWq2 @ Pc.T, c["ccw_caches"], use_bn)
+        dr_cb, dPs_cb, dbn_cb = _cpg_context_backward(dbq @ Pcb.T, c["ccb_caches"], use_bn)
+        g["conv1_weights_proj"] = dPs_cw + [out["ccw"].T @ dWq2]
+        g["conv1_bias_proj"] = dPs_cb + [out["ccb"].T @ dbq]
+        g["conv1_weights_bn"] = [None if t is None else {"gamma": t[0], "beta": t[1]} for t in dbn_cw]
+        g["conv1_bias_bn"] = [None if t is None else {"gamma": t[0], "beta": t[1]} for t in dbn_cb]
+        dr = dr + dr_cw + dr_cb
+    else:
+        g["conv1_bias"] = dZ.sum(axis=(0, 1, 2))
+        Wc = p["conv1_weights"][:, :, 0, :]
+        dWc = np.zeros_like(Wc)
+        for i in range(KH):
+            for j in range(KW):
+                dWc[i, j] = np.einsum("bhw,bhwc->c", X[:, i:i + OH, j:j + OW], dZ)
+                dX[:, i:i + OH, j:j + OW] += dZ @ Wc[i, j]
+        g["conv1_weights"] = dWc[:, :, None, :]
     H = cfg.conv_in_height
     if variant == "plain":                                     # tf.concat backward: the two halves of the image
         dx0, dr = dX[:, :H].reshape(B, d), dX[:, H:].reshape(B, d)

@@ -108,6 +108,11 @@ CASES = {
                          variant="param_lookup"),
     "lookup_eval": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, B=7, d=30, C=8,
                         variant="param_lookup"),
+    # conv filter and bias generated per query too (context_rel_conv, models.py:216-241, 375-380)
+    "cpgconv_train": dict(ctx=[6], ctx_conv=[5], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9,
+                          d=30, C=8),
+    "cpgconv_eval": dict(ctx=[], ctx_conv=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, B=7,
+                         d=30, C=8),
 }
 
 
@@ -118,18 +123,20 @@ def gen_model(tf, models, name, case, n_steps=1):
     d, C = case["d"], case["C"]
     variant = case.get("variant", "cpg")
     dr = d if variant == "plain" else 5
+    ctx_conv = case.get("ctx_conv")
     cfg = O.OracleConfig(num_ent=97, num_rel=6, ent_emb_size=d, rel_emb_size=dr, context_rel_out=ctx, variant=variant,
-                         conv_num_channels=C, hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
+                         context_rel_conv=ctx_conv, conv_num_channels=C, hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
                          context_rel_dropout=case["drop"][2], context_rel_use_batch_norm=case["usebn"],
                          batch_norm_train_stats=case["bn_train"], batch_norm_momentum=0.9)
     p = O.init_params(cfg, seed=11, bias_noise=0.1)
     save = {}
-    init = {"ent_emb": p["ent_emb"], "conv1_weights": p["conv1_weights"],
-            "conv1_bias": p["conv1_bias"], "pred_bias": p["pred_bias"]}
+    init = {"ent_emb": p["ent_emb"], "pred_bias": p["pred_bias"]}
+    if ctx_conv is None:
+        init["conv1_weights"], init["conv1_bias"] = p["conv1_weights"], p["conv1_bias"]
     if variant != "param_lookup":
         init["rel_emb"] = p["rel_emb"]
     F = cfg.fc_input_size
-    for which in ("fc_weights", "fc_bias"):
+    for which in ("fc_weights", "fc_bias") + (("conv1_weights", "conv1_bias") if ctx_conv is not None else ()):
         if variant == "plain":            # plain tf variables fc_weights [F, d], fc_bias [d] (models.py:334-340)
             init[which] = p[which + "_proj"][0].reshape((F, d) if which == "fc_weights" else (d,))
             continue
@@ -161,7 +168,12 @@ def gen_model(tf, models, name, case, n_steps=1):
                 for i, n in enumerate(ctx or [])]
         m_cb = [DH.keep_mask(B * n, 1 - case["drop"][2], sd, DH.ctx_salt(1, i)).reshape(B, n)
                 for i, n in enumerate(ctx or [])]
-        # tf.nn.dropout call order in models.py: conv1 (:390), fc_weights CPG hidden, fc_bias CPG hidden, fc (:414)
+        m_ccw = [DH.keep_mask(B * n, 1 - case["drop"][2], sd, DH.ctx_salt(2, i)).reshape(B, n)
+                 for i, n in enumerate(ctx_conv or [])]
+        m_ccb = [DH.keep_mask(B * n, 1 - case["drop"][2], sd, DH.ctx_salt(3, i)).reshape(B, n)
+                 for i, n in enumerate(ctx_conv or [])]
+        # tf.nn.dropout call order in models.py: [conv1_weights CPG hidden, conv1_bias CPG hidden (:367),] conv1
+        # (:390), fc_weights CPG hidden, fc_bias CPG hidden, fc (:414)
         tf.state.reset() if step == 0 else None
         st = tf.state
         if step > 0:
@@ -180,13 +192,13 @@ def gen_model(tf, models, name, case, n_steps=1):
             lookup[:, -1] = lookup[:, 0]                         # a repeated id inside every row
             labels = dense[np.arange(B)[:, None], lookup].astype(np.float32)
             st.batch["e2_multi"], st.batch["lookup_values"] = labels, lookup
-        st.dropout_masks = [m_fm] + m_cw + m_cb + [m_out]
+        st.dropout_masks = m_ccw + m_ccb + [m_fm] + m_cw + m_cb + [m_out]
         st.dropout_calls = 0
         model = models.ConvE(model_descriptors={
             "use_negative_sampling": bool(case.get("sampled")), "label_smoothing_epsilon": 0.1, "num_ent": cfg.num_ent,
             "num_rel": cfg.num_rel, "ent_emb_size": d, "rel_emb_size": dr, "concat_rel": False,
             "conv_num_channels": C,
-            "context_rel_conv": None, "context_rel_out": ctx, "context_rel_dropout": case["drop"][2],
+            "context_rel_conv": ctx_conv, "context_rel_out": ctx, "context_rel_dropout": case["drop"][2],
             "context_rel_use_batch_norm": case["usebn"], "input_dropout": 0.2, "hidden_dropout": case["drop"][0],
             "output_dropout": case["drop"][1], "learning_rate": 1e-2, "batch_size": B, "add_loss_summaries": False,
             "add_variable_summaries": False, "add_tensor_summaries": False, "batch_norm_momentum": 0.9,
@@ -197,6 +209,8 @@ def gen_model(tf, models, name, case, n_steps=1):
         save[pre + "mask_fm"], save[pre + "mask_out"] = m_fm, m_out
         for i, (a, b) in enumerate(zip(m_cw, m_cb)):
             save[pre + "mask_cw%d" % i], save[pre + "mask_cb%d" % i] = a, b
+        for i, (a, b) in enumerate(zip(m_ccw, m_ccb)):
+            save[pre + "mask_ccw%d" % i], save[pre + "mask_ccb%d" % i] = a, b
         if L:
             save[pre + "lookup"], save[pre + "labels"] = lookup, labels
             save[pre + "predictions_lookup"] = model.predictions_lookup.detach().numpy()

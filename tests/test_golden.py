@@ -34,8 +34,20 @@ CASE_CFG = {
                          variant="param_lookup"),
     "lookup_eval": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, d=30, C=8,
                         variant="param_lookup"),
+    "cpgconv_train": dict(ctx=[6], ctx_conv=[5], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, d=30,
+                          C=8),
+    "cpgconv_eval": dict(ctx=[], ctx_conv=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, d=30,
+                         C=8),
 }
 LR = 1e-2
+
+
+def generators_of(case):
+    """(oracle key, reference variable prefix, hidden sizes) of every ContextualParameterGenerator of the case."""
+    gens = [("fc_weights", case["ctx"] or []), ("fc_bias", case["ctx"] or [])]
+    if case.get("ctx_conv") is not None:
+        gens += [("conv1_weights", case["ctx_conv"]), ("conv1_bias", case["ctx_conv"])]
+    return gens
 
 
 def variant_of(case):
@@ -62,7 +74,7 @@ def assert_grads_close(grads, z, case, tol=2e-4):
 def cfg_of(case):
     return O.OracleConfig(num_ent=97, num_rel=6, ent_emb_size=case["d"],
                           rel_emb_size=case["d"] if variant_of(case) == "plain" else 5, context_rel_out=case["ctx"],
-                          variant=variant_of(case), conv_num_channels=case["C"], hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
+                          variant=variant_of(case), context_rel_conv=case.get("ctx_conv"), conv_num_channels=case["C"], hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
                           context_rel_dropout=case["drop"][2], context_rel_use_batch_norm=case["usebn"],
                           batch_norm_train_stats=case["bn_train"], batch_norm_momentum=0.9)
 
@@ -77,8 +89,9 @@ def _bn(z, pre, name, n):
 def params_of(z, pre, case):
     n = len(case["ctx"] or []) + 1
     p = {k: z[pre + k] for k in ("ent_emb", "rel_emb", "conv1_weights", "conv1_bias", "pred_bias")
-         if not (k == "rel_emb" and variant_of(case) == "param_lookup")}
-    for which in ("fc_weights", "fc_bias"):
+         if pre + k in z.files}
+    for which, hidden in generators_of(case):
+        n = len(hidden) + 1
         if variant_of(case) != "cpg":
             # plain tf variables [F, d] / [d] or ParameterLookup tables [R', F*d] / [R', d]: the oracle holds them as
             # the single projection of a generator with a constant / one-hot context
@@ -87,7 +100,7 @@ def params_of(z, pre, case):
             p[which + "_bn"] = []
             continue
         p[which + "_proj"] = [z[pre + "%s/CPG/Projection%d" % (which, i)] for i in range(n)]
-        p[which + "_bn"] = [_bn(z, pre, "%s/CPG/Projection%d/BatchNorm" % (which, i), case["ctx"][i])
+        p[which + "_bn"] = [_bn(z, pre, "%s/CPG/Projection%d/BatchNorm" % (which, i), hidden[i])
                             for i in range(n - 1)]
     p["Conv1BN"] = _bn(z, pre, "Conv1BN", case["C"])
     p["FCBN"] = _bn(z, pre, "FCBN", case["d"])
@@ -99,17 +112,19 @@ def masks_of(z, step, case):
     m = {"feature_map": z[pre + "mask_fm"], "output": z[pre + "mask_out"]}
     m["ctx_w"] = [z[pre + "mask_cw%d" % i] for i in range(len(case["ctx"] or []))]
     m["ctx_b"] = [z[pre + "mask_cb%d" % i] for i in range(len(case["ctx"] or []))]
+    m["ctx_cw"] = [z[pre + "mask_ccw%d" % i] for i in range(len(case.get("ctx_conv") or []))]
+    m["ctx_cb"] = [z[pre + "mask_ccb%d" % i] for i in range(len(case.get("ctx_conv") or []))]
     return m
 
 
 def named_grads(g, case):
     """oracle.backward output keyed by the reference's variable names."""
-    out = {"ent_emb": g["ent_emb"], "conv1_weights": g["conv1_weights"],
-           "conv1_bias": g["conv1_bias"], "pred_bias": g["pred_bias"], "Conv1BN/gamma": g["Conv1BN"]["gamma"],
+    out = {"ent_emb": g["ent_emb"], "pred_bias": g["pred_bias"], "Conv1BN/gamma": g["Conv1BN"]["gamma"],
            "Conv1BN/beta": g["Conv1BN"]["beta"], "FCBN/gamma": g["FCBN"]["gamma"], "FCBN/beta": g["FCBN"]["beta"]}
-    if "rel_emb" in g:
-        out["rel_emb"] = g["rel_emb"]
-    for which in ("fc_weights", "fc_bias"):
+    for k in ("rel_emb", "conv1_weights", "conv1_bias"):
+        if k in g:
+            out[k] = g[k]
+    for which, _ in generators_of(case):
         if variant_of(case) != "cpg":
             out[which] = g[which + "_proj"][0]
             continue
@@ -126,7 +141,7 @@ def named_params(p, case):
     out = {k: p[k] for k in ("ent_emb", "rel_emb", "conv1_weights", "conv1_bias", "pred_bias") if k in p}
     for nm in ("Conv1BN", "FCBN"):
         out[nm + "/gamma"], out[nm + "/beta"] = p[nm]["gamma"], p[nm]["beta"]
-    for which in ("fc_weights", "fc_bias"):
+    for which, _ in generators_of(case):
         if variant_of(case) != "cpg":
             out[which] = p[which + "_proj"][0]
             continue
@@ -205,8 +220,9 @@ def test_oracle_multi_step_training_matches_reference(name):
                   sparse={k: (th[k], v, i) for k, v, i in zip(sp_names, sp_clipped, sp_idx)})
         for nm in ("Conv1BN", "FCBN"):
             p[nm]["moving_mean"], p[nm]["moving_var"] = out["moving"][nm]
-        for which, key in (("fc_weights", "ctx_w"), ("fc_bias", "ctx_b")):
-            for i, upd in enumerate(out["moving"][key]):
+        for which, key in (("fc_weights", "ctx_w"), ("fc_bias", "ctx_b"), ("conv1_weights", "ctx_cw"),
+                           ("conv1_bias", "ctx_cb")):
+            for i, upd in enumerate(out["moving"].get(key, [])):
                 if upd is not None:
                     p[which + "_bn"][i]["moving_mean"], p[which + "_bn"][i]["moving_var"] = upd
         after = params_of(z, pre + "after/", case)
