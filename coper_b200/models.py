@@ -123,9 +123,11 @@ class ConvE:
         #                 279-287), no relation embedding (models.py:210, 180)
         # Both of the latter run on the SAME fused generate-and-apply kernels: shared weights are a linear generator
         # applied to the constant context [1], table rows one applied to one-hot(rel) (adding exact zeros).
-        if self.context_rel_conv is not None or self.concat_rel:
-            raise NotImplementedError("per-query conv filters (context_rel_conv) and concat_rel are not built: no "
-                                      "shipped configuration uses them (SURVEY §8f-4)")
+        if self.concat_rel:
+            raise NotImplementedError("concat_rel is not built: no shipped configuration uses it (SURVEY §8f-4)")
+        if self.context_rel_conv is not None and (self.is_parameter_lookup or self.context_rel_out is None):
+            raise NotImplementedError("generated conv filters (context_rel_conv) are built together with generated "
+                                      "FC weights (context_rel_out: [...]) only")
         if self.is_parameter_lookup:
             if self.context_rel_out is None:
                 raise NotImplementedError("do_parameter_lookup needs context_rel_out: [] (config_*_param_lookup.yaml)")
@@ -199,10 +201,21 @@ class ConvE:
             self.rel_emb = torch.empty(self.num_rel, dr, dtype=f32)
             _xavier_(self.rel_emb, gen)
             self.rel_emb = self.rel_emb.to(dev)
-        w = torch.empty(self.conv_filter_height, self.conv_filter_width, 1, self.C, dtype=f32)
-        _xavier_(w, gen)
-        self.conv1_weights = w.to(dev)
-        self.conv1_bias = torch.zeros(self.C, dtype=f32, device=dev)
+        self.conv_w_gen = self.conv_b_gen = None
+        if self.context_rel_conv is None:
+            w = torch.empty(self.conv_filter_height, self.conv_filter_width, 1, self.C, dtype=f32)
+            _xavier_(w, gen)
+            self.conv1_weights = w.to(dev)
+            self.conv1_bias = torch.zeros(self.C, dtype=f32, device=dev)
+        else:
+            # conv filter / bias generated per query (models.py:216-241); applied per example (models.py:375-381)
+            cctx = [dr] + list(self.context_rel_conv)
+            self.conv_w_gen = ContextualParameterGenerator(
+                cctx, "conv1_weights", [self.conv_filter_height, self.conv_filter_width, 1, self.C], False,
+                self.context_rel_use_batch_norm, dev, gen)
+            self.conv_b_gen = ContextualParameterGenerator(cctx, "conv1_bias", [self.C], True,
+                                                           self.context_rel_use_batch_norm, dev, gen)
+            self.conv1_weights, self.conv1_bias = self.conv_w_gen, self.conv_b_gen
         if self.variant == "cpg":
             ctx = [dr] + list(self.context_rel_out)
         else:                      # constant context [1] (shared weights) / one-hot(rel) (table rows)
@@ -215,6 +228,8 @@ class ConvE:
             w = torch.empty(self.F, d, dtype=f32)
             _xavier_(w, gen)
             self.fc_weights.projections[0].copy_(w.view(1, -1))
+        self.generators = [self.fc_weights, self.fc_bias] + \
+            ([self.conv_w_gen, self.conv_b_gen] if self.conv_w_gen is not None else [])
         self.conv1_bn = _BatchNorm(self.C, dev)
         self.fc_bn = _BatchNorm(d, dev)
         self.pred_bias = torch.zeros(self.shard.rows, dtype=f32, device=dev)
@@ -245,12 +260,13 @@ class ConvE:
         tr = [("ent_emb", self.ent_emb, True), ("pred_bias", self.pred_bias, True)]
         if self.rel_emb is not None:
             tr.append(("rel_emb", self.rel_emb, False))
-        tr += [("conv1_weights", self.conv1_weights, False), ("conv1_bias", self.conv1_bias, False)]
+        if self.conv_w_gen is None:
+            tr += [("conv1_weights", self.conv1_weights, False), ("conv1_bias", self.conv1_bias, False)]
         self._last_w_name = "fc_weights/CPG/Projection%d" % (len(self.fc_weights.projections) - 1)
         self._last_b_name = "fc_bias/CPG/Projection%d" % (len(self.fc_bias.projections) - 1)
         if self.variant != "cpg":        # tf variable names: 'fc_weights' / 'fc_bias' (models.py:334-340, 86)
             self._last_w_name, self._last_b_name = "fc_weights", "fc_bias"
-        for cpg in (self.fc_weights, self.fc_bias):
+        for cpg in self.generators:
             if self.variant != "cpg":
                 tr.append((cpg.name, cpg.projections[0], False))
                 continue
@@ -354,9 +370,10 @@ class ConvE:
         put(self.pred_bias, params["pred_bias"][s.lo:s.hi])
         if self.rel_emb is not None:
             put(self.rel_emb, params["rel_emb"])
-        put(self.conv1_weights, params["conv1_weights"])
-        put(self.conv1_bias, params["conv1_bias"])
-        for cpg, key in ((self.fc_weights, "fc_weights"), (self.fc_bias, "fc_bias")):
+        if self.conv_w_gen is None:
+            put(self.conv1_weights, params["conv1_weights"])
+            put(self.conv1_bias, params["conv1_bias"])
+        for cpg, key in [(g, g.name) for g in self.generators]:
             for t, a in zip(cpg.projections, params[key + "_proj"]):
                 put(t, a)
             for bn, b in zip(cpg.bns, params[key + "_bn"]):
@@ -373,7 +390,7 @@ class ConvE:
         sd.update({"m/" + n: v for n, v in self.m.items()})
         sd.update({"v/" + n: v for n, v in self.v.items()})
         bns = [("Conv1BN", self.conv1_bn), ("FCBN", self.fc_bn)]
-        for cpg in (self.fc_weights, self.fc_bias):
+        for cpg in self.generators:
             bns += [("%s/CPG/Projection%d/BatchNorm" % (cpg.name, i), bn) for i, bn in enumerate(cpg.bns)]
         for nm, bn in bns:
             sd["bn/%s/moving_mean" % nm], sd["bn/%s/moving_var" % nm] = bn.moving_mean, bn.moving_var
@@ -452,7 +469,7 @@ class ConvE:
         b.dq, b.dy, b.df, b.dz, b.dx0, b.dr = z(B, d), z(B, d), z(B, F), z(B, F), z(B, d), z(B, dr)
         R1 = B * self.OH * self.OW
         nch = max(lib.coper_colstats_chunks(R1), lib.coper_colstats_chunks(B))
-        maxC = max([C, d] + self.fc_weights.hidden)
+        maxC = max([C, d] + [n for gcp in self.generators for n in gcp.hidden])
         b.stat = z(nch * maxC * 2)
         b.stat1 = z(maxC * 2)
         # allocated on first use (each exactly once, so captured graphs keep valid pointers):
@@ -480,10 +497,15 @@ class ConvE:
         b.ws_bytes = ws
         # context nets: activations per hidden layer for the two generators
         b.ctx = {}
-        for cpg in (self.fc_weights, self.fc_bias):
+        for cpg in self.generators:
             b.ctx[cpg.name] = {"pre": [z(B, n) for n in cpg.hidden], "act": [z(B, n) for n in cpg.hidden],
                                "dact": [z(B, n) for n in cpg.hidden], "dpre": [z(B, n) for n in cpg.hidden]}
         b.dcw, b.dcb = z(B, dcw), z(B, dcb)
+        if self.conv_w_gen is not None:      # per-query filters [B, KH*KW*C], biases [B, C], context gradients
+            KK = self.conv_filter_height * self.conv_filter_width * C
+            b.wq, b.bq = z(B, KK), z(B, C)
+            b.dccw = z(B, self.conv_w_gen.projections[-1].shape[0])
+            b.dccb = z(B, self.conv_b_gen.projections[-1].shape[0])
         if self.variant == "plain":          # the stacked [entity image; relation image] and its gradient
             b.xc, b.dxc = z(B, d + dr), z(B, d + dr)
             b.cconst = torch.ones(B, 1, dtype=f32, device=dev)
@@ -714,8 +736,18 @@ class ConvE:
         elif self.variant == "param_lookup":
             b.cconst.zero_()
             b.cconst.scatter_(1, b.rel.view(-1, 1), 1.0)
-        call("coper_conv_fwd", ptr(x_img), B, self.H, self.W, ptr(self.conv1_weights), ptr(self.conv1_bias),
-             self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.z))
+        if self.conv_w_gen is None:
+            call("coper_conv_fwd", ptr(x_img), B, self.H, self.W, ptr(self.conv1_weights), ptr(self.conv1_bias),
+                 self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.z))
+        else:
+            KK = self.conv_filter_height * self.conv_filter_width * C
+            b.ccw = self._ctx_forward(self.conv_w_gen, 2, b, is_train)
+            b.ccb = self._ctx_forward(self.conv_b_gen, 3, b, is_train)
+            Pc, Pcb = self.conv_w_gen.projections[-1], self.conv_b_gen.projections[-1]
+            call("coper_sgemm", 0, 0, B, KK, Pc.shape[0], ptr(b.ccw), Pc.shape[0], ptr(Pc), KK, ptr(b.wq), KK, 0)
+            call("coper_sgemm", 0, 0, B, C, Pcb.shape[0], ptr(b.ccb), Pcb.shape[0], ptr(Pcb), C, ptr(b.bq), C, 0)
+            call("coper_conv_fwd", ptr(x_img), B, self.H, self.W, ptr(b.wq), ptr(b.bq),
+                 self.conv_filter_height, self.conv_filter_width, C, 1, ptr(b.z))
         use_batch = self.batch_norm_train_stats and is_train
         keep1 = 1.0 - (self.hidden_dropout if is_train else 0.0)
         self._bn_forward(self.conv1_bn, b.z, B * self.OH * self.OW, C, b, use_batch, is_train, True, True, keep1,
@@ -815,17 +847,30 @@ class ConvE:
         g["Conv1BN/gamma"].copy_(self.conv1_bn.dgamma)
         g["Conv1BN/beta"].copy_(self.conv1_bn.dbeta)
         plain = self.variant == "plain"
-        call("coper_conv_bwd", ptr(b.dz), ptr(b.xc if plain else b.x0), B, self.H, self.W, ptr(self.conv1_weights),
-             self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.dxc if plain else b.dx0), ptr(b.dwc_part),
-             ptr(b.dbc_part))
-        if plain:                            # tf.concat backward: the two halves of the stacked image
-            b.dx0.copy_(b.dxc[:, :d])
-            b.dr.copy_(b.dxc[:, d:])
         KK = self.conv_filter_height * self.conv_filter_width * C
-        slabs = _lib.load().coper_conv_bwd_slabs(B, self.H, self.W, self.conv_filter_height, self.conv_filter_width,
-                                                 C, 0)
-        call("coper_reduce_partials", ptr(b.dwc_part), slabs, KK, 1.0, 0, ptr(g["conv1_weights"]))
-        call("coper_reduce_partials", ptr(b.dbc_part), slabs, C, 1.0, 0, ptr(g["conv1_bias"]))
+        if self.conv_w_gen is not None:
+            # per-example filters: dz -> dx0 and, per query, dWq [B, KK] / dbq [B, C]; then back through the generators
+            call("coper_conv_bwd", ptr(b.dz), ptr(b.x0), B, self.H, self.W, ptr(b.wq), self.conv_filter_height,
+                 self.conv_filter_width, C, 1, ptr(b.dx0), ptr(b.dwc_part), ptr(b.dbc_part))
+            for gen_, ctx_, dq_, dctx_, width, net in ((self.conv_w_gen, b.ccw, b.dwc_part, b.dccw, KK, 2),
+                                                       (self.conv_b_gen, b.ccb, b.dbc_part, b.dccb, C, 3)):
+                Pl = gen_.projections[-1]
+                dcc = Pl.shape[0]
+                last = "%s/CPG/Projection%d" % (gen_.name, len(gen_.projections) - 1)
+                call("coper_sgemm", 1, 0, dcc, width, B, ptr(ctx_), dcc, ptr(dq_), width, ptr(g[last]), width, 0)
+                call("coper_sgemm", 0, 1, B, dcc, width, ptr(dq_), width, ptr(Pl), width, ptr(dctx_), dcc, 0)
+                self._ctx_backward(gen_, net, b, dctx_, b.dr, True)
+        else:
+            call("coper_conv_bwd", ptr(b.dz), ptr(b.xc if plain else b.x0), B, self.H, self.W, ptr(self.conv1_weights),
+                 self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.dxc if plain else b.dx0),
+                 ptr(b.dwc_part), ptr(b.dbc_part))
+            if plain:                            # tf.concat backward: the two halves of the stacked image
+                b.dx0.copy_(b.dxc[:, :d])
+                b.dr.copy_(b.dxc[:, d:])
+            slabs = _lib.load().coper_conv_bwd_slabs(B, self.H, self.W, self.conv_filter_height,
+                                                     self.conv_filter_width, C, 0)
+            call("coper_reduce_partials", ptr(b.dwc_part), slabs, KK, 1.0, 0, ptr(g["conv1_weights"]))
+            call("coper_reduce_partials", ptr(b.dbc_part), slabs, C, 1.0, 0, ptr(g["conv1_bias"]))
         # gradients of the two embedding gathers (models.py:176-178): deterministic segmented scatter
         # IndexedSlices bookkeeping (rel_emb always; ent_emb with sampled labels): the same pass also accumulates the
         # per-row sums of the SQUARED slices (slice-wise global norm + sparse AMSGrad rule)

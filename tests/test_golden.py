@@ -261,7 +261,8 @@ def _model(case, p, lr=LR):
           "num_rel": 6,
           "ent_emb_size": case["d"], "rel_emb_size": case["d"] if variant_of(case) == "plain" else 5,
           "concat_rel": False, "conv_num_channels": case["C"],
-          "context_rel_conv": None, "context_rel_out": case["ctx"], "context_rel_dropout": case["drop"][2],
+          "context_rel_conv": case.get("ctx_conv"), "context_rel_out": case["ctx"],
+          "context_rel_dropout": case["drop"][2],
           "context_rel_use_batch_norm": case["usebn"], "input_dropout": 0.2, "hidden_dropout": case["drop"][0],
           "output_dropout": case["drop"][1], "learning_rate": lr, "batch_size": 0, "add_loss_summaries": False,
           "add_variable_summaries": False, "add_tensor_summaries": False, "batch_norm_momentum": 0.9,
@@ -312,7 +313,9 @@ def test_cuda_training_matches_reference_model(name):
     for k, ref in after.items():
         if k == "conv1_bias" and case["bn_train"]:
             continue       # noise-driven under batch-stat BN (see the CPU test above)
-        assert relerr(got[k].reshape(ref.shape), ref) < 5e-4, k
+        # AMSGrad as written steps by ~ lr * g / (sqrt(g^2) + 1e-8): on entries whose gradient is near the 1e-8 scale
+        # fp32 summation-order noise is amplified to a fraction of a step (step-0 gradients are compared at 2e-4 above)
+        assert relerr(got[k].reshape(ref.shape), ref) < 1e-3, k
     assert relerr(m.conv1_bn.moving_var.cpu().numpy(), z["step2/after/Conv1BN/moving_variance"]) < 1e-4
     assert relerr(m.fc_bn.moving_mean.cpu().numpy(), z["step2/after/FCBN/moving_mean"]) < 1e-4
     assert relerr(m.vhat["ent_emb"].cpu().numpy(), z["step2/after/ent_emb/AMSGrad/v_hat"]) < 1e-3

@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 def descriptors(cfg: O.OracleConfig, lr=1e-3):
     return {"use_negative_sampling": False, "label_smoothing_epsilon": cfg.label_smoothing_epsilon,
             "num_ent": cfg.num_ent, "num_rel": cfg.num_rel, "ent_emb_size": cfg.ent_emb_size,
-            "rel_emb_size": cfg.rel_emb_size, "concat_rel": False, "context_rel_conv": None,
+            "rel_emb_size": cfg.rel_emb_size, "concat_rel": False,
+            "context_rel_conv": None if cfg.context_rel_conv is None else list(cfg.context_rel_conv),
             "context_rel_out": None if cfg.variant == "plain" else list(cfg.context_rel_out or []),
             "context_rel_dropout": cfg.context_rel_dropout,
             "context_rel_use_batch_norm": cfg.context_rel_use_batch_norm, "input_dropout": 0.2,
@@ -64,6 +65,10 @@ def export_masks(model, cfg, B):
         for key, net in (("ctx_w", 0), ("ctx_b", 1)):
             masks[key] = [mask(B * n, 1 - cfg.context_rel_dropout, M.SALT_CTX + ((net * 64 + i) << 32)).reshape(B, n)
                           for i, n in enumerate(cfg.context_rel_out)]
+    if cfg.context_rel_dropout > 0 and cfg.context_rel_conv:
+        for key, net in (("ctx_cw", 2), ("ctx_cb", 3)):
+            masks[key] = [mask(B * n, 1 - cfg.context_rel_dropout, M.SALT_CTX + ((net * 64 + i) << 32)).reshape(B, n)
+                          for i, n in enumerate(cfg.context_rel_conv)]
     return masks
 
 
@@ -85,11 +90,19 @@ def compare_grads(model, g, cfg, tol=2e-4):
     mg = grads_by_name(model)
     nw = len(g["fc_weights_proj"])
     checks = [("ent_emb", g["ent_emb"]), ("pred_bias", g["pred_bias"]),
-              ("conv1_weights", g["conv1_weights"]), ("conv1_bias", g["conv1_bias"]),
               ("FCBN/gamma", g["FCBN"]["gamma"]), ("FCBN/beta", g["FCBN"]["beta"]),
               ("Conv1BN/gamma", g["Conv1BN"]["gamma"]), ("Conv1BN/beta", g["Conv1BN"]["beta"])]
-    if "rel_emb" in g:
-        checks.append(("rel_emb", g["rel_emb"]))
+    for k in ("rel_emb", "conv1_weights", "conv1_bias"):
+        if k in g:
+            checks.append((k, g[k]))
+    if cfg.context_rel_conv is not None:
+        for which in ("conv1_weights", "conv1_bias"):
+            for i, a in enumerate(g[which + "_proj"]):
+                checks.append(("%s/CPG/Projection%d" % (which, i), a))
+            if cfg.context_rel_use_batch_norm:
+                for i, t in enumerate(g[which + "_bn"]):
+                    checks.append(("%s/CPG/Projection%d/BatchNorm/gamma" % (which, i), t["gamma"]))
+                    checks.append(("%s/CPG/Projection%d/BatchNorm/beta" % (which, i), t["beta"]))
     for i in range(nw):
         if cfg.variant != "cpg":        # plain tf variables / ParameterLookup tables carry the generator's name
             checks.append(("fc_weights", g["fc_weights_proj"][0]))
@@ -132,6 +145,13 @@ CASES = {
                         output_dropout=0.2), 130),
     "big_batch": (dict(num_ent=2047, num_rel=11, ent_emb_size=40, rel_emb_size=4, context_rel_out=[],
                        batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 4096),
+    # conv filter + bias generated per query as well (context_rel_conv, models.py:216-241, 375-381)
+    "cpgconv_glinear": (dict(num_ent=131, num_rel=6, ent_emb_size=40, rel_emb_size=5, context_rel_out=[],
+                             context_rel_conv=[], batch_norm_train_stats=True, hidden_dropout=0.3,
+                             output_dropout=0.2), 33),
+    "cpgconv_gmlp_d200": (dict(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[6],
+                               context_rel_conv=[7, 5], context_rel_use_batch_norm=True, context_rel_dropout=0.2,
+                               batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 130),
     # the other two shipped model types (config_*_plain.yaml, config_*_param_lookup.yaml)
     "plain_toy": (dict(num_ent=131, num_rel=6, ent_emb_size=40, rel_emb_size=40, context_rel_out=None, variant="plain",
                        batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 33),
@@ -208,7 +228,7 @@ def test_dense_label_schema_equals_csr():
 
 
 @pytest.mark.parametrize("name", ["toy_glinear_eval_stats", "toy_gmlp_bn_dropout", "ragged_mid", "d256_16x16",
-                                  "plain_toy", "lookup_toy"])
+                                  "plain_toy", "lookup_toy", "cpgconv_gmlp_d200"])
 def test_eval_scores_and_ranks(name):
     kw, B = CASES[name]
     cfg = O.OracleConfig(**kw)
@@ -312,7 +332,7 @@ TC_TOL = {  # prec: (q, loss, dq/dy/df, parameter grads)
 
 @pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
 @pytest.mark.parametrize("name", ["toy_glinear_batch_stats", "toy_gmlp_bn_dropout", "ragged_mid", "d256_16x16",
-                                  "plain_d200", "lookup_d200", "lookup_toy"])
+                                  "plain_d200", "lookup_d200", "lookup_toy", "cpgconv_gmlp_d200"])
 def test_train_step_parity_tensor_pipe(name, prec):
     """Same step as test_train_step_parity with the CPG contraction and the scorer on tcgen05."""
     kw, B = CASES[name]
