@@ -269,8 +269,13 @@ def main():
         sb_dev = [{k: torch.as_tensor(v).cuda() for k, v in hb.items()} for hb in sb_host]
         t_ms, n_l = timed(lambda i: ms.train_step(sb_dev[i % n_batches]), K, W)
         e2e_ms, _ = timed(lambda i: float(ms.train_step(sb_host[i % n_batches]).item()), K, W)
+        # labels drawn on the device (coper_sample_labels) from host CSR batches: only ids + id lists cross PCIe
+        dev_host = [dict(hb, sample_on_device=(args.num_labels, 10.0)) for hb in host]
+        ds_ms, _ = timed(lambda i: float(ms.train_step(dev_host[i % n_batches]).item()), K, W)
         sampled = {"num_labels": args.num_labels, "value": B / t_ms * 1e3, "unit": "train rows/s", "ms_per_step": t_ms,
                    "e2e_value": B / e2e_ms * 1e3, "e2e_ms_per_step": e2e_ms,
+                   "device_sampling_e2e_value": B / ds_ms * 1e3, "device_sampling_e2e_ms_per_step": ds_ms,
+                   "device_sampling_h2d_bytes_per_step": h2d,
                    "h2d_bytes_per_step": int(B * 16 + B * args.num_labels * 8), "gpu_launches_per_step": n_l / K,
                    "gather_bytes_per_step": int(B * args.num_labels * s["ent_emb_size"] * 4)}
     cpu = None

@@ -139,6 +139,103 @@ __global__ void sampled_scatter_kernel(const int32_t* __restrict__ keys, const i
   }
 }
 
+// ---- on-device label sampling (data.py:228-277, _sample_negatives) ------------------------------------------------
+// Two keyed random permutations of [0, n):
+//   n <= kSampleSmall: ORDER of the n hashes hash32(key, i) (ties broken by i): position of element i = its rank.
+//     Uniform over all n! orders for an ideal hash; O(n^2 / threads) per row, n is tiny (a row's positives; the
+//     entity set of the toy datasets).
+//   larger n: 6-round balanced Feistel network over the next even power of two, restricted to [0, n) by cycle walking
+//     (a bijection of the larger domain walked until it lands inside stays a bijection); O(1) per drawn element.
+constexpr int kSampleSmall = 1024;
+__device__ __forceinline__ uint32_t prp(uint32_t x, uint32_t n, uint64_t key) {
+  int bits = 2;
+  while (bits < 32 && (1ull << bits) < (uint64_t)n) bits += 2;
+  const int half = bits >> 1;
+  const uint32_t mask = (1u << half) - 1u;
+  do {
+    uint32_t l = x >> half, r = x & mask;
+#pragma unroll
+    for (int round = 0; round < 6; ++round) {
+      const uint32_t t = l ^ (hash32(key, ((uint64_t)round << 32) | r) & mask);
+      l = r;
+      r = t;
+    }
+    x = (l << half) | r;
+  } while (x >= n);
+  return x;
+}
+
+// rank permutation: every element i < n whose rank is < count writes out(rank, i)
+template <class Out>
+__device__ __forceinline__ void rank_permute(uint32_t* sh, int n, int count, uint64_t key, Out out) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = hash32(key, (uint64_t)i);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t hi = sh[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const uint32_t hj = sh[j];
+      r += (hj < hi) || (hj == hi && j < i);
+    }
+    if (r < count) out(r, i);
+  }
+  __syncthreads();
+}
+
+constexpr int kSampleThreads = 128;
+__global__ void __launch_bounds__(kSampleThreads) sample_labels_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int L, int n_pos_needed,
+    const uint64_t* __restrict__ seed_dev, uint64_t salt, int32_t* __restrict__ lookup, float* __restrict__ labels) {
+  __shared__ int32_t spos[kSampleSmall];       // the row's positives (membership test)
+  __shared__ uint32_t sh[kSampleSmall];        // hashes of the rank permutation
+  const int b = blockIdx.x;
+  const int p0 = rowptr[b], P = rowptr[b + 1] - p0;
+  const int32_t* cols = col + p0;
+  for (int i = threadIdx.x; i < P && i < kSampleSmall; i += blockDim.x) spos[i] = cols[i];
+  __syncthreads();
+  // data.py:244-268: all positives when there are at most n_pos_needed of them, otherwise as many as are left after
+  // min(N, L - n_pos_needed) negatives; the rest of the row is the prefix of a random permutation of ALL entities
+  int n_pos = P;
+  if (P > n_pos_needed) {
+    const int64_t want_neg = (int64_t)L - n_pos_needed;
+    n_pos = L - (int)(want_neg < N ? want_neg : N);
+  }
+  n_pos = n_pos < P ? n_pos : P;
+  n_pos = n_pos < L ? n_pos : L;
+  const int n_neg = L - n_pos;
+  const uint64_t seed = *seed_dev + salt;
+  const uint64_t key_pos = ((uint64_t)hash32(seed, 2 * (uint64_t)b) << 32) | hash32(seed ^ 0x5bd1e995u, 2 * (uint64_t)b);
+  const uint64_t key_neg = ((uint64_t)hash32(seed, 2 * (uint64_t)b + 1) << 32) |
+                           hash32(seed ^ 0x5bd1e995u, 2 * (uint64_t)b + 1);
+  int32_t* lrow = lookup + (int64_t)b * L;
+  // positives: tf.random_shuffle(correct_e2s)[:n_pos]
+  if (P <= kSampleSmall) {
+    rank_permute(sh, P, n_pos, key_pos, [&](int r, int i) { lrow[r] = spos[i]; });
+  } else {
+    for (int l = threadIdx.x; l < n_pos; l += blockDim.x) lrow[l] = cols[prp((uint32_t)l, (uint32_t)P, key_pos)];
+  }
+  // sampled entities: tf.random_shuffle(tf.range(num_ent))[:L - n_pos]
+  if (N <= kSampleSmall) {
+    rank_permute(sh, (int)N, n_neg, key_neg, [&](int r, int i) { lrow[n_pos + r] = i; });
+  } else {
+    for (int l = threadIdx.x; l < n_neg; l += blockDim.x)
+      lrow[n_pos + l] = (int32_t)prp((uint32_t)l, (uint32_t)N, key_neg);
+  }
+  __syncthreads();
+  // labels = gather(dense multi-hot, ids): a sampled entity that is a true tail keeps its label 1
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    float lab = l < n_pos ? 1.0f : 0.0f;
+    if (l >= n_pos) {
+      const int32_t id = lrow[l];
+      for (int i = 0; i < P; ++i) {
+        const int32_t c = i < kSampleSmall ? spos[i] : cols[i];
+        if (c == id) lab = 1.0f;
+      }
+    }
+    labels[(int64_t)b * L + l] = lab;
+  }
+}
+
 struct SampLayout {
   size_t off_loss, off_keys_out, off_pos_in, off_pos_out, off_cub, cub_bytes, total;
 };
@@ -163,6 +260,15 @@ static SampLayout samp_layout(int B, int L) {
 using namespace coper;
 
 extern "C" {
+
+int coper_sample_labels(const int32_t* rowptr, const int32_t* col, int B, int64_t N, int L, int n_pos_needed,
+                        const uint64_t* seed_dev, uint64_t salt, int32_t* lookup, float* labels, coper_stream_t stream) {
+  COPER_CHECK_ARG(rowptr && col && seed_dev && lookup && labels && B > 0 && L > 0 && n_pos_needed >= 0);
+  COPER_CHECK_ARG(N > 0 && N < (int64_t(1) << 31) && (int64_t)L <= N);
+  sample_labels_kernel<<<B, kSampleThreads, 0, as_stream(stream)>>>(rowptr, col, N, L, n_pos_needed, seed_dev, salt,
+                                                                    lookup, labels);
+  return check_launch();
+}
 
 size_t coper_score_sampled_workspace_bytes(int B, int L) { return (B <= 0 || L <= 0) ? 256 : samp_layout(B, L).total; }
 

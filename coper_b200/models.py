@@ -37,6 +37,7 @@ BN_EPS = 1e-3           # tf.layers.batch_normalization default epsilon (models.
 CLIP_NORM = 5.0         # models.py:199
 SALT_FEATURE_MAP = 1 << 40
 SALT_OUTPUT = 2 << 40
+SALT_SAMPLE = 4 << 40   # on-device label sampling (coper_sample_labels)
 SALT_CTX = 3 << 40      # + (net_id * 64 + layer) << 32
 
 
@@ -550,6 +551,7 @@ class ConvE:
         if b.csr_cap < nnz:
             cap = max(1024, int(nnz * 1.5))
             b.col = torch.zeros(cap, dtype=torch.int32, device=self.dev)
+            b.csr_gen = getattr(b, "csr_gen", 0) + 1     # graphs that captured the old pointer must not be replayed
             b.h_col = torch.zeros(cap, dtype=torch.int32).pin_memory()
             b.h_col_np = b.h_col.numpy()
             b.csr_cap = cap
@@ -929,6 +931,11 @@ class ConvE:
         sb, g, gsq = b.cur_samp, self.grads, self.grad_sq
         for t in (g["ent_emb"], gsq["ent_emb"], g["pred_bias"], gsq["pred_bias"]):
             t.zero_()
+        if b.cur_sampling is not None:       # labels drawn on the device from the staged CSR positives (data.py:228-277)
+            L, prop_negatives = b.cur_sampling
+            call("coper_sample_labels", ptr(b.rowptr), ptr(b.col), b.B, self.num_ent, L,
+                 int(1.0 / (1.0 + prop_negatives) * L), ptr(self.seed_dev), SALT_SAMPLE, ptr(sb.lookup),
+                 ptr(sb.labels))
         call("coper_score_sampled_bce_fwd_bwd", ptr(b.q), ptr(self.ent_emb), ptr(self.pred_bias), ptr(sb.lookup),
              ptr(sb.labels), b.B, sb.L, self.num_ent, self.ent_emb_size, 1.0 - self.label_smoothing_epsilon,
              1.0 / self.num_ent, 1.0 / (float(b.B) * float(sb.L)), ptr(b.loss_sum), ptr(sb.scores), ptr(sb.g),
@@ -995,18 +1002,34 @@ class ConvE:
     def _train_step_sampled(self, batch: Dict, apply_update: bool):
         """Sampled-label step: ``batch['lookup_values']`` int32 [B, L] entity ids and ``batch['e2_multi']`` fp32 [B, L]
         their labels (data.py:228-312 produce them; models.py:165,438-443 consume them)."""
-        lookup, labels = batch["lookup_values"], batch["e2_multi"]
-        if lookup is None or len(lookup.shape) != 2 or lookup.shape[1] == 0 or tuple(labels.shape) != tuple(lookup.shape):
-            raise ValueError("sampled-label training needs lookup_values [B, L] and e2_multi [B, L] (L = num_labels)")
-        b = self.stage_batch({k: batch[k] for k in ("e1", "rel", "e2") if k in batch})
-        sb = self._sampled_buffers(b, int(lookup.shape[1]))
-        for src, dev_t, host_t, dt in ((lookup, sb.lookup, sb.h_lookup, torch.int32),
-                                      (labels, sb.labels, sb.h_labels, torch.float32)):
-            if isinstance(src, torch.Tensor) and src.is_cuda:
-                dev_t.copy_(src)
-            else:
-                host_t.copy_(torch.as_tensor(np.asarray(src), dtype=dt))
-                dev_t.copy_(host_t, non_blocking=True)
+        sampling = batch.get("sample_on_device")
+        if sampling is not None:
+            # (num_labels, prop_negatives): the batch carries the CSR id lists of the known-true tails instead of
+            # pre-sampled [B, L] ids / labels; coper_sample_labels draws them inside the (graph-captured) device step
+            L = int(sampling[0])
+            if not 0 < L <= self.num_ent or "e2_multi_rowptr" not in batch:
+                raise ValueError("sample_on_device=(num_labels, prop_negatives) needs e2_multi_rowptr / e2_multi_col "
+                                 "and 0 < num_labels <= num_ent")
+            b = self.stage_batch({k: batch[k] for k in ("e1", "rel", "e2", "e2_multi_rowptr", "e2_multi_col")
+                                  if k in batch})
+            sb = self._sampled_buffers(b, L)
+            b.cur_sampling = (L, float(sampling[1]))
+        else:
+            lookup, labels = batch["lookup_values"], batch["e2_multi"]
+            if lookup is None or len(lookup.shape) != 2 or lookup.shape[1] == 0 \
+                    or tuple(labels.shape) != tuple(lookup.shape):
+                raise ValueError("sampled-label training needs lookup_values [B, L] and e2_multi [B, L] "
+                                 "(L = num_labels)")
+            b = self.stage_batch({k: batch[k] for k in ("e1", "rel", "e2") if k in batch})
+            sb = self._sampled_buffers(b, int(lookup.shape[1]))
+            b.cur_sampling = None
+            for src, dev_t, host_t, dt in ((lookup, sb.lookup, sb.h_lookup, torch.int32),
+                                          (labels, sb.labels, sb.h_labels, torch.float32)):
+                if isinstance(src, torch.Tensor) and src.is_cuda:
+                    dev_t.copy_(src)
+                else:
+                    host_t.copy_(torch.as_tensor(np.asarray(src), dtype=dt))
+                    dev_t.copy_(host_t, non_blocking=True)
         b.h2d_event.record()
         b.cur_samp = sb
         if not apply_update:
@@ -1017,7 +1040,8 @@ class ConvE:
             finally:
                 self._clip_and_apply = saved
         else:
-            self._run_graphed(("train_sampled", b.B, sb.L), lambda: self._train_device(b))
+            key = ("train_sampled", b.B, sb.L, b.cur_sampling, getattr(b, "csr_gen", 0) if b.cur_sampling else 0)
+            self._run_graphed(key, lambda: self._train_device(b))
         self.global_step += 1
         return b.loss_sum[0] / (float(b.B) * float(sb.L))
 

@@ -193,6 +193,18 @@ int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prep
  *   dE_sum, dE_sq [N, d], dbias_sum, dbias_sq [N] are ACCUMULATED (zero them first; the e1-gather slices are added on
  *   top with coper_segscatter_add).  Exact fp32 (gather-bound, no tensor-pipe variant); deterministic. */
 size_t coper_score_sampled_workspace_bytes(int B, int L);
+
+/* SURVEY §8f-2, on-device label sampling — replaces the input pipeline's _sample_negatives map (data.py:228-277) and
+ * its [B, L] host->device copies.  Per query row b, from the CSR list of its known-true tails (rowptr int32 [B+1],
+ * col int32 [nnz]; the e2_multi id lists, data.py:574-594), with n_pos_needed = int(1/(1+prop_negatives) * L):
+ *   P <= n_pos_needed : all P positives in random order, then L - P sampled entities            (data.py:244-251)
+ *   P >  n_pos_needed : n_pos = L - min(N, L - n_pos_needed) randomly chosen positives, then the rest (data.py:253-263)
+ * The sampled entities are the prefix of a keyed pseudorandom PERMUTATION of [0, N) (4-round Feistel network + cycle
+ * walking; key = *seed_dev + salt, row): distinct within a row and, as in the reference, positives are not removed
+ * from them - a sampled entity that is a true tail gets label 1.  lookup int32 [B, L], labels fp32 [B, L] are the
+ * batch['lookup_values'] / batch['e2_multi'] of models.py:135-152,165.  Needs L <= N < 2^31. */
+int coper_sample_labels(const int32_t* rowptr, const int32_t* col, int B, int64_t N, int L, int n_pos_needed,
+                        const uint64_t* seed_dev, uint64_t salt, int32_t* lookup, float* labels, coper_stream_t stream);
 int coper_score_sampled_bce_fwd_bwd(const float* q, const float* E, const float* bias, const int32_t* lookup,
                                     const float* labels, int B, int L, int64_t N, int d, float one_minus_eps,
                                     float inv_num_ent, float inv_count, double* loss_sum, float* scores, float* g,

@@ -449,3 +449,54 @@ def test_reduce_partials_fixed_order(L):
         L.call("coper_reduce_partials", L.ptr(dev(x)), S, n, 0.5, 1, L.ptr(out))
         ref = 7.0 + 0.5 * x.astype(np.float64).sum(0)
         assert np.abs(out.cpu().numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("N,L,needed", [(5000, 100, 9), (14, 10, 3), (200, 200, 18), (70001, 1000, 90)])
+def test_sample_labels_bit_exact_and_well_formed(N, L, needed):
+    """coper_sample_labels (data.py:228-277 on the device) vs the NumPy restatement, plus the properties the reference's
+    sampler guarantees: positives first (all of them, or the computed share), sampled entities distinct, labels ==
+    membership in the row's true tails."""
+    from coper_b200 import _lib as L_
+    from oracle import dropout_hash as DH
+    lib = L_.load()
+    rng = np.random.default_rng(N + L)
+    B = 96
+    k = np.minimum(rng.geometric(0.2, B), N)
+    k[:6] = [0, 1, min(needed, N), min(needed + 1, N), min(60, N), min(1500, N)]     # empty row ... > 1024 positives
+    rowptr = np.zeros(B + 1, np.int32)
+    rowptr[1:] = np.cumsum(k)
+    col = np.concatenate([rng.choice(N, int(kk), replace=False) for kk in k]).astype(np.int32)
+    trp, tcol = torch.as_tensor(rowptr).cuda(), torch.as_tensor(col).cuda()
+    for seed in (1, 987654321012345):
+        sd = torch.tensor([seed], dtype=torch.int64, device="cuda")
+        lookup = torch.full((B, L), -1, dtype=torch.int32, device="cuda")
+        labels = torch.full((B, L), -1.0, device="cuda")
+        L_.call("coper_sample_labels", L_.ptr(trp), L_.ptr(tcol), B, N, L, needed, L_.ptr(sd), DH.SALT_SAMPLE,
+                L_.ptr(lookup), L_.ptr(labels))
+        lk, lab = lookup.cpu().numpy(), labels.cpu().numpy()
+        ref_lk, ref_lab = DH.sample_labels(rowptr, col, N, L, needed, seed)
+        assert np.array_equal(lk, ref_lk) and np.array_equal(lab, ref_lab)
+        for b in range(B):
+            pos = col[rowptr[b]:rowptr[b + 1]]
+            P = len(pos)
+            n_pos = P if P <= needed else L - min(L - needed, N)
+            n_pos = min(n_pos, P, L)
+            assert set(lk[b, :n_pos].tolist()) <= set(pos.tolist()) and len(set(lk[b, :n_pos].tolist())) == n_pos
+            neg = lk[b, n_pos:]
+            assert len(set(neg.tolist())) == L - n_pos and neg.min(initial=0) >= 0 and neg.max(initial=0) < N
+            assert np.array_equal(lab[b], np.isin(lk[b], pos).astype(np.float32) if P else np.zeros(L, np.float32))
+    # the sampled entities are uniform over [0, N): chi-square of their histogram over all rows and 20 seeds
+    if N == 5000:
+        cnt = np.zeros(N)
+        for seed in range(20):
+            sd = torch.tensor([seed * 104729 + 7], dtype=torch.int64, device="cuda")
+            L_.call("coper_sample_labels", L_.ptr(trp), L_.ptr(tcol), B, N, L, needed, L_.ptr(sd), DH.SALT_SAMPLE,
+                    L_.ptr(lookup), L_.ptr(labels))
+            lk = lookup.cpu().numpy()
+            for b in range(B):
+                P = int(k[b])
+                n_pos = min(P if P <= needed else L - min(L - needed, N), P, L)
+                np.add.at(cnt, lk[b, n_pos:], 1)
+        e = cnt.sum() / N
+        chi2 = ((cnt - e) ** 2 / e).sum()
+        assert abs(chi2 - (N - 1)) < 6 * np.sqrt(2 * (N - 1)), chi2

@@ -519,3 +519,44 @@ def test_sampled_label_step_parity(L):
     assert relerr(model.ent_emb.cpu().numpy(), p64["ent_emb"]) < 1e-3
     assert relerr(model.pred_bias.cpu().numpy(), p64["pred_bias"]) < 1e-3
     assert relerr(model.rel_emb.cpu().numpy(), p64["rel_emb"]) < 1e-3
+
+
+def test_device_sampled_step_matches_restatement_and_oracle():
+    """Labels drawn ON THE DEVICE (coper_sample_labels; data.py:228-277) inside the captured train step: the drawn ids /
+    labels equal the NumPy restatement bit for bit for the step's seed, and the step computed from them equals the
+    oracle's step on those ids (two steps: the second runs from the captured graph with a new seed)."""
+    from oracle import dropout_hash as DH
+    from coper_b200.models import ConvE
+    kw, B = CASES["ragged_mid"]
+    cfg = O.OracleConfig(**kw)
+    params = O.init_params(cfg, seed=3, bias_noise=0.05)
+    e1, rel, e2, rowptr, col = O.synthetic_batch(cfg, B, seed=5, mean_pos=6.0)
+    L, prop = 40, 4.0
+    md = descriptors(cfg, lr=1e-2)
+    md["use_negative_sampling"] = True
+    model = ConvE(md, conv_in_height=cfg.conv_in_height)
+    model.load_variables(params)
+    batch = {"e1": e1, "rel": rel, "e2": e2, "e2_multi_rowptr": rowptr, "e2_multi_col": col,
+             "sample_on_device": (L, prop)}
+    loss = float(model.train_step(batch, apply_update=False).item())
+    sb = model._bufs[B].samp[L]
+    lookup, labels = sb.lookup.cpu().numpy(), sb.labels.cpu().numpy()
+    lk_ref, lab_ref = DH.sample_labels(rowptr, col, cfg.num_ent, L, int(1.0 / (1.0 + prop) * L),
+                                       int(model.seed_dev.item()))
+    assert np.array_equal(lookup, lk_ref) and np.array_equal(labels, lab_ref)
+    dense = O.csr_to_dense(rowptr, col, cfg.num_ent)
+    assert np.array_equal(labels, dense[np.arange(B)[:, None], lookup].astype(np.float32))
+    masks = export_masks(model, cfg, B)
+    out = O.forward(params, cfg, e1, rel, True, masks, labels, np.float64, lookup=lookup)
+    g = O.backward(out, cfg)
+    assert abs(loss - out["loss"]) < 1e-6 * abs(out["loss"])
+    assert relerr(model.grads["ent_emb"].cpu().numpy(), g["ent_emb"]) < 2e-4
+    compare_grads(model, g, cfg)
+    draws = []
+    for _ in range(3):               # eager, capture, replay: a fresh draw every step
+        assert np.isfinite(float(model.train_step(batch).item()))
+        lk = sb.lookup.cpu().numpy()
+        ref, _ = DH.sample_labels(rowptr, col, cfg.num_ent, L, int(1.0 / (1.0 + prop) * L), int(model.seed_dev.item()))
+        assert np.array_equal(lk, ref)
+        draws.append(lk)
+    assert not np.array_equal(draws[0], draws[1]) and not np.array_equal(draws[1], draws[2])
