@@ -242,10 +242,19 @@ class _DataLoader(Loader):
     def train_dataset(self, directory, batch_size, include_inv_relations=True, num_parallel_readers=32,
                       num_parallel_batches=32, buffer_size=1024 * 1024, prefetch_buffer_size=10, prop_negatives=10.0,
                       num_labels=None, cache=False, one_positive_label_per_sample=True, seed=0,
-                      dense=False) -> Iterator[Dict[str, np.ndarray]]:
+                      dense=False, device_sampling=False) -> Iterator[Dict[str, np.ndarray]]:
         """Endless iterator of training batches (``data.py:89-166``: repeat -> labels -> shuffle -> batch).
-        The reference shuffles with a 1000-element buffer; here every epoch is a seeded full permutation."""
+        The reference shuffles with a 1000-element buffer; here every epoch is a seeded full permutation.
+        ``device_sampling`` (with ``num_labels``, not with ``one_positive_label_per_sample``): batches carry the CSR id
+        lists plus ``sample_on_device = (num_labels, prop_negatives)``; ``ConvE.train_step`` then draws the
+        ``[B, num_labels]`` ids / labels of ``_sample_negatives`` (``data.py:228-277``) on the GPU."""
         c = self.load_and_preprocess(directory, buffer_size)
+        on_device = None
+        if num_labels is not None and device_sampling and not one_positive_label_per_sample:
+            if num_labels > self.num_ent:
+                raise ValueError("Parameter `num_labels` needs to be at most the total number of entities.")
+            on_device = (int(num_labels), float(prop_negatives))
+            num_labels = None
         if num_labels is not None:
             if num_labels > self.num_ent:                         # data.py:149
                 raise ValueError("Parameter `num_labels` needs to be at most the total number of entities.")
@@ -262,8 +271,11 @@ class _DataLoader(Loader):
                 order = rng.permutation(sel)
                 for s in range(0, len(order), batch_size):
                     idx = order[s:s + batch_size]
-                    yield self._make_batch(split.e1[idx], split.rel[idx], np.full(len(idx), -1, np.int64),
-                                           idx, split.rowptr, split.col, dense)
+                    bt = self._make_batch(split.e1[idx], split.rel[idx], np.full(len(idx), -1, np.int64),
+                                          idx, split.rowptr, split.col, dense)
+                    if on_device is not None:
+                        bt["sample_on_device"] = on_device
+                    yield bt
         return gen()
 
     # ------------------------------------------------------------------------------------------ sampled labels

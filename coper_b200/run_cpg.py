@@ -67,6 +67,8 @@ def main(argv=None):
     ap.add_argument("--working-dir", default=None)
     ap.add_argument("--synthetic", default=None, help="run on a synthetic KG of this BASELINE shape instead of files")
     ap.add_argument("--full-1n", action="store_true", help="train with full 1-N labels (num_labels: null)")
+    ap.add_argument("--device-sampling", action="store_true",
+                    help="sampled-label configs: draw the [B, num_labels] ids / labels on the GPU (coper_sample_labels)")
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--eval-batches", type=int, default=None, help="cap the number of eval batches (synthetic runs)")
     ap.add_argument("--prec", default="tf32x3", choices=["fp32", "tf32x3", "bf16"])
@@ -127,7 +129,8 @@ def main(argv=None):
         train_batches = loader.train_dataset(
             directory=data_dir, batch_size=B, include_inv_relations=True, prop_negatives=cfg.training.prop_negatives,
             num_labels=cfg.training.num_labels, cache=cfg.training.cache_data,
-            one_positive_label_per_sample=cfg.training.get("one_positive_label_per_sample", False), seed=args.seed)
+            one_positive_label_per_sample=cfg.training.get("one_positive_label_per_sample", False), seed=args.seed,
+            device_sampling=args.device_sampling)
 
         def make_eval(which):
             it = loader.eval_dataset(directory=data_dir, dataset_type=which, batch_size=B, include_inv_relations=False)

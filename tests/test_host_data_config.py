@@ -144,6 +144,34 @@ def test_sampled_label_pipelines(tmp_path, one_pos):
         ld.train_dataset(str(tmp_path), batch_size=4, num_labels=10 ** 6)
 
 
+def test_device_sampling_pipeline_and_restatement(tmp_path):
+    """device_sampling=True: the loader hands out the CSR id lists + (num_labels, prop_negatives); the sampler the GPU
+    kernel implements (NumPy restatement, oracle/dropout_hash.sample_labels) builds rows with the reference's shape:
+    positives first, distinct sampled entities, labels == membership (data.py:228-277)."""
+    from oracle import dropout_hash as DH
+    _big_graph(str(tmp_path))
+    ld = _loader()
+    L, B, prop = 16, 8, 3.0
+    it = ld.train_dataset(str(tmp_path), batch_size=B, num_labels=L, prop_negatives=prop,
+                          one_positive_label_per_sample=False, device_sampling=True)
+    b = next(it)
+    assert b["sample_on_device"] == (L, prop) and b["lookup_values"].shape == (B, 0)
+    rowptr, col = b["e2_multi_rowptr"], b["e2_multi_col"]
+    n_needed = int(1.0 / (1.0 + prop) * L)
+    lk, lab = DH.sample_labels(rowptr, col, ld.num_ent, L, n_needed, seed_dev=12345)
+    for i in range(B):
+        pos = set(col[rowptr[i]:rowptr[i + 1]].tolist())
+        n_pos = len(pos) if len(pos) <= n_needed else L - min(ld.num_ent, L - n_needed)
+        assert set(lk[i, :n_pos].tolist()) <= pos and len(set(lk[i, n_pos:].tolist())) == L - n_pos
+        assert np.array_equal(lab[i], np.isin(lk[i], list(pos)).astype(np.float32))
+    lk2, _ = DH.sample_labels(rowptr, col, ld.num_ent, L, n_needed, seed_dev=12346)
+    assert not np.array_equal(lk, lk2)
+    # one_positive_label_per_sample keeps the host sampler (a different row expansion, data.py:279-312)
+    b1 = next(ld.train_dataset(str(tmp_path), batch_size=B, num_labels=L, prop_negatives=prop,
+                               one_positive_label_per_sample=True, device_sampling=True, prefetch_buffer_size=2))
+    assert b1["lookup_values"].shape == (B, L) and "sample_on_device" not in b1
+
+
 def test_nell995_fixture_format_if_present():
     """The only dataset files the reference ships (dev / test of nell-995, 3 tab-separated columns)."""
     path = "/root/reference/CoPER_ConvE/data/nell-995/dev.txt"
