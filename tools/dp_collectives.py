@@ -13,7 +13,7 @@ def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    B, d, F, dc = 512, 200, 10368, 8
+    B, d, F, dc = 512, 200, 4608, 8
     f32 = dict(dtype=torch.float32, device="cuda")
     big = torch.zeros(dc * F * d + 4096, **f32)
     xg, xl = torch.zeros(B * world, d, **f32), torch.zeros(B, d, **f32)
