@@ -88,7 +88,9 @@ def test_tc_gemm_all_layouts(prec, M, N, K):
 
 @pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
 @pytest.mark.parametrize("B,N,d", [(512, 40943, 200), (7, 97, 40), (130, 1003, 200), (33, 5000, 256), (128, 70001, 256),
-                                   (4096, 5118, 200)])     # last: one rank's share of 8-way data-parallel WN18RR
+                                   (4096, 5118, 200),      # one rank's share of 8-way data-parallel WN18RR
+                                   # BASELINE.json configs at full size: FB15k-237, NELL-995, YAGO3-10 (B = 128)
+                                   (512, 14541, 200), (512, 75492, 200), (128, 123182, 200)])
 def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     """scorer + label-smoothed BCE + gradient on tcgen05 (models.py:433-437,448-453,198): loss, dq, dE, dbias.
     tf32x3: fp32-class (loss 1e-5 rel, gradients 2e-5 of max); bf16: vs fp64 arithmetic on bf16-rounded q, E
@@ -143,7 +145,8 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
 
 @pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
 @pytest.mark.parametrize("B,N,d,lo", [(512, 40943, 200, 0), (7, 97, 40, 0), (130, 1003, 200, 0), (33, 5000, 256, 0),
-                                      (64, 70001, 256, 123456), (300, 33, 64, 0), (4096, 5118, 200, 5118)])
+                                      (64, 70001, 256, 123456), (300, 33, 64, 0), (4096, 5118, 200, 5118),
+                                      (512, 14541, 200, 0), (512, 75492, 200, 0), (128, 123182, 200, 0)])
 def test_fused_score_rank_equals_two_pass(prec, B, N, d, lo):
     """scorer + filtered rank fused (logits stay in TMEM) == scoring into HBM + coper_filtered_rank, bit for bit:
     the gold logits from the gather+diagonal pass equal the stored logits, and the integer counts agree — including
