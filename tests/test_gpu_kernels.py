@@ -500,3 +500,34 @@ def test_sample_labels_bit_exact_and_well_formed(N, L, needed):
         e = cnt.sum() / N
         chi2 = ((cnt - e) ** 2 / e).sum()
         assert abs(chi2 - (N - 1)) < 6 * np.sqrt(2 * (N - 1)), chi2
+
+
+@pytest.mark.parametrize("B,dc,F,d,prec", [(64, 8, 128, 64, "auto"), (33, 5, 50, 300, "auto"), (130, 6, 96, 200, "bf16"),
+                                           (16, 3, 64, 800 // 4, "fp32")])
+def test_generate_and_apply_autograd_matches_torch_einsum(B, dc, F, d, prec):
+    """coper_b200.generate_apply (the ConvE path's fused kernels as a torch op) vs the materialising formulation of
+    CoPER_MINERVA/src/rl/graph_search/pn.py:125 — einsum('ij,ijk->ik', X, reshape(Q @ P, [B, F, d])) + Q @ Pb — and
+    its autograd gradients, in fp64 torch."""
+    from coper_b200.generate_apply import generate_and_apply
+    g = torch.Generator().manual_seed(B + F)
+    Q = torch.randn(B, dc, generator=g)
+    X = torch.relu(torch.randn(B, F, generator=g))
+    P = (torch.rand(dc, F * d, generator=g) - 0.5) * 0.2
+    Pb = (torch.rand(dc, d, generator=g) - 0.5) * 0.2
+    dY = torch.randn(B, d, generator=g)
+    ref_in = [t.double().requires_grad_(True) for t in (Q, X, P, Pb)]
+    q64, x64, p64, pb64 = ref_in
+    y_ref = torch.einsum("ij,ijk->ik", x64, (q64 @ p64).reshape(B, F, d)) + q64 @ pb64
+    y_ref.backward(dY.double())
+    dev_in = [t.cuda().requires_grad_(True) for t in (Q, X, P, Pb)]
+    qd, xd, pd, pbd = dev_in
+    y = generate_and_apply(qd, xd, pd, pbd, prec=prec)
+    y.backward(dY.cuda())
+    tol = 5e-2 if prec == "bf16" else 2e-5
+    assert relerr(y.detach().cpu().numpy(), y_ref.detach().numpy()) < tol
+    for got, ref in zip(dev_in, ref_in):
+        assert relerr(got.grad.cpu().numpy(), ref.grad.numpy()) < (5e-2 if prec == "bf16" else 1e-4)
+    # no bias term
+    y0 = generate_and_apply(qd.detach(), xd.detach(), pd.detach(), prec=prec)
+    y0_ref = torch.einsum("ij,ijk->ik", x64.detach(), (q64.detach() @ p64.detach()).reshape(B, F, d))
+    assert relerr(y0.cpu().numpy(), y0_ref.numpy()) < tol
