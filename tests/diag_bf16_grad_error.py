@@ -1,3 +1,5 @@
+"""Diagnostic (not collected by pytest): how far the bf16 engine's downstream gradients sit from the fp64 oracle.
+Lives under tests/ because it uses the oracle (only tests/, smoke() and bench.py's CPU legs may)."""
 import sys; sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np, torch
 from oracle import conve_oracle as O
