@@ -422,6 +422,18 @@ class ConvE:
         self.global_step = int(ck["global_step"])
         self.refresh_prepared()
 
+    def full_entity_table(self) -> torch.Tensor:
+        """[num_ent, d] on every rank: all-gather of the (padded) row shards (run_cpg.py:245-248 pickles the table)."""
+        if self.world == 1:
+            return self.ent_emb
+        import torch.distributed as dist
+        per, d = self.shard.per, self.ent_emb_size
+        mine = torch.zeros(per, d, dtype=torch.float32, device=self.dev)
+        mine[:self.shard.rows].copy_(self.ent_emb)
+        out = torch.empty(self.world * per, d, dtype=torch.float32, device=self.dev)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out[:self.num_ent]
+
     def refresh_prepared(self):
         """(Re)build the tensor-pipe operand copies after the variables were written from outside the optimizer."""
         if self.E_prep is None:
@@ -1048,7 +1060,7 @@ class ConvE:
     def predict_all(self, batch: Dict):
         """Logits of every query against this rank's entity rows: [B, rows] view (metrics.py:40-42)."""
         b = self.stage_batch(batch)
-        if self.dp:
+        if self.dp and b.B % self.world == 0:
             self._forward_q_dp(b, self._local_buffers(b), False)
         else:
             self._forward_q(b, False)
@@ -1080,7 +1092,9 @@ class ConvE:
         return b.n_greater + 1, b.n_equal
 
     def _rank_device(self, b):
-        if self.dp:
+        # (evaluation uses moving statistics and no dropout: a batch that does not split evenly over the ranks simply
+        # runs the front end replicated, with identical results)
+        if self.dp and b.B % self.world == 0:
             self._forward_q_dp(b, self._local_buffers(b), False)
         else:
             self._forward_q(b, False)

@@ -2,6 +2,7 @@
 
     python -m coper_b200.run_cpg --dataset WN18RR --model-type cpg --data-dir temp/WN18RR/data/WN18RR
     python -m coper_b200.run_cpg --synthetic wn18rr --max-steps 200          # no dataset files needed
+    torchrun --nproc-per-node 8 -m coper_b200.run_cpg --dataset YAGO3-10 --full-1n   # entity-sharded over 8 GPUs
 
 Where the reference edits flags in source (``run_cpg.py:38-46``: ``use_cpg``, ``use_parameter_lookup``,
 ``save_best_embeddings``, ``model_load_path``, the loader instance) they are command-line options here; everything else
@@ -11,6 +12,11 @@ next to the outputs (``:87-105``), the step loop with loss logging every ``log_s
 ``eval_steps`` on dev / test through ``ranking_and_hits`` (``:18-35,226-236``), best-dev checkpoint + embedding pickle
 (``:238-252``) and ``--model-load-path`` = restore, evaluate test, exit (``:205-208``).  TensorBoard summaries are
 replaced by the log lines.
+
+Under ``torchrun`` (one process per GPU) the entity table is sharded by entity id and the batch (the config's
+``batch_size``, unchanged) is split over the ranks (``ConvE(..., shard=..., data_parallel=True)``): every rank reads the
+same batches from its own, identically seeded loader; rank 0 logs and writes the config / embedding pickle, every rank
+saves the checkpoint of its own rows.  Full 1-N labels only (``--full-1n`` for the sampled-label configs).
 """
 from __future__ import annotations
 
@@ -82,6 +88,17 @@ def main(argv=None):
 
     from . import configs, data, synthetic
     from .models import ConvE
+    from .sharding import EntityShard
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if rank != 0:
+            logging.getLogger().setLevel(logging.WARNING)
     use_cpg, use_parameter_lookup = args.model_type == "cpg", args.model_type == "param_lookup"
     dataset_name = args.dataset
     cfg = configs.load_config(args.config) if args.config else configs.load_config(dataset_name, args.model_type)
@@ -149,11 +166,16 @@ def main(argv=None):
         os.makedirs(d, exist_ok=True)
     ckpt_path = os.path.join(ckpt_dir, "model_weights.ckpt")
     embed_file = os.path.join(eval_path, "best_embeddings.ckpt")
-    with open(os.path.join(config_save_dir, "config.yml"), "w") as outfile:
-        yaml.dump(_plain(cfg), outfile, default_flow_style=False)
+    if rank == 0:
+        with open(os.path.join(config_save_dir, "config.yml"), "w") as outfile:
+            yaml.dump(_plain(cfg), outfile, default_flow_style=False)
 
     md = configs.model_descriptors(cfg, num_ent, num_rel, use_cpg, use_parameter_lookup)
-    model = ConvE(md, seed=args.seed, prec=args.prec, conv_in_height=conv_h, init_fast=num_ent > 1_000_000)
+    if world > 1 and md["use_negative_sampling"]:
+        raise SystemExit("sampled-label configurations train on one GPU; pass --full-1n for the entity-sharded 1-N path")
+    split_batch = world > 1 and cfg.training.batch_size % world == 0 and not use_parameter_lookup
+    model = ConvE(md, seed=args.seed, prec=args.prec, conv_in_height=conv_h, init_fast=num_ent > 1_000_000,
+                  shard=EntityShard(num_ent, rank, world), data_parallel=split_batch, graphs_multi_gpu=True)
     logger.info("Number of entities: %d", num_ent)
     logger.info("Number of relations: %d", num_rel)
 
@@ -165,10 +187,13 @@ def main(argv=None):
     if args.model_load_path is not None:
         model.load_checkpoint(args.model_load_path)
         _evaluate(model, make_eval("test"), "test", eval_path, 0)
-        return 0
+        return _finish(world)
     loss = None
     for step in range(cfg.training.max_steps):
-        loss_dev = model.train_step(next(train_batches))
+        batch = next(train_batches)
+        while split_batch and len(batch["e1"]) % world:      # the short batch that ends an epoch cannot be split evenly
+            batch = next(train_batches)
+        loss_dev = model.train_step(batch)
         if step % cfg.eval.log_steps == 0:
             loss = float(loss_dev.item())
             logger.info("Step %6d | Loss: %10.4f", step, loss)
@@ -185,10 +210,11 @@ def main(argv=None):
                 if improved:
                     best_dev, test_at_best, best_iter = metrics_dev, metrics_test, step
                     if not args.no_save_best_embeddings:
-                        ent = model.variables["ent_emb"].cpu().numpy()
+                        ent = model.full_entity_table().cpu().numpy()          # (a collective when sharded)
                         obj = ent if use_parameter_lookup else [model.variables["rel_emb"].cpu().numpy(), ent]
-                        with open(embed_file, "wb") as fh:
-                            pickle.dump(obj, fh)
+                        if rank == 0:
+                            with open(embed_file, "wb") as fh:
+                                pickle.dump(obj, fh)
                     logger.info("Step %d. Saving checkpoint at %s...", step, ckpt_path)
                     model.save_checkpoint(ckpt_path)
                 logger.info("Best dev %s so far is at step %s. Best dev metrics: %s", validation_metric, best_iter,
@@ -196,6 +222,19 @@ def main(argv=None):
                 logger.info("Test metrics at best dev: %s", str(test_at_best))
     if loss is not None:
         logger.info("final logged loss %.6f; best dev step %s", loss, best_iter)
+    return _finish(world)
+
+
+def _finish(world):
+    """Multi-process runs leave without tearing NCCL down: destroy_process_group() blocks once collectives have been
+    captured into CUDA graphs; everything is synchronised and flushed first."""
+    if world > 1:
+        import torch
+        torch.cuda.synchronize()
+        logging.shutdown()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -224,3 +224,33 @@ def test_data_parallel_front_end_matches_oracle(prec, tmp_path):
     # replicated variables identical on both ranks after the bucketed all-reduce + update
     assert np.array_equal(outs[0]["rel_emb_new"], outs[1]["rel_emb_new"])
     assert np.array_equal(outs[0]["P_new"], outs[1]["P_new"])
+
+
+def test_run_cpg_entry_point_under_torchrun(tmp_path):
+    """The train / evaluate entry point launched one process per GPU: entity-sharded table, batch split over the ranks,
+    rank 0 writes the config and the (all-gathered) embedding pickle, every rank its checkpoint shard; the saved shards
+    restore and evaluate."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import glob
+    import pickle
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    wd = str(tmp_path)
+    base = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "-m", "coper_b200.run_cpg",
+            "--synthetic", "toy", "--working-dir", wd, "--eval-batches", "2", "--prec", "tf32x3"]
+    out = subprocess.run(base + ["--max-steps", "12"], cwd=root, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "Step      0 | Loss" in out.stderr and "MRR" in out.stderr
+    shards = sorted(glob.glob(os.path.join(wd, "checkpoints", "*", "model_weights.ckpt", "model_weights.ckpt.rank*")))
+    assert len(shards) == world
+    emb = glob.glob(os.path.join(wd, "evaluation", "*", "best_embeddings.ckpt"))
+    rel_emb, ent_emb = pickle.load(open(emb[0], "rb"))
+    assert ent_emb.shape == (997, 40) and rel_emb.shape == (6, 5) and np.abs(ent_emb[-1]).max() > 0
+    out = subprocess.run(base + ["--model-load-path", shards[0][:-len(".rank0")]], cwd=root, capture_output=True,
+                         text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "test" in out.stderr and "MRR" in out.stderr
