@@ -100,3 +100,55 @@ def test_amsgrad_oracle_matches_port_and_bug():
     lr_t = 1e-2 * np.sqrt(1 - 0.999) / (1 - 0.9)
     exp = 1 - lr_t * 0.1 * g / (np.sqrt(0.001 * g * g) + 1e-8)
     assert np.allclose(th, exp)
+
+
+@pytest.mark.parametrize("variant,kw", [
+    ("plain", dict(rel_emb_size=40, context_rel_out=None)),
+    ("param_lookup", dict(rel_emb_size=5, context_rel_out=[])),
+    ("cpg", dict(rel_emb_size=5, context_rel_out=[6], context_rel_conv=[7], context_rel_use_batch_norm=True)),
+])
+def test_other_model_types_backward_matches_finite_differences(variant, kw):
+    """plain ConvE, ParameterLookup tables and generated conv filters: the analytic backward of the oracle against
+    central differences of its own fp64 forward (dropout masks fixed, batch-statistics BN)."""
+    cfg = O.OracleConfig(num_ent=31, num_rel=4, ent_emb_size=40, conv_num_channels=4, batch_norm_train_stats=True,
+                         hidden_dropout=0.3, output_dropout=0.2, context_rel_dropout=0.2, variant=variant, **kw)
+    p = O.cast_params(O.init_params(cfg, 1, 0.1), np.float64)
+    B = 6
+    e1, rel, e2, rp, col = O.synthetic_batch(cfg, B, 2)
+    dense = O.csr_to_dense(rp, col, cfg.num_ent, np.float64)
+    rng = np.random.default_rng(0)
+    OH, OW = cfg.conv_out_hw
+    masks = {"feature_map": rng.random((B, OH, OW, 4)) < 0.7, "output": rng.random((B, 40)) < 0.8,
+             "ctx_w": [rng.random((B, 6)) < 0.8], "ctx_b": [rng.random((B, 6)) < 0.8],
+             "ctx_cw": [rng.random((B, 7)) < 0.8], "ctx_cb": [rng.random((B, 7)) < 0.8]}
+
+    def loss_of():
+        return O.forward(p, cfg, e1, rel, True, masks, dense, np.float64)["loss"]
+    g = O.backward(O.forward(p, cfg, e1, rel, True, masks, dense, np.float64), cfg)
+    checks = [(p["ent_emb"], g["ent_emb"]), (p["fc_weights_proj"][-1], g["fc_weights_proj"][-1]),
+              (p["fc_bias_proj"][-1], g["fc_bias_proj"][-1]), (p["FCBN"]["gamma"], g["FCBN"]["gamma"])]
+    if variant != "param_lookup":
+        checks.append((p["rel_emb"], g["rel_emb"]))
+    if cfg.context_rel_conv is not None:
+        for i in range(2):
+            checks.append((p["conv1_weights_proj"][i], g["conv1_weights_proj"][i]))
+            checks.append((p["conv1_bias_proj"][i], g["conv1_bias_proj"][i]))
+        checks.append((p["conv1_weights_bn"][0]["gamma"], g["conv1_weights_bn"][0]["gamma"]))
+    else:
+        checks.append((p["conv1_weights"], g["conv1_weights"]))
+    for arr, grad in checks:
+        idxs = np.argwhere(np.abs(grad) > 0.1 * np.abs(grad).max())
+        for idx in idxs[rng.choice(len(idxs), 3)]:
+            idx, h = tuple(idx), 1e-5
+            old = arr[idx]
+            arr[idx] = old + h
+            lp = loss_of()
+            arr[idx] = old - h
+            lm = loss_of()
+            arr[idx] = old
+            assert abs((lp - lm) / (2 * h) - grad[idx]) < 1e-6 * abs(grad[idx]) + 1e-12
+    if variant == "param_lookup":       # the IndexedSlices of the tables sum to the dense gradients
+        vals, idx = g["_sparse"]["fc_weights"][0]
+        dense_g = np.zeros_like(g["fc_weights_proj"][0])
+        np.add.at(dense_g, idx, vals)
+        assert np.abs(dense_g - g["fc_weights_proj"][0]).max() < 1e-15
