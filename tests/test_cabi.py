@@ -46,3 +46,18 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md is the map from the C ABI to the reference call sites: every function of include/coper.h must be
+    named in it."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "coper.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(coper_[A-Za-z0-9_]+)\s*\(", header)))
+    # `coper_bn_*`-style wildcards and `coper_conv_fwd`, `coper_conv_bwd` lists both count
+    wild = [w[:-1] for w in re.findall(r"`(coper_[a-z0-9_]*\*)", doc)]
+    missing = [s for s in syms if s not in doc and not any(s.startswith(w) for w in wild)]
+    assert not missing, missing
