@@ -66,7 +66,8 @@ int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int wi
  * wc [KH,KW,C] / bc [C], or [B,KH,KW,C] / [B,C] when per_query != 0. */
 int coper_conv_fwd(const float* x0, int B, int H, int W, const float* wc, const float* bc, int KH, int KW,
                    int C, int per_query, float* z, coper_stream_t stream);
-/* backward of the above: dz [B,OH*OW*C] -> dx0 [B,H*W]; shared filters: per-sample partials
+/* backward of the above (what TF autodiff derives for models.py:375-385 at models.py:198):
+ * dz [B,OH*OW*C] -> dx0 [B,H*W]; shared filters: per-sample partials
  * dwc_part [S, KH*KW*C], dbc_part [S, C] with S = coper_conv_bwd_slabs(...) <= B slabs (reduce over S with
  * coper_reduce_partials; the 3x3 x 32-channel fast path emits one slab per 4 images);
  * per_query: S = B and the same buffers ARE the per-query gradients. */
@@ -102,7 +103,8 @@ int coper_bn_act_bwd_apply(const float* dout, const float* x, int64_t R, int C, 
                            const float* mean, const float* invstd, const float* c1, const float* c2, int relu,
                            float keep_post, const uint64_t* seed_dev, uint64_t salt_post, float keep_pre,
                            uint64_t salt_pre, float* dx, coper_stream_t stream);
-/* mask[i] = 1.0f if element i is kept (same hash as the kernels) — exported for the oracle/tests */
+/* mask[i] = 1.0f if element i is kept (same hash as the kernels) — the tf.nn.dropout draws of models.py:67-68,
+ * 390-391,414-415 made reproducible; exported for the oracle/tests */
 int coper_dropout_mask(int64_t n, float keep, const uint64_t* seed_dev, uint64_t salt, float* mask,
                        coper_stream_t stream);
 /* x[i] = x[i] * mask(i)/keep (used for the CPG hidden-layer dropout, models.py:67-68) */
@@ -144,7 +146,8 @@ size_t coper_score1n_workspace_bytes(int B, int64_t Ns, int d, int prec);
 int coper_score1n_fwd(const float* q, const float* E, const float* bias, int B, int64_t Ns, int d, float* scores,
                       int64_t ld_scores, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
 
-/* Tensor-pipe operand preparation (COPER_PREC_BF16 / COPER_PREC_TF32X3).  The tcgen05 kernels consume operands in
+/* Tensor-pipe operand preparation (COPER_PREC_BF16 / COPER_PREC_TF32X3) for the operands of the tf.matmul calls
+ * at models.py:70-73,412,433-437.  The tcgen05 kernels consume operands in
  * "prepared" form: a bf16 copy [rows, ldp] (ldp = cols rounded up to 8), or two fp32 planes (hi = tf32-rounded value,
  * lo = x - hi) of [rows, ldp] (ldp = cols rounded up to 4).  Prepare the entity table once per evaluation pass /
  * optimizer step and reuse it across calls with coper_score1n_fwd_prepared (coper_score1n_fwd prepares per call). */
@@ -154,7 +157,8 @@ int coper_prepare_operand(const float* src, int64_t rows, int cols, int64_t ld_s
 int coper_score1n_fwd_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
                                float* scores, int64_t ld_scores, int prec, coper_stream_t stream);
 
-/* C = op(A).op(B) on the tensor pipe (tcgen05, fp32 accumulate in TMEM); same layout flags as coper_sgemm.
+/* C = op(A).op(B) on the tensor pipe (tcgen05, fp32 accumulate in TMEM); same layout flags as coper_sgemm
+ * (tf.matmul, models.py:60, and its autodiff twins).
  * Operands are prepared into the workspace on every call (bf16 copy or tf32 hi/lo planes). */
 size_t coper_tc_gemm_workspace_bytes(int M, int N, int K, int prec);
 int coper_tc_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
@@ -217,7 +221,8 @@ int coper_csr_to_bits(const int32_t* rowptr, const int32_t* col, int B, int64_t 
                       uint32_t* bits, coper_stream_t stream);
 /* dense fp32 multi-hot [B, N] (the reference batch schema, models.py:144) -> bits (value == 1.0f) */
 int coper_dense_to_bits(const float* dense, int B, int64_t N, uint32_t* bits, coper_stream_t stream);
-/* ENTITY-MAJOR bit matrix used by the tensor-pipe scorers (one entity per epilogue thread):
+/* ENTITY-MAJOR bit matrix (the multi-hot e2_multi of models.py:144 / the filter of metrics.py:44-46, one bit per
+ * pair) used by the tensor-pipe scorers (one entity per epilogue thread):
  *   bits_t [ent_hi - ent_lo, ceil(B/32)]: bit (b & 31) of word (n, b >> 5) = 1 iff entity ent_lo + n is a positive /
  *   filtered tail of query b.  coper_bits_t_set ORs in the bits (ent[b], b) - used to add the gold entity to the
  *   filter set so the fused ranking kernel needs no per-element identity test. */
@@ -263,7 +268,8 @@ int coper_score1n_rank_prepared(const void* q_prep, const void* E_prep, const fl
  *   (sort by key, warp per segment, fixed summation order) -> deterministic. */
 size_t coper_segscatter_workspace_bytes(int M);
 /* M <= 4096 (one batch of gathers): sort-free variant that can also accumulate the per-row sums of the SQUARED source
- * rows into dst_sq (NULL = skip) - the IndexedSlices bookkeeping of the sparse AMSGrad rule / slice-wise global norm.
+ * rows into dst_sq (NULL = skip) - the IndexedSlices bookkeeping of the sparse AMSGrad rule (utils/amsgrad.py:161-189)
+ * and of tf.clip_by_global_norm's slice-wise norm (models.py:199).
  * Same summation order (index order) as coper_segscatter_add, which uses this path for small M. */
 int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int width, float* dst, float* dst_sq,
                             int64_t row_lo, int64_t row_hi, coper_stream_t stream);
