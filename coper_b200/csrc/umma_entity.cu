@@ -13,6 +13,7 @@
 // Three epilogues share the pipeline (umma_gemm.cuh):  ScoreEpiT (logits out), BceEpiT (loss + G + dbias partials),
 // RankEpiT (filtered-rank counts; logits never leave TMEM) plus DiagEpiT for the bit-identical gold logits.
 #include "umma_gemm.cuh"
+#include "bce_math.cuh"
 
 namespace coper {
 using namespace umma;
@@ -24,6 +25,20 @@ TcOperand tc_operand(const void* prep, int64_t rows, int cols, int prec);       
 int tc_gemm_store(int prec, bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, const GemmProblem& p,
                   bool split, const StoreEpi& epi, cudaStream_t st);
 int tc_plan_splits(int prec, GemmProblem p, bool split);
+// fused scorer + BCE + dq kernel (umma_fused.cu)
+bool umma_fused_ok(int B, int64_t Ns, int d, int prec);
+void umma_fused_plan(int B, int64_t Ns, int* QB, int* R);
+int umma_bce_dq_fused(const TcOperand& E, const TcOperand& Q, const float* bias, const uint32_t* bitsT, int B, int64_t Ns,
+                      int d, float pos, float neg, float inv_count, void* GT, int64_t ldGT, float* dq_part,
+                      float* dbias_part, double* loss_part, int* grid_out, cudaStream_t st);
+// COPER_FUSED_SCORER=0 selects the three-kernel schedule (A/B measurements); read once
+static bool fused_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("COPER_FUSED_SCORER");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 constexpr int kEntEpiWarps = 16;
 constexpr int kBceEpiWarps = 16;   // the BCE epilogue is MUFU / latency bound: 4 warps per scheduler
@@ -112,35 +127,16 @@ struct BceEpiT : EpiBase {
   __device__ __forceinline__ void tile_prefetch(const GemmProblem& p, const TileCoord&, int row, int col0) { rs.prefetch(p, row, col0); }
 
   // GENERAL: label bits and the column-valid mask vm are honoured; otherwise every element is a negative and all 32
-  // columns exist.  g[j] = sigmoid(s) - z' (unscaled), 0 for columns that do not exist.
+  // columns exist.  g[j] = (sigmoid(s) - z') * inv_count, 0 for columns that do not exist; gsum = sum_j g[j];
+  // lsum = sum_j of the per-element loss (tf.nn.sigmoid_cross_entropy_with_logits, unscaled).
   template <bool GENERAL>
-  __device__ __forceinline__ void body(const uint32_t (&r)[32], uint32_t w, uint32_t vm, float (&g)[32], float& lsum) const {
-    float ssum = 0.f, psum = 0.f, msum = 0.f, lgsum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float s = __uint_as_float(r[j]) + rs.bias_cur;
-      if (GENERAL) s = ((vm >> j) & 1u) ? s : 0.f;       // non-existent column: s = 0 (its ln 2 is removed below)
-      // tf.nn.sigmoid_cross_entropy_with_logits: max(s,0) - s z + log1p(exp(-|s|))
-      float e, u, rc, lg;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(s) * 1.4426950408889634f));
-      u = 1.0f + e;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(u));
-      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
-      const float sig = rc * ((s >= 0.f) ? 1.0f : e);
-      ssum += s;
-      msum += fmaxf(s, 0.f);
-      lgsum += lg;
-      if (GENERAL) {
-        const bool on = (w >> j) & 1u;
-        psum += on ? s : 0.f;
-        g[j] = ((vm >> j) & 1u) ? sig - (on ? pos : neg) : 0.f;
-      } else {
-        g[j] = sig - neg;
-      }
+  __device__ __forceinline__ void body(const uint32_t (&r)[32], uint32_t w, uint32_t vm, float (&g)[32], float& lsum,
+                                       float& gsum) const {
+    if (GENERAL) {
+      bce_chunk_general(r, rs.bias_cur, w, vm, pos, neg, inv_count, g, lsum, gsum);
+    } else {
+      bce_chunk_dense(r, rs.bias_cur, neg, inv_count, g, lsum, gsum);
     }
-    // sum of max(s,0) - s z + ln2 * lg2(1+e)   with z = neg + [positive] (pos - neg)
-    if (GENERAL) lgsum -= (float)(32 - __popc(vm));      // lg2(1 + e^0) = 1 for every masked column
-    lsum = fmaf(lgsum, 0.6931471805599453f, msum) - neg * ssum - (pos - neg) * psum;
   }
   __device__ __forceinline__ void chunk(const GemmProblem& p, const TileCoord&, int row, int col, const uint32_t (&r)[32],
                                         int ci) {
@@ -149,19 +145,13 @@ struct BceEpiT : EpiBase {
     const uint32_t vm = ncol >= 32 ? 0xFFFFFFFFu : ((1u << ncol) - 1u);
     const uint32_t w = rowok ? (rs.w_cur[ci] & vm) : 0u;
     float g[32];
-    float lsum;
-    if (ncol < 32 || __any_sync(0xffffffffu, w != 0u)) body<true>(r, w, vm, g, lsum);
-    else body<false>(r, w, vm, g, lsum);
+    float lsum, gsum;
+    if (ncol < 32 || __any_sync(0xffffffffu, w != 0u)) body<true>(r, w, vm, g, lsum, gsum);
+    else body<false>(r, w, vm, g, lsum, gsum);
     uint4 pk[4];
     if (rowok) {
       loss_acc += (double)lsum;
-      float rs_ = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        g[j] *= inv_count;
-        rs_ += g[j];
-      }
-      rsum += rs_;
+      rsum += gsum;
       if (PREC == PREC_BF16) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -515,10 +505,17 @@ static BceTcLayout bce_tc_layout(int B, int64_t Ns, int d, int prec) {
   L.splits = tc_plan_splits(prec, p, true);
   int bn = ent_block_n(d, prec, Ns, B);
   L.dbias_slabs = ((B + bn - 1) / bn) * (kBceEpiWarps / 4);
+  size_t dq_rows = (size_t)L.splits * B;
+  if (umma_fused_ok(B, Ns, d, prec)) {               // fused kernel: one [128, d] dq block per CTA, QB dbias slabs
+    int QB, R;
+    umma_fused_plan(B, Ns, &QB, &R);
+    if ((size_t)R * B > dq_rows) dq_rows = (size_t)R * B;
+    if (QB > L.dbias_slabs) L.dbias_slabs = QB;
+  }
   size_t o = 0;
   L.off_q = o; o = align_up(o + tc_prepared_bytes(B, d, prec), 256);
   L.off_E = o; o = align_up(o + tc_prepared_bytes(Ns, d, prec), 256);
-  L.off_dq = o; o = align_up(o + (size_t)L.splits * B * d * sizeof(float), 256);
+  L.off_dq = o; o = align_up(o + dq_rows * d * sizeof(float), 256);
   L.off_dbias = o; o = align_up(o + (size_t)L.dbias_slabs * Ns * sizeof(float), 256);
   L.off_loss = o; o = align_up(o + (size_t)148 * kBceEpiWarps * sizeof(double), 256);
   L.total = o;
@@ -569,6 +566,25 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
   if ((rc = tc_prepare(q, B, d, d, prec, qp, st))) return rc;
   if (!E_prepared && (rc = tc_prepare(E, Ns, d, d, prec, w + L.off_E, st))) return rc;
   TcOperand Qo = tc_operand(qp, B, d, prec), Eo = tc_operand(Ep, Ns, d, prec);
+  if (fused_enabled() && umma_fused_ok(B, Ns, d, prec)) {
+    // ---- single pass over E: scores -> loss, dbias, G (TMA store, entity-major) AND dq (G consumed from shared memory)
+    int QB, R, grid = 0;
+    umma_fused_plan(B, Ns, &QB, &R);
+    if ((rc = umma_bce_dq_fused(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT, dq_part, dbias_part,
+                                loss_part, &grid, st)))
+      return rc;
+    sum_doubles_kernel<<<1, 256, 0, st>>>(loss_part, grid * kBceEpiWarps, loss_sum);
+    if ((rc = check_launch())) return rc;
+    if ((rc = coper_reduce_partials(dbias_part, QB, Ns, 1.0f, 0, dbias, (coper_stream_t)st))) return rc;
+    if ((rc = coper_reduce_partials(dq_part, R, (int64_t)B * d, 1.0f, 0, dq, (coper_stream_t)st))) return rc;
+    // ---- dE = G^T . q from the entity-major G the kernel stored
+    TcOperand Go;
+    Go.main = G; Go.lo = nullptr; Go.pitch = (uint64_t)ldGT; Go.rows = (uint64_t)Ns; Go.cols = (uint64_t)B;
+    GemmProblem pe{};
+    pe.M = (int)Ns; pe.N = d; pe.K = B; pe.groups = 1; pe.groups_inner = 0;
+    StoreEpi epi = make_store_epi(dE, d, 0, 0);
+    return tc_gemm_store(prec, false, true, Go, Qo, pe, false, epi, st);
+  }
   // ---- pass 1: scores -> loss, G, dbias partials
   int grid = 0;
   auto run_bce = [&]() -> int {

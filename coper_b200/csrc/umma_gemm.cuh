@@ -126,98 +126,67 @@ __device__ __forceinline__ void cta_teardown(uint32_t tmem_base) {
 template <class Cfg>
 __device__ __forceinline__ void produce_stage(const SmemLayout<Cfg>& sm, int stage, const CUtensorMap* tA,
                                               const CUtensorMap* tAlo, const CUtensorMap* tB, const CUtensorMap* tBlo,
-                                              int a_mn0, int b_mn0, int a_k0, int b_k0) {
+                                              int a_mn0, int b_mn0, int a_k0, int b_k0, bool leader) {
+  // called warp-uniformly; only the leader lane issues (see elect_one in umma.cuh)
   uint64_t* bar = &sm.full[stage];
-  mbar_expect_tx(bar, Cfg::STAGE_BYTES);
+  if (leader) mbar_expect_tx(bar, Cfg::STAGE_BYTES);
 #pragma unroll
   for (int t = 0; t < Cfg::TERMS; ++t) {
     const CUtensorMap* ma = t ? tAlo : tA;
     const CUtensorMap* mb = t ? tBlo : tB;
     if (!Cfg::A_MN) {
-      tma_load_2d(sm.a_plane(stage, t), ma, bar, a_k0, a_mn0);
+      if (leader) tma_load_2d(sm.a_plane(stage, t), ma, bar, a_k0, a_mn0);
     } else {
 #pragma unroll
       for (int c = 0; c < BLOCK_M / Cfg::CHUNK; ++c)
-        tma_load_2d(sm.a_plane(stage, t) + c * (Cfg::BLOCK_K * 128), ma, bar, a_mn0 + c * Cfg::CHUNK, a_k0);
+        if (leader) tma_load_2d(sm.a_plane(stage, t) + c * (Cfg::BLOCK_K * 128), ma, bar, a_mn0 + c * Cfg::CHUNK, a_k0);
     }
     if (Cfg::RES_KB > 0) {
       // B is resident: nothing to stream
     } else if (!Cfg::B_MN) {
-      tma_load_2d(sm.b_plane(stage, t), mb, bar, b_k0, b_mn0);
+      if (leader) tma_load_2d(sm.b_plane(stage, t), mb, bar, b_k0, b_mn0);
     } else {
 #pragma unroll
       for (int c = 0; c < Cfg::BLOCK_N / Cfg::CHUNK; ++c)
-        tma_load_2d(sm.b_plane(stage, t) + c * (Cfg::BLOCK_K * 128), mb, bar, b_mn0 + c * Cfg::CHUNK, b_k0);
+        if (leader) tma_load_2d(sm.b_plane(stage, t) + c * (Cfg::BLOCK_K * 128), mb, bar, b_mn0 + c * Cfg::CHUNK, b_k0);
     }
   }
 }
 
-// MMA issuer: consume one stage (kvalid = number of valid k elements in it, <= BLOCK_K).
-// `first` = this is the first stage of the accumulation (overwrite instead of accumulate).
-template <class Cfg>
-__device__ __forceinline__ void issue_stage(const SmemLayout<Cfg>& sm, int stage, uint32_t tmem_d, int kvalid,
-                                            bool first) {
-  int nk = (kvalid + Cfg::UMMA_K - 1) / Cfg::UMMA_K;
-  uint32_t a_addr[2], b_addr[2];
-#pragma unroll
-  for (int t = 0; t < Cfg::TERMS; ++t) {
-    a_addr[t] = smem_u32(sm.a_plane(stage, t));
-    b_addr[t] = smem_u32(sm.b_plane(stage, t));
-  }
-  for (int k = 0; k < nk; ++k) {
-    // K-major: step 32 bytes inside the 128-byte swizzle row; MN-major: step UMMA_K k-rows of 128 bytes
-    uint32_t a_off = Cfg::A_MN ? k * Cfg::UMMA_K * 128 : k * 32;
-    uint32_t b_off = Cfg::B_MN ? k * Cfg::UMMA_K * 128 : k * 32;
-    uint64_t da[2], db[2];
-#pragma unroll
-    for (int t = 0; t < Cfg::TERMS; ++t) {
-      da[t] = Cfg::A_MN ? make_desc(a_addr[t] + a_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                        : make_desc_kmajor(a_addr[t] + a_off);
-      db[t] = Cfg::B_MN ? make_desc(b_addr[t] + b_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                        : make_desc_kmajor(b_addr[t] + b_off);
-    }
-    uint32_t acc = (first && k == 0) ? 0u : 1u;
-    if (Cfg::PREC == PREC_BF16) {
-      mma_bf16(tmem_d, da[0], db[0], Cfg::IDESC, acc);
-    } else {
-      mma_tf32(tmem_d, da[1], db[0], Cfg::IDESC, acc);   // lo * hi
-      mma_tf32(tmem_d, da[0], db[1], Cfg::IDESC, 1u);    // hi * lo
-      mma_tf32(tmem_d, da[0], db[0], Cfg::IDESC, 1u);    // hi * hi
-    }
-  }
-}
-
-// same as issue_stage but with a run-time instruction descriptor (N of the last tile may be < BLOCK_N)
+// same as issue_stage but with a run-time instruction descriptor (N of the last tile may be < BLOCK_N).
+// Called warp-uniformly; only the leader lane issues.  The descriptors of the stage bases are built once, a k-step only
+// adds to the start-address field (>> 4 units; shared-memory addresses are < 256 KB, so the 14-bit field cannot carry).
 template <class Cfg>
 __device__ __forceinline__ void issue_stage_rt(const SmemLayout<Cfg>& sm, int stage, uint32_t tmem_d, int kvalid,
-                                               bool first, uint32_t idesc, int kb_res = 0) {
-  int nk = (kvalid + Cfg::UMMA_K - 1) / Cfg::UMMA_K;
-  uint32_t a_addr[2], b_addr[2];
+                                               bool first, uint32_t idesc, int kb_res, bool leader) {
+  const int nk = (kvalid + Cfg::UMMA_K - 1) / Cfg::UMMA_K;
+  uint64_t da[2], db[2];
 #pragma unroll
   for (int t = 0; t < Cfg::TERMS; ++t) {
-    a_addr[t] = smem_u32(sm.a_plane(stage, t));
-    b_addr[t] = smem_u32(Cfg::RES_KB > 0 ? sm.res_plane(kb_res, t) : sm.b_plane(stage, t));
+    const uint32_t a_addr = smem_u32(sm.a_plane(stage, t));
+    const uint32_t b_addr = smem_u32(Cfg::RES_KB > 0 ? sm.res_plane(kb_res, t) : sm.b_plane(stage, t));
+    da[t] = Cfg::A_MN ? make_desc(a_addr, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT) : make_desc_kmajor(a_addr);
+    db[t] = Cfg::B_MN ? make_desc(b_addr, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT) : make_desc_kmajor(b_addr);
   }
-  for (int k = 0; k < nk; ++k) {
-    uint32_t a_off = Cfg::A_MN ? k * Cfg::UMMA_K * 128 : k * 32;
-    uint32_t b_off = Cfg::B_MN ? k * Cfg::UMMA_K * 128 : k * 32;
-    uint64_t da[2], db[2];
+  // K-major: step 32 bytes inside the 128-byte swizzle row; MN-major: step UMMA_K k-rows of 128 bytes
+  constexpr uint64_t a_step = (Cfg::A_MN ? Cfg::UMMA_K * 128 : 32) >> 4, b_step = (Cfg::B_MN ? Cfg::UMMA_K * 128 : 32) >> 4;
+  constexpr int NK_MAX = Cfg::BLOCK_K / Cfg::UMMA_K;
+  if (leader) {
 #pragma unroll
-    for (int t = 0; t < Cfg::TERMS; ++t) {
-      da[t] = Cfg::A_MN ? make_desc(a_addr[t] + a_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                        : make_desc_kmajor(a_addr[t] + a_off);
-      db[t] = Cfg::B_MN ? make_desc(b_addr[t] + b_off, Cfg::BLOCK_K * 128, Cfg::MN_SBO, Cfg::MN_LAYOUT)
-                        : make_desc_kmajor(b_addr[t] + b_off);
-    }
-    uint32_t acc = (first && k == 0) ? 0u : 1u;
-    if (Cfg::PREC == PREC_BF16) {
-      mma_bf16(tmem_d, da[0], db[0], idesc, acc);
-    } else {
-      mma_tf32(tmem_d, da[1], db[0], idesc, acc);   // lo * hi
-      mma_tf32(tmem_d, da[0], db[1], idesc, 1u);    // hi * lo
-      mma_tf32(tmem_d, da[0], db[0], idesc, 1u);    // hi * hi
+    for (int k = 0; k < NK_MAX; ++k) {
+      if (k < nk) {
+        const uint32_t acc = (first && k == 0) ? 0u : 1u;
+        if (Cfg::PREC == PREC_BF16) {
+          mma_bf16(tmem_d, da[0] + k * a_step, db[0] + k * b_step, idesc, acc);
+        } else {
+          mma_tf32(tmem_d, da[1] + k * a_step, db[0] + k * b_step, idesc, acc);   // lo * hi
+          mma_tf32(tmem_d, da[0] + k * a_step, db[1] + k * b_step, idesc, 1u);    // hi * lo
+          mma_tf32(tmem_d, da[0] + k * a_step, db[0] + k * b_step, idesc, 1u);    // hi * hi
+        }
+      }
     }
   }
+  __syncwarp();
 }
 
 struct PipeState {
@@ -311,89 +280,95 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   SmemLayout<Cfg> sm(smem_raw);
   uint32_t tmem_base = cta_setup<Cfg>(sm);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const long long supers = gemm_supers(p);
   const int g_loop = p.groups_inner ? p.groups : 1;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: the loop is warp-uniform, only the leader lane issues
+    const bool leader = elect_one();
+    if (leader) {
       tma_prefetch_desc(&tA);
       tma_prefetch_desc(&tB);
-      PipeState ps;
-      int res_nblk = -1;
-      for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
-        for (int g = 0; g < g_loop; ++g) {
-          TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
-          int a_mn0 = t.m_blk * BLOCK_M + t.group * p.a_group_mn;
-          int b_mn0 = t.n_blk * Cfg::BLOCK_N + t.group * p.b_group_mn;
-          if (Cfg::RES_KB > 0 && t.n_blk != res_nblk) {
-            // new n-block: wait until every MMA that reads the old resident B has completed (all stages drained),
-            // then load the whole K extent of the new B tile
-            PipeState q = ps;
-            for (int i = 0; i < Cfg::STAGES; ++i) {
-              mbar_wait(&sm.empty[q.stage], q.phase ^ 1);
-              q.template advance<Cfg::STAGES>();
-            }
-            const int kbn = t.kb1 - t.kb0;
-            mbar_expect_tx(sm.bfull, (uint32_t)(kbn * Cfg::TERMS * Cfg::B_BYTES));
-            for (int kb = t.kb0; kb < t.kb1; ++kb)
+    }
+    PipeState ps;
+    int res_nblk = -1;
+    for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
+      for (int g = 0; g < g_loop; ++g) {
+        TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
+        int a_mn0 = t.m_blk * BLOCK_M + t.group * p.a_group_mn;
+        int b_mn0 = t.n_blk * Cfg::BLOCK_N + t.group * p.b_group_mn;
+        if (Cfg::RES_KB > 0 && t.n_blk != res_nblk) {
+          // new n-block: wait until every MMA that reads the old resident B has completed (all stages drained),
+          // then load the whole K extent of the new B tile
+          PipeState q = ps;
+          for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_wait(&sm.empty[q.stage], q.phase ^ 1);
+            q.template advance<Cfg::STAGES>();
+          }
+          const int kbn = t.kb1 - t.kb0;
+          if (leader) mbar_expect_tx(sm.bfull, (uint32_t)(kbn * Cfg::TERMS * Cfg::B_BYTES));
+          for (int kb = t.kb0; kb < t.kb1; ++kb)
 #pragma unroll
-              for (int tm = 0; tm < Cfg::TERMS; ++tm) {
-                if (!Cfg::B_MN) {
+            for (int tm = 0; tm < Cfg::TERMS; ++tm) {
+              if (!Cfg::B_MN) {
+                if (leader)
                   tma_load_2d(sm.res_plane(kb - t.kb0, tm), tm ? &tBlo : &tB, sm.bfull, kb * Cfg::BLOCK_K, b_mn0);
-                } else {
+              } else {
 #pragma unroll
-                  for (int c = 0; c < Cfg::BLOCK_N / Cfg::CHUNK; ++c)
+                for (int c = 0; c < Cfg::BLOCK_N / Cfg::CHUNK; ++c)
+                  if (leader)
                     tma_load_2d(sm.res_plane(kb - t.kb0, tm) + c * (Cfg::BLOCK_K * 128), tm ? &tBlo : &tB, sm.bfull,
                                 b_mn0 + c * Cfg::CHUNK, kb * Cfg::BLOCK_K);
-                }
               }
-            res_nblk = t.n_blk;
-          }
-          for (int kb = t.kb0; kb < t.kb1; ++kb) {
-            mbar_wait(&sm.empty[ps.stage], ps.phase ^ 1);
-            produce_stage<Cfg>(sm, ps.stage, &tA, &tAlo, &tB, &tBlo, a_mn0, b_mn0,
-                               kb * Cfg::BLOCK_K + t.group * p.a_group_k, kb * Cfg::BLOCK_K + t.group * p.b_group_k);
-            ps.template advance<Cfg::STAGES>();
-          }
+            }
+          res_nblk = t.n_blk;
+        }
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&sm.empty[ps.stage], ps.phase ^ 1);
+          produce_stage<Cfg>(sm, ps.stage, &tA, &tAlo, &tB, &tBlo, a_mn0, b_mn0,
+                             kb * Cfg::BLOCK_K + t.group * p.a_group_k, kb * Cfg::BLOCK_K + t.group * p.b_group_k, leader);
+          ps.template advance<Cfg::STAGES>();
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      PipeState ps;
-      int as = 0;
-      uint32_t aphase = 0;
-      int res_nblk = -1;
-      uint32_t bphase = 0;
-      for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
-        for (int g = 0; g < g_loop; ++g) {
-          TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
-          if (Cfg::RES_KB > 0 && t.n_blk != res_nblk) {
-            mbar_wait(sm.bfull, bphase);
-            bphase ^= 1;
-            res_nblk = t.n_blk;
-          }
-          int n_rem = p.N - t.n_blk * Cfg::BLOCK_N;
-          int n_eff = min(Cfg::BLOCK_N, (n_rem + 15) & ~15);
-          uint32_t idesc = make_idesc(Cfg::FMT, BLOCK_M, (uint32_t)n_eff, Cfg::A_MN ? 1u : 0u, Cfg::B_MN ? 1u : 0u);
-          const int chain = Cfg::PROMOTE_KB > 0 ? Cfg::PROMOTE_KB : (t.kb1 - t.kb0);
-          for (int kc = t.kb0; kc < t.kb1; kc += chain) {
-            int kce = min(t.kb1, kc + chain);
-            mbar_wait(&sm.tempty[as], aphase ^ 1);
+    // MMA issuer: warp-uniform loop, the leader lane issues tcgen05.mma / tcgen05.commit
+    const bool leader = elect_one();
+    PipeState ps;
+    int as = 0;
+    uint32_t aphase = 0;
+    int res_nblk = -1;
+    uint32_t bphase = 0;
+    for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
+      for (int g = 0; g < g_loop; ++g) {
+        TileCoord t = gemm_decode(p, s, g, Cfg::BLOCK_K);
+        if (Cfg::RES_KB > 0 && t.n_blk != res_nblk) {
+          mbar_wait(sm.bfull, bphase);
+          bphase ^= 1;
+          res_nblk = t.n_blk;
+        }
+        int n_rem = p.N - t.n_blk * Cfg::BLOCK_N;
+        int n_eff = min(Cfg::BLOCK_N, (n_rem + 15) & ~15);
+        uint32_t idesc = make_idesc(Cfg::FMT, BLOCK_M, (uint32_t)n_eff, Cfg::A_MN ? 1u : 0u, Cfg::B_MN ? 1u : 0u);
+        const int chain = Cfg::PROMOTE_KB > 0 ? Cfg::PROMOTE_KB : (t.kb1 - t.kb0);
+        for (int kc = t.kb0; kc < t.kb1; kc += chain) {
+          int kce = min(t.kb1, kc + chain);
+          mbar_wait(&sm.tempty[as], aphase ^ 1);
+          tc_fence_after();
+          for (int kb = kc; kb < kce; ++kb) {
+            mbar_wait(&sm.full[ps.stage], ps.phase);
             tc_fence_after();
-            for (int kb = kc; kb < kce; ++kb) {
-              mbar_wait(&sm.full[ps.stage], ps.phase);
-              tc_fence_after();
-              int kvalid = min(Cfg::BLOCK_K, p.K - kb * Cfg::BLOCK_K);
-              issue_stage_rt<Cfg>(sm, ps.stage, tmem_base + as * Cfg::BLOCK_N, kvalid, kb == kc, idesc, kb - t.kb0);
-              mma_commit(&sm.empty[ps.stage]);
-              ps.template advance<Cfg::STAGES>();
-            }
-            mma_commit(&sm.tfull[as]);
-            as ^= 1;
-            if (as == 0) aphase ^= 1;
+            int kvalid = min(Cfg::BLOCK_K, p.K - kb * Cfg::BLOCK_K);
+            issue_stage_rt<Cfg>(sm, ps.stage, tmem_base + as * Cfg::BLOCK_N, kvalid, kb == kc, idesc, kb - t.kb0, leader);
+            if (leader) mma_commit(&sm.empty[ps.stage]);
+            ps.template advance<Cfg::STAGES>();
           }
+          if (leader) mma_commit(&sm.tfull[as]);
+          __syncwarp();
+          as ^= 1;
+          if (as == 0) aphase ^= 1;
         }
       }
     }
