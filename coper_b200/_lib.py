@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcoper_sm100.so")
 
-PREC = {"fp32": 0, "bf16": 1, "tf32x3": 2}
+PREC = {"fp32": 0, "bf16": 1, "tf32x3": 2, "fp16x3": 3}
 
 vp, i32, i64, u64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 

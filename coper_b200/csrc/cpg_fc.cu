@@ -282,8 +282,14 @@ int coper_sgemm(int transA, int transB, int M, int N, int K, const float* A, int
   return check_launch();
 }
 
+// The tcgen05 kernels cover F % 32 == 0 and d <= 256 (every shipped configuration); any other shape runs on the
+// exact-fp32 CUDA-core engine below whatever `prec` asks for (more accurate, slower - never a host fallback).
+static inline bool cpg_on_tensor_pipe(int F, int d, int prec) {
+  return (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3 || prec == COPER_PREC_FP16X3) && F % 32 == 0 && d <= 256;
+}
+
 size_t coper_cpg_fc_fwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
-  if (prec != COPER_PREC_FP32) return umma_cpg_fwd_workspace_bytes(B, dc, F, d, prec);
+  if (cpg_on_tensor_pipe(F, d, prec)) return umma_cpg_fwd_workspace_bytes(B, dc, F, d, prec);
   return cpg_fwd_layout(B, dc, F, d).total;
 }
 
@@ -297,10 +303,10 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
   float* part = nullptr;
   int n_slabs = 0;
   int rc;
-  if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3) {
+  if (cpg_on_tensor_pipe(F, d, prec)) {
     if ((rc = umma_cpg_fwd_partials(c, f, P, P_prepared, B, dc, F, d, workspace, workspace_bytes, prec, st, &part, &n_slabs)))
       return rc;
-  } else if (prec == COPER_PREC_FP32) {
+  } else if (prec >= COPER_PREC_FP32 && prec <= COPER_PREC_FP16X3) {
     CpgLayout L = cpg_fwd_layout(B, dc, F, d);
     if (workspace_bytes < L.total) return COPER_ERR_WORKSPACE;
     part = static_cast<float*>(workspace);
@@ -319,7 +325,7 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
 }
 
 size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
-  if (prec != COPER_PREC_FP32) return umma_cpg_bwd_workspace_bytes(B, dc, F, d, prec);
+  if (cpg_on_tensor_pipe(F, d, prec)) return umma_cpg_bwd_workspace_bytes(B, dc, F, d, prec);
   return align_up((size_t)ceil_div(F, BN) * B * dc * sizeof(float), 256);
 }
 
@@ -332,11 +338,11 @@ int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void*
   if (workspace_bytes < coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, prec)) return COPER_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   int rc;
-  if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3) {
+  if (cpg_on_tensor_pipe(F, d, prec)) {
     if ((rc = umma_cpg_bwd(c, f, P, P_prepared, dy, B, dc, F, d, dP, df, dc_out, workspace, workspace_bytes, prec,
                            reuse_fwd_operands, st)))
       return rc;
-  } else if (prec == COPER_PREC_FP32) {
+  } else if (prec >= COPER_PREC_FP32 && prec <= COPER_PREC_FP16X3) {
     float* dc_part = static_cast<float*>(workspace);
     int ftiles = ceil_div(F, BN);
     cpg_bwd_T_kernel<<<dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st>>>(c, f, P, dy, B, dc, F, d, df, dc_part);

@@ -246,7 +246,7 @@ int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prep
                               void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
   COPER_CHECK_ARG(q && E && bias && label_bits && loss_sum && Gv && dq && dE && dbias && workspace);
   COPER_CHECK_ARG(B > 0 && Ns > 0 && d > 0 && ldG >= Ns);
-  if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3)
+  if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3 || prec == COPER_PREC_FP16X3)
     return umma_score1n_bce_fwd_bwd(q, E, E_prepared, bias, label_bits, B, Ns, d, pos_target, neg_target, inv_count, loss_sum, Gv,
                                     ldG, dq, dE, dbias, workspace, workspace_bytes, prec, as_stream(stream));
   if (prec != COPER_PREC_FP32) return COPER_ERR_UNSUPPORTED;

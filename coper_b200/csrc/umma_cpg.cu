@@ -11,6 +11,7 @@
 // Backward:
 //   T_k = dy . P[k]^T  (per group, never stored)   df = sum_k c[:,k] * T_k     dc[:,k] = rowsum(f * T_k)
 //   dP[k] = f^T . (c[:,k] * dy)                     (grouped GEMM over k with a pre-scaled dy operand)
+#include <cuda_fp16.h>
 #include "umma_gemm.cuh"
 
 namespace coper {
@@ -20,6 +21,7 @@ size_t tc_prepared_bytes(int64_t rows, int cols, int prec);                     
 int tc_prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst, cudaStream_t st);
 int64_t tc_prepared_ld(int cols, int prec);
 TcOperand tc_operand(const void* prep, int64_t rows, int cols, int prec);       // umma_gemm.cu
+void* tc_fp16x3_trailer(const void* prep, int64_t rows, int cols);
 int tc_gemm_store(int prec, bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, const GemmProblem& p,
                   bool split, const StoreEpi& epi, cudaStream_t st);
 
@@ -51,8 +53,10 @@ struct CpgFwdEpi : EpiBase {
 };
 
 // N = d <= 256 in one tile.  tf32x3: chains cut every 4 k-blocks (see umma_gemm.cuh)
+// fp16x3: 64 k-elements per k-block (two fp16 planes) -> the same chain length is 2 k-blocks
 template <int PREC>
-using CpgFwdCfg = GemmCfg<PREC, 256, (PREC == PREC_BF16 ? 4 : 2), 8, false, true, (PREC == PREC_BF16 ? 0 : 4)>;
+using CpgFwdCfg = GemmCfg<PREC, 256, (PREC == PREC_BF16 ? 4 : 2), 8, false, true,
+                          (PREC == PREC_BF16 ? 0 : PREC == PREC_FP16X3 ? 2 : 4)>;
 
 struct CpgFwdPlan {
   GemmProblem p;
@@ -64,6 +68,7 @@ static CpgFwdPlan cpg_fwd_plan(int B, int dc, int F, int d, int prec) {
   p.M = B; p.N = d; p.K = F; p.groups = dc; p.groups_inner = 1;
   p.a_group_mn = 0; p.a_group_k = 0; p.b_group_mn = 0; p.b_group_k = F;
   if (prec == COPER_PREC_BF16) plan_gemm<CpgFwdCfg<PREC_BF16>>(p, true);
+  else if (prec == COPER_PREC_FP16X3) plan_gemm<CpgFwdCfg<PREC_FP16X3>>(p, true);
   else plan_gemm<CpgFwdCfg<PREC_TF32X3>>(p, true);
   L.p = p;
   size_t o = 0;
@@ -129,11 +134,37 @@ constexpr int kBwdTBlockN = 128;
 template <int PREC>
 using CpgBwdTCfg = GemmCfg<PREC, kBwdTBlockN, (PREC == PREC_BF16 ? 4 : 3), kBwdTEpiWarps, false, false, 0>;
 
+// fp16x3: max |dy[b,j] * c[b,g]| = max_b (max_j |dy[b,:]| * max_g |c[b,:]|); one warp per row, result (float bits) in
+// trailer[1] (zeroed before the launch)
+__global__ void absmax_scaled_kernel(const float* __restrict__ dy, const float* __restrict__ c, int B, int d, int dc,
+                                     uint32_t* __restrict__ trailer) {
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.x * (blockDim.x >> 5)) {
+    float my = 0.f, mc = 0.f;
+    for (int j = lane; j < d; j += 32) my = fmaxf(my, fabsf(__ldg(dy + (int64_t)b * d + j)));
+    for (int g = lane; g < dc; g += 32) mc = fmaxf(mc, fabsf(__ldg(c + (int64_t)b * dc + g)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, o));
+      mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    }
+    const float m = my * mc;
+    if (lane == 0 && m > 0.f) atomicMax(trailer + 1, __float_as_uint(m));
+  }
+}
 // dyc[(g*B + b), j] = dy[b,j] * c[b,g] in prepared operand form
 __global__ void prepare_scaled_kernel(const float* __restrict__ dy, const float* __restrict__ c, int B, int d, int dc,
-                                      int64_t ldp, int prec, void* __restrict__ dst) {
+                                      int64_t ldp, int prec, void* __restrict__ dst, uint32_t* __restrict__ trailer) {
   int64_t n = (int64_t)dc * B * ldp;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float sc = 1.0f;
+  if (prec == COPER_PREC_FP16X3) {                      // same exponent rule as coper_prepare_operand (umma_score.cu)
+    const float m = __uint_as_float(trailer[1]);
+    int ex = (m > 0.f && isfinite(m)) ? 10 - ilogbf(m) : 0;
+    ex = max(-100, min(100, ex));
+    if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(trailer)[0] = ex;
+    sc = exp2f((float)ex);
+  }
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
     int64_t r = e / ldp;
     int j = (int)(e - r * ldp);
@@ -141,6 +172,11 @@ __global__ void prepare_scaled_kernel(const float* __restrict__ dy, const float*
     float x = j < d ? __ldg(dy + (int64_t)b * d + j) * __ldg(c + (int64_t)b * dc + g) : 0.f;
     if (prec == COPER_PREC_BF16) {
       static_cast<__nv_bfloat16*>(dst)[e] = __float2bfloat16_rn(x);
+    } else if (prec == COPER_PREC_FP16X3) {
+      const float xs = x * sc;
+      const __half h = __float2half_rn(xs);
+      static_cast<__half*>(dst)[e] = h;
+      static_cast<__half*>(dst)[n + e] = __float2half_rn(xs - __half2float(h));
     } else {
       uint32_t h;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
@@ -193,6 +229,7 @@ int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, const 
   epi.c = c; epi.dc = dc; epi.out = out; epi.ld = d; epi.split_stride = (long long)B * d;
   TcOperand A = tc_operand(fp, B, F, prec), Bo = tc_operand(Pp, (int64_t)dc * F, d, prec);
   if (prec == COPER_PREC_BF16) rc = launch_gemm<CpgFwdCfg<PREC_BF16>, CpgFwdEpi>(A, Bo, L.p, epi, st);
+  else if (prec == COPER_PREC_FP16X3) rc = launch_gemm<CpgFwdCfg<PREC_FP16X3>, CpgFwdEpi>(A, Bo, L.p, epi, st);
   else rc = launch_gemm<CpgFwdCfg<PREC_TF32X3>, CpgFwdEpi>(A, Bo, L.p, epi, st);
   *slabs = out;
   *n_slabs = L.p.splits;
@@ -223,8 +260,15 @@ int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_p
   {
     int64_t ldp = tc_prepared_ld(d, prec);
     int64_t n = (int64_t)dc * B * ldp;
-    int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-    prepare_scaled_kernel<<<grid, 256, 0, st>>>(dy, c, B, d, dc, ldp, prec, dycp);
+    int grid = (int)((n + 255) / 256 < sm_count() * 8 ? (n + 255) / 256 : sm_count() * 8);
+    uint32_t* trailer = nullptr;
+    if (prec == COPER_PREC_FP16X3) {
+      trailer = static_cast<uint32_t*>(tc_fp16x3_trailer(dycp, (int64_t)dc * B, d));
+      if ((rc = check_cuda(cudaMemsetAsync(trailer, 0, 8, st)))) return rc;
+      absmax_scaled_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, c, B, d, dc, trailer);
+      if ((rc = check_launch())) return rc;
+    }
+    prepare_scaled_kernel<<<grid, 256, 0, st>>>(dy, c, B, d, dc, ldp, prec, dycp, trailer);
     if ((rc = check_launch())) return rc;
   }
   // ---- T kernel: df, dc partials
@@ -238,6 +282,9 @@ int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_p
     if (prec == COPER_PREC_BF16) {
       plan_gemm<CpgBwdTCfg<PREC_BF16>>(p, false);
       rc = launch_gemm<CpgBwdTCfg<PREC_BF16>, CpgBwdTEpi>(A, Bo, p, epi, st);
+    } else if (prec == COPER_PREC_FP16X3) {
+      plan_gemm<CpgBwdTCfg<PREC_FP16X3>>(p, false);
+      rc = launch_gemm<CpgBwdTCfg<PREC_FP16X3>, CpgBwdTEpi>(A, Bo, p, epi, st);
     } else {
       plan_gemm<CpgBwdTCfg<PREC_TF32X3>>(p, false);
       rc = launch_gemm<CpgBwdTCfg<PREC_TF32X3>, CpgBwdTEpi>(A, Bo, p, epi, st);

@@ -12,6 +12,7 @@
 //
 // Three epilogues share the pipeline (umma_gemm.cuh):  ScoreEpiT (logits out), BceEpiT (loss + G + dbias partials),
 // RankEpiT (filtered-rank counts; logits never leave TMEM) plus DiagEpiT for the bit-identical gold logits.
+#include <cuda_fp16.h>
 #include "umma_gemm.cuh"
 #include "bce_math.cuh"
 
@@ -22,6 +23,7 @@ size_t tc_prepared_bytes(int64_t rows, int cols, int prec);                     
 int tc_prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst, cudaStream_t st);
 int64_t tc_prepared_ld(int cols, int prec);
 TcOperand tc_operand(const void* prep, int64_t rows, int cols, int prec);       // umma_gemm.cu
+void* tc_fp16x3_trailer(const void* prep, int64_t rows, int cols);
 int tc_gemm_store(int prec, bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, const GemmProblem& p,
                   bool split, const StoreEpi& epi, cudaStream_t st);
 int tc_plan_splits(int prec, GemmProblem p, bool split);
@@ -113,8 +115,9 @@ struct ScoreEpiT : EpiBase {
 template <int PREC, int NCH>
 struct BceEpiT : EpiBase {
   RowState<NCH> rs;
-  float pos, neg, inv_count;
-  void* GT;                 // bf16 [M, ldGT]  |  fp32 hi plane [M, ldGT] followed by the lo plane
+  float pos, neg, inv_count;  // inv_count: factor applied to g (fp16x3: 2^10, the true 1/count is applied downstream)
+  float rsum_scale;           // dbias = rsum_scale * sum g  (1 unless fp16x3)
+  void* GT;                 // bf16 [M, ldGT] | fp16 hi plane [M, ldGT] + lo plane | fp32 hi plane [N, ldGT] + lo plane
   int64_t ldGT;             // >= N, multiple of 8 (bf16) / 4 (tf32)
   float* dbias_part;        // [n_tiles * col_groups][M]
   double* loss_part;        // [grid * epi_warps]
@@ -149,10 +152,28 @@ struct BceEpiT : EpiBase {
     if (ncol < 32 || __any_sync(0xffffffffu, w != 0u)) body<true>(r, w, vm, g, lsum, gsum);
     else body<false>(r, w, vm, g, lsum, gsum);
     uint4 pk[4];
+    uint4 pk2[4];
     if (rowok) {
       loss_acc += (double)lsum;
-      rsum += gsum;
-      if (PREC == PREC_BF16) {
+      rsum += gsum * rsum_scale;
+      if (PREC == PREC_FP16X3) {
+        // (sigmoid - z') * 2^10 as fp16 hi / lo planes, entity-major like the bf16 path
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float a = g[8 * v + 2 * k], b = g[8 * v + 2 * k + 1];
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+            hw[k] = *reinterpret_cast<const uint32_t*>(&h);
+            lw[k] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          pk[v] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          pk2[v] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      } else if (PREC == PREC_BF16) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           __nv_bfloat162 t0 = __floats2bfloat162_rn(g[8 * v], g[8 * v + 1]);
@@ -162,7 +183,7 @@ struct BceEpiT : EpiBase {
           pk[v].x = *reinterpret_cast<uint32_t*>(&t0); pk[v].y = *reinterpret_cast<uint32_t*>(&t1);
           pk[v].z = *reinterpret_cast<uint32_t*>(&t2); pk[v].w = *reinterpret_cast<uint32_t*>(&t3);
         }
-      } else {
+      } else if (PREC == PREC_TF32X3) {
         // tf32x3: 8 bytes per element in two planes - QUERY-major G[b, n] so that every store instruction of the warp
         // covers 32 consecutive entities (128 B); ldGT is the [N, ld] pitch here
         float* hi = static_cast<float*>(GT) + (int64_t)col * ldGT + row;
@@ -180,26 +201,29 @@ struct BceEpiT : EpiBase {
         }
       }
     }
-    if (PREC == PREC_BF16) {
-      // stage the warp's [32 entities x 32 queries] bf16 block (64 B per row) through shared memory so that every
+    if (PREC == PREC_BF16 || PREC == PREC_FP16X3) {
+      // stage the warp's [32 entities x 32 queries] 16-bit block (64 B per row) through shared memory so that every
       // store instruction writes 8 rows x 64 contiguous bytes (full sectors) instead of 32 rows x 16 bytes
       __shared__ uint4 stage_g[kBceEpiWarps][128];
       uint4* st = stage_g[(threadIdx.x >> 5) - 4];
       const int lane = threadIdx.x & 31;
-#pragma unroll
-      for (int v = 0; v < 4; ++v) st[lane * 4 + (v ^ ((lane >> 1) & 3))] = pk[v];
-      __syncwarp();
       const int row0 = row - lane;
-      uint4* o0 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(GT) + (int64_t)row0 * ldGT + col);
       const int64_t ld16 = ldGT / 8;                    // row pitch in 16-byte units
       const int gq = lane & 3;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int rr = 8 * k + (lane >> 2);
-        const uint4 x = st[rr * 4 + (gq ^ ((rr >> 1) & 3))];
-        if (row0 + rr < p.M) o0[(int64_t)rr * ld16 + gq] = x;   // the pitch is padded to 32 queries: whole chunks writable
+      for (int plane = 0; plane < (PREC == PREC_FP16X3 ? 2 : 1); ++plane) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) st[lane * 4 + (v ^ ((lane >> 1) & 3))] = plane ? pk2[v] : pk[v];
+        __syncwarp();
+        uint4* o0 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(GT) + ((int64_t)plane * p.M + row0) * ldGT + col);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rr = 8 * k + (lane >> 2);
+          const uint4 x = st[rr * 4 + (gq ^ ((rr >> 1) & 3))];
+          if (row0 + rr < p.M) o0[(int64_t)rr * ld16 + gq] = x;   // the pitch is padded to 32 queries: whole chunks writable
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   __device__ __forceinline__ void tile_done(const GemmProblem& p, const TileCoord& t, int row, int col_group, int col_groups) {
@@ -346,8 +370,10 @@ struct DiagEpiT : EpiBase {
 
 // rows e2[b] - ent_lo of a prepared operand [Ns, ldp] -> [B, ldp] (zero rows when not owned); 16-byte vectors
 __global__ void gather_prepared_kernel(const uint4* __restrict__ src, int64_t Ns, int vec_per_row, int planes,
-                                       const int64_t* __restrict__ e2, int64_t ent_lo, int B, uint4* __restrict__ dst) {
+                                       const int64_t* __restrict__ e2, int64_t ent_lo, int B, uint4* __restrict__ dst,
+                                       const int* __restrict__ src_exp, int* __restrict__ dst_exp) {
   int b = blockIdx.x;
+  if (src_exp && b == 0 && threadIdx.x == 0) *dst_exp = *src_exp;      // fp16x3: the gathered rows keep E's exponent
   int64_t l = e2[b] - ent_lo;
   bool owned = l >= 0 && l < Ns;
   for (int pl = 0; pl < planes; ++pl) {
@@ -377,6 +403,8 @@ template <>
 struct EntSel<PREC_BF16, false> { using Cfg = GemmCfg<PREC_BF16, 128, 6, kEntEpiWarps, false, false, 0, 0>; };
 template <>
 struct EntSel<PREC_TF32X3, false> { using Cfg = GemmCfg<PREC_TF32X3, 128, 3, kEntEpiWarps, false, false, 0, 0>; };
+template <>
+struct EntSel<PREC_FP16X3, false> { using Cfg = GemmCfg<PREC_FP16X3, 128, 3, kEntEpiWarps, false, false, 0, 0>; };
 // the BCE epilogue is MUFU / latency bound: 16 epilogue warps (4 per scheduler) hide the TMEM-load and SFU latencies
 template <int PREC, bool RES>
 struct BceSel;
@@ -386,6 +414,8 @@ template <>
 struct BceSel<PREC_BF16, false> { using Cfg = GemmCfg<PREC_BF16, 128, 5, kBceEpiWarps, false, false, 0, 0>; };
 template <>
 struct BceSel<PREC_TF32X3, false> { using Cfg = GemmCfg<PREC_TF32X3, 128, 3, kBceEpiWarps, false, false, 0, 0>; };
+template <>
+struct BceSel<PREC_FP16X3, false> { using Cfg = GemmCfg<PREC_FP16X3, 128, 3, kBceEpiWarps, false, false, 0, 0>; };
 template <class Cfg>
 constexpr int ent_nch() { return Cfg::BLOCK_N / (Cfg::EPI_WARPS / 4) / 32; }
 // the resident-query-block configuration pays a 128 KB fill per CTA: worth it once a CTA processes >= 8 tiles
@@ -393,7 +423,7 @@ constexpr int ent_nch() { return Cfg::BLOCK_N / (Cfg::EPI_WARPS / 4) / 32; }
 static inline bool ent_resident(int d, int prec, int64_t Ns, int B) {
   if (prec != COPER_PREC_BF16 || d > 256) return false;
   const int64_t tiles = ((Ns + BLOCK_M - 1) / BLOCK_M) * ((B + 255) / 256);
-  return tiles >= 8 * 148;
+  return tiles >= 8 * (int64_t)sm_count();
 }
 static inline int ent_block_n(int d, int prec, int64_t Ns, int B) { return ent_resident(d, prec, Ns, B) ? 256 : 128; }
 
@@ -411,7 +441,8 @@ static GemmProblem ent_problem(int B, int64_t Ns, int d, int block_n) {
 // grid <= m_tiles a CTA changes its query block at most n_tiles - 1 times
 static int ent_grid(const GemmProblem& p) {
   long long supers = (long long)p.m_tiles * p.n_tiles;
-  int grid = (int)(supers < 148 ? supers : 148);
+  const int sms = sm_count();
+  int grid = (int)(supers < sms ? supers : sms);
   if (p.n_tiles <= grid) grid = grid / p.n_tiles * p.n_tiles;    // multiple of n_tiles: fixed n-block per CTA
   return grid;
 }
@@ -432,6 +463,7 @@ static int score_t_impl(const TcOperand& E, const TcOperand& Q, const float* bia
     if (prec == COPER_PREC_BF16 && ent_resident(d, prec, Ns, B)) return FN<EntSel<PREC_BF16, true>::Cfg>(__VA_ARGS__);  \
     if (prec == COPER_PREC_BF16) return FN<EntSel<PREC_BF16, false>::Cfg>(__VA_ARGS__);                   \
     if (prec == COPER_PREC_TF32X3) return FN<EntSel<PREC_TF32X3, false>::Cfg>(__VA_ARGS__);               \
+    if (prec == COPER_PREC_FP16X3) return FN<EntSel<PREC_FP16X3, false>::Cfg>(__VA_ARGS__);               \
     return COPER_ERR_UNSUPPORTED;                                                                          \
   } while (0)
 int umma_score1n_fwd_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
@@ -458,10 +490,17 @@ int umma_score1n_gold(const void* q_prep, const void* E_prep, const float* bias,
   if (!ws || ws_bytes < umma_rank_workspace_bytes(B, d, prec) || (reinterpret_cast<uintptr_t>(ws) & 255))
     return COPER_ERR_WORKSPACE;
   int64_t ldp = tc_prepared_ld(d, prec);
-  int elem = prec == COPER_PREC_BF16 ? 2 : 4;
+  int elem = prec == COPER_PREC_TF32X3 ? 4 : 2;
   int vec_per_row = (int)(ldp * elem / 16);
+  const int* src_exp = nullptr;
+  int* dst_exp = nullptr;
+  if (prec == COPER_PREC_FP16X3) {
+    src_exp = static_cast<const int*>(tc_fp16x3_trailer(E_prep, Ns, d));
+    dst_exp = static_cast<int*>(tc_fp16x3_trailer(ws, B, d));
+  }
   gather_prepared_kernel<<<B, 64, 0, st>>>(static_cast<const uint4*>(E_prep), Ns, vec_per_row,
-                                           prec == COPER_PREC_BF16 ? 1 : 2, e2, ent_lo, B, static_cast<uint4*>(ws));
+                                           prec == COPER_PREC_BF16 ? 1 : 2, e2, ent_lo, B, static_cast<uint4*>(ws),
+                                           src_exp, dst_exp);
   int rc = check_launch();
   if (rc) return rc;
   TcOperand Q = tc_operand(q_prep, B, d, prec), Eg = tc_operand(ws, B, d, prec);
@@ -517,7 +556,7 @@ static BceTcLayout bce_tc_layout(int B, int64_t Ns, int d, int prec) {
   L.off_E = o; o = align_up(o + tc_prepared_bytes(Ns, d, prec), 256);
   L.off_dq = o; o = align_up(o + dq_rows * d * sizeof(float), 256);
   L.off_dbias = o; o = align_up(o + (size_t)L.dbias_slabs * Ns * sizeof(float), 256);
-  L.off_loss = o; o = align_up(o + (size_t)148 * kBceEpiWarps * sizeof(double), 256);
+  L.off_loss = o; o = align_up(o + (size_t)sm_count() * kBceEpiWarps * sizeof(double), 256);
   L.total = o;
   return L;
 }
@@ -526,6 +565,7 @@ size_t umma_bce_workspace_bytes(int B, int64_t Ns, int d, int prec) { return bce
 static inline int64_t gt_pitch(int B) { return (B + 31) / 32 * 32; }
 size_t umma_bce_G_bytes(int B, int64_t Ns, int prec) {
   if (prec == COPER_PREC_BF16) return (size_t)Ns * gt_pitch(B) * 2;
+  if (prec == COPER_PREC_FP16X3) return (size_t)Ns * gt_pitch(B) * 2 * 2;    // entity-major fp16 hi / lo planes
   return (size_t)B * ((Ns + 31) / 32 * 32) * 8;      // tf32x3: query-major hi / lo planes
 }
 
@@ -538,7 +578,11 @@ static int bce_impl(const TcOperand& E, const TcOperand& Q, const float* bias, c
   constexpr int PREC = Cfg::PREC;
   BceEpiT<PREC, kEntNCH> epi;
   epi.rs.init(bias, bitsT, (B + 31) / 32);
-  epi.pos = pos; epi.neg = neg; epi.inv_count = inv_count; epi.GT = GT; epi.ldGT = ldGT;
+  epi.pos = pos; epi.neg = neg; epi.GT = GT; epi.ldGT = ldGT;
+  // fp16x3 carries dL/dS as (sigmoid - z') * 2^10 in fp16 hi / lo planes (values in (-2^10, 2^10)); the true 1/count
+  // (far below the fp16 range) is applied by the dq / dE epilogues and to the dbias row sums
+  epi.inv_count = PREC == PREC_FP16X3 ? 1024.0f : inv_count;
+  epi.rsum_scale = PREC == PREC_FP16X3 ? inv_count * (1.0f / 1024.0f) : 1.0f;
   epi.dbias_part = dbias_part; epi.loss_part = loss_part; epi.loss_acc = 0.0; epi.rsum = 0.f;
   *grid_out = ent_grid(p);
   return launch_gemm<Cfg, BceEpiT<PREC, kEntNCH>>(E, Q, p, epi, st, *grid_out);
@@ -551,8 +595,9 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
   if (Ns > 0x7fffffff - 512) return COPER_ERR_UNSUPPORTED;
   (void)ldG;                                          // the tensor-pipe engines lay G out entity-major themselves
   if (reinterpret_cast<uintptr_t>(G) & 127) return COPER_ERR_INVALID_ARG;
-  const bool entity_major = prec == COPER_PREC_BF16;
+  const bool entity_major = prec != COPER_PREC_TF32X3;
   const int64_t ldGT = entity_major ? gt_pitch(B) : (Ns + 31) / 32 * 32;
+  const float g_post = prec == COPER_PREC_FP16X3 ? inv_count * (1.0f / 1024.0f) : 0.f;   // see bce_impl
   BceTcLayout L = bce_tc_layout(B, Ns, d, prec);
   if (!ws || ws_bytes < L.total) return COPER_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(ws) & 255) return COPER_ERR_INVALID_ARG;
@@ -579,7 +624,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     if ((rc = coper_reduce_partials(dq_part, R, (int64_t)B * d, 1.0f, 0, dq, (coper_stream_t)st))) return rc;
     // ---- dE = G^T . q from the entity-major G the kernel stored
     TcOperand Go;
-    Go.main = G; Go.lo = nullptr; Go.pitch = (uint64_t)ldGT; Go.rows = (uint64_t)Ns; Go.cols = (uint64_t)B;
+    Go.main = G; Go.lo = nullptr; Go.exp = nullptr; Go.pitch = (uint64_t)ldGT; Go.rows = (uint64_t)Ns; Go.cols = (uint64_t)B;
     GemmProblem pe{};
     pe.M = (int)Ns; pe.N = d; pe.K = B; pe.groups = 1; pe.groups_inner = 0;
     StoreEpi epi = make_store_epi(dE, d, 0, 0);
@@ -594,6 +639,9 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     if (prec == COPER_PREC_BF16)
       return bce_impl<BceSel<PREC_BF16, false>::Cfg>(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT,
                                                      dbias_part, loss_part, st, &grid);
+    if (prec == COPER_PREC_FP16X3)
+      return bce_impl<BceSel<PREC_FP16X3, false>::Cfg>(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT,
+                                                       dbias_part, loss_part, st, &grid);
     return bce_impl<BceSel<PREC_TF32X3, false>::Cfg>(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT,
                                                      dbias_part, loss_part, st, &grid);
   };
@@ -605,8 +653,9 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
   TcOperand Go;
   Go.main = G;
   Go.pitch = (uint64_t)ldGT;
+  Go.exp = nullptr;
   if (entity_major) {
-    Go.lo = nullptr;
+    Go.lo = prec == COPER_PREC_FP16X3 ? static_cast<const void*>(static_cast<const uint16_t*>(G) + Ns * ldGT) : nullptr;
     Go.rows = (uint64_t)Ns; Go.cols = (uint64_t)B;
   } else {
     Go.lo = static_cast<const void*>(static_cast<const float*>(G) + (int64_t)B * ldGT);
@@ -616,6 +665,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
   {
     GemmProblem p{};
     p.M = B; p.N = d; p.K = (int)Ns; p.groups = 1; p.groups_inner = 0;
+    p.post_scale = g_post;
     StoreEpi epi = make_store_epi(dq_part, d, 0, (long long)B * d);
     if ((rc = tc_gemm_store(prec, entity_major, true, Go, Eo, p, true, epi, st))) return rc;
     if ((rc = coper_reduce_partials(dq_part, L.splits, (int64_t)B * d, 1.0f, 0, dq, (coper_stream_t)st))) return rc;
@@ -624,6 +674,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
   {
     GemmProblem p{};
     p.M = (int)Ns; p.N = d; p.K = B; p.groups = 1; p.groups_inner = 0;
+    p.post_scale = g_post;
     StoreEpi epi = make_store_epi(dE, d, 0, 0);
     if ((rc = tc_gemm_store(prec, !entity_major, true, Go, Qo, p, false, epi, st))) return rc;
   }
@@ -637,7 +688,7 @@ using namespace coper;
 extern "C" {
 
 size_t coper_score1n_rank_workspace_bytes(int B, int d, int prec) {
-  if (prec != COPER_PREC_BF16 && prec != COPER_PREC_TF32X3) return 0;
+  if (prec != COPER_PREC_BF16 && prec != COPER_PREC_TF32X3 && prec != COPER_PREC_FP16X3) return 0;
   return umma_rank_workspace_bytes(B, d, prec);
 }
 int coper_score1n_gold_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,

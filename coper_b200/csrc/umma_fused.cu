@@ -49,7 +49,9 @@ struct Params {
   float* dq_part;            // [R][B][d]
   float* dbias_part;         // [QB][Ns]
   double* loss_part;         // [grid][kEpiWarps]
+  long long* trace;          // optional [tiles][8] clock64 stamps of CTA 0 (pipeline timeline, dev tool); NULL = off
 };
+enum { TR_S_ISSUE = 0, TR_S_ISSUED, TR_G_SEEN, TR_DQ_ISSUED, TR_E_FREE_SEEN, TR_S_SEEN, TR_EPI_MATH_DONE, TR_G_WRITTEN };
 }  // namespace fz
 
 __global__ void __launch_bounds__(fz::kThreads, 1)
@@ -103,7 +105,14 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
       if (leader) tma_load_2d(smQ + kb * kTile, &tQ, &bar[B_QFULL], kb * 64, qb * 128);
     for (int i = 0; i < T; ++i) {
       const int buf = i & 1, n = i >> 1;
+      // only two entity-tile buffers fit beside the resident query block, so the load of tile i cannot be issued before
+      // the dq MMAs of tile i-2 have completed; pulling the tile into L2 two tiles ahead turns the exposed part of that
+      // load from an HBM round trip into an L2 hit (query block 0 prefetches for the QB CTAs that share the tile)
+      if (qb == 0 && i + 2 < T)
+        for (int kb = 0; kb < p.KB; ++kb)
+          if (leader) tma_prefetch_l2_2d(&tE, kb * 64, (t0 + i + 2) * 128);
       mbar_wait_guarded(&bar[B_EEMPTY + buf], (uint32_t)((n & 1) ^ 1));
+      if (p.trace && blockIdx.x == 0 && leader) p.trace[i * 8 + TR_E_FREE_SEEN] = clock64();
       for (int kb = 0; kb < p.KB; ++kb) {
         uint64_t* fb = &bar[B_EFULL + buf * 4 + kb];
         if (leader) {
@@ -126,6 +135,7 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
     const int nk_last = (min(64, p.d - (p.KB - 1) * 64) + 15) >> 4;
     auto issue_S = [&](int j) {
       const int buf = j & 1, n = j >> 1;
+      if (p.trace && blockIdx.x == 0 && leader) p.trace[j * 8 + TR_S_ISSUE] = clock64();
       mbar_wait_guarded(&bar[B_SEMPTY + buf], (uint32_t)((n & 1) ^ 1));
       tc_fence_after();
       const uint32_t tS = tmem + kColS + buf * 128;
@@ -143,6 +153,7 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
         __syncwarp();
       }
       if (leader) mma_commit(&bar[B_SFULL + buf]);
+      if (p.trace && blockIdx.x == 0 && leader) p.trace[j * 8 + TR_S_ISSUED] = clock64();
       __syncwarp();
     };
     mbar_wait_guarded(&bar[B_QFULL], 0);
@@ -152,6 +163,7 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
       if (i + 1 < T) issue_S(i + 1);             // keeps the tensor pipe busy while the epilogue works on tile i
       mbar_wait_guarded(&bar[B_GFULL], (uint32_t)(i & 1));
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && leader) p.trace[i * 8 + TR_G_SEEN] = clock64();
       // dq[128 queries, Nd] += G^T[queries, 128 entities] . E_t[128 entities, Nd]: both operands MN-major
       // (A: two 64-query chunks 16 KB apart; B: d/64 column chunks 16 KB apart; 16 entity rows = 2048 B per MMA)
       const uint64_t db = dEm + (uint64_t)(((i & 1) * kEBuf) >> 4);
@@ -160,6 +172,7 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
         for (int k = 0; k < 8; ++k) mma_bf16(tmem, dGm + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idescD, (i | k) ? 1u : 0u);
         mma_commit(&bar[B_EEMPTY + (i & 1)]);
         mma_commit(&bar[B_GEMPTY]);
+        if (p.trace && blockIdx.x == 0) p.trace[i * 8 + TR_DQ_ISSUED] = clock64();
       }
       __syncwarp();
     }
@@ -211,6 +224,8 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
       const bool rowok = row < p.Ns;
       mbar_wait_guarded(&bar[B_SFULL + sb], (uint32_t)(n & 1));
       tc_fence_after();
+      const bool tr = p.trace && blockIdx.x == 0 && ew == 0 && lane == 0;
+      if (tr) p.trace[i * 8 + TR_S_SEEN] = clock64();
       uint32_t r[32];
       tmem_ld32(tmem + kColS + sb * 128 + cg * 32 + lane_base, r);
       tmem_ld_wait();
@@ -240,6 +255,7 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
         pk[v].x = *reinterpret_cast<uint32_t*>(&a0); pk[v].y = *reinterpret_cast<uint32_t*>(&a1);
         pk[v].z = *reinterpret_cast<uint32_t*>(&a2); pk[v].w = *reinterpret_cast<uint32_t*>(&a3);
       }
+      if (tr) p.trace[i * 8 + TR_EPI_MATH_DONE] = clock64();
       // the G tile of the previous entity tile must have been consumed (dq MMAs + TMA store) before it is overwritten
       mbar_wait_guarded(&bar[B_GEMPTY], (uint32_t)((i & 1) ^ 1));
 #pragma unroll
@@ -247,6 +263,7 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
       fence_proxy_async();                                     // generic-proxy writes -> visible to tcgen05.mma / TMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[B_GFULL]);
+      if (tr) p.trace[i * 8 + TR_G_WRITTEN] = clock64();
       // dbias[n] = sum over the CTA's 128 queries: column groups 1..3 hand their row sums to group 0
       if (cg > 0) {
         mbar_wait_guarded(&bar[B_DBFREE], (uint32_t)((i & 1) ^ 1));
@@ -298,13 +315,14 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------ host side
+static long long* g_fused_trace = nullptr;      // dev tool (tools/fused_trace.py): device buffer [tiles of CTA 0][8]
 bool umma_fused_ok(int B, int64_t Ns, int d, int prec) {
   return prec == COPER_PREC_BF16 && d <= 64 * fz::kKbMax && B >= 1 && Ns >= 1 && Ns <= 0x7fffffff - 512;
 }
 void umma_fused_plan(int B, int64_t Ns, int* QB, int* R) {
   const int qb = (B + 127) / 128;
   const int64_t m_tiles = (Ns + 127) / 128;
-  int r = 148 / qb;
+  int r = sm_count() / qb;
   if (r < 1) r = 1;
   if (r > m_tiles) r = (int)m_tiles;
   *QB = qb;
@@ -328,6 +346,7 @@ int umma_bce_dq_fused(const TcOperand& E, const TcOperand& Q, const float* bias,
   p.bias = bias; p.bitsT = bitsT; p.wordsB = (B + 31) / 32;
   p.pos = pos; p.neg = neg; p.ic = inv_count;
   p.dq_part = dq_part; p.dbias_part = dbias_part; p.loss_part = loss_part;
+  p.trace = g_fused_trace;
   int dev = 0;
   if ((rc = check_cuda(cudaGetDevice(&dev)))) return rc;
   static bool attr_done[64] = {};
@@ -345,3 +364,5 @@ int umma_bce_dq_fused(const TcOperand& E, const TcOperand& Q, const float* bias,
 }
 
 }  // namespace coper
+
+extern "C" void coper_debug_set_fused_trace(long long* device_buffer) { coper::g_fused_trace = device_buffer; }

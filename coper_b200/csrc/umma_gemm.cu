@@ -8,12 +8,14 @@ using namespace umma;
 size_t tc_prepared_bytes(int64_t rows, int cols, int prec);                     // umma_score.cu
 int tc_prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst, cudaStream_t st);
 int64_t tc_prepared_ld(int cols, int prec);
+void* tc_fp16x3_trailer(const void* prep, int64_t rows, int cols);
 
 // N-is-small configurations (N = d <= 256 in one tile): BLOCK_N = 256
 // tf32x3: 8 epilogue warps (128 promoted accumulators per thread), chains cut every 4 k-blocks (48 MMAs)
+// fp16x3: a k-block holds 64 k-elements (2 x 16 KB planes per operand tile row block): chains cut every 2 k-blocks
 template <int PREC, bool A_MN, bool B_MN>
 using StoreCfg = GemmCfg<PREC, 256, (PREC == PREC_BF16 ? 4 : 2), (PREC == PREC_BF16 ? 4 : 8), A_MN, B_MN,
-                         (PREC == PREC_BF16 ? 0 : 4)>;
+                         (PREC == PREC_BF16 ? 0 : PREC == PREC_FP16X3 ? 2 : 4)>;
 
 template <int PREC>
 static int dispatch_layout(bool a_mn, bool b_mn, const TcOperand& A, const TcOperand& B, GemmProblem p, bool split,
@@ -45,11 +47,13 @@ int tc_gemm_store(int prec, bool a_mn, bool b_mn, const TcOperand& A, const TcOp
   // for reference only)
   if (prec == COPER_PREC_BF16) return dispatch_layout<PREC_BF16>(a_mn, b_mn, A, B, p, split, epi, st);
   if (prec == COPER_PREC_TF32X3) return dispatch_layout<PREC_TF32X3>(a_mn, b_mn, A, B, p, split, epi, st);
+  if (prec == COPER_PREC_FP16X3) return dispatch_layout<PREC_FP16X3>(a_mn, b_mn, A, B, p, split, epi, st);
   return COPER_ERR_UNSUPPORTED;
 }
 // number of split-K slabs tc_gemm_store will produce for this problem (all StoreCfg share BLOCK_N / BLOCK_K per prec)
 int tc_plan_splits(int prec, GemmProblem p, bool split) {
   if (prec == COPER_PREC_BF16) plan_gemm<StoreCfg<PREC_BF16, false, false>>(p, split);
+  else if (prec == COPER_PREC_FP16X3) plan_gemm<StoreCfg<PREC_FP16X3, false, false>>(p, split);
   else plan_gemm<StoreCfg<PREC_TF32X3, false, false>>(p, split);
   return p.splits;
 }
@@ -58,7 +62,10 @@ TcOperand tc_operand(const void* prep, int64_t rows, int cols, int prec) {
   TcOperand o;
   int64_t ldp = tc_prepared_ld(cols, prec);
   o.main = prep;
-  o.lo = prec == COPER_PREC_TF32X3 ? static_cast<const void*>(static_cast<const float*>(prep) + rows * ldp) : nullptr;
+  o.lo = prec == COPER_PREC_TF32X3 ? static_cast<const void*>(static_cast<const float*>(prep) + rows * ldp)
+         : prec == COPER_PREC_FP16X3 ? static_cast<const void*>(static_cast<const uint16_t*>(prep) + rows * ldp)
+                                     : nullptr;
+  o.exp = prec == COPER_PREC_FP16X3 ? static_cast<const int*>(tc_fp16x3_trailer(prep, rows, cols)) : nullptr;
   o.rows = (uint64_t)rows;
   o.cols = (uint64_t)cols;
   o.pitch = (uint64_t)ldp;
@@ -80,7 +87,7 @@ size_t coper_tc_gemm_workspace_bytes(int M, int N, int K, int prec) {
 int coper_tc_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                   float* C, int ldc, int prec, void* workspace, size_t workspace_bytes, coper_stream_t stream) {
   COPER_CHECK_ARG(A && B && C && workspace && M > 0 && N > 0 && K > 0 && ldc >= N);
-  if (prec != COPER_PREC_BF16 && prec != COPER_PREC_TF32X3) return COPER_ERR_UNSUPPORTED;
+  if (prec != COPER_PREC_BF16 && prec != COPER_PREC_TF32X3 && prec != COPER_PREC_FP16X3) return COPER_ERR_UNSUPPORTED;
   if (workspace_bytes < coper_tc_gemm_workspace_bytes(M, N, K, prec)) return COPER_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));

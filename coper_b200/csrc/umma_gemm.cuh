@@ -8,6 +8,10 @@
 //   PREC_BF16  : bf16 operands, 1 MMA per k-step (kind::f16)
 //   PREC_TF32X3: fp32 operands pre-split into (hi, lo) tf32 planes, 3 MMAs per k-step
 //                (lo*hi + hi*lo + hi*hi; kind::tf32) -> fp32-class accuracy on the tensor pipe.
+//   PREC_FP16X3: the same 3-term scheme on IEEE fp16 (hi, lo) planes of x * 2^e (kind::f16: twice the MMA rate, half the
+//                operand bytes).  fp16 carries tf32's 11-bit significand; the per-operand exponents e (device int32,
+//                written by the operand preparation from the operand's max |x|) are removed from the accumulators
+//                right after they are read from TMEM (acc * 2^-(ea+eb) * post_scale).
 // Operands may be K-major (rows x 128 B tiles) or MN-major (k-rows x 128 B chunks); see umma.cuh.
 #pragma once
 #include "umma.cuh"
@@ -15,7 +19,7 @@
 namespace coper {
 namespace umma {
 
-constexpr int PREC_BF16 = COPER_PREC_BF16, PREC_TF32X3 = COPER_PREC_TF32X3;
+constexpr int PREC_BF16 = COPER_PREC_BF16, PREC_TF32X3 = COPER_PREC_TF32X3, PREC_FP16X3 = COPER_PREC_FP16X3;
 constexpr int BLOCK_M = 128;
 constexpr int NUM_NON_EPI_THREADS = 128;
 
@@ -33,11 +37,12 @@ struct GemmCfg {
   static constexpr int RES_KB = RES_KB_;
   static constexpr int PREC = PREC_, BLOCK_N = BLOCK_N_, STAGES = STAGES_, EPI_WARPS = EPI_WARPS_;
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
-  static constexpr int ELEM = (PREC == PREC_BF16) ? 2 : 4;
+  static constexpr int ELEM = (PREC == PREC_TF32X3) ? 4 : 2;
   static constexpr int CHUNK = 128 / ELEM;          // elements per 128-byte swizzle row: 64 bf16 / 32 tf32
   static constexpr int BLOCK_K = CHUNK;             // k elements per pipeline stage
   static constexpr int UMMA_K = 32 / ELEM;          // 16 bf16 / 8 tf32
-  static constexpr int TERMS = (PREC == PREC_TF32X3) ? 2 : 1;   // operand planes (hi, lo)
+  static constexpr int TERMS = (PREC == PREC_BF16) ? 1 : 2;     // operand planes (hi, lo)
+  static constexpr bool SCALED = (PREC == PREC_FP16X3);         // accumulators carry 2^(ea+eb)
   static constexpr int A_BYTES = BLOCK_M * 128;     // one plane of the A tile (BLOCK_M x BLOCK_K or BLOCK_K x BLOCK_M)
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = RES_KB_ > 0 ? TERMS * A_BYTES : TERMS * (A_BYTES + B_BYTES);
@@ -47,7 +52,7 @@ struct GemmCfg {
   static constexpr int THREADS = NUM_NON_EPI_THREADS + EPI_WARPS * 32;
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-  static constexpr uint32_t FMT = (PREC == PREC_BF16) ? FMT_BF16 : FMT_TF32;
+  static constexpr uint32_t FMT = (PREC == PREC_BF16) ? FMT_BF16 : (PREC == PREC_FP16X3) ? FMT_F16 : FMT_TF32;
   // MN-major smem layout: 16-bit types use the plain 128B swizzle (8-row k atoms); tf32 must use the
   // 128B swizzle with 32-byte atoms (4-row k atoms)
   static constexpr bool MN_ATOM32 = (PREC == PREC_TF32X3);
@@ -178,6 +183,10 @@ __device__ __forceinline__ void issue_stage_rt(const SmemLayout<Cfg>& sm, int st
         const uint32_t acc = (first && k == 0) ? 0u : 1u;
         if (Cfg::PREC == PREC_BF16) {
           mma_bf16(tmem_d, da[0] + k * a_step, db[0] + k * b_step, idesc, acc);
+        } else if (Cfg::PREC == PREC_FP16X3) {                                    // kind::f16 on fp16 planes
+          mma_bf16(tmem_d, da[1] + k * a_step, db[0] + k * b_step, idesc, acc);   // lo * hi
+          mma_bf16(tmem_d, da[0] + k * a_step, db[1] + k * b_step, idesc, 1u);    // hi * lo
+          mma_bf16(tmem_d, da[0] + k * a_step, db[0] + k * b_step, idesc, 1u);    // hi * hi
         } else {
           mma_tf32(tmem_d, da[1] + k * a_step, db[0] + k * b_step, idesc, acc);   // lo * hi
           mma_tf32(tmem_d, da[0] + k * a_step, db[1] + k * b_step, idesc, 1u);    // hi * lo
@@ -216,6 +225,9 @@ struct GemmProblem {
                                 //    (m_blk, n_blk, split) consecutively (epilogue may accumulate across groups)
   int a_group_mn, a_group_k;    // per-group coordinate offsets into the operand tensor maps
   int b_group_mn, b_group_k;
+  const int* exp_a;             // PREC_FP16X3: device exponents of the two operands (NULL = 0) and a host-known
+  const int* exp_b;             //   factor: accumulators are multiplied by 2^-(*exp_a + *exp_b) * post_scale
+  float post_scale;             //   (0 is read as 1)
   int n_fastest;                // 0: tiles enumerated m-block fastest (default); 1: n-block fastest - with a grid that
                                 //    is a multiple of n_tiles every CTA keeps ONE n-block (resident B is loaded once)
                                 //    and neighbouring CTAs work on the same m-block at the same time, so the A tile
@@ -382,6 +394,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    // PREC_FP16X3: the operands were stored as x * 2^e -> every accumulator read from TMEM is multiplied by
+    // 2^-(ea+eb) * post_scale before the epilogue sees it
+    float acc_scale = 1.0f;
+    if (Cfg::SCALED) {
+      const int e = (p.exp_a ? __ldg(p.exp_a) : 0) + (p.exp_b ? __ldg(p.exp_b) : 0);
+      acc_scale = exp2f((float)-e) * (p.post_scale != 0.f ? p.post_scale : 1.0f);
+    }
     for (long long s = blockIdx.x; s < supers; s += gridDim.x) {
       TileCoord t = gemm_decode(p, s, 0, Cfg::BLOCK_K);
       const int row = t.m_blk * BLOCK_M + quarter * 32 + lane;
@@ -402,6 +421,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
             uint32_t r[32];
             tmem_ld32(tmem_base + as * Cfg::BLOCK_N + group_c * COLS + i * 32 + lane_base, r);
             tmem_ld_wait();
+            if (Cfg::SCALED) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * acc_scale);
+            }
             epi.chunk(p, t, row, col, r, i);
           }
         }
@@ -433,6 +456,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
                   uint32_t r[16];
                   tmem_ld16(tmem_base + as * Cfg::BLOCK_N + group_c * COLS + i * 32 + h * 16 + lane_base, r);
                   tmem_ld_wait();
+                  if (Cfg::SCALED) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * acc_scale);
+                  }
                   epi.group_vals(p, t, row, col0 + i * 32 + h * 16, r, i * 2 + h);
 #pragma unroll
                   for (int j = 0; j < 16; ++j) accr[i][h * 16 + j] = fmaf(scale, __uint_as_float(r[j]), accr[i][h * 16 + j]);
@@ -468,7 +495,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__
 // Host-side description of a prepared operand (see coper_prepare_operand)
 struct TcOperand {
   const void* main;
-  const void* lo;        // tf32x3 only
+  const void* lo;        // tf32x3 / fp16x3 only
+  const int* exp;        // fp16x3 only: device exponent e of the stored planes (x * 2^e); NULL = 0
   uint64_t rows, cols;   // extents of the stored row-major matrix (cols contiguous)
   uint64_t pitch;        // elements between rows
 };
@@ -478,7 +506,7 @@ struct TcOperand {
 template <class Cfg>
 int make_gemm_tmaps(const TcOperand& A, const TcOperand& B, CUtensorMap* tA, CUtensorMap* tAlo, CUtensorMap* tB,
                     CUtensorMap* tBlo) {
-  constexpr bool bf16 = Cfg::PREC == PREC_BF16;
+  constexpr bool bf16 = Cfg::ELEM == 2;      // any 16-bit plane: TMA only moves bytes
   int rc;
   uint32_t a_box_rows = Cfg::A_MN ? Cfg::BLOCK_K : BLOCK_M;
   uint32_t b_box_rows = Cfg::B_MN ? Cfg::BLOCK_K : Cfg::BLOCK_N;
@@ -487,10 +515,10 @@ int make_gemm_tmaps(const TcOperand& A, const TcOperand& B, CUtensorMap* tA, CUt
   if ((rc = make_tmap_2d(tB, B.main, Cfg::ELEM, bf16, B.rows, B.cols, B.pitch, Cfg::CHUNK, b_box_rows, b32))) return rc;
   *tAlo = *tA;
   *tBlo = *tB;
-  if (!bf16) {
+  if (Cfg::TERMS == 2) {
     if (!A.lo || !B.lo) return COPER_ERR_INVALID_ARG;
-    if ((rc = make_tmap_2d(tAlo, A.lo, 4, false, A.rows, A.cols, A.pitch, Cfg::CHUNK, a_box_rows, a32))) return rc;
-    if ((rc = make_tmap_2d(tBlo, B.lo, 4, false, B.rows, B.cols, B.pitch, Cfg::CHUNK, b_box_rows, b32))) return rc;
+    if ((rc = make_tmap_2d(tAlo, A.lo, Cfg::ELEM, bf16, A.rows, A.cols, A.pitch, Cfg::CHUNK, a_box_rows, a32))) return rc;
+    if ((rc = make_tmap_2d(tBlo, B.lo, Cfg::ELEM, bf16, B.rows, B.cols, B.pitch, Cfg::CHUNK, b_box_rows, b32))) return rc;
   }
   return COPER_OK;
 }
@@ -504,24 +532,34 @@ int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, co
   CUtensorMap tA, tAlo, tB, tBlo;
   int rc = make_gemm_tmaps<Cfg>(A, B, &tA, &tAlo, &tB, &tBlo);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  int dev = 0;
+  if ((rc = check_cuda(cudaGetDevice(&dev)))) return rc;
+  static bool attr_done[64] = {};               // the attribute is per device
+  if (dev < 0 || dev >= 64) return COPER_ERR_UNSUPPORTED;
+  if (!attr_done[dev]) {
     rc = check_cuda(cudaFuncSetAttribute(umma_gemm_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::SMEM_BYTES));
     if (rc) return rc;
-    attr_done = true;
+    attr_done[dev] = true;
   }
+  GemmProblem pp = p;
+  if (Cfg::SCALED) {                            // operand exponents travel with the operands
+    if (!pp.exp_a) pp.exp_a = A.exp;
+    if (!pp.exp_b) pp.exp_b = B.exp;
+  }
+  const int sms = sm_count();
   long long supers = (long long)p.m_tiles * p.n_tiles * p.splits * (p.groups_inner ? 1 : p.groups);
-  int grid = (int)(supers < 148 ? supers : 148);
+  int grid = (int)(supers < sms ? supers : sms);
   if (grid_override > 0 && grid_override < grid) grid = grid_override;
   if (grid < 1) return COPER_ERR_INVALID_ARG;
-  umma_gemm_kernel<Cfg, Epi><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tAlo, tB, tBlo, p, epi);
+  umma_gemm_kernel<Cfg, Epi><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tAlo, tB, tBlo, pp, epi);
   return check_launch();
 }
 
 // Fill the tiling fields of a problem; split-K chosen so that ~`target_ctas` work items exist.
 template <class Cfg>
-inline void plan_gemm(GemmProblem& p, bool allow_split, int target_ctas = 148) {
+inline void plan_gemm(GemmProblem& p, bool allow_split, int target_ctas = 0) {
+  if (target_ctas <= 0) target_ctas = sm_count();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
   int kb_total = (p.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;

@@ -5,13 +5,14 @@
 //
 // Operands are consumed in "prepared" form (coper_prepare_operand): bf16 copy, or (hi, lo) tf32 planes —
 // the entity table is prepared once per evaluation pass / per optimizer step, not per call.
+#include <cuda_fp16.h>
 #include "umma_gemm.cuh"
 
 namespace coper {
 using namespace umma;
 
 // ------------------------------------------------------------------------------------------ operand preparation
-static inline int64_t prepared_ld(int cols, int prec) { return prec == COPER_PREC_BF16 ? (cols + 7) / 8 * 8 : (cols + 3) / 4 * 4; }
+static inline int64_t prepared_ld(int cols, int prec) { return prec == COPER_PREC_TF32X3 ? (cols + 3) / 4 * 4 : (cols + 7) / 8 * 8; }
 
 // block = (64 column lanes) x (4 rows); grid-stride over rows; each lane converts VEC consecutive columns per pass
 // (VEC = 8 bf16 / 4 tf32 -> one 16-byte store per plane); no integer division anywhere
@@ -61,14 +62,98 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
   }
 }
 
+// ---- COPER_PREC_FP16X3: hi / lo IEEE fp16 planes of x * 2^e with ONE exponent per operand.
+// fp16 keeps 11 significand bits per plane (like tf32) but only 5 exponent bits, so the operand is first scaled by a
+// power of two (exact) that puts its largest magnitude at [2^10, 2^11): far from the fp16 overflow (2^16) and with
+// 12 binades of headroom before the lo plane of an element leaves the normal range (an element 2^12 below the max
+// still carries 22 bits; smaller ones lose lo bits they contribute negligibly to any dot product).  e lives in the
+// 256-byte trailer of the prepared buffer (int32 at offset 0; the max |x| as float bits at offset 4) and is removed
+// from the accumulators by the consuming kernels (umma_gemm.cuh, SCALED).
+constexpr int kFp16TargetExp = 10;
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src,
+                                                     uint32_t* __restrict__ trailer) {
+  float m = 0.f;
+  if (ld_src == cols) {                                // dense: one flat stream (16-byte loads when aligned)
+    const int64_t n = rows * cols;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n / 4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = __ldg(s4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+      for (int64_t i = (n / 4) * 4 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        m = fmaxf(m, fabsf(__ldg(src + i)));
+    } else {
+      for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        m = fmaxf(m, fabsf(__ldg(src + i)));
+    }
+  } else {
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
+      for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, fabsf(__ldg(src + r * ld_src + c)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // non-negative floats order like their bit patterns; a NaN / Inf input makes the exponent choice fall back to 0
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(trailer + 1, __float_as_uint(m));
+}
+__device__ __forceinline__ int fp16x3_exponent(uint32_t absmax_bits) {
+  const float m = __uint_as_float(absmax_bits);
+  if (!(m > 0.f) || !isfinite(m)) return 0;
+  int e = kFp16TargetExp - ilogbf(m);
+  return max(-100, min(100, e));
+}
+__global__ void __launch_bounds__(256) prepare_fp16x3_kernel(const float* __restrict__ src, int64_t rows, int cols,
+                                                             int64_t ld_src, __half* __restrict__ dst, int64_t ldp,
+                                                             uint32_t* __restrict__ trailer) {
+  const int e = fp16x3_exponent(trailer[1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(trailer)[0] = e;
+  const float sc = exp2f((float)e);
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int nvec = (int)(ldp / 8);
+  const bool vec_src = ((ld_src & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  __half* lo_plane = dst + rows * ldp;
+  for (int64_t r = (int64_t)blockIdx.x * 4 + ty; r < rows; r += (int64_t)gridDim.x * 4) {
+    const float* srow = src + r * ld_src;
+    for (int v = tx; v < nvec; v += 64) {
+      const int c0 = v * 8;
+      float x[8];
+      if (vec_src && c0 + 8 <= cols) {
+#pragma unroll
+        for (int k = 0; k < 8; k += 4) {
+          float4 t = __ldg(reinterpret_cast<const float4*>(srow + c0 + k));
+          x[k] = t.x; x[k + 1] = t.y; x[k + 2] = t.z; x[k + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (c0 + k < cols) ? __ldg(srow + c0 + k) : 0.f;
+      }
+      __half2 h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = x[2 * k] * sc, b = x[2 * k + 1] * sc;
+        h[k] = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h[k]);
+        l[k] = __floats2half2_rn(a - hf.x, b - hf.y);            // the residuals are exact in fp32
+      }
+      *reinterpret_cast<uint4*>(dst + r * ldp + c0) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(lo_plane + r * ldp + c0) = *reinterpret_cast<uint4*>(l);
+    }
+  }
+}
+
 // entity-major scorer kernels: umma_entity.cu
 int umma_score1n_fwd_prepared(const void* q_prep, const void* E_prep, const float* bias, int B, int64_t Ns, int d,
                               float* scores, int64_t ld, int prec, cudaStream_t st);
 
 static size_t prepared_bytes(int64_t rows, int cols, int prec) {
   int64_t ldp = prepared_ld(cols, prec);
+  if (prec == COPER_PREC_FP16X3) return align_up((size_t)rows * ldp * 2 * 2, 256) + 256;    // 2 fp16 planes + trailer
   size_t b = prec == COPER_PREC_BF16 ? (size_t)rows * ldp * 2 : (size_t)rows * ldp * 4 * 2;
   return align_up(b, 256);
+}
+// device address of the 256-byte trailer {int32 e, float-bits max |x|} of an FP16X3 operand
+void* tc_fp16x3_trailer(const void* prep, int64_t rows, int cols) {
+  return const_cast<char*>(static_cast<const char*>(prep)) + align_up((size_t)rows * prepared_ld(cols, COPER_PREC_FP16X3) * 4, 256);
 }
 
 size_t umma_score1n_workspace_bytes(int B, int64_t Ns, int d, int prec) {
@@ -84,7 +169,16 @@ static int prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int
     prepare_kernel<COPER_PREC_BF16><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ldp);
   else if (prec == COPER_PREC_TF32X3)
     prepare_kernel<COPER_PREC_TF32X3><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ldp);
-  else
+  else if (prec == COPER_PREC_FP16X3) {
+    uint32_t* trailer = static_cast<uint32_t*>(tc_fp16x3_trailer(dst, rows, cols));
+    int rc = check_cuda(cudaMemsetAsync(trailer, 0, 8, st));
+    if (rc) return rc;
+    const int64_t n = rows * cols;
+    int g1 = (int)((n + 2047) / 2048 < sm_count() * 8 ? (n + 2047) / 2048 : sm_count() * 8);
+    absmax_kernel<<<g1 < 1 ? 1 : g1, 256, 0, st>>>(src, rows, cols, ld_src, trailer);
+    if ((rc = check_launch())) return rc;
+    prepare_fp16x3_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, static_cast<__half*>(dst), ldp, trailer);
+  } else
     return COPER_ERR_UNSUPPORTED;
   return check_launch();
 }
@@ -112,7 +206,7 @@ using namespace coper;
 
 extern "C" {
 size_t coper_prepared_bytes(int64_t rows, int cols, int prec) {
-  if (prec != COPER_PREC_BF16 && prec != COPER_PREC_TF32X3) return 0;
+  if (prec != COPER_PREC_BF16 && prec != COPER_PREC_TF32X3 && prec != COPER_PREC_FP16X3) return 0;
   return prepared_bytes(rows, cols, prec);
 }
 int coper_prepare_operand(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst,

@@ -99,7 +99,9 @@ class _DataLoader(Loader):
 
     # ------------------------------------------------------------------------------------------ preprocessing
     def _read_triples(self, directory) -> Dict[str, List[tuple]]:
-        if self.maybe_extract(directory):
+        if all(os.path.exists(os.path.join(directory, "%s.txt" % ft)) for ft in self.filetypes):
+            pass                                  # the split files are already here: no archive needed
+        elif self.maybe_extract(directory):
             directory = os.path.join(directory, self.dataset_name)      # the archive adds one directory level
         out = {}
         for ft in self.filetypes:
@@ -120,10 +122,14 @@ class _DataLoader(Loader):
         cache_file = os.path.join(directory, "coper_cache_%s%s.npz" % (
             self.dataset_name, "_clean" if self.needs_test_set_cleaning else ""))
         if os.path.exists(cache_file):
-            z = np.load(cache_file, allow_pickle=False)
-            self._cache = {k: z[k] for k in z.files}
-            self.num_ent, self.num_rel = int(self._cache["num_ent"]), int(self._cache["num_rel"])
-            return self._cache
+            try:
+                z = np.load(cache_file, allow_pickle=False)
+                cache = {k: z[k] for k in z.files}
+                self.num_ent, self.num_rel = int(cache["num_ent"]), int(cache["num_rel"])
+                self._cache = cache
+                return self._cache
+            except Exception as exc:              # truncated / corrupt file (e.g. an interrupted writer): rebuild it
+                logger.warning("ignoring unreadable cache %s (%r); preprocessing again", cache_file, exc)
         logger.info("Loading and preprocessing the '%s' dataset.", self.dataset_name)
         triples, data_dir = self._read_triples(directory)
         # graphs keyed by (e1, rel) -> set(e2); reverse edges per split as in data.py:427-439
@@ -186,8 +192,10 @@ class _DataLoader(Loader):
             cache["eval_%s_inv" % out_name] = np.array([k[1].endswith("_reverse") for k in keys], bool)
             cache["eval_%s_rowptr" % out_name] = frowptr
             cache["eval_%s_col" % out_name] = fcol
-        try:
-            np.savez(cache_file, **cache)
+        try:                                                          # temp file + rename: readers never see half a file
+            tmp = "%s.tmp%d.npz" % (cache_file, os.getpid())
+            np.savez(tmp, **cache)
+            os.replace(tmp, cache_file)
         except OSError:                                               # read-only dataset directory: keep in memory
             logger.warning("could not write %s; keeping the preprocessed graphs in memory", cache_file)
         self._cache = cache
@@ -223,9 +231,11 @@ class _DataLoader(Loader):
         for path, ids in ((ent_file, ent_ids), (rel_file, rel_ids)):
             if not os.path.exists(path):
                 try:
-                    with open(path, "w") as handle:
+                    tmp = "%s.tmp%d" % (path, os.getpid())
+                    with open(tmp, "w") as handle:
                         for name, _ in sorted(ids.items(), key=lambda kv: kv[1]):
                             handle.write(name + "\n")
+                    os.replace(tmp, path)
                 except OSError:
                     pass
         return ent_ids, rel_ids
@@ -335,24 +345,41 @@ class _DataLoader(Loader):
                 for p in pos:
                     yield r, p
 
+        def rows_one_positive_forever():
+            """repeat() comes before the per-positive expansion in the reference (data.py:147): an endless row stream"""
+            while True:
+                yield from gen_rows_one_positive(rng.permutation(sel))
+
+        def shuffled(stream, buffer_size=1000):
+            """tf.data shuffle(buffer_size) (data.py:160): a row leaves the buffer at a uniformly random position, so
+            the consecutive positives of one high-degree query are spread over ~buffer_size rows instead of filling a
+            batch"""
+            buf = []
+            for item in stream:
+                if len(buf) < buffer_size:
+                    buf.append(item)
+                    continue
+                j = int(rng.integers(0, buffer_size))
+                out, buf[j] = buf[j], item
+                yield out
+
         def gen():
+            if one_pos:
+                buf_r, buf_p = [], []
+                for r, p in shuffled(rows_one_positive_forever()):     # never truncated at an epoch boundary
+                    buf_r.append(r)
+                    buf_p.append(p)
+                    if len(buf_r) == batch_size:
+                        rows = np.array(buf_r)
+                        lookup = np.concatenate([np.array(buf_p, np.int64)[:, None],
+                                                 self._distinct_random(rng, N, len(rows), num_labels - 1)], axis=1)
+                        yield self._sampled_batch(e1a, rela, rows, lookup, labels_of(rows, lookup))
+                        buf_r, buf_p = [], []
             while True:
                 order = rng.permutation(sel)
-                if not one_pos:
-                    for s0 in range(0, len(order), batch_size):
-                        rows, lookup = batch_sample_negatives(order[s0:s0 + batch_size])
-                        yield self._sampled_batch(e1a, rela, rows, lookup, labels_of(rows, lookup))
-                else:
-                    buf_r, buf_p = [], []
-                    for r, p in gen_rows_one_positive(order):
-                        buf_r.append(r)
-                        buf_p.append(p)
-                        if len(buf_r) == batch_size:
-                            rows = np.array(buf_r)
-                            lookup = np.concatenate([np.array(buf_p, np.int64)[:, None],
-                                                     self._distinct_random(rng, N, len(rows), num_labels - 1)], axis=1)
-                            yield self._sampled_batch(e1a, rela, rows, lookup, labels_of(rows, lookup))
-                            buf_r, buf_p = [], []
+                for s0 in range(0, len(order), batch_size):
+                    rows, lookup = batch_sample_negatives(order[s0:s0 + batch_size])
+                    yield self._sampled_batch(e1a, rela, rows, lookup, labels_of(rows, lookup))
         return _prefetch(gen(), prefetch)
 
     @staticmethod

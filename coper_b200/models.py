@@ -321,7 +321,8 @@ class ConvE:
         lib = _lib.load()
         d = self.ent_emb_size
         # emission from inside the optimizer kernel needs operand pitch == row length; otherwise re-convert per step
-        self._emit_prepared = d % (8 if self.prec == PREC["bf16"] else 4) == 0
+        # (fp16x3 operands carry a data-dependent exponent: they are re-converted after every update, see refresh_prepared)
+        self._emit_prepared = d % (8 if self.prec == PREC["bf16"] else 4) == 0 and self.prec != PREC["fp16x3"]
         if self.prec != 0:
             Pw = self.fc_weights.projections[-1]
             self.E_prep = torch.zeros(lib.coper_prepared_bytes(self.shard.rows, d, self.prec), dtype=torch.uint8,

@@ -69,7 +69,7 @@ def main(argv=None):
     ap.add_argument("--dataset", default="WN18RR", help="one of: " + ", ".join(sorted(LOADERS)))
     ap.add_argument("--model-type", default="cpg", choices=["cpg", "plain", "param_lookup"])
     ap.add_argument("--config", default=None, help="YAML file overriding the shipped config of (dataset, model type)")
-    ap.add_argument("--data-dir", default=None, help="directory holding train/valid|dev/test.txt (or the .tar.gz)")
+    ap.add_argument("--data-dir", default=None, help="directory holding the split files train/valid|dev/test.txt, or <dataset>.tar.gz (extracted on first use)")
     ap.add_argument("--working-dir", default=None)
     ap.add_argument("--synthetic", default=None, help="run on a synthetic KG of this BASELINE shape instead of files")
     ap.add_argument("--full-1n", action="store_true", help="train with full 1-N labels (num_labels: null)")
@@ -77,7 +77,7 @@ def main(argv=None):
                     help="sampled-label configs: draw the [B, num_labels] ids / labels on the GPU (coper_sample_labels)")
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--eval-batches", type=int, default=None, help="cap the number of eval batches (synthetic runs)")
-    ap.add_argument("--prec", default="tf32x3", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--prec", default="tf32x3", choices=["fp32", "tf32x3", "fp16x3", "bf16"])
     ap.add_argument("--is-test", action="store_true")
     ap.add_argument("--needs-test-set-cleaning", action="store_true")
     ap.add_argument("--no-save-best-embeddings", action="store_true")
@@ -140,7 +140,13 @@ def main(argv=None):
         dataset_name = loader.dataset_name
         working = args.working_dir or os.path.join(os.getcwd(), "temp", dataset_name)
         data_dir = args.data_dir or os.path.join(working, "data", dataset_name)
+        # rank 0 extracts / parses / writes the id files and the CSR cache (atomically); the other ranks wait at the
+        # barrier and then load the finished cache, so every rank sees the same ids and num_ent
+        if world > 1 and rank != 0:
+            dist.barrier()
         loader.maybe_create_tf_record_files(data_dir)
+        if world > 1 and rank == 0:
+            dist.barrier()
         num_ent, num_rel = loader.num_ent, loader.num_rel
         B = cfg.training.batch_size
         train_batches = loader.train_dataset(

@@ -16,7 +16,10 @@
  *   - `prec` selects the arithmetic of the GEMM-shaped kernels: COPER_PREC_FP32 = CUDA-core FFMA,
  *     fp32 operands and accumulation (parity path, <=1e-5 rel); COPER_PREC_BF16 = tcgen05 kind::f16 with
  *     bf16 operands / fp32 TMEM accumulators; COPER_PREC_TF32X3 = tcgen05 kind::tf32 with 3-term error
- *     compensation (hi*hi + hi*lo + lo*hi), fp32-class accuracy on the tensor pipe.
+ *     compensation (hi*hi + hi*lo + lo*hi), fp32-class accuracy on the tensor pipe; COPER_PREC_FP16X3 = the same
+ *     3-term compensation on IEEE fp16 (hi, lo) planes (kind::f16: twice the MMA rate and half the operand bytes of
+ *     tf32; fp16 has tf32's 11-bit significand, its 5-bit exponent is handled by one power-of-two scale per
+ *     operand, chosen from the operand's max |x| when it is prepared and removed again in the epilogue).
  *   - dropout is a counter-based hash of (seed, element index): keep iff hash32 < keep * 2^32
  *     (coper_dropout_mask exports the same mask for the oracle).  keep >= 1 disables it.  The seed is
  *     (*seed_dev + salt): seed_dev is a device uint64 the step-state kernel bumps once per step (so a
@@ -42,7 +45,7 @@ typedef enum {
   COPER_ERR_WORKSPACE = -4
 } coper_status;
 
-enum { COPER_PREC_FP32 = 0, COPER_PREC_BF16 = 1, COPER_PREC_TF32X3 = 2 };
+enum { COPER_PREC_FP32 = 0, COPER_PREC_BF16 = 1, COPER_PREC_TF32X3 = 2, COPER_PREC_FP16X3 = 3 };
 
 int coper_version(void);
 const char* coper_status_string(int status);
@@ -149,7 +152,8 @@ int coper_score1n_fwd(const float* q, const float* E, const float* bias, int B, 
 /* Tensor-pipe operand preparation (COPER_PREC_BF16 / COPER_PREC_TF32X3) for the operands of the tf.matmul calls
  * at models.py:70-73,412,433-437.  The tcgen05 kernels consume operands in
  * "prepared" form: a bf16 copy [rows, ldp] (ldp = cols rounded up to 8), or two fp32 planes (hi = tf32-rounded value,
- * lo = x - hi) of [rows, ldp] (ldp = cols rounded up to 4).  Prepare the entity table once per evaluation pass /
+ * lo = x - hi) of [rows, ldp] (ldp = cols rounded up to 4), or (FP16X3) two fp16 planes of [rows, ldp] (ldp = cols
+ * rounded up to 8) holding hi / lo of x * 2^e followed by a 256-byte trailer whose first int32 is e.  Prepare the entity table once per evaluation pass /
  * optimizer step and reuse it across calls with coper_score1n_fwd_prepared (coper_score1n_fwd prepares per call). */
 size_t coper_prepared_bytes(int64_t rows, int cols, int prec);
 int coper_prepare_operand(const float* src, int64_t rows, int cols, int64_t ld_src, int prec, void* dst,

@@ -255,7 +255,7 @@ def test_dropout_hash_restatement_is_uniform():
 
 
 # ================================================================================================ GPU: CUDA vs goldens
-def _model(case, p, lr=LR):
+def _model(case, p, lr=LR, prec="fp32"):
     from coper_b200.models import ConvE
     md = {"use_negative_sampling": bool(case.get("sampled")), "label_smoothing_epsilon": 0.1, "num_ent": 97,
           "num_rel": 6,
@@ -267,9 +267,24 @@ def _model(case, p, lr=LR):
           "output_dropout": case["drop"][1], "learning_rate": lr, "batch_size": 0, "add_loss_summaries": False,
           "add_variable_summaries": False, "add_tensor_summaries": False, "batch_norm_momentum": 0.9,
           "batch_norm_train_stats": case["bn_train"], "do_parameter_lookup": variant_of(case) == "param_lookup"}
-    m = ConvE(md, seed=0)
+    m = ConvE(md, seed=0, prec=prec)
     m.load_variables(p)
     return m
+
+
+def elementwise_err(a, b, floor):
+    """max |a - b| / max(|b|, floor): every element is held to a relative bound, with an absolute floor for the entries
+    near zero (the max-norm `relerr` only bounds the error against the LARGEST entry)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return (np.abs(a - b) / np.maximum(np.abs(b), floor)).max()
+
+
+# tolerance of each engine against the reference-run goldens (fp32 TensorFlow semantics): the fp32 FFMA engine and the
+# fp32-class tf32x3 tensor-pipe engine share the 1e-5 bar; bf16 (operands rounded to 8 mantissa bits) states its own
+ENGINES = ["fp32", "tf32x3", "fp16x3", "bf16"]
+SCORE_TOL = {"fp32": 1e-5, "tf32x3": 1e-5, "fp16x3": 1e-5, "bf16": 1e-2}
+GRAD_TOL = {"fp32": 2e-4, "tf32x3": 2e-4, "fp16x3": 2e-4, "bf16": 5e-2}
+LOSS_TOL = {"fp32": 2e-6, "tf32x3": 2e-6, "fp16x3": 2e-6, "bf16": 2e-3}
 
 
 def _batch(z, step):
@@ -282,14 +297,54 @@ def _batch(z, step):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("prec", ENGINES)
 @pytest.mark.parametrize("name", [n for n in MODEL_CASES if not CASE_CFG[n]["is_train"]])
-def test_cuda_eval_scores_match_reference_model(name):
+def test_cuda_eval_scores_match_reference_model(name, prec):
+    """Every engine (FFMA fp32, tcgen05 tf32x3, tcgen05 bf16) against the logits the reference's models.py produced."""
     case = CASE_CFG[name]
     z = np.load(os.path.join(GOLD, "ref_model_%s.npz" % name))
-    m = _model(case, params_of(z, "init/", case))
+    m = _model(case, params_of(z, "init/", case), prec=prec)
     S = m.predict_all(_batch(z, 0)).cpu().numpy()
-    assert relerr(S, z["step0/predictions_all"]) < 1e-5
-    assert relerr(m._bufs[len(z["step0/e1"])].q.cpu().numpy(), z["step0/predicted_e2_emb"]) < 1e-5
+    ref = z["step0/predictions_all"]
+    assert relerr(S, ref) < SCORE_TOL[prec]
+    # element-wise: each logit within the tolerance of ITS magnitude (floor: 1 % of the largest logit)
+    assert elementwise_err(S, ref, 1e-2 * np.abs(ref).max()) < 100 * SCORE_TOL[prec]
+    assert relerr(m._bufs[len(z["step0/e1"])].q.cpu().numpy(), z["step0/predicted_e2_emb"]) < SCORE_TOL[prec]
+    # filtered ranks of the golden's own logits vs the engine's fused rank path: bit-exact wherever the engine's logits
+    # order the candidates like the golden's (always for the fp32-class engines on these tie-free cases)
+    if prec != "bf16":
+        rank, n_equal = m.filtered_ranks(_batch(z, 0))
+        dense = O.csr_to_dense(z["step0/rowptr"], z["step0/col"], 97)
+        cnt, ne = O.rank_count(ref, z["step0/e2"], dense)
+        assert np.array_equal(rank.cpu().numpy(), cnt) and int(n_equal.sum().item()) == int(ne.sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["tf32x3", "fp16x3", "bf16"])
+@pytest.mark.parametrize("name", [n for n in MODEL_CASES if CASE_CFG[n]["is_train"] and not CASE_CFG[n].get("sampled")])
+def test_cuda_tensor_pipe_gradients_match_reference_model(name, prec):
+    """Step-0 loss and every gradient of the tensor-pipe engines against the reference-run goldens."""
+    case = CASE_CFG[name]
+    z = np.load(os.path.join(GOLD, "ref_model_%s.npz" % name))
+    m = _model(case, params_of(z, "init/", case), prec=prec)
+    loss = m.train_step(_batch(z, 0), apply_update=False).item()
+    assert abs(loss - float(z["step0/loss"])) < LOSS_TOL[prec] * abs(loss)
+    grads = {k: v.cpu().numpy() for k, v in m.grads.items()}
+    if prec == "bf16":
+        # the bf16 forward flips the FC ReLU units whose pre-activation lies within rounding of zero; every gradient
+        # behind the batch-stat FCBN backward then differs from the fp32 reference in those few elements by the full
+        # common part of dq (tests/test_gpu_model.py checks the backward at the engine's own activation pattern).
+        # Against the fixed goldens: scorer-side gradient to the stated tolerance, every other one by direction.
+        ref = z["step0/grad/pred_bias"]
+        assert relerr(grads["pred_bias"].reshape(ref.shape), ref) < GRAD_TOL[prec]
+        for k, v in grads.items():
+            ref = z["step0/grad/" + k].ravel().astype(np.float64)
+            if np.abs(ref).max() < 1e-4 * max(np.abs(g_).max() for g_ in grads.values()):
+                continue                              # analytically ~0 (conv bias under batch-stat BN)
+            v = v.ravel().astype(np.float64)
+            assert (v * ref).sum() / (np.linalg.norm(v) * np.linalg.norm(ref) + 1e-30) > 0.97, k
+        return
+    assert_grads_close(grads, z, case, tol=GRAD_TOL[prec])
 
 
 @pytest.mark.gpu

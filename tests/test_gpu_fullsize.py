@@ -17,7 +17,7 @@ def _model(shape, prec):
     return ConvE(synthetic.descriptors(shape, dropout=True), seed=0, prec=prec, conv_in_height=s["H"])
 
 
-@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("shape", ["fb15k-237", "wn18rr", "nell-995", "yago3-10"])
 def test_full_size_step_is_reproducible_and_ranks_follow_the_counting_rule(shape, prec):
     from coper_b200 import synthetic

@@ -144,7 +144,7 @@ def _bf16r(x):
     return torch.as_tensor(np.asarray(x), dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("B,dc,F,d", [(512, 8, 4608, 200), (7, 5, 192, 40), (130, 3, 1000, 72), (64, 32, 512, 200),
                                       (512, 32, 6272, 256)])
 def test_cpg_fc_fwd_bwd(L, B, dc, F, d, prec):

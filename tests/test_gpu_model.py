@@ -326,11 +326,12 @@ def test_train_step_is_deterministic():
 # ------------------------------------------------------------------------------------------ tensor-pipe engines
 TC_TOL = {  # prec: (q, loss, dq/dy/df, parameter grads)
     "tf32x3": (1e-5, 1e-5, 1e-4, 2e-4),       # fp32-class: same bars as the CUDA-core fp32 engine
+    "fp16x3": (1e-5, 1e-5, 1e-4, 2e-4),
     "bf16": (2e-2, 2e-3, 5e-2, 5e-2),         # stated tolerance of the bf16 path (operands rounded to 8 mantissa bits)
 }
 
 
-@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("name", ["toy_glinear_batch_stats", "toy_gmlp_bn_dropout", "ragged_mid", "d256_16x16",
                                   "plain_d200", "lookup_d200", "lookup_toy", "cpgconv_gmlp_d200"])
 def test_train_step_parity_tensor_pipe(name, prec):
@@ -353,21 +354,33 @@ def test_train_step_parity_tensor_pipe(name, prec):
     assert relerr(b.dq.cpu().numpy(), g["_dq"]) < ta
     mg = grads_by_name(model)
     if prec == "bf16":
-        # dL/dS is carried in bf16: the scorer-side gradients meet the stated bar; everything behind the batch-stat
-        # FCBN backward sees the per-query variation of dq (the common part cancels) and is only required to point
-        # the same way as the oracle gradient.
+        # The bf16 forward (q within 2e-2 of the oracle) flips the few FC ReLU units whose pre-activation lies within
+        # rounding of zero (measured: 0-25 of 26 000).  Each flip moves that element of the ReLU/FCBN backward input
+        # by the FULL common part of dq, which batch-stat BN would otherwise cancel - so against the unmodified oracle
+        # the max-norm error of dy is dominated by those few elements (direction check only), while the GRADIENT CHECK
+        # proper evaluates the oracle backward at the engine's own activation pattern: every gradient within 2e-2.
         assert relerr(mg["pred_bias"], g["pred_bias"]) < tg
         cos = lambda a, r: float((a.ravel() * r.ravel()).sum() / (np.linalg.norm(a) * np.linalg.norm(r) + 1e-30))
         assert cos(mg["ent_emb"], g["ent_emb"]) > 0.99
         assert cos(b.dy.cpu().numpy(), g["_dy"]) > 0.9
         assert cos(mg[model._last_w_name].reshape(-1), g["fc_weights_proj"][-1].reshape(-1)) > 0.9
+        active = b.q.cpu().numpy() > 0
+        flips = int((active != (out["_cache"]["relu2"] > 0)).sum())
+        assert flips <= max(2, active.size // 500), flips
+        out["_cache"]["relu2"] = active.astype(np.float64)
+        g2 = O.backward(out, cfg)
+        assert relerr(b.dy.cpu().numpy(), g2["_dy"]) < 2e-2
+        assert relerr(b.df.cpu().numpy(), g2["_df"]) < 2e-2
+        assert relerr(mg["ent_emb"], g2["ent_emb"]) < 2e-2
+        assert relerr(mg[model._last_w_name].reshape(-1), g2["fc_weights_proj"][-1].reshape(-1)) < 2e-2
+        compare_grads(model, g2, cfg, tol=tg)
         return
     assert relerr(b.dy.cpu().numpy(), g["_dy"]) < ta
     assert relerr(b.df.cpu().numpy(), g["_df"]) < ta
     compare_grads(model, g, cfg, tol=tg)
 
 
-@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("name", ["toy_glinear_eval_stats", "ragged_mid", "d256_16x16", "plain_d200", "lookup_d200"])
 def test_eval_scores_and_ranks_tensor_pipe(name, prec):
     kw, B = CASES[name]
@@ -379,11 +392,11 @@ def test_eval_scores_and_ranks_tensor_pipe(name, prec):
     batch = batch_of(e1, rel, e2, rowptr, col)
     S = model.predict_all(batch).cpu().numpy()
     out = O.forward(params, cfg, e1, rel, False, None, None, np.float64)
-    assert relerr(S, out["scores"]) < (1e-5 if prec == "tf32x3" else 2e-2)
+    assert relerr(S, out["scores"]) < (1e-5 if prec != "bf16" else 2e-2)
     rank, n_equal = model.filtered_ranks(batch)
     cnt, ne = O.rank_count(S, e2, dense)                      # ranks are bit-exact given the device logits
     assert (n_equal.cpu().numpy() == ne).all() and (rank.cpu().numpy() == cnt).all()
-    if prec == "tf32x3" and ne.sum() == 0:
+    if prec != "bf16" and ne.sum() == 0:
         ref_rank = O.rank_literal(out["scores"].astype(np.float32), e2, dense)
         assert (rank.cpu().numpy() == ref_rank).mean() > 0.98  # fp32-class logits: ranks agree except near-ties
 

@@ -10,7 +10,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-PREC = {"bf16": 1, "tf32x3": 2}
+PREC = {"bf16": 1, "tf32x3": 2, "fp16x3": 3}
+FP32_CLASS = ("tf32x3", "fp16x3")      # 3-term compensated engines: fp32-class accuracy on the tensor pipe
 
 
 def relerr(a, b):
@@ -22,7 +23,7 @@ def bf16_round(x):
     return torch.as_tensor(x, dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
 
 
-@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("B,N,d", [(512, 40943, 200), (7, 97, 40), (130, 1003, 200), (33, 5000, 256), (512, 70001, 256),
                                    (128, 256, 64), (1, 1, 8)])
 def test_score1n_fwd_tensor_pipe(prec, B, N, d):
@@ -41,7 +42,7 @@ def test_score1n_fwd_tensor_pipe(prec, B, N, d):
     got = S[:, :N].cpu().numpy()
     assert np.isfinite(got).all()
     exact = q.astype(np.float64) @ E.astype(np.float64).T + bias
-    if prec == "tf32x3":
+    if prec in FP32_CLASS:
         assert relerr(got, exact) < 1e-5
     else:
         rounded = bf16_round(q) @ bf16_round(E).T + bias
@@ -57,7 +58,7 @@ def test_score1n_fwd_tensor_pipe(prec, B, N, d):
     assert torch.equal(S2[:, :N], S[:, :N])
 
 
-@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("M,N,K", [(130, 77, 301), (512, 200, 4608), (128, 200, 512), (300, 201, 100), (5, 8, 8),
                                    (1000, 256, 64)])
 def test_tc_gemm_all_layouts(prec, M, N, K):
@@ -80,13 +81,13 @@ def test_tc_gemm_all_layouts(prec, M, N, K):
                    L.ptr(ws), ws.numel())
             got = c.cpu().numpy()
             assert np.isfinite(got).all(), (ta, tb)
-            if prec == "tf32x3":
+            if prec in FP32_CLASS:
                 assert relerr(got, exact) < 1e-5, (ta, tb, relerr(got, exact))
             else:
                 assert relerr(got, rounded) < 1e-5, (ta, tb, relerr(got, rounded))
 
 
-@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("B,N,d", [(512, 40943, 200), (7, 97, 40), (130, 1003, 200), (33, 5000, 256), (128, 70001, 256),
                                    (4096, 5118, 200),      # one rank's share of 8-way data-parallel WN18RR
                                    # BASELINE.json configs at full size: FB15k-237, NELL-995, YAGO3-10 (B = 128)
@@ -122,7 +123,7 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     L.call("coper_score1n_bce_fwd_bwd", L.ptr(tq), L.ptr(tE), None, L.ptr(tb), L.ptr(bits), B, N, d, float(pos), float(neg),
            inv, L.ptr(loss), L.ptr(G), ld, L.ptr(dq), L.ptr(dE), L.ptr(db), L.ptr(ws), ws.numel(), p)
     torch.cuda.synchronize()
-    if prec == "tf32x3":
+    if prec in FP32_CLASS:
         qq, EE = q.astype(np.float64), E.astype(np.float64)
     else:
         qq, EE = bf16_round(q), bf16_round(E)
@@ -130,7 +131,7 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     el = np.maximum(Sr, 0) - Sr * zs + np.log1p(np.exp(-np.abs(Sr)))
     Gr = (O.sigmoid(Sr) - zs) * inv
     assert abs(loss.item() - el.sum()) < 1e-5 * el.sum()
-    gtol = 2e-5 if prec == "tf32x3" else 1e-2
+    gtol = 2e-5 if prec in FP32_CLASS else 1e-2
     for got, ref in ((dq, Gr @ EE), (dE, Gr.T @ qq), (db, Gr.sum(0))):
         got = got.cpu().numpy()
         assert np.isfinite(got).all()
@@ -143,7 +144,7 @@ def test_score1n_bce_fwd_bwd_tensor_pipe(prec, B, N, d):
     assert torch.equal(dq, dq2) and torch.equal(dE, dE2) and torch.equal(db, db2) and torch.equal(loss, loss2)
 
 
-@pytest.mark.parametrize("prec", ["bf16", "tf32x3"])
+@pytest.mark.parametrize("prec", ["bf16", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("B,N,d,lo", [(512, 40943, 200, 0), (7, 97, 40, 0), (130, 1003, 200, 0), (33, 5000, 256, 0),
                                       (64, 70001, 256, 123456), (300, 33, 64, 0), (4096, 5118, 200, 5118),
                                       (512, 14541, 200, 0), (512, 75492, 200, 0), (128, 123182, 200, 0)])

@@ -73,7 +73,7 @@ def bce(B, N, d, precs=("fp32", "bf16", "tf32x3")):
         print("score1n_bce_fwd_bwd B=%d N=%d d=%d %-7s %.3f ms %.1f TF/s" % (B, N, d, name, t, fl / t / 1e9))
 
 
-def rankf(B, N, d, precs=("bf16", "tf32x3")):
+def rankf(B, N, d, precs=("bf16", "tf32x3", "fp16x3")):
     q = torch.randn(B, d, device="cuda").clamp_(min=0)
     E = (torch.rand(N, d, device="cuda") - 0.5) * 0.1
     bias = torch.zeros(N, device="cuda")
@@ -97,7 +97,7 @@ def rankf(B, N, d, precs=("bf16", "tf32x3")):
         print("score1n_rank_fused B=%d N=%d d=%d %-7s gold %.3f ms, rank %.3f ms %.1f TF/s" % (B, N, d, name, t0, t, fl / t / 1e9))
 
 
-def cpg(B, dc, F, d, precs=("fp32", "bf16", "tf32x3")):
+def cpg(B, dc, F, d, precs=("fp32", "bf16", "tf32x3", "fp16x3")):
     c, f = torch.randn(B, dc, device="cuda"), torch.randn(B, F, device="cuda").clamp_(min=0)
     P, Pb = torch.randn(dc, F * d, device="cuda") * 0.01, torch.randn(dc, d, device="cuda")
     dy = torch.randn(B, d, device="cuda")
@@ -127,7 +127,7 @@ if __name__ == "__main__":
         bce(512, 40943, 200, precs=(sys.argv[2],))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rank":
-        precs = tuple(sys.argv[2:]) or ("bf16", "tf32x3")
+        precs = tuple(sys.argv[2:]) or ("bf16", "tf32x3", "fp16x3")
         rankf(512, 40943, 200, precs)
         rankf(512, 1000000, 256, precs)
         sys.exit(0)
