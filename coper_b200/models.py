@@ -427,12 +427,11 @@ class ConvE:
         """[num_ent, d] on every rank: all-gather of the (padded) row shards (run_cpg.py:245-248 pickles the table)."""
         if self.world == 1:
             return self.ent_emb
-        import torch.distributed as dist
         per, d = self.shard.per, self.ent_emb_size
         mine = torch.zeros(per, d, dtype=torch.float32, device=self.dev)
         mine[:self.shard.rows].copy_(self.ent_emb)
         out = torch.empty(self.world * per, d, dtype=torch.float32, device=self.dev)
-        dist.all_gather_into_tensor(out, mine, group=self.group)
+        sharding.gather_batch(out, mine, self.world, self.group)
         return out[:self.num_ent]
 
     def refresh_prepared(self):

@@ -94,9 +94,17 @@ def main(argv=None):
         import torch
         import torch.distributed as dist
         local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        # one GPU per rank over NCCL; if the box has fewer devices than local ranks (the single-GPU test tier) the
+        # ranks share a device and the exchange steps run over gloo (host-staged, coper_b200/sharding.py)
+        ndev = torch.cuda.device_count()
+        shared_device = ndev < int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        local = local % max(ndev, 1) if shared_device else local
         torch.cuda.set_device(local)
         if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            if shared_device:
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         if rank != 0:
             logging.getLogger().setLevel(logging.WARNING)
     use_cpg, use_parameter_lookup = args.model_type == "cpg", args.model_type == "param_lookup"
@@ -181,7 +189,8 @@ def main(argv=None):
         raise SystemExit("sampled-label configurations train on one GPU; pass --full-1n for the entity-sharded 1-N path")
     split_batch = world > 1 and cfg.training.batch_size % world == 0 and not use_parameter_lookup
     model = ConvE(md, seed=args.seed, prec=args.prec, conv_in_height=conv_h, init_fast=num_ent > 1_000_000,
-                  shard=EntityShard(num_ent, rank, world), data_parallel=split_batch, graphs_multi_gpu=True)
+                  shard=EntityShard(num_ent, rank, world), data_parallel=split_batch,
+                  graphs_multi_gpu=not (world > 1 and dist.get_backend() == "gloo"))
     logger.info("Number of entities: %d", num_ent)
     logger.info("Number of relations: %d", num_rel)
 

@@ -23,7 +23,9 @@ rank's entity rows.  Additional exchange steps:
   scatter_dq             reduce-scatter of the per-shard partial dq [Bg, d] -> each rank has the summed dq of its rows
   reduce_replicated_grads all-reduce(sum) of the flat bucket of replicated-parameter gradients
 
-All functions work on tensors of any device (NCCL on GPU; gloo on CPU in the unit tests).
+All functions work on tensors of any device (NCCL on GPU; gloo on CPU in the unit tests).  A gloo group given CUDA
+tensors stages every collective through host memory: that is how the world-2 parity tests run as two processes on ONE
+GPU (NCCL refuses two ranks on the same device), so a single-GPU box still exercises the sharded schedule end to end.
 """
 from __future__ import annotations
 
@@ -56,19 +58,58 @@ def _active(world, group):
     return world > 1 and dist.is_available() and dist.is_initialized()
 
 
+def _staged(t: torch.Tensor, group) -> bool:
+    """CUDA tensor on a gloo group: run the collective on a host copy (test path, see the module docstring)."""
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+class _Done:
+    def wait(self):
+        return True
+
+
+def _all_reduce(t, group, async_op=False):
+    if _staged(t, group):
+        h = t.detach().cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(h)
+        return _Done() if async_op else None
+    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def _reduce_scatter(out, inp, group):
+    if _staged(inp, group):
+        hi = inp.detach().cpu()
+        dist.all_reduce(hi, op=dist.ReduceOp.SUM, group=group)          # gloo has no reduce-scatter: reduce, then slice
+        r, n = dist.get_rank(group), out.numel()
+        out.copy_(hi.reshape(-1)[r * n:(r + 1) * n].reshape(out.shape))
+        return
+    dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+
+
+def _all_gather(out, inp, group):
+    if _staged(inp, group):
+        hi = inp.detach().cpu().contiguous()
+        parts = [torch.empty_like(hi) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, hi, group=group)
+        out.copy_(torch.cat([p.reshape(-1) for p in parts]).reshape(out.shape))
+        return
+    dist.all_gather_into_tensor(out, inp, group=group)
+
+
 def exchange_rows(x_masked: torch.Tensor, world: int, group=None) -> torch.Tensor:
     """x_masked [B, d]: rows owned by this rank filled, all others exactly zero.  Adding zeros is exact in
     fp32, so one all-reduce(sum) delivers every row bit-exactly to every rank."""
     if _active(world, group):
-        dist.all_reduce(x_masked, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(x_masked, group)
     return x_masked
 
 
 def reduce_scorer_partials(loss_sum: torch.Tensor, dq: torch.Tensor, world: int, group=None):
     """Each rank scored all queries against its rows: the loss and dq = sum over shards of G_s . E_s add up."""
     if _active(world, group):
-        dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(dq, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(loss_sum, group)
+        _all_reduce(dq, group)
     return loss_sum, dq
 
 
@@ -76,22 +117,22 @@ def reduce_sharded_sumsq(sumsq_sharded: torch.Tensor, world: int, group=None) ->
     """Squared-norm partials of the row-sharded gradients add across ranks; replicated gradients are identical on
     every rank and are counted once (they are NOT passed here)."""
     if _active(world, group):
-        dist.all_reduce(sumsq_sharded, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(sumsq_sharded, group)
     return sumsq_sharded
 
 
 def reduce_gold(gold: torch.Tensor, world: int, group=None) -> torch.Tensor:
     """gold [B]: the logit of e2[b] on the rank that owns entity e2[b], 0 elsewhere."""
     if _active(world, group):
-        dist.all_reduce(gold, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(gold, group)
     return gold
 
 
 def reduce_counts(n_greater: torch.Tensor, n_equal: torch.Tensor, world: int, group=None):
     """Integer partial counts add exactly -> ranks are bit-identical for any number of shards."""
     if _active(world, group):
-        dist.all_reduce(n_greater, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(n_equal, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(n_greater, group)
+        _all_reduce(n_equal, group)
     return n_greater, n_equal
 
 
@@ -100,7 +141,7 @@ def scatter_rows(x_masked_global: torch.Tensor, x_local: torch.Tensor, world: in
     """x_masked_global [Bg, d] as in exchange_rows; rank r receives rows [r*Bl, (r+1)*Bl) summed over the owners
     (bit-exact: one owner, zeros elsewhere)."""
     if _active(world, group):
-        dist.reduce_scatter_tensor(x_local, x_masked_global, op=dist.ReduceOp.SUM, group=group)
+        _reduce_scatter(x_local, x_masked_global, group)
     else:
         x_local.copy_(x_masked_global)
     return x_local
@@ -109,7 +150,7 @@ def scatter_rows(x_masked_global: torch.Tensor, x_local: torch.Tensor, world: in
 def gather_batch(x_global: torch.Tensor, x_local: torch.Tensor, world: int, group=None) -> torch.Tensor:
     """Per-rank rows [Bl, w] -> [Bg, w] in batch order on every rank."""
     if _active(world, group):
-        dist.all_gather_into_tensor(x_global, x_local, group=group)
+        _all_gather(x_global, x_local, group)
     else:
         x_global.copy_(x_local)
     return x_global
@@ -119,7 +160,7 @@ def gather_stat_partials(all_partials: torch.Tensor, partials: torch.Tensor, wor
     """partials [nchunk, C, 2] (per-chunk sums the stats kernels write) -> [P*nchunk, C, 2]; the finalise kernels
     then run with nchunk*P chunks and R*P rows: the statistics of the global batch, identical on every rank."""
     if _active(world, group):
-        dist.all_gather_into_tensor(all_partials, partials, group=group)
+        _all_gather(all_partials, partials, group)
     else:
         all_partials.copy_(partials)
     return all_partials
@@ -128,8 +169,8 @@ def gather_stat_partials(all_partials: torch.Tensor, partials: torch.Tensor, wor
 def scatter_dq(dq_partial_global: torch.Tensor, dq_local: torch.Tensor, loss_sum: torch.Tensor, world: int, group=None):
     """Entity-sharded scorer over all Bg queries: partial dq [Bg, d] sums over shards; each rank keeps its rows."""
     if _active(world, group):
-        dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)
-        dist.reduce_scatter_tensor(dq_local, dq_partial_global, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(loss_sum, group)
+        _reduce_scatter(dq_local, dq_partial_global, group)
     else:
         dq_local.copy_(dq_partial_global)
     return dq_local
@@ -138,5 +179,5 @@ def scatter_dq(dq_partial_global: torch.Tensor, dq_local: torch.Tensor, loss_sum
 def reduce_replicated_grads(flat: torch.Tensor, world: int, group=None, async_op: bool = False):
     """Gradients of replicated parameters are partial sums over the rank's rows of the batch."""
     if _active(world, group):
-        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return _all_reduce(flat, group, async_op=async_op)
     return None
