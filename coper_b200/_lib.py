@@ -52,6 +52,8 @@ SIGNATURES = {
     "coper_score1n_bce_G_bytes": (sz, [i32, i64, i32]),
     "coper_score1n_bce_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
                                         sz, i32, vp]),
+    "coper_score1n_bce_fwd_bwd_norm": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
+                                             vp, sz, i32, vp]),
     "coper_sample_labels": (i32, [vp, vp, i32, i64, i32, i32, vp, u64, vp, vp, vp]),
     "coper_score_sampled_workspace_bytes": (sz, [i32, i32]),
     "coper_score_sampled_bce_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, f32, f32, vp, vp, vp, vp, vp,
@@ -68,11 +70,13 @@ SIGNATURES = {
     "coper_bits_t_set": (i32, [vp, i32, i64, i64, vp, vp]),
     "coper_segscatter_workspace_bytes": (sz, [i32]),
     "coper_segscatter_add_sq": (i32, [vp, i32, vp, i32, vp, vp, i64, i64, vp]),
+    "coper_segscatter_add_norm": (i32, [vp, i32, vp, i32, vp, vp, i64, i64, vp, vp]),
     "coper_segscatter_add": (i32, [vp, i32, vp, i32, vp, i64, i64, vp, sz, vp]),
     "coper_reduce_partials": (i32, [vp, i32, i64, f32, i32, vp, vp]),
     "coper_sumsq": (i32, [vp, i64, i32, vp, vp]),
     "coper_clip_scale": (i32, [vp, i32, f32, vp, vp]),
     "coper_step_state_advance": (i32, [vp, vp, f32, f32, f32, vp]),
+    "coper_sumsq_combine": (i32, [vp, i32, vp, i32, vp, vp]),
     "coper_mt_sumsq": (i32, [vp, i32, vp, i32, vp, vp, vp, vp]),
     "coper_clip_scale_n": (i32, [vp, i32, f32, vp, vp]),
     "coper_mt_amsgrad": (i32, [vp, vp, i32, vp, f32, f32, f32, vp, i32, vp]),

@@ -264,7 +264,10 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
       return check_launch();
     }
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};            // the attribute is per device, not per process
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return COPER_ERR_CUDA;
+  bool& attr_set = attr_set_dev[dev];
   if (smem > 48 * 1024 && !attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (rc) return rc;

@@ -105,7 +105,16 @@ __global__ void cpg_fwd_finalize_kernel(const float* __restrict__ part, int S, c
   if (e >= n) return;
   int b = (int)(e / d), j = (int)(e % d);
   double acc = 0.0;
-  for (int s = 0; s < S; ++s) acc += (double)part[(int64_t)s * n + e];
+  // slabs are summed in slab order (deterministic); the loads of 8 slabs are issued together, the adds stay ordered
+  int s = 0;
+  for (; s + 8 <= S; s += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (int64_t)(s + u) * n + e);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += (double)v[u];
+  }
+  for (; s < S; ++s) acc += (double)__ldg(part + (int64_t)s * n + e);
   float bias = 0.f;
   for (int k = 0; k < dcb; ++k) bias = fmaf(__ldg(cb + (int64_t)b * dcb + k), __ldg(Pb + (int64_t)k * d + j), bias);
   float v = (float)acc + bias;

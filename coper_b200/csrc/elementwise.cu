@@ -2,6 +2,8 @@
 // deterministic reductions, global-norm clip and AMSGrad.  All kernels are streaming: coalesced,
 // 128-bit vectorised where the shape allows, grids sized in multiples of the SM count.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace coper {
@@ -401,7 +403,9 @@ __global__ void __launch_bounds__(256) mt_sumsq_kernel(const coper_param_desc* _
   const int64_t end = start + COPER_MT_CHUNK < d.n ? start + COPER_MT_CHUNK : d.n;
   const float* x = d.grad;
   float p = 0.f;
-  if (d.mode == COPER_GRAD_INDEXED_SLICES) {
+  if (d.mode & COPER_GRAD_NORM_EXTERNAL) {
+    // the squared norm of this gradient is supplied by its producer (coper_sumsq_combine): nothing to read
+  } else if (d.mode == COPER_GRAD_INDEXED_SLICES) {
     // IndexedSlices: norm over the slice values = sum of the per-row sums of squared slices
     for (int64_t j = start + threadIdx.x; j < end; j += 256) p += d.grad_sq[j];
   } else if (((reinterpret_cast<uintptr_t>(x) & 15) == 0) && end - start == COPER_MT_CHUNK) {
@@ -418,15 +422,30 @@ __global__ void __launch_bounds__(256) mt_sumsq_kernel(const coper_param_desc* _
   if (threadIdx.x == 0) chunk_partials[blockIdx.x] = tsum;
 }
 // tensor_sumsq[t] = sum of the chunk partials of tensor t (fixed order); chunk_offsets [n_tensors + 1]
-__global__ void mt_tensor_sums_kernel(const double* __restrict__ chunk_partials, const int32_t* __restrict__ chunk_offsets,
-                                      int n_tensors, double* __restrict__ tensor_sumsq) {
+__device__ __forceinline__ uint32_t* fp16x3_trailer_of(const coper_param_desc& d) {
+  // the optimizer emits operands whose pitch equals the row length: 2 fp16 planes of n elements, then the trailer
+  return reinterpret_cast<uint32_t*>(static_cast<char*>(d.prepared) + (((size_t)d.n * 4 + 255) / 256) * 256);
+}
+__global__ void mt_tensor_sums_kernel(const coper_param_desc* __restrict__ descs, const double* __restrict__ chunk_partials,
+                                      const int32_t* __restrict__ chunk_offsets, int n_tensors,
+                                      double* __restrict__ tensor_sumsq) {
   // one warp per tensor: lanes stride over the tensor's chunks, fixed-order shuffle combine
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n_tensors) return;
   double acc = 0.0;
   for (int c = chunk_offsets[t] + lane; c < chunk_offsets[t + 1]; c += 32) acc += chunk_partials[c];
   acc = warp_sum_d(acc);
-  if (lane == 0) tensor_sumsq[t] = acc;
+  if (lane == 0) {
+    tensor_sumsq[t] = acc;
+    // fp16x3 operand copies re-emitted by the update kernel that follows: roll the exponent to the magnitude the
+    // variable has NOW (running max of the previous emission / of the full preparation) and restart the running max
+    const coper_param_desc d = descs[t];
+    if (d.prepared && d.prepared_prec == COPER_PREC_FP16X3) {
+      uint32_t* tr = fp16x3_trailer_of(d);
+      reinterpret_cast<int*>(tr)[0] = fp16x3_exponent_of(__uint_as_float(tr[2]));
+      tr[2] = 0u;
+    }
+  }
 }
 __device__ __forceinline__ void amsgrad_elem(float g, float& th, float* m, float* v, float& vh, int64_t i, float lr_t,
                                              float b1, float b2, float omb1, float omb2, float eps, int bug_compat) {
@@ -443,9 +462,14 @@ __device__ __forceinline__ void amsgrad_elem(float g, float& th, float* m, float
   vh = fmaxf(vh, vt);
   th -= lr_t * mt / (sqrtf(vh) + eps);
 }
-__device__ __forceinline__ void emit_prepared(const coper_param_desc& d, int64_t i, float th) {
+__device__ __forceinline__ void emit_prepared(const coper_param_desc& d, int64_t i, float th, float sc = 1.0f) {
   if (d.prepared_prec == COPER_PREC_BF16) {
     static_cast<__nv_bfloat16*>(d.prepared)[i] = __float2bfloat16_rn(th);
+  } else if (d.prepared_prec == COPER_PREC_FP16X3) {
+    const float xs = th * sc;
+    const __half h = __float2half_rn(xs);
+    static_cast<__half*>(d.prepared)[i] = h;
+    static_cast<__half*>(d.prepared)[d.n + i] = __float2half_rn(xs - __half2float(h));
   } else {
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(th));
@@ -466,7 +490,12 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
   const float lr_t = step_state[0];
   const float cs = clip_scale ? *clip_scale : 1.0f;
   const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
-  if (d.mode == COPER_GRAD_INDEXED_SLICES) {                 // utils/amsgrad.py:161-189 (slots accumulate)
+  // fp16x3 operand copy: the exponent was rolled by mt_tensor_sums_kernel; max |theta_new| goes to the running max
+  const bool f16x3 = d.prepared && d.prepared_prec == COPER_PREC_FP16X3;
+  uint32_t* trailer = f16x3 ? fp16x3_trailer_of(d) : nullptr;
+  const float sc = f16x3 ? exp2f((float)reinterpret_cast<const int*>(trailer)[0]) : 1.0f;
+  float amax = 0.f;
+  if ((d.mode & 1) == COPER_GRAD_INDEXED_SLICES) {           // utils/amsgrad.py:161-189 (slots accumulate)
     for (int64_t i = start + threadIdx.x; i < end; i += 256) {
       const float g1 = d.grad[i] * cs, g2 = d.grad_sq[i] * cs * cs;
       const float mt = d.m[i] * b1 + g1 * omb1;
@@ -477,7 +506,12 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
       d.vhat[i] = vh;
       const float th = d.theta[i] - lr_t * mt / (sqrtf(vh) + eps);
       d.theta[i] = th;
-      if (d.prepared) emit_prepared(d, i, th);
+      if (d.prepared) emit_prepared(d, i, th, sc);
+      amax = fmaxf(amax, fabsf(th));
+    }
+    if (f16x3) {
+      amax = warp_max(amax);
+      if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(trailer + 2, __float_as_uint(amax));
     }
     return;
   }
@@ -488,7 +522,7 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
     float4* th4 = reinterpret_cast<float4*>(d.theta + start);
     const float4* g4 = reinterpret_cast<const float4*>(d.grad + start);
     float4* vh4 = reinterpret_cast<float4*>(d.vhat + start);
-#pragma unroll 2
+#pragma unroll 4
     for (int j = threadIdx.x; j < COPER_MT_CHUNK / 4; j += 256) {
       float4 g = g4[j], th = th4[j], vh = vh4[j];
       amsgrad_elem(g.x * cs, th.x, nullptr, nullptr, vh.x, 0, lr_t, b1, b2, omb1, omb2, eps, 1);
@@ -505,6 +539,21 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
           u.x = *reinterpret_cast<uint32_t*>(&p0);
           u.y = *reinterpret_cast<uint32_t*>(&p1);
           *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(d.prepared) + i) = u;
+        } else if (d.prepared_prec == COPER_PREC_FP16X3 && (d.n & 3) == 0) {
+          const float a0 = th.x * sc, a1 = th.y * sc, a2 = th.z * sc, a3 = th.w * sc;
+          const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          const __half2 l0 = __floats2half2_rn(a0 - f0.x, a1 - f0.y), l1 = __floats2half2_rn(a2 - f1.x, a3 - f1.y);
+          uint2 uh, ul;
+          uh.x = *reinterpret_cast<const uint32_t*>(&h0); uh.y = *reinterpret_cast<const uint32_t*>(&h1);
+          ul.x = *reinterpret_cast<const uint32_t*>(&l0); ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(static_cast<__half*>(d.prepared) + i) = uh;
+          *reinterpret_cast<uint2*>(static_cast<__half*>(d.prepared) + d.n + i) = ul;
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(th.x), fabsf(th.y))), fmaxf(fabsf(th.z), fabsf(th.w)));
+        } else if (d.prepared_prec == COPER_PREC_FP16X3) {
+          emit_prepared(d, i, th.x, sc); emit_prepared(d, i + 1, th.y, sc); emit_prepared(d, i + 2, th.z, sc);
+          emit_prepared(d, i + 3, th.w, sc);
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(th.x), fabsf(th.y))), fmaxf(fabsf(th.z), fabsf(th.w)));
         } else if ((d.n & 3) == 0) {
           float h[4] = {th.x, th.y, th.z, th.w}, l[4];
 #pragma unroll
@@ -529,9 +578,25 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
       amsgrad_elem(d.grad[i] * cs, th, d.m, d.v, vh, i, lr_t, b1, b2, omb1, omb2, eps, bug_compat);
       d.theta[i] = th;
       d.vhat[i] = vh;
-      if (d.prepared) emit_prepared(d, i, th);
+      if (d.prepared) emit_prepared(d, i, th, sc);
+      amax = fmaxf(amax, fabsf(th));
     }
   }
+  if (f16x3) {
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(trailer + 2, __float_as_uint(amax));
+  }
+}
+
+// out[0] = sum(parts[0..n_parts)) + sum(deltas[0..n_deltas)) in a fixed order (one block)
+__global__ void sumsq_combine_kernel(const double* __restrict__ parts, int n_parts, const double* __restrict__ deltas,
+                                     int n_deltas, double* __restrict__ out) {
+  __shared__ double smd[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) acc += parts[i];
+  for (int i = threadIdx.x; i < n_deltas; i += blockDim.x) acc += deltas[i];
+  const double t = block_sum<double>(acc, smd);
+  if (threadIdx.x == 0) *out = t > 0.0 ? t : 0.0;
 }
 
 static inline int grid_for(int64_t n, int threads, int per_sm = 8) {
@@ -734,8 +799,8 @@ int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* 
   mt_sumsq_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, chunk_partials);
   int rc = check_launch();
   if (rc) return rc;
-  mt_tensor_sums_kernel<<<(n_tensors * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(chunk_partials, chunk_offsets, n_tensors,
-                                                                            tensor_sumsq);
+  mt_tensor_sums_kernel<<<(n_tensors * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(descs, chunk_partials, chunk_offsets,
+                                                                            n_tensors, tensor_sumsq);
   return check_launch();
 }
 int coper_mt_amsgrad(const coper_param_desc* descs, const int32_t* chunks, int n_chunks, const float* step_state,
@@ -744,6 +809,12 @@ int coper_mt_amsgrad(const coper_param_desc* descs, const int32_t* chunks, int n
   COPER_CHECK_ARG(descs && chunks && step_state && n_chunks > 0);
   mt_amsgrad_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, step_state, beta1, beta2, eps, clip_scale,
                                                             bug_compat);
+  return check_launch();
+}
+int coper_sumsq_combine(const double* parts, int n_parts, const double* deltas, int n_deltas, double* out,
+                        coper_stream_t stream) {
+  COPER_CHECK_ARG(out && n_parts >= 0 && n_deltas >= 0 && (parts || n_parts == 0) && (deltas || n_deltas == 0));
+  sumsq_combine_kernel<<<1, 256, 0, as_stream(stream)>>>(parts, n_parts, deltas, n_deltas, out);
   return check_launch();
 }
 int coper_step_state_advance(float* step_state, uint64_t* seed_dev, float lr, float beta1, float beta2,

@@ -21,7 +21,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
                              const uint32_t* label_bits, int B,
                              int64_t Ns, int d, float pos, float neg, float inv_count, double* loss_sum, void* G,
                              int64_t ldG, float* dq, float* dE, float* dbias, void* ws, size_t ws_bytes, int prec,
-                             cudaStream_t st);
+                             double* dE_sumsq, cudaStream_t st);
 
 using namespace simt;
 
@@ -239,17 +239,17 @@ size_t coper_score1n_bce_G_bytes(int B, int64_t Ns, int prec) {
   return (size_t)B * ((Ns + 31) / 32 * 32) * sizeof(float);
 }
 
-int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
-                              const uint32_t* label_bits, int B,
-                              int64_t Ns, int d, float pos_target, float neg_target, float inv_count,
-                              double* loss_sum, void* Gv, int64_t ldG, float* dq, float* dE, float* dbias,
-                              void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
+static int score1n_bce_impl(const float* q, const float* E, const void* E_prepared, const float* bias,
+                            const uint32_t* label_bits, int B, int64_t Ns, int d, float pos_target, float neg_target,
+                            float inv_count, double* loss_sum, void* Gv, int64_t ldG, float* dq, float* dE, float* dbias,
+                            void* workspace, size_t workspace_bytes, int prec, double* dE_sumsq, coper_stream_t stream) {
   COPER_CHECK_ARG(q && E && bias && label_bits && loss_sum && Gv && dq && dE && dbias && workspace);
   COPER_CHECK_ARG(B > 0 && Ns > 0 && d > 0 && ldG >= Ns);
   if (prec == COPER_PREC_BF16 || prec == COPER_PREC_TF32X3 || prec == COPER_PREC_FP16X3)
     return umma_score1n_bce_fwd_bwd(q, E, E_prepared, bias, label_bits, B, Ns, d, pos_target, neg_target, inv_count, loss_sum, Gv,
-                                    ldG, dq, dE, dbias, workspace, workspace_bytes, prec, as_stream(stream));
+                                    ldG, dq, dE, dbias, workspace, workspace_bytes, prec, dE_sumsq, as_stream(stream));
   if (prec != COPER_PREC_FP32) return COPER_ERR_UNSUPPORTED;
+  if (dE_sumsq) return COPER_ERR_UNSUPPORTED;         // the CUDA-core engine does not fuse the norm (callers pass NULL)
   float* G = static_cast<float*>(Gv);
   BceLayout L = bce_layout(B, Ns, d);
   if (workspace_bytes < L.total) return COPER_ERR_WORKSPACE;
@@ -272,6 +272,23 @@ int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prep
   if (rc) return rc;
   dE_kernel<<<dim3(ceil_div(Ns, BM), ceil_div(d, BN)), THREADS, 0, st>>>(G, ldG, q, B, Ns, d, dE);
   return check_launch();
+}
+
+int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
+                              const uint32_t* label_bits, int B, int64_t Ns, int d, float pos_target, float neg_target,
+                              float inv_count, double* loss_sum, void* Gv, int64_t ldG, float* dq, float* dE,
+                              float* dbias, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
+  return score1n_bce_impl(q, E, E_prepared, bias, label_bits, B, Ns, d, pos_target, neg_target, inv_count, loss_sum, Gv,
+                          ldG, dq, dE, dbias, workspace, workspace_bytes, prec, nullptr, stream);
+}
+int coper_score1n_bce_fwd_bwd_norm(const float* q, const float* E, const void* E_prepared, const float* bias,
+                                   const uint32_t* label_bits, int B, int64_t Ns, int d, float pos_target,
+                                   float neg_target, float inv_count, double* loss_sum, void* Gv, int64_t ldG, float* dq,
+                                   float* dE, float* dbias, double* dE_sumsq, void* workspace, size_t workspace_bytes,
+                                   int prec, coper_stream_t stream) {
+  COPER_CHECK_ARG(dE_sumsq);
+  return score1n_bce_impl(q, E, E_prepared, bias, label_bits, B, Ns, d, pos_target, neg_target, inv_count, loss_sum, Gv,
+                          ldG, dq, dE, dbias, workspace, workspace_bytes, prec, dE_sumsq, stream);
 }
 
 }  // extern "C"

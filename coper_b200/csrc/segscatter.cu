@@ -40,12 +40,16 @@ __global__ void segscatter_kernel(const int64_t* __restrict__ keys, const int32_
 // sort would give): same result bit for bit as the sorted path, one launch, no workspace.
 // dst_sq (optional): sum of the SQUARED source rows per destination row (the IndexedSlices bookkeeping).
 constexpr int kSegSmallM = 4096;
+// norm_delta (optional, [M] doubles): position i receives sum_c (new_c^2 - old_c^2) of the destination row it updated
+// (0 if it is not a segment head / not owned) - the correction that turns a sum of squares taken BEFORE the scatter
+// (by the kernel that produced dst) into the sum of squares of the final gradient.
 __global__ void segscatter_small_kernel(const int64_t* __restrict__ idx, int M, const float* __restrict__ src, int width,
                                         float* __restrict__ dst, float* __restrict__ dst_sq, int64_t row_lo,
-                                        int64_t row_hi) {
+                                        int64_t row_hi, double* __restrict__ norm_delta) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= M) return;
+  if (norm_delta && lane == 0) norm_delta[i] = 0.0;
   const int64_t key = idx[i];
   if (key < row_lo || key >= row_hi) return;
   bool dup = false;
@@ -56,6 +60,7 @@ __global__ void segscatter_small_kernel(const int64_t* __restrict__ idx, int M, 
   if (__any_sync(0xffffffffu, dup)) return;          // an earlier position owns this row
   float* drow = dst + (key - row_lo) * (int64_t)width;
   float* qrow = dst_sq ? dst_sq + (key - row_lo) * (int64_t)width : nullptr;
+  double delta = 0.0;
   for (int c0 = 0; c0 < width; c0 += 32 * 4) {       // 4 columns per lane per pass
     float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j0 = (i / 32) * 32; j0 < M; j0 += 32) {
@@ -79,10 +84,16 @@ __global__ void segscatter_small_kernel(const int64_t* __restrict__ idx, int M, 
     for (int k = 0; k < 4; ++k) {
       const int c = c0 + lane + 32 * k;
       if (c < width) {
-        drow[c] += a[k];
+        const float old = drow[c], nw = old + a[k];
+        drow[c] = nw;
+        delta += (double)nw * (double)nw - (double)old * (double)old;
         if (qrow) qrow[c] += q[k];
       }
     }
+  }
+  if (norm_delta) {
+    delta = warp_sum_d(delta);
+    if (lane == 0) norm_delta[i] = delta;
   }
 }
 
@@ -116,7 +127,18 @@ int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int wid
   COPER_CHECK_ARG(idx && src && dst && M >= 0 && width > 0 && row_hi >= row_lo);
   if (M > kSegSmallM) return COPER_ERR_UNSUPPORTED;
   if (M == 0) return COPER_OK;
-  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(idx, M, src, width, dst, dst_sq, row_lo, row_hi);
+  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(idx, M, src, width, dst, dst_sq, row_lo, row_hi,
+                                                                         nullptr);
+  return check_launch();
+}
+
+int coper_segscatter_add_norm(const int64_t* idx, int M, const float* src, int width, float* dst, float* dst_sq,
+                              int64_t row_lo, int64_t row_hi, double* norm_delta, coper_stream_t stream) {
+  COPER_CHECK_ARG(idx && src && dst && norm_delta && M >= 0 && width > 0 && row_hi >= row_lo);
+  if (M > kSegSmallM) return COPER_ERR_UNSUPPORTED;
+  if (M == 0) return COPER_OK;
+  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(idx, M, src, width, dst, dst_sq, row_lo, row_hi,
+                                                                         norm_delta);
   return check_launch();
 }
 

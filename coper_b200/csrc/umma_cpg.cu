@@ -159,9 +159,7 @@ __global__ void prepare_scaled_kernel(const float* __restrict__ dy, const float*
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float sc = 1.0f;
   if (prec == COPER_PREC_FP16X3) {                      // same exponent rule as coper_prepare_operand (umma_score.cu)
-    const float m = __uint_as_float(trailer[1]);
-    int ex = (m > 0.f && isfinite(m)) ? 10 - ilogbf(m) : 0;
-    ex = max(-100, min(100, ex));
+    const int ex = fp16x3_exponent_of(__uint_as_float(trailer[1]));
     if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(trailer)[0] = ex;
     sc = exp2f((float)ex);
   }

@@ -533,8 +533,25 @@ int umma_score1n_rank(const void* q_prep, const void* E_prep, const float* bias,
 }
 
 // ------------------------------------------------------------------------------------------ training scorer
+// dE = G^T . q; with dE_sumsq != NULL the store epilogue also sums the squares of what it writes (per-warp partials,
+// fixed-order final sum): the global-norm clip then does not re-read the [Ns, d] gradient
+static int dE_gemm(int prec, bool a_mn, const TcOperand& Go, const TcOperand& Qo, const GemmProblem& p, StoreEpi epi,
+                   double* dE_sumsq, double* ss_part, cudaStream_t st) {
+  int rc;
+  const int n_part = sm_count() * 16;
+  if (dE_sumsq) {
+    if ((rc = check_cuda(cudaMemsetAsync(ss_part, 0, (size_t)n_part * sizeof(double), st)))) return rc;
+    epi.sumsq_part = ss_part;
+  }
+  if ((rc = tc_gemm_store(prec, a_mn, true, Go, Qo, p, false, epi, st))) return rc;
+  if (dE_sumsq) {
+    sum_doubles_kernel<<<1, 256, 0, st>>>(ss_part, n_part, dE_sumsq);
+    rc = check_launch();
+  }
+  return rc;
+}
 struct BceTcLayout {
-  size_t off_q, off_E, off_dq, off_dbias, off_loss, total;
+  size_t off_q, off_E, off_dq, off_dbias, off_loss, off_ss, total;
   int splits, dbias_slabs;
 };
 static BceTcLayout bce_tc_layout(int B, int64_t Ns, int d, int prec) {
@@ -557,6 +574,7 @@ static BceTcLayout bce_tc_layout(int B, int64_t Ns, int d, int prec) {
   L.off_dq = o; o = align_up(o + dq_rows * d * sizeof(float), 256);
   L.off_dbias = o; o = align_up(o + (size_t)L.dbias_slabs * Ns * sizeof(float), 256);
   L.off_loss = o; o = align_up(o + (size_t)sm_count() * kBceEpiWarps * sizeof(double), 256);
+  L.off_ss = o; o = align_up(o + (size_t)sm_count() * 16 * sizeof(double), 256);      // sum-of-squares partials of dE
   L.total = o;
   return L;
 }
@@ -591,7 +609,7 @@ static int bce_impl(const TcOperand& E, const TcOperand& Q, const float* bias, c
 int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
                              const uint32_t* label_bits_t, int B, int64_t Ns, int d, float pos, float neg,
                              float inv_count, double* loss_sum, void* G, int64_t ldG, float* dq, float* dE,
-                             float* dbias, void* ws, size_t ws_bytes, int prec, cudaStream_t st) {
+                             float* dbias, void* ws, size_t ws_bytes, int prec, double* dE_sumsq, cudaStream_t st) {
   if (Ns > 0x7fffffff - 512) return COPER_ERR_UNSUPPORTED;
   (void)ldG;                                          // the tensor-pipe engines lay G out entity-major themselves
   if (reinterpret_cast<uintptr_t>(G) & 127) return COPER_ERR_INVALID_ARG;
@@ -628,7 +646,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     GemmProblem pe{};
     pe.M = (int)Ns; pe.N = d; pe.K = B; pe.groups = 1; pe.groups_inner = 0;
     StoreEpi epi = make_store_epi(dE, d, 0, 0);
-    return tc_gemm_store(prec, false, true, Go, Qo, pe, false, epi, st);
+    return dE_gemm(prec, false, Go, Qo, pe, epi, dE_sumsq, reinterpret_cast<double*>(w + L.off_ss), st);
   }
   // ---- pass 1: scores -> loss, G, dbias partials
   int grid = 0;
@@ -676,7 +694,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     p.M = (int)Ns; p.N = d; p.K = B; p.groups = 1; p.groups_inner = 0;
     p.post_scale = g_post;
     StoreEpi epi = make_store_epi(dE, d, 0, 0);
-    if ((rc = tc_gemm_store(prec, !entity_major, true, Go, Qo, p, false, epi, st))) return rc;
+    if ((rc = dE_gemm(prec, !entity_major, Go, Qo, p, epi, dE_sumsq, reinterpret_cast<double*>(w + L.off_ss), st))) return rc;
   }
   return COPER_OK;
 }

@@ -610,10 +610,21 @@ struct StoreEpi : EpiBase {
   const float* col_bias;    // optional [N]
   int extra_col;            // if >= 0: column index whose values go to extra_out[row] instead (e.g. dbias)
   float* extra_out;
+  double* sumsq_part;       // optional [grid * epilogue warps]: sum of the squares of everything this warp stored
+  double ss_acc;            //   (the gradient-norm pass of the optimizer then need not re-read the output)
   __device__ __forceinline__ void chunk(const GemmProblem& p, const TileCoord& t, int row, int col,
-                                        const uint32_t (&r)[32], int) const {
+                                        const uint32_t (&r)[32], int) {
     const int lane = threadIdx.x & 31;
     const int n_out = extra_col >= 0 ? min(p.N, extra_col) : p.N;
+    if (sumsq_part && row < p.M) {           // plain-store uses only (no row scale / bias): squares of the raw values
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = __uint_as_float(r[j]);
+        ss = (col + j < n_out) ? fmaf(v, v, ss) : ss;
+      }
+      ss_acc += (double)ss;
+    }
     float* base = out + t.group * group_stride + t.split * split_stride;
     float* o0 = base + (long long)(row - lane) * ld + col;          // (first row of this warp, col)
     // warp-uniform: whole float4 granules, 16-byte aligned rows
@@ -638,12 +649,18 @@ struct StoreEpi : EpiBase {
       }
     }
   }
+  __device__ __forceinline__ void finish(int epi_thread, int epi_threads) {
+    if (!sumsq_part) return;
+    const double t = warp_sum_d(ss_acc);
+    if ((epi_thread & 31) == 0) sumsq_part[(long long)blockIdx.x * (epi_threads >> 5) + (epi_thread >> 5)] = t;
+  }
 };
 
 inline StoreEpi make_store_epi(float* out, long long ld, long long group_stride, long long split_stride) {
   StoreEpi e;
   e.out = out; e.ld = ld; e.group_stride = group_stride; e.split_stride = split_stride;
   e.row_scale = nullptr; e.row_scale_ld = 0; e.col_bias = nullptr; e.extra_col = -1; e.extra_out = nullptr;
+  e.sumsq_part = nullptr; e.ss_acc = 0.0;
   return e;
 }
 

@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
 // still carries 22 bits; smaller ones lose lo bits they contribute negligibly to any dot product).  e lives in the
 // 256-byte trailer of the prepared buffer (int32 at offset 0; the max |x| as float bits at offset 4) and is removed
 // from the accumulators by the consuming kernels (umma_gemm.cuh, SCALED).
-constexpr int kFp16TargetExp = 10;
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src,
                                                      uint32_t* __restrict__ trailer) {
   float m = 0.f;
@@ -96,17 +95,15 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ s
   // non-negative floats order like their bit patterns; a NaN / Inf input makes the exponent choice fall back to 0
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(trailer + 1, __float_as_uint(m));
 }
-__device__ __forceinline__ int fp16x3_exponent(uint32_t absmax_bits) {
-  const float m = __uint_as_float(absmax_bits);
-  if (!(m > 0.f) || !isfinite(m)) return 0;
-  int e = kFp16TargetExp - ilogbf(m);
-  return max(-100, min(100, e));
-}
+__device__ __forceinline__ int fp16x3_exponent(uint32_t absmax_bits) { return fp16x3_exponent_of(__uint_as_float(absmax_bits)); }
 __global__ void __launch_bounds__(256) prepare_fp16x3_kernel(const float* __restrict__ src, int64_t rows, int cols,
                                                              int64_t ld_src, __half* __restrict__ dst, int64_t ldp,
                                                              uint32_t* __restrict__ trailer) {
   const int e = fp16x3_exponent(trailer[1]);
-  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(trailer)[0] = e;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    reinterpret_cast<int*>(trailer)[0] = e;
+    trailer[2] = trailer[1];                           // seeds the optimizer's running max (common.cuh)
+  }
   const float sc = exp2f((float)e);
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int nvec = (int)(ldp / 8);
@@ -134,6 +131,61 @@ __global__ void __launch_bounds__(256) prepare_fp16x3_kernel(const float* __rest
         h[k] = __floats2half2_rn(a, b);
         const float2 hf = __half22float2(h[k]);
         l[k] = __floats2half2_rn(a - hf.x, b - hf.y);            // the residuals are exact in fp32
+      }
+      *reinterpret_cast<uint4*>(dst + r * ldp + c0) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(lo_plane + r * ldp + c0) = *reinterpret_cast<uint4*>(l);
+    }
+  }
+}
+
+// Small operands (activations / gradients of one batch: q, f, dy): max |x| and the split in ONE launch.  Every block
+// reduces its share of the max into the trailer, a grid-wide arrive counter (trailer[3]) tells when all shares are in,
+// then each block converts its rows.  The grid is capped so that all blocks are co-resident (the spin cannot wait on a
+// block that has not been scheduled); a stuck barrier traps instead of hanging the GPU.
+__global__ void __launch_bounds__(256) prepare_fp16x3_fused_kernel(const float* __restrict__ src, int64_t rows, int cols,
+                                                                   int64_t ld_src, __half* __restrict__ dst, int64_t ldp,
+                                                                   uint32_t* __restrict__ trailer) {
+  __shared__ float wmax[8];
+  float m = 0.f;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
+    for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, fabsf(__ldg(src + r * ld_src + c)));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wmax[w]);
+    if (m > 0.f) atomicMax(trailer + 1, __float_as_uint(m));
+    __threadfence();
+    atomicAdd(trailer + 3, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile uint32_t*>(trailer + 3) < gridDim.x) {     // plain polling load, no RMW traffic
+      if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const uint32_t mbits = *reinterpret_cast<volatile uint32_t*>(trailer + 1);
+  const int e = fp16x3_exponent(mbits);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    reinterpret_cast<int*>(trailer)[0] = e;
+    trailer[2] = mbits;
+  }
+  const float sc = exp2f((float)e);
+  __half* lo_plane = dst + rows * ldp;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* srow = src + r * ld_src;
+    for (int c0 = threadIdx.x * 8; c0 < ldp; c0 += 256 * 8) {
+      float x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = (c0 + k < cols) ? __ldg(srow + c0 + k) : 0.f;   // second touch: L1 / L2 hits
+      __half2 h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = x[2 * k] * sc, b = x[2 * k + 1] * sc;
+        h[k] = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h[k]);
+        l[k] = __floats2half2_rn(a - hf.x, b - hf.y);
       }
       *reinterpret_cast<uint4*>(dst + r * ldp + c0) = *reinterpret_cast<uint4*>(h);
       *reinterpret_cast<uint4*>(lo_plane + r * ldp + c0) = *reinterpret_cast<uint4*>(l);
@@ -171,9 +223,14 @@ static int prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int
     prepare_kernel<COPER_PREC_TF32X3><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ldp);
   else if (prec == COPER_PREC_FP16X3) {
     uint32_t* trailer = static_cast<uint32_t*>(tc_fp16x3_trailer(dst, rows, cols));
-    int rc = check_cuda(cudaMemsetAsync(trailer, 0, 8, st));
+    int rc = check_cuda(cudaMemsetAsync(trailer, 0, 16, st));
     if (rc) return rc;
     const int64_t n = rows * cols;
+    if (n <= (int64_t)4 << 20) {                          // per-batch operands: one launch (see the kernel)
+      int g = (int)(rows < (int64_t)sm_count() ? rows : (int64_t)sm_count());      // <= 1 block per SM: all co-resident
+      prepare_fp16x3_fused_kernel<<<g, 256, 0, st>>>(src, rows, cols, ld_src, static_cast<__half*>(dst), ldp, trailer);
+      return check_launch();
+    }
     int g1 = (int)((n + 2047) / 2048 < sm_count() * 8 ? (n + 2047) / 2048 : sm_count() * 8);
     absmax_kernel<<<g1 < 1 ? 1 : g1, 256, 0, st>>>(src, rows, cols, ld_src, trailer);
     if ((rc = check_launch())) return rc;

@@ -153,6 +153,9 @@ class ConvE:
         self.shard = shard or EntityShard(self.num_ent)
         self.group = process_group
         self.world = self.shard.world
+        if self.shard.rows <= 0:
+            raise ValueError("%r owns no entity rows: %d entities cannot be sharded %d ways in blocks of %d rows - use "
+                             "fewer ranks for this table" % (self.shard, self.num_ent, self.world, self.shard.per))
         if self.use_negative_sampling and self.world > 1:
             raise NotImplementedError("sampled-label training is single-GPU (the 1-N path is the entity-sharded one)")
         # data-parallel front end: every rank receives the GLOBAL batch [Bg], runs lookups' conv / CPG /
@@ -321,8 +324,8 @@ class ConvE:
         lib = _lib.load()
         d = self.ent_emb_size
         # emission from inside the optimizer kernel needs operand pitch == row length; otherwise re-convert per step
-        # (fp16x3 operands carry a data-dependent exponent: they are re-converted after every update, see refresh_prepared)
-        self._emit_prepared = d % (8 if self.prec == PREC["bf16"] else 4) == 0 and self.prec != PREC["fp16x3"]
+        # (fp16x3: the kernel also tracks max |theta| and rolls the operand's power-of-two scale, csrc/common.cuh)
+        self._emit_prepared = d % (4 if self.prec == PREC["tf32x3"] else 8) == 0
         if self.prec != 0:
             Pw = self.fc_weights.projections[-1]
             self.E_prep = torch.zeros(lib.coper_prepared_bytes(self.shard.rows, d, self.prec), dtype=torch.uint8,
@@ -350,6 +353,17 @@ class ConvE:
             chunks += [(i, c) for c in range(nch)]
             offsets.append(len(chunks))
         self.mt_desc = torch.from_numpy(desc.view(np.uint8).copy()).to(self.dev)
+        # tensor-pipe engines with full 1-N labels: the dE GEMM epilogue and the head-entity scatter hand over the
+        # squared norm of the entity gradient (coper.h: COPER_GRAD_NORM_EXTERNAL), so the clip does not re-read [N, d]
+        self._norm_fused = self.prec != 0 and not self.use_negative_sampling
+        desc_ext = desc.copy()
+        desc_ext[0]["mode"] |= 2
+        assert tr[0][0] == "ent_emb"
+        self.mt_desc_ext = torch.from_numpy(desc_ext.view(np.uint8).copy()).to(self.dev)
+        self.dE_sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.norm_delta = torch.zeros(4096, dtype=torch.float64, device=self.dev)
+        self._norm_fused_now = False
+        self._norm_delta_n = 0
         self.mt_chunks = torch.tensor(chunks, dtype=torch.int32).to(self.dev)
         self.mt_offsets = torch.tensor(offsets, dtype=torch.int32).to(self.dev)
         self.mt_nchunks = len(chunks)
@@ -814,8 +828,14 @@ class ConvE:
                          + np.float32(1.0 / self.num_ent))                     # models.py:450 in fp32
         neg = np.float32(1.0 / self.num_ent)
         inv_count = 1.0 / (float(bg.B) * float(self.num_ent))                # mean over B*N (models.py:451)
+        self._norm_fused_now = self._norm_fused and bg.B <= 4096       # (the scatter correction is the small-M kernel's)
         if self.use_negative_sampling:
             self._sampled_scorer(b)
+        elif self._norm_fused_now:
+            call("coper_score1n_bce_fwd_bwd_norm", ptr(bg.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
+                 ptr(bg.bitsT), bg.B, Ns, d, float(pos), float(neg), inv_count, ptr(bg.loss_sum),
+                 ptr(self._grad_buf(bg)), bg.ld, ptr(bg.dq), ptr(g["ent_emb"]), ptr(g["pred_bias"]), ptr(self.dE_sumsq),
+                 ptr(bg.ws), bg.ws_bytes, self.prec)
         else:
             call("coper_score1n_bce_fwd_bwd", ptr(bg.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
                  ptr(bg.bits if self.prec == 0 else bg.bitsT), bg.B, Ns, d, float(pos), float(neg), inv_count,
@@ -892,7 +912,11 @@ class ConvE:
         gsq_e = self.grad_sq["ent_emb"] if self.use_negative_sampling else None
         if dp:      # every shard needs dx0 of ALL queries whose head entity it owns
             sharding.gather_batch(bg.dx0, b.dx0, self.world, self.group)
-        if bg.B <= 4096:
+        if self._norm_fused_now:
+            call("coper_segscatter_add_norm", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi,
+                 ptr(self.norm_delta))
+            self._norm_delta_n = bg.B
+        elif bg.B <= 4096:
             call("coper_segscatter_add_sq", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi)
         else:
             call("coper_segscatter_add", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), s.lo, s.hi, ptr(bg.ws),
@@ -958,8 +982,12 @@ class ConvE:
         """tf.clip_by_global_norm(5.0) (models.py:199) + AMSGrad apply (amsgrad.py:130-159): one multi-tensor
         launch per phase over the whole variable list."""
         nt = len(self.trainables)
-        call("coper_mt_sumsq", ptr(self.mt_desc), nt, ptr(self.mt_chunks), self.mt_nchunks, ptr(self.mt_offsets),
-             ptr(self.mt_partials), ptr(self.sumsq))
+        fused = self._norm_fused_now
+        call("coper_mt_sumsq", ptr(self.mt_desc_ext if fused else self.mt_desc), nt, ptr(self.mt_chunks), self.mt_nchunks,
+             ptr(self.mt_offsets), ptr(self.mt_partials), ptr(self.sumsq))
+        if fused:       # |dE|^2 from the dE GEMM epilogue + the change the head-entity scatter made to it
+            call("coper_sumsq_combine", ptr(self.dE_sumsq), 1, ptr(self.norm_delta), self._norm_delta_n,
+                 ptr(self.sumsq))
         # trainables 0,1 (ent_emb, pred_bias) are row-sharded: their squared norms add across ranks;
         # every other gradient is replicated (identical on all ranks) and is counted once.
         sharding.reduce_sharded_sumsq(self.sumsq[:2], self.world, self.group)

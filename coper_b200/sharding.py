@@ -55,7 +55,20 @@ class EntityShard:
 
 
 def _active(world, group):
-    return world > 1 and dist.is_available() and dist.is_initialized()
+    """Whether an exchange step has anything to exchange.  A shard that claims world > 1 without an initialised
+    process group would silently keep its non-owned rows at zero, so that is an error (the CPU unit tests that
+    exercise one rank's arithmetic in isolation set ALLOW_UNINITIALISED)."""
+    if world <= 1:
+        return False
+    if dist.is_available() and dist.is_initialized():
+        return True
+    if ALLOW_UNINITIALISED:
+        return False
+    raise RuntimeError("EntityShard.world = %d but torch.distributed is not initialised: the exchange steps of the "
+                       "sharded path cannot run (launch one process per GPU, e.g. with torchrun)" % world)
+
+
+ALLOW_UNINITIALISED = False
 
 
 def _staged(t: torch.Tensor, group) -> bool:

@@ -189,6 +189,15 @@ int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prep
                               double* loss_sum, void* G, int64_t ldG, float* dq, float* dE, float* dbias,
                               void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
 
+/* coper_score1n_bce_fwd_bwd that additionally writes *dE_sumsq = sum of the squares of the dE it stored (fp64, fixed
+ * order; tensor-pipe precisions only - the dE GEMM epilogue accumulates it): the global-norm clip (models.py:199) then
+ * does not re-read the [Ns, d] gradient.  See COPER_GRAD_NORM_EXTERNAL. */
+int coper_score1n_bce_fwd_bwd_norm(const float* q, const float* E, const void* E_prepared, const float* bias,
+                                   const uint32_t* label_bits, int B, int64_t Ns, int d, float pos_target,
+                                   float neg_target, float inv_count, double* loss_sum, void* G, int64_t ldG, float* dq,
+                                   float* dE, float* dbias, double* dE_sumsq, void* workspace, size_t workspace_bytes,
+                                   int prec, coper_stream_t stream);
+
 /* a8 / SURVEY §8f-2 — SAMPLED-label scorer (models.py:438-443), loss (:448-453) and gradients: what the shipped
  * big-dataset configs train with (training.num_labels = 100 / 1000).  lookup int32 [B, L] entity ids
  * (batch['lookup_values'], models.py:165), labels fp32 [B, L] (batch['e2_multi'] in sampled mode):
@@ -277,6 +286,11 @@ size_t coper_segscatter_workspace_bytes(int M);
  * Same summation order (index order) as coper_segscatter_add, which uses this path for small M. */
 int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int width, float* dst, float* dst_sq,
                             int64_t row_lo, int64_t row_hi, coper_stream_t stream);
+/* coper_segscatter_add_sq that also reports, per position i of idx, norm_delta[i] = sum_c (new^2 - old^2) over the
+ * destination row position i updated (0 for non-heads / rows of other shards): the correction of a squared gradient
+ * norm that was taken before this scatter (tf.clip_by_global_norm over the dense ent_emb gradient, models.py:198-199). */
+int coper_segscatter_add_norm(const int64_t* idx, int M, const float* src, int width, float* dst, float* dst_sq,
+                              int64_t row_lo, int64_t row_hi, double* norm_delta, coper_stream_t stream);
 int coper_segscatter_add(const int64_t* idx, int M, const float* src, int width, float* dst, int64_t row_lo,
                          int64_t row_hi, void* workspace, size_t workspace_bytes, coper_stream_t stream);
 
@@ -329,7 +343,11 @@ int coper_amsgrad_step(float* theta, const float* grad, float* m, float* v, floa
  *   coper_clip_scale_n(tensor_sumsq, n_tensors, ...) -> {clip / max(norm, clip), norm}
  *   coper_mt_amsgrad -> the update of coper_amsgrad_step for every tensor. */
 #define COPER_MT_CHUNK 16384
-enum { COPER_GRAD_DENSE = 0, COPER_GRAD_INDEXED_SLICES = 1 };
+/* COPER_GRAD_NORM_EXTERNAL (OR-ed into mode): coper_mt_sumsq does not read this gradient - its squared norm is written
+ * into tensor_sumsq[t] by coper_sumsq_combine AFTER coper_mt_sumsq, from the partial sums the kernel that produced the
+ * gradient emitted (coper_score1n_bce_fwd_bwd_norm) and the corrections of the scatter that touched it afterwards
+ * (coper_segscatter_add_norm): the [N, d] entity gradient is then read once (by the update), not twice. */
+enum { COPER_GRAD_DENSE = 0, COPER_GRAD_INDEXED_SLICES = 1, COPER_GRAD_NORM_EXTERNAL = 2 };
 typedef struct {
   float* theta;
   const float* grad;
@@ -342,6 +360,10 @@ typedef struct {
   int32_t prepared_prec;
   int32_t mode;
 } coper_param_desc;
+/* out[0] = sum(parts) + sum(deltas), fp64, fixed order, clamped at 0 (tf.clip_by_global_norm, models.py:199: the
+ * squared norm of one gradient assembled from its producers' partial sums). */
+int coper_sumsq_combine(const double* parts, int n_parts, const double* deltas, int n_deltas, double* out,
+                        coper_stream_t stream);
 int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
                    const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, coper_stream_t stream);
 int coper_clip_scale_n(const double* sums, int n, float clip_norm, float* out2, coper_stream_t stream);
