@@ -10,8 +10,10 @@ clip -> AMSGrad.  `value` = train rows/s with inputs resident in HBM; `eval` = f
 with the loss / ranks read back every step.  One JSON line on stdout (rank 0).
 
 Workloads (BASELINE.json configs):
-  N = 1   headline = WN18RR shape (configs[1]), fp32-class tf32x3 engine; `configs` holds one block per other named
-          shape (FB15k-237, NELL-995, YAGO3-10 in tf32x3; synth-10m in bf16) with value / e2e / eval / per-stage
+  N = 1   headline = WN18RR shape (configs[1]), fp32-class fp16x3 engine (3-term compensated fp16 planes on tcgen05:
+          same accuracy class and the same 1e-5 parity bar as tf32x3, which stays selectable with --prec); `configs`
+          holds one block per other named shape (FB15k-237, NELL-995, YAGO3-10 in fp16x3; synth-10m in bf16) with
+          value / e2e / eval / per-stage
           rooflines; `rooflines` has EVERY stage of the headline (tensor-bound stages against the measured bf16 peak,
           HBM-bound ones against the measured copy bandwidth); `hbm_kernels` times gather / segmented scatter /
           filtered rank at sizes where HBM bandwidth (not launch latency) is what is measured.
@@ -420,7 +422,9 @@ def kernel_breakdown(model, batch, peaks, prec, shape="wn18rr", reps=10):
             "note": "isolated launches of the C-ABI stage (its tcgen05 kernels + reductions), CUDA events on the launching "
                     "stream; prec=%s%s; traffic = DRAM bytes of the stage from the committed ncu capture (%s)" % (
                         prec, " (3 tf32 MMAs per product: tensor-pipe time = 6x the bf16-equivalent of the algorithmic "
-                              "FLOPs)" if prec == "tf32x3" else "", traffic_src)}
+                              "FLOPs)" if prec == "tf32x3" else
+                        " (3 fp16 MMAs per product: tensor-pipe time = 3x the bf16-equivalent of the algorithmic FLOPs)"
+                        if prec == "fp16x3" else "", traffic_src)}
     return out, roofs, roof
 
 
@@ -491,7 +495,7 @@ def main():
     ap.add_argument("--shape", default=os.environ.get("COPER_BENCH_SHAPE"),
                     help="default: wn18rr at N = 1, synth-10m at N > 1")
     ap.add_argument("--prec", default=os.environ.get("COPER_BENCH_PREC"),
-                    help="default: tf32x3 (fp32-class) for the named datasets, bf16 for synth-10m")
+                    help="default: fp16x3 (fp32-class) for the named datasets, bf16 for synth-10m")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -521,7 +525,7 @@ def main():
     multi = max(world, args.gpus) > 1
     explicit = args.shape is not None
     shape = args.shape or ("synth-10m" if multi else "wn18rr")
-    prec = args.prec or ("bf16" if shape == "synth-10m" else "tf32x3")
+    prec = args.prec or ("bf16" if shape == "synth-10m" else "fp16x3")
     front = args.front_end or ("replicated" if shape == "synth-10m" else "data-parallel")
     dp = multi and front == "data-parallel"
     from coper_b200 import synthetic
@@ -616,7 +620,7 @@ def main():
                 if other == shape:
                     continue
                 try:
-                    blk, m_o, _ = measure(ctx, other, "bf16" if other == "synth-10m" else "tf32x3", Kc, Wc, peaks,
+                    blk, m_o, _ = measure(ctx, other, "bf16" if other == "synth-10m" else "fp16x3", Kc, Wc, peaks,
                                           e2e=True, breakdown=not args.no_breakdown)
                     blk.pop("_B")
                     blk["steps"], blk["warmup"] = Kc, Wc
@@ -643,7 +647,7 @@ def main():
             Kc, Wc = max(5, min(K, 10)), max(3, min(W, 5))
             # ---- the data-parallel WN18RR weak-scaling numbers (global batch N * 512), all ranks
             try:
-                weak, m_w, _ = measure(ctx, "wn18rr", "tf32x3", K, W, peaks, sharded=True, dp=True, e2e=True,
+                weak, m_w, _ = measure(ctx, "wn18rr", "fp16x3", K, W, peaks, sharded=True, dp=True, e2e=True,
                                        breakdown=False, graphs_multi=not args.no_graph_multi, overlap=not args.no_overlap)
                 weak.pop("_B")
                 weak["scaling"] = "weak"

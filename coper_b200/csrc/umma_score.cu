@@ -146,9 +146,29 @@ __global__ void __launch_bounds__(256) prepare_fp16x3_fused_kernel(const float* 
                                                                    int64_t ld_src, __half* __restrict__ dst, int64_t ldp,
                                                                    uint32_t* __restrict__ trailer) {
   __shared__ float wmax[8];
+  // work unit = one 8-column group of one row (ldp / 8 groups per row); consecutive threads take consecutive groups
+  const int gpr = (int)(ldp / 8);
+  const int64_t units = rows * gpr;
+  const bool vec = ((ld_src & 3) == 0) && ((cols & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  auto load8 = [&](int64_t u, float (&x)[8]) {
+    const int64_t r = u / gpr;
+    const int c0 = (int)(u - r * gpr) * 8;
+    const float* p = src + r * ld_src + c0;
+    if (vec) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = (c0 + k < cols) ? __ldg(p + k) : 0.f;
+    }
+  };
   float m = 0.f;
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
-    for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, fabsf(__ldg(src + r * ld_src + c)));
+  for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < units; u += (int64_t)gridDim.x * 256) {
+    float x[8];
+    load8(u, x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(x[k]));
+  }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -173,23 +193,19 @@ __global__ void __launch_bounds__(256) prepare_fp16x3_fused_kernel(const float* 
   }
   const float sc = exp2f((float)e);
   __half* lo_plane = dst + rows * ldp;
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-    const float* srow = src + r * ld_src;
-    for (int c0 = threadIdx.x * 8; c0 < ldp; c0 += 256 * 8) {
-      float x[8];
+  for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < units; u += (int64_t)gridDim.x * 256) {
+    float x[8];
+    load8(u, x);                                       // second touch of the same addresses: L1 / L2 hits
+    __half2 h[4], l[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = (c0 + k < cols) ? __ldg(srow + c0 + k) : 0.f;   // second touch: L1 / L2 hits
-      __half2 h[4], l[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = x[2 * k] * sc, b = x[2 * k + 1] * sc;
-        h[k] = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(h[k]);
-        l[k] = __floats2half2_rn(a - hf.x, b - hf.y);
-      }
-      *reinterpret_cast<uint4*>(dst + r * ldp + c0) = *reinterpret_cast<uint4*>(h);
-      *reinterpret_cast<uint4*>(lo_plane + r * ldp + c0) = *reinterpret_cast<uint4*>(l);
+    for (int k = 0; k < 4; ++k) {
+      const float a = x[2 * k] * sc, b = x[2 * k + 1] * sc;
+      h[k] = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(h[k]);
+      l[k] = __floats2half2_rn(a - hf.x, b - hf.y);
     }
+    *reinterpret_cast<uint4*>(dst + u * 8) = *reinterpret_cast<uint4*>(h);        // u * 8 == r * ldp + c0
+    *reinterpret_cast<uint4*>(lo_plane + u * 8) = *reinterpret_cast<uint4*>(l);
   }
 }
 
@@ -227,7 +243,10 @@ static int prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int
     if (rc) return rc;
     const int64_t n = rows * cols;
     if (n <= (int64_t)4 << 20) {                          // per-batch operands: one launch (see the kernel)
-      int g = (int)(rows < (int64_t)sm_count() ? rows : (int64_t)sm_count());      // <= 1 block per SM: all co-resident
+      // <= 2 blocks of 256 threads per SM: always co-resident (an SM holds 8 of them), which the grid barrier needs
+      const int64_t want = (rows * (ldp / 8) + 256 * 4 - 1) / (256 * 4);
+      int g = (int)(want < (int64_t)sm_count() * 2 ? want : (int64_t)sm_count() * 2);
+      if (g < 1) g = 1;
       prepare_fp16x3_fused_kernel<<<g, 256, 0, st>>>(src, rows, cols, ld_src, static_cast<__half*>(dst), ldp, trailer);
       return check_launch();
     }

@@ -14,12 +14,18 @@ PyTorch is used only for device memory, streams, CUDA graphs and torch.distribut
 arithmetic step of the hot path is a call into the C ABI (``include/coper.h``).  There is no
 CPU / PyTorch fallback: without the CUDA library or a GPU this raises.
 
-Supported configuration = the one every shipped ``*_cpg.yaml`` uses: ``context_rel_conv: null``
-(shared conv filters), ``context_rel_out: [...]`` (g_linear ``[]`` or g_MLP ``[n, ...]``),
-``concat_rel: False``; training with full 1-N labels (``num_labels: null``, entity-sharded across GPUs) or with
-sampled labels (``use_negative_sampling``, ``models.py:438-443``: ``batch['lookup_values']`` [B, L], single GPU).
-Evaluation is always 1-N.  ``do_parameter_lookup``, CPG-generated conv filters and ``concat_rel`` raise
-NotImplementedError.
+Supported configurations = the three model types the reference ships configs for: ``cpg`` (``context_rel_out: [...]``,
+g_linear ``[]`` or g_MLP ``[n, ...]``), ``plain`` (``context_rel_out: null``: shared FC weights, relation image stacked
+under the entity image) and ``param_lookup`` (``do_parameter_lookup``: per-relation tables), plus CPG-generated conv
+filters (``context_rel_conv: [...]`` together with ``context_rel_out``); training with full 1-N labels
+(``num_labels: null``, entity-sharded across GPUs) or with sampled labels (``use_negative_sampling``,
+``models.py:438-443``: ``batch['lookup_values']`` [B, L] or labels drawn on the device; single GPU).  Evaluation is
+always 1-N.  ``concat_rel`` and generated conv filters combined with shared FC weights / parameter tables raise
+NotImplementedError (no shipped configuration uses them).
+
+Engines (``prec``): ``fp32`` (CUDA-core FFMA, the on-device parity reference), ``tf32x3`` / ``fp16x3`` (fp32-class
+3-term compensated tcgen05 engines), ``bf16`` (tcgen05, the 10 M-entity throughput path; its scorer + BCE + dq run as
+one fused kernel).
 """
 from __future__ import annotations
 
@@ -303,6 +309,14 @@ class ConvE:
                 off += sz
             self._flat_gsq_rel = self.flat_grads[off:off + self.rel_emb.numel()].view(self.rel_emb.shape)
             self.flat_big, self.flat_small = self.flat_grads[:sizes[0]], self.flat_grads[sizes[0]:]
+        # the batch-norm backward kernels write dgamma / dbeta straight into the gradient list (no copies in the step)
+        for nm, bn in (("Conv1BN", self.conv1_bn), ("FCBN", self.fc_bn)):
+            bn.dgamma, bn.dbeta = self.grads[nm + "/gamma"], self.grads[nm + "/beta"]
+        for cpg in self.generators:
+            if self.variant == "cpg" and cpg.use_batch_norm:
+                for i, bn in enumerate(cpg.bns):
+                    bn.dgamma = self.grads["%s/CPG/Projection%d/BatchNorm/gamma" % (cpg.name, i)]
+                    bn.dbeta = self.grads["%s/CPG/Projection%d/BatchNorm/beta" % (cpg.name, i)]
         self.vhat = {n: torch.zeros_like(p) for n, p, _ in tr}
         # variables read only through embedding_lookup get an IndexedSlices gradient in TF -> sparse AMSGrad rule
         # (slots accumulate) and a slice-wise contribution to the global norm (include/coper.h, coper_param_desc)
@@ -719,8 +733,6 @@ class ConvE:
                 use_batch = self.batch_norm_train_stats
                 self._bn_backward(bn, dh, bufs["pre"][i], B, n, b, use_batch, True, keep, salt, 1.0, 0,
                                   bufs["dpre"][i])
-                self.grads["%s/CPG/Projection%d/BatchNorm/gamma" % (cpg.name, i)].copy_(bn.dgamma)
-                self.grads["%s/CPG/Projection%d/BatchNorm/beta" % (cpg.name, i)].copy_(bn.dbeta)
             else:
                 one, zero = self._ident(n)
                 call("coper_bn_act_bwd_apply", ptr(dh), ptr(bufs["pre"][i]), B, n, ptr(one), ptr(zero), ptr(zero),
@@ -851,8 +863,6 @@ class ConvE:
         keep1, keep2 = 1.0 - self.hidden_dropout, 1.0 - self.output_dropout
         # FC block backward: relu -> FCBN -> output dropout (models.py:414-419)
         self._bn_backward(self.fc_bn, b.dq, b.y, B, d, b, use_batch, True, 1.0, 0, keep2, SALT_OUTPUT, b.dy)
-        g["FCBN/gamma"].copy_(self.fc_bn.dgamma)
-        g["FCBN/beta"].copy_(self.fc_bn.dbeta)
         Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
         nw, nb = len(self.fc_weights.projections) - 1, len(self.fc_bias.projections) - 1
         call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(b.cb), ptr(Pb), ptr(b.dy), B,
@@ -878,8 +888,6 @@ class ConvE:
         # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)
         R1 = B * self.OH * self.OW
         self._bn_backward(self.conv1_bn, b.df, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz)
-        g["Conv1BN/gamma"].copy_(self.conv1_bn.dgamma)
-        g["Conv1BN/beta"].copy_(self.conv1_bn.dbeta)
         plain = self.variant == "plain"
         KK = self.conv_filter_height * self.conv_filter_width * C
         if self.conv_w_gen is not None:
