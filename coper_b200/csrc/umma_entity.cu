@@ -405,6 +405,10 @@ template <>
 struct EntSel<PREC_TF32X3, false> { using Cfg = GemmCfg<PREC_TF32X3, 128, 3, kEntEpiWarps, false, false, 0, 0>; };
 template <>
 struct EntSel<PREC_FP16X3, false> { using Cfg = GemmCfg<PREC_FP16X3, 128, 3, kEntEpiWarps, false, false, 0, 0>; };
+// fp16x3 with the 128-query block RESIDENT (2 planes x 4 k-blocks x 16 KB = 128 KB): per 128 x 128 tile only the entity
+// planes stream (128 KB instead of 256 KB), which is what bounds the streaming configuration (~42 B/clk/SM of TMA)
+template <>
+struct EntSel<PREC_FP16X3, true> { using Cfg = GemmCfg<PREC_FP16X3, 128, 2, kEntEpiWarps, false, false, 0, 4>; };   // (3 stages + the rank epilogue's 2 KB would exceed 227 KB by 256 B)
 // the BCE epilogue is MUFU / latency bound: 16 epilogue warps (4 per scheduler) hide the TMEM-load and SFU latencies
 template <int PREC, bool RES>
 struct BceSel;
@@ -416,16 +420,22 @@ template <>
 struct BceSel<PREC_TF32X3, false> { using Cfg = GemmCfg<PREC_TF32X3, 128, 3, kBceEpiWarps, false, false, 0, 0>; };
 template <>
 struct BceSel<PREC_FP16X3, false> { using Cfg = GemmCfg<PREC_FP16X3, 128, 3, kBceEpiWarps, false, false, 0, 0>; };
+// (2 stages: the BCE epilogue's 32 KB store staging tile shares the 227 KB with the 128 KB resident block)
+template <>
+struct BceSel<PREC_FP16X3, true> { using Cfg = GemmCfg<PREC_FP16X3, 128, 2, kBceEpiWarps, false, false, 0, 4>; };
 template <class Cfg>
 constexpr int ent_nch() { return Cfg::BLOCK_N / (Cfg::EPI_WARPS / 4) / 32; }
 // the resident-query-block configuration pays a 128 KB fill per CTA: worth it once a CTA processes >= 8 tiles
 // (WN18RR: 640 tiles / 148 CTAs -> streaming configuration; 1 M entities: 106 tiles per CTA -> resident)
 static inline bool ent_resident(int d, int prec, int64_t Ns, int B) {
-  if (prec != COPER_PREC_BF16 || d > 256) return false;
-  const int64_t tiles = ((Ns + BLOCK_M - 1) / BLOCK_M) * ((B + 255) / 256);
+  if ((prec != COPER_PREC_BF16 && prec != COPER_PREC_FP16X3) || d > 256) return false;
+  const int bn = prec == COPER_PREC_BF16 ? 256 : 128;
+  const int64_t tiles = ((Ns + BLOCK_M - 1) / BLOCK_M) * ((B + bn - 1) / bn);
   return tiles >= 8 * (int64_t)sm_count();
 }
-static inline int ent_block_n(int d, int prec, int64_t Ns, int B) { return ent_resident(d, prec, Ns, B) ? 256 : 128; }
+static inline int ent_block_n(int d, int prec, int64_t Ns, int B) {
+  return (prec == COPER_PREC_BF16 && ent_resident(d, prec, Ns, B)) ? 256 : 128;
+}
 
 static GemmProblem ent_problem(int B, int64_t Ns, int d, int block_n) {
   GemmProblem p{};
@@ -463,6 +473,7 @@ static int score_t_impl(const TcOperand& E, const TcOperand& Q, const float* bia
     if (prec == COPER_PREC_BF16 && ent_resident(d, prec, Ns, B)) return FN<EntSel<PREC_BF16, true>::Cfg>(__VA_ARGS__);  \
     if (prec == COPER_PREC_BF16) return FN<EntSel<PREC_BF16, false>::Cfg>(__VA_ARGS__);                   \
     if (prec == COPER_PREC_TF32X3) return FN<EntSel<PREC_TF32X3, false>::Cfg>(__VA_ARGS__);               \
+    if (prec == COPER_PREC_FP16X3 && ent_resident(d, prec, Ns, B)) return FN<EntSel<PREC_FP16X3, true>::Cfg>(__VA_ARGS__); \
     if (prec == COPER_PREC_FP16X3) return FN<EntSel<PREC_FP16X3, false>::Cfg>(__VA_ARGS__);               \
     return COPER_ERR_UNSUPPORTED;                                                                          \
   } while (0)
@@ -657,6 +668,9 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     if (prec == COPER_PREC_BF16)
       return bce_impl<BceSel<PREC_BF16, false>::Cfg>(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT,
                                                      dbias_part, loss_part, st, &grid);
+    if (prec == COPER_PREC_FP16X3 && ent_resident(d, prec, Ns, B))
+      return bce_impl<BceSel<PREC_FP16X3, true>::Cfg>(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT,
+                                                      dbias_part, loss_part, st, &grid);
     if (prec == COPER_PREC_FP16X3)
       return bce_impl<BceSel<PREC_FP16X3, false>::Cfg>(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT,
                                                        dbias_part, loss_part, st, &grid);

@@ -130,8 +130,9 @@ class ConvE:
         #                 279-287), no relation embedding (models.py:210, 180)
         # Both of the latter run on the SAME fused generate-and-apply kernels: shared weights are a linear generator
         # applied to the constant context [1], table rows one applied to one-hot(rel) (adding exact zeros).
-        if self.concat_rel:
-            raise NotImplementedError("concat_rel is not built: no shipped configuration uses it (SURVEY §8f-4)")
+        if self.concat_rel and self.is_parameter_lookup:
+            raise NotImplementedError("concat_rel needs the relation embedding, which do_parameter_lookup does not "
+                                      "create (models.py:180, 406-407 would fail the same way)")
         if self.context_rel_conv is not None and (self.is_parameter_lookup or self.context_rel_out is None):
             raise NotImplementedError("generated conv filters (context_rel_conv) are built together with generated "
                                       "FC weights (context_rel_out: [...]) only")
@@ -154,7 +155,9 @@ class ConvE:
             self.H = 2 * H_ent                                      # models.py:264-265
         self.OH, self.OW = self.H - self.conv_filter_height + 1, self.W - self.conv_filter_width + 1
         self.C = self.conv_num_channels
-        self.F = self.OH * self.OW * self.C                          # models.py:268
+        self.F_conv = self.OH * self.OW * self.C                     # models.py:268
+        # concat_rel (models.py:270-271, 406-407): the relation embedding is appended to the flattened conv features
+        self.F = self.F_conv + (self.rel_emb_size if self.concat_rel else 0)
         self.prec = PREC[prec]                                       # scorer / CPG contraction arithmetic
         self.shard = shard or EntityShard(self.num_ent)
         self.group = process_group
@@ -502,12 +505,17 @@ class ConvE:
         b.h_idx_np = b.h_head_np[:6 * B].view(np.int64).reshape(3, B)
         b.h_rowptr_np = b.h_head_np[6 * B:6 * B + B + 1]
         b.x0, b.r = z(B, d), z(B, dr)
-        b.z, b.f = z(B, F), z(B, F)
+        Fc = self.F_conv
+        b.z, b.f = z(B, Fc), z(B, F)
+        # concat_rel: the conv block works on contiguous [B, F_conv] buffers; b.f / b.df hold [conv features | rel_emb]
+        b.fconv, b.dfconv = (z(B, Fc), z(B, Fc)) if self.concat_rel else (b.f, None)
         b.y, b.q = z(B, d), z(B, d)
         b.q_prep = None
         if self.E_prep is not None:
             b.q_prep = torch.zeros(lib.coper_prepared_bytes(B, d, self.prec), dtype=torch.uint8, device=dev)
-        b.dq, b.dy, b.df, b.dz, b.dx0, b.dr = z(B, d), z(B, d), z(B, F), z(B, F), z(B, d), z(B, dr)
+        b.dq, b.dy, b.df, b.dz, b.dx0, b.dr = z(B, d), z(B, d), z(B, F), z(B, Fc), z(B, d), z(B, dr)
+        if not self.concat_rel:
+            b.dfconv = b.df
         R1 = B * self.OH * self.OW
         nch = max(lib.coper_colstats_chunks(R1), lib.coper_colstats_chunks(B))
         maxC = max([C, d] + [n for gcp in self.generators for n in gcp.hidden])
@@ -791,7 +799,10 @@ class ConvE:
         use_batch = self.batch_norm_train_stats and is_train
         keep1 = 1.0 - (self.hidden_dropout if is_train else 0.0)
         self._bn_forward(self.conv1_bn, b.z, B * self.OH * self.OW, C, b, use_batch, is_train, True, True, keep1,
-                         SALT_FEATURE_MAP, b.f)
+                         SALT_FEATURE_MAP, b.fconv)
+        if self.concat_rel:                  # tf.concat([fc_input, rel_emb], axis=1)  (models.py:406-407)
+            b.f[:, :self.F_conv].copy_(b.fconv)
+            b.f[:, self.F_conv:].copy_(b.r)
         if self.variant == "cpg":
             cw = self._ctx_forward(self.fc_weights, 0, b, is_train)
             cb = self._ctx_forward(self.fc_bias, 1, b, is_train)
@@ -887,7 +898,11 @@ class ConvE:
             self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
         # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)
         R1 = B * self.OH * self.OW
-        self._bn_backward(self.conv1_bn, b.df, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz)
+        if self.concat_rel:                  # tf.concat backward: conv part | d rel_emb (added to the generators' part)
+            b.dfconv.copy_(b.df[:, :self.F_conv])
+            if self.variant == "cpg":
+                b.dr.add_(b.df[:, self.F_conv:])
+        self._bn_backward(self.conv1_bn, b.dfconv, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz)
         plain = self.variant == "plain"
         KK = self.conv_filter_height * self.conv_filter_width * C
         if self.conv_w_gen is not None:
@@ -909,6 +924,8 @@ class ConvE:
             if plain:                            # tf.concat backward: the two halves of the stacked image
                 b.dx0.copy_(b.dxc[:, :d])
                 b.dr.copy_(b.dxc[:, d:])
+                if self.concat_rel:
+                    b.dr.add_(b.df[:, self.F_conv:])
             slabs = _lib.load().coper_conv_bwd_slabs(B, self.H, self.W, self.conv_filter_height,
                                                      self.conv_filter_width, C, 0)
             call("coper_reduce_partials", ptr(b.dwc_part), slabs, KK, 1.0, 0, ptr(g["conv1_weights"]))

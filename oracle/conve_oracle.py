@@ -85,6 +85,9 @@ class OracleConfig:
     # "param_lookup" do_parameter_lookup (*_param_lookup.yaml): FC weights / bias are rows of per-relation tables
     #                (ParameterLookup, models.py:79-94, 279-287); there is no relation embedding (models.py:210, 180)
     variant: str = "cpg"
+    # models.py:270-271, 406-407: the relation embedding is concatenated to the flattened conv features before the FC
+    # layer (fc_input_size grows by rel_emb_size); not used by a shipped configuration
+    concat_rel: bool = False
 
     @property
     def conv_in_width(self) -> int:
@@ -104,9 +107,13 @@ class OracleConfig:
                 self.conv_in_width - self.conv_filter_width + 1)
 
     @property
-    def fc_input_size(self) -> int:  # models.py:266-271 (concat_rel unsupported here)
+    def conv_feature_size(self) -> int:  # models.py:266-269
         oh, ow = self.conv_out_hw
         return oh * ow * self.conv_num_channels
+
+    @property
+    def fc_input_size(self) -> int:  # models.py:266-271
+        return self.conv_feature_size + (self.rel_emb_size if self.concat_rel else 0)
 
     @property
     def context_sizes(self) -> List[int]:  # models.py:294: [rel_emb_size] + context_rel_out
@@ -361,7 +368,9 @@ def forward(params, cfg: OracleConfig, e1, rel, is_train=False, masks=None, labe
     m1 = masks.get("feature_map") if keep1 < 1.0 else None
     if m1 is not None:
         A1 = A1 * m1.reshape(-1, C).astype(dtype) / dt(keep1)
-    f = A1.reshape(B, F)                                      # models.py:404  (h,w,c) order
+    f = A1.reshape(B, cfg.conv_feature_size)                  # models.py:404  (h,w,c) order
+    if cfg.concat_rel:                                        # models.py:406-407
+        f = np.concatenate([f, r], axis=1)
 
     # CPG (models.py:338-352, 56-76): weights and bias generators own separate hidden nets.
     if variant == "cpg":
@@ -499,6 +508,10 @@ def backward(out, cfg: OracleConfig):
     g["fc_weights_bn"] = [None if t is None else {"gamma": t[0], "beta": t[1]} for t in dbn_w]
     g["fc_bias_bn"] = [None if t is None else {"gamma": t[0], "beta": t[1]} for t in dbn_b]
     # conv block backward: feature-map dropout -> relu -> Conv1BN -> bias -> conv
+    if cfg.concat_rel:                                         # tf.concat backward (models.py:407): the tail is d rel_emb
+        Fc = cfg.conv_feature_size
+        dr = df[:, Fc:] if dr is None else dr + df[:, Fc:]
+        df_full, df = df, df[:, :Fc]
     dA1 = df.reshape(-1, C)
     if c["m1"] is not None:
         dA1 = dA1 * c["m1"].reshape(-1, C).astype(dA1.dtype) / dA1.dtype.type(c["keep1"])
@@ -536,12 +549,13 @@ def backward(out, cfg: OracleConfig):
         g["conv1_weights"] = dWc[:, :, None, :]
     H = cfg.conv_in_height
     if variant == "plain":                                     # tf.concat backward: the two halves of the image
-        dx0, dr = dX[:, :H].reshape(B, d), dX[:, H:].reshape(B, d)
+        dx0 = dX[:, :H].reshape(B, d)
+        dr = dX[:, H:].reshape(B, d) + (dr if cfg.concat_rel else 0)
     else:
         dx0 = dX.reshape(B, d)
     np.add.at(dE, c["e1"], dx0)                               # gather gradient (IndexedSlices -> dense)
     g["ent_emb"] = dE
-    g["_dq"], g["_dy"], g["_df"], g["_dr"], g["_dx0"], g["_G"] = dq, dy, df, dr, dx0, G
+    g["_dq"], g["_dy"], g["_df"], g["_dr"], g["_dx0"], g["_G"] = dq, dy, (df_full if cfg.concat_rel else df), dr, dx0, G
     if "_sparse" in g:
         g["_sparse"]["ent_emb"].append((dx0, c["e1"]))         # the e1 gather (models.py:176)
     if variant == "param_lookup":

@@ -2,6 +2,7 @@
 where /root/reference exists — the GPU box never needs it, it reads the committed .npz files).
 
     python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+    python oracle/gen_golden.py concat_train concat_eval      # only the named model cases
 
 What runs:
   * ``/root/reference/CoPER_ConvE/qa_cpg/metrics.py`` — UNMODIFIED, with real NumPy; the fake ``tensorflow``
@@ -113,6 +114,14 @@ CASES = {
                           d=30, C=8),
     "cpgconv_eval": dict(ctx=[], ctx_conv=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, B=7,
                          d=30, C=8),
+    # concat_rel (models.py:270-271, 406-407): rel_emb appended to the flattened conv features, for the generated-FC
+    # and the shared-FC model types
+    "concat_train": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9, d=30, C=8,
+                         concat=True),
+    "concat_eval": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, B=7, d=30, C=8,
+                        concat=True),
+    "concat_plain_train": dict(ctx=None, bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, B=9, d=30, C=8,
+                               variant="plain", concat=True),
 }
 
 
@@ -126,6 +135,7 @@ def gen_model(tf, models, name, case, n_steps=1):
     ctx_conv = case.get("ctx_conv")
     cfg = O.OracleConfig(num_ent=97, num_rel=6, ent_emb_size=d, rel_emb_size=dr, context_rel_out=ctx, variant=variant,
                          context_rel_conv=ctx_conv, conv_num_channels=C, hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
+                         concat_rel=bool(case.get("concat")),
                          context_rel_dropout=case["drop"][2], context_rel_use_batch_norm=case["usebn"],
                          batch_norm_train_stats=case["bn_train"], batch_norm_momentum=0.9)
     p = O.init_params(cfg, seed=11, bias_noise=0.1)
@@ -196,7 +206,7 @@ def gen_model(tf, models, name, case, n_steps=1):
         st.dropout_calls = 0
         model = models.ConvE(model_descriptors={
             "use_negative_sampling": bool(case.get("sampled")), "label_smoothing_epsilon": 0.1, "num_ent": cfg.num_ent,
-            "num_rel": cfg.num_rel, "ent_emb_size": d, "rel_emb_size": dr, "concat_rel": False,
+            "num_rel": cfg.num_rel, "ent_emb_size": d, "rel_emb_size": dr, "concat_rel": bool(case.get("concat")),
             "conv_num_channels": C,
             "context_rel_conv": ctx_conv, "context_rel_out": ctx, "context_rel_dropout": case["drop"][2],
             "context_rel_use_batch_norm": case["usebn"], "input_dropout": 0.2, "hidden_dropout": case["drop"][0],
@@ -231,10 +241,14 @@ def gen_model(tf, models, name, case, n_steps=1):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     tf, models, metrics = _import_reference()
-    gen_metrics(tf, metrics, "small", [16, 16, 5], 211, seed=1, filt_p=0.05)
-    gen_metrics(tf, metrics, "dense_filter", [8], 64, seed=2, filt_p=0.5)
-    gen_metrics(tf, metrics, "single", [1], 10, seed=3, filt_p=0.2)
+    only = set(sys.argv[1:])
+    if not only:
+        gen_metrics(tf, metrics, "small", [16, 16, 5], 211, seed=1, filt_p=0.05)
+        gen_metrics(tf, metrics, "dense_filter", [8], 64, seed=2, filt_p=0.5)
+        gen_metrics(tf, metrics, "single", [1], 10, seed=3, filt_p=0.2)
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         gen_model(tf, models, name, case, n_steps=3 if case["is_train"] else 1)
 
 

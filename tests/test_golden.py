@@ -38,6 +38,12 @@ CASE_CFG = {
                           C=8),
     "cpgconv_eval": dict(ctx=[], ctx_conv=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, d=30,
                          C=8),
+    "concat_train": dict(ctx=[6], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, d=30, C=8,
+                         concat=True),
+    "concat_eval": dict(ctx=[], bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=False, d=30, C=8,
+                        concat=True),
+    "concat_plain_train": dict(ctx=None, bn_train=True, usebn=True, drop=(0.3, 0.2, 0.2), is_train=True, d=30, C=8,
+                               variant="plain", concat=True),
 }
 LR = 1e-2
 
@@ -75,6 +81,7 @@ def cfg_of(case):
     return O.OracleConfig(num_ent=97, num_rel=6, ent_emb_size=case["d"],
                           rel_emb_size=case["d"] if variant_of(case) == "plain" else 5, context_rel_out=case["ctx"],
                           variant=variant_of(case), context_rel_conv=case.get("ctx_conv"), conv_num_channels=case["C"], hidden_dropout=case["drop"][0], output_dropout=case["drop"][1],
+                          concat_rel=bool(case.get("concat")),
                           context_rel_dropout=case["drop"][2], context_rel_use_batch_norm=case["usebn"],
                           batch_norm_train_stats=case["bn_train"], batch_norm_momentum=0.9)
 
@@ -230,9 +237,12 @@ def test_oracle_multi_step_training_matches_reference(name):
             if k == "conv1_bias" and case["bn_train"]:
                 continue   # its gradient is pure rounding noise under batch-stat BN; AMSGrad's g/sqrt(g^2) amplifies it
             ref = named_params(after, case)[k]
-            assert relerr(v.reshape(ref.shape), ref) < 2e-4, (step, k)
+            # (concat_rel: the generator rows that multiply the appended rel_emb columns see gradients near the 1e-8
+            # scale of AMSGrad's epsilon, where fp32-vs-fp64 summation noise is amplified to a fraction of a step;
+            # the step-0 gradients themselves are compared at 2e-4 by the test above)
+            assert relerr(v.reshape(ref.shape), ref) < (1e-3 if case.get("concat") else 2e-4), (step, k)
         assert relerr(p["Conv1BN"]["moving_var"], after["Conv1BN"]["moving_var"]) < 1e-5
-        assert relerr(p["FCBN"]["moving_mean"], after["FCBN"]["moving_mean"]) < 1e-5
+        assert relerr(p["FCBN"]["moving_mean"], after["FCBN"]["moving_mean"]) < (5e-5 if case.get("concat") else 1e-5)
         # the reference's dense AMSGrad never accumulates m / v (amsgrad.py:142-151)
         dense_var = "conv1_weights" if case.get("sampled") else "ent_emb"
         assert np.abs(z[pre + "after/%s/AMSGrad/m" % dense_var]).max() == 0.0
@@ -260,7 +270,7 @@ def _model(case, p, lr=LR, prec="fp32"):
     md = {"use_negative_sampling": bool(case.get("sampled")), "label_smoothing_epsilon": 0.1, "num_ent": 97,
           "num_rel": 6,
           "ent_emb_size": case["d"], "rel_emb_size": case["d"] if variant_of(case) == "plain" else 5,
-          "concat_rel": False, "conv_num_channels": case["C"],
+          "concat_rel": bool(case.get("concat")), "conv_num_channels": case["C"],
           "context_rel_conv": case.get("ctx_conv"), "context_rel_out": case["ctx"],
           "context_rel_dropout": case["drop"][2],
           "context_rel_use_batch_norm": case["usebn"], "input_dropout": 0.2, "hidden_dropout": case["drop"][0],

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 def descriptors(cfg: O.OracleConfig, lr=1e-3):
     return {"use_negative_sampling": False, "label_smoothing_epsilon": cfg.label_smoothing_epsilon,
             "num_ent": cfg.num_ent, "num_rel": cfg.num_rel, "ent_emb_size": cfg.ent_emb_size,
-            "rel_emb_size": cfg.rel_emb_size, "concat_rel": False,
+            "rel_emb_size": cfg.rel_emb_size, "concat_rel": bool(cfg.concat_rel),
             "context_rel_conv": None if cfg.context_rel_conv is None else list(cfg.context_rel_conv),
             "context_rel_out": None if cfg.variant == "plain" else list(cfg.context_rel_out or []),
             "context_rel_dropout": cfg.context_rel_dropout,
@@ -152,6 +152,13 @@ CASES = {
     "cpgconv_gmlp_d200": (dict(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[6],
                                context_rel_conv=[7, 5], context_rel_use_batch_norm=True, context_rel_dropout=0.2,
                                batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 130),
+    # concat_rel (models.py:270-271, 406-407): rel_emb appended to the flattened conv features (generated and shared FC)
+    "concat_gmlp_d200": (dict(num_ent=1003, num_rel=22, ent_emb_size=200, rel_emb_size=8, context_rel_out=[6],
+                              context_rel_use_batch_norm=True, context_rel_dropout=0.2, concat_rel=True,
+                              batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 130),
+    "concat_plain_toy": (dict(num_ent=131, num_rel=6, ent_emb_size=40, rel_emb_size=40, context_rel_out=None,
+                              variant="plain", concat_rel=True, batch_norm_train_stats=True, hidden_dropout=0.3,
+                              output_dropout=0.2), 33),
     # the other two shipped model types (config_*_plain.yaml, config_*_param_lookup.yaml)
     "plain_toy": (dict(num_ent=131, num_rel=6, ent_emb_size=40, rel_emb_size=40, context_rel_out=None, variant="plain",
                        batch_norm_train_stats=True, hidden_dropout=0.3, output_dropout=0.2), 33),
@@ -333,7 +340,7 @@ TC_TOL = {  # prec: (q, loss, dq/dy/df, parameter grads)
 
 @pytest.mark.parametrize("prec", ["tf32x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("name", ["toy_glinear_batch_stats", "toy_gmlp_bn_dropout", "ragged_mid", "d256_16x16",
-                                  "plain_d200", "lookup_d200", "lookup_toy", "cpgconv_gmlp_d200"])
+                                  "plain_d200", "lookup_d200", "lookup_toy", "cpgconv_gmlp_d200", "concat_gmlp_d200"])
 def test_train_step_parity_tensor_pipe(name, prec):
     """Same step as test_train_step_parity with the CPG contraction and the scorer on tcgen05."""
     kw, B = CASES[name]
