@@ -288,6 +288,26 @@ __global__ void dense_to_bits_t_kernel(const float* __restrict__ dense, int B, i
 }
 
 // ------------------------------------------------------------------ deterministic reductions
+// Few slabs (S <= 8), many outputs (dbias of a sharded table, 4 slabs x 10 M floats): one thread per 4 outputs, float4
+// loads, slabs added in slab order in fp64 - the same order (and bits) as the general kernel below gives for S <= 8.
+__global__ void __launch_bounds__(256) reduce_partials_few_kernel(const float* __restrict__ in, int S, int64_t n,
+                                                                  float scale, int accumulate, float* __restrict__ out) {
+  const int64_t i4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int s = 0; s < S; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + (int64_t)s * n + i4));
+    a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+  }
+  float4 r = make_float4((float)(a0 * (double)scale), (float)(a1 * (double)scale), (float)(a2 * (double)scale),
+                         (float)(a3 * (double)scale));
+  float4* o = reinterpret_cast<float4*>(out + i4);
+  if (accumulate) {
+    const float4 p = *o;
+    r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+  }
+  *o = r;
+}
 // out[i] = scale * sum_s in[s, i]: block = 32 outputs x 8 slab lanes; every thread sums the slabs s = ty, ty+8, ...
 // in fp64, the 8 lane sums are added in a fixed order -> deterministic, and the slab loop is 8x shorter / pipelined
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ in, int S, int64_t n,
@@ -400,12 +420,13 @@ __global__ void __launch_bounds__(256) mt_sumsq_kernel(const coper_param_desc* _
   const int t = chunks[2 * blockIdx.x];
   const int64_t start = (int64_t)chunks[2 * blockIdx.x + 1] * COPER_MT_CHUNK;
   const coper_param_desc d = descs[t];
+  // the squared norm of this gradient is supplied by its producer (coper_sumsq_combine): nothing to read, and its
+  // chunk partials are never summed (mt_tensor_sums_kernel)
+  if (d.mode & COPER_GRAD_NORM_EXTERNAL) return;
   const int64_t end = start + COPER_MT_CHUNK < d.n ? start + COPER_MT_CHUNK : d.n;
   const float* x = d.grad;
   float p = 0.f;
-  if (d.mode & COPER_GRAD_NORM_EXTERNAL) {
-    // the squared norm of this gradient is supplied by its producer (coper_sumsq_combine): nothing to read
-  } else if (d.mode == COPER_GRAD_INDEXED_SLICES) {
+  if (d.mode == COPER_GRAD_INDEXED_SLICES) {
     // IndexedSlices: norm over the slice values = sum of the per-row sums of squared slices
     for (int64_t j = start + threadIdx.x; j < end; j += 256) p += d.grad_sq[j];
   } else if (((reinterpret_cast<uintptr_t>(x) & 15) == 0) && end - start == COPER_MT_CHUNK) {
@@ -429,11 +450,13 @@ __device__ __forceinline__ uint32_t* fp16x3_trailer_of(const coper_param_desc& d
 __global__ void mt_tensor_sums_kernel(const coper_param_desc* __restrict__ descs, const double* __restrict__ chunk_partials,
                                       const int32_t* __restrict__ chunk_offsets, int n_tensors,
                                       double* __restrict__ tensor_sumsq) {
-  // one warp per tensor: lanes stride over the tensor's chunks, fixed-order shuffle combine
+  // one warp per tensor: lanes stride over the tensor's chunks, fixed-order shuffle combine.  A tensor whose norm is
+  // supplied by its producer (COPER_GRAD_NORM_EXTERNAL) has no partials to add (160 k of them at 10 M entities).
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n_tensors) return;
   double acc = 0.0;
-  for (int c = chunk_offsets[t] + lane; c < chunk_offsets[t + 1]; c += 32) acc += chunk_partials[c];
+  if (!(descs[t].mode & COPER_GRAD_NORM_EXTERNAL))
+    for (int c = chunk_offsets[t] + lane; c < chunk_offsets[t + 1]; c += 32) acc += chunk_partials[c];
   acc = warp_sum_d(acc);
   if (lane == 0) {
     tensor_sumsq[t] = acc;
@@ -775,7 +798,11 @@ int coper_dense_to_bits_t(const float* dense, int B, int64_t N, int64_t ld_dense
 int coper_reduce_partials(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
                           coper_stream_t stream) {
   COPER_CHECK_ARG(in && out && S > 0 && n > 0);
-  reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate, out);
+  if (S <= 8 && n >= (1 << 16) && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    reduce_partials_few_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate,
+                                                                                        out);
+  else
+    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate, out);
   return check_launch();
 }
 int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_stream_t stream) {

@@ -377,6 +377,12 @@ class ConvE:
         desc_ext[0]["mode"] |= 2
         assert tr[0][0] == "ent_emb"
         self.mt_desc_ext = torch.from_numpy(desc_ext.view(np.uint8).copy()).to(self.dev)
+        # ... and the norm pass does not even launch blocks for that tensor's chunks (160 k of them at 10 M entities)
+        chunks_ext = [c for c in chunks if c[0] != 0]
+        n0 = len(chunks) - len(chunks_ext)
+        self.mt_chunks_ext = torch.tensor(chunks_ext or [(1, 0)], dtype=torch.int32).to(self.dev)
+        self.mt_offsets_ext = torch.tensor([0] + [max(0, o - n0) for o in offsets[1:]], dtype=torch.int32).to(self.dev)
+        self.mt_nchunks_ext = len(chunks_ext)
         self.dE_sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.norm_delta = torch.zeros(4096, dtype=torch.float64, device=self.dev)
         self._norm_fused_now = False
@@ -1008,8 +1014,12 @@ class ConvE:
         launch per phase over the whole variable list."""
         nt = len(self.trainables)
         fused = self._norm_fused_now
-        call("coper_mt_sumsq", ptr(self.mt_desc_ext if fused else self.mt_desc), nt, ptr(self.mt_chunks), self.mt_nchunks,
-             ptr(self.mt_offsets), ptr(self.mt_partials), ptr(self.sumsq))
+        if fused and self.mt_nchunks_ext > 0:
+            call("coper_mt_sumsq", ptr(self.mt_desc_ext), nt, ptr(self.mt_chunks_ext), self.mt_nchunks_ext,
+                 ptr(self.mt_offsets_ext), ptr(self.mt_partials), ptr(self.sumsq))
+        else:
+            call("coper_mt_sumsq", ptr(self.mt_desc_ext if fused else self.mt_desc), nt, ptr(self.mt_chunks),
+                 self.mt_nchunks, ptr(self.mt_offsets), ptr(self.mt_partials), ptr(self.sumsq))
         if fused:       # |dE|^2 from the dE GEMM epilogue + the change the head-entity scatter made to it
             call("coper_sumsq_combine", ptr(self.dE_sumsq), 1, ptr(self.norm_delta), self._norm_delta_n,
                  ptr(self.sumsq))

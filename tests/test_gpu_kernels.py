@@ -443,7 +443,8 @@ def test_multi_tensor_optimizer_matches_per_tensor(L, bug_compat):
 
 def test_reduce_partials_fixed_order(L):
     rng = np.random.default_rng(0)
-    for S, n in ((37, 102400), (512, 288), (1, 5), (16, 40943), (144, 4096)):
+    # (4, 1 << 20) / (8, 65536): the few-slabs float4 path (dbias of a sharded table); (4, 65538): n % 4 != 0 -> general path
+    for S, n in ((37, 102400), (512, 288), (1, 5), (16, 40943), (144, 4096), (4, 1 << 20), (8, 65536), (4, 65538)):
         x = rng.normal(size=(S, n)).astype(np.float32)
         out = torch.full((n,), 7.0, device="cuda")
         L.call("coper_reduce_partials", L.ptr(dev(x)), S, n, 0.5, 1, L.ptr(out))
