@@ -77,7 +77,7 @@ def main(argv=None):
                     help="sampled-label configs: draw the [B, num_labels] ids / labels on the GPU (coper_sample_labels)")
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--eval-batches", type=int, default=None, help="cap the number of eval batches (synthetic runs)")
-    ap.add_argument("--prec", default="tf32x3", choices=["fp32", "tf32x3", "fp16x3", "bf16"])
+    ap.add_argument("--prec", default="fp16x3", choices=["fp32", "tf32x3", "fp16x3", "bf16"])
     ap.add_argument("--is-test", action="store_true")
     ap.add_argument("--needs-test-set-cleaning", action="store_true")
     ap.add_argument("--no-save-best-embeddings", action="store_true")
