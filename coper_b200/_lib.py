@@ -54,6 +54,7 @@ SIGNATURES = {
                                         sz, i32, vp]),
     "coper_score1n_bce_fwd_bwd_norm": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
                                              vp, sz, i32, vp]),
+    "coper_score1n_bce_dE": (i32, [vp, i32, i64, i32, f32, vp, vp, vp, sz, i32, vp]),
     "coper_sample_labels": (i32, [vp, vp, i32, i64, i32, i32, vp, u64, vp, vp, vp]),
     "coper_score_sampled_workspace_bytes": (sz, [i32, i32]),
     "coper_score_sampled_bce_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, f32, f32, vp, vp, vp, vp, vp,

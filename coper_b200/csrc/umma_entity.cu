@@ -624,6 +624,40 @@ static int bce_impl(const TcOperand& E, const TcOperand& Q, const float* bias, c
   return launch_gemm<Cfg, BceEpiT<PREC, kEntNCH>>(E, Q, p, epi, st, *grid_out);
 }
 
+// dL/dS as a tensor-pipe operand: bf16 / fp16x3 GT stored entity-major [Ns, B]; tf32x3 G stored query-major [B, Ns]
+static TcOperand g_operand(const void* G, int B, int64_t Ns, int prec) {
+  const bool entity_major = prec != COPER_PREC_TF32X3;
+  const int64_t ldGT = entity_major ? gt_pitch(B) : (Ns + 31) / 32 * 32;
+  TcOperand Go;
+  Go.main = G;
+  Go.pitch = (uint64_t)ldGT;
+  Go.exp = nullptr;
+  if (entity_major) {
+    Go.lo = prec == COPER_PREC_FP16X3 ? static_cast<const void*>(static_cast<const uint16_t*>(G) + Ns * ldGT) : nullptr;
+    Go.rows = (uint64_t)Ns; Go.cols = (uint64_t)B;
+  } else {
+    Go.lo = static_cast<const void*>(static_cast<const float*>(G) + (int64_t)B * ldGT);
+    Go.rows = (uint64_t)B; Go.cols = (uint64_t)Ns;
+  }
+  return Go;
+}
+
+// Pass 3 on its own: dE = G^T . q from the G and the prepared q that umma_score1n_bce_fwd_bwd (called with dE == NULL)
+// left in `G` / `ws`.  Independent of dq and of everything the front-end backward does, so the host may enqueue it on a
+// second stream and let the HBM-bound GEMM run under the latency-bound backward chain.
+int umma_score1n_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq, void* ws,
+                    size_t ws_bytes, int prec, cudaStream_t st) {
+  BceTcLayout L = bce_tc_layout(B, Ns, d, prec);
+  if (!ws || ws_bytes < L.total) return COPER_ERR_WORKSPACE;
+  char* w = static_cast<char*>(ws);
+  TcOperand Qo = tc_operand(w + L.off_q, B, d, prec), Go = g_operand(G, B, Ns, prec);
+  GemmProblem p{};
+  p.M = (int)Ns; p.N = d; p.K = B; p.groups = 1; p.groups_inner = 0;
+  p.post_scale = prec == COPER_PREC_FP16X3 ? inv_count * (1.0f / 1024.0f) : 0.f;
+  StoreEpi epi = make_store_epi(dE, d, 0, 0);
+  return dE_gemm(prec, prec == COPER_PREC_TF32X3, Go, Qo, p, epi, dE_sumsq, reinterpret_cast<double*>(w + L.off_ss), st);
+}
+
 int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepared, const float* bias,
                              const uint32_t* label_bits_t, int B, int64_t Ns, int d, float pos, float neg,
                              float inv_count, double* loss_sum, void* G, int64_t ldG, float* dq, float* dE,
@@ -658,13 +692,9 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     if ((rc = check_launch())) return rc;
     if ((rc = coper_reduce_partials(dbias_part, QB, Ns, 1.0f, 0, dbias, (coper_stream_t)st))) return rc;
     if ((rc = coper_reduce_partials(dq_part, R, (int64_t)B * d, 1.0f, 0, dq, (coper_stream_t)st))) return rc;
-    // ---- dE = G^T . q from the entity-major G the kernel stored
-    TcOperand Go;
-    Go.main = G; Go.lo = nullptr; Go.exp = nullptr; Go.pitch = (uint64_t)ldGT; Go.rows = (uint64_t)Ns; Go.cols = (uint64_t)B;
-    GemmProblem pe{};
-    pe.M = (int)Ns; pe.N = d; pe.K = B; pe.groups = 1; pe.groups_inner = 0;
-    StoreEpi epi = make_store_epi(dE, d, 0, 0);
-    return dE_gemm(prec, false, Go, Qo, pe, epi, dE_sumsq, reinterpret_cast<double*>(w + L.off_ss), st);
+    // ---- dE = G^T . q from the entity-major G the kernel stored (dE == NULL: the caller runs umma_score1n_dE itself)
+    if (!dE) return COPER_OK;
+    return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, ws, ws_bytes, prec, st);
   }
   // ---- pass 1: scores -> loss, G, dbias partials
   int grid = 0;
@@ -688,18 +718,7 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
   sum_doubles_kernel<<<1, 256, 0, st>>>(loss_part, grid * kBceEpiWarps, loss_sum);
   if ((rc = check_launch())) return rc;
   if ((rc = coper_reduce_partials(dbias_part, L.dbias_slabs, Ns, 1.0f, 0, dbias, (coper_stream_t)st))) return rc;
-  // ---- dL/dS as a tensor-pipe operand: bf16 GT stored [Ns, B]; tf32x3 G stored [B, Ns]
-  TcOperand Go;
-  Go.main = G;
-  Go.pitch = (uint64_t)ldGT;
-  Go.exp = nullptr;
-  if (entity_major) {
-    Go.lo = prec == COPER_PREC_FP16X3 ? static_cast<const void*>(static_cast<const uint16_t*>(G) + Ns * ldGT) : nullptr;
-    Go.rows = (uint64_t)Ns; Go.cols = (uint64_t)B;
-  } else {
-    Go.lo = static_cast<const void*>(static_cast<const float*>(G) + (int64_t)B * ldGT);
-    Go.rows = (uint64_t)B; Go.cols = (uint64_t)Ns;
-  }
+  TcOperand Go = g_operand(G, B, Ns, prec);
   // ---- pass 2: dq = G . E   (A(b, n): GT is the MN-major form, G the K-major form; B = E stored [K, N] -> MN-major)
   {
     GemmProblem p{};
@@ -710,14 +729,8 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     if ((rc = coper_reduce_partials(dq_part, L.splits, (int64_t)B * d, 1.0f, 0, dq, (coper_stream_t)st))) return rc;
   }
   // ---- pass 3: dE = G^T . q (A(n, b): GT is the K-major form, G the MN-major form; B = q stored [K, N] -> MN-major)
-  {
-    GemmProblem p{};
-    p.M = (int)Ns; p.N = d; p.K = B; p.groups = 1; p.groups_inner = 0;
-    p.post_scale = g_post;
-    StoreEpi epi = make_store_epi(dE, d, 0, 0);
-    if ((rc = dE_gemm(prec, !entity_major, Go, Qo, p, epi, dE_sumsq, reinterpret_cast<double*>(w + L.off_ss), st))) return rc;
-  }
-  return COPER_OK;
+  if (!dE) return COPER_OK;                            // the caller runs umma_score1n_dE itself (second stream)
+  return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, ws, ws_bytes, prec, st);
 }
 
 }  // namespace coper

@@ -95,7 +95,7 @@ class ConvE:
                  shard: Optional[EntityShard] = None, reference_bug_compat: bool = True,
                  conv_in_height: int = 10, process_group=None, use_graphs: bool = True,
                  init_fast: bool = False, graphs_multi_gpu: bool = False, data_parallel: bool = False,
-                 overlap_grad_allreduce: bool = True):
+                 overlap_grad_allreduce: bool = True, overlap_entity_grad: bool = True):
         md = model_descriptors
         _lib.load()
         if not torch.cuda.is_available():
@@ -180,6 +180,11 @@ class ConvE:
             ranks = dist.get_process_group_ranks(process_group) if process_group is not None else None
             self.group_big = dist.new_group(ranks=ranks)          # collective: every rank builds its model here
         self.bug_compat = bool(reference_bug_compat)
+        # the entity-gradient GEMM dE = G^T.q (HBM-bound) depends on nothing the rest of the backward pass produces and
+        # nothing there depends on it until the head-entity scatter: it is enqueued on a second stream and runs under
+        # the latency-bound FC / CPG / conv backward chain (fork / join are captured into the step's CUDA graph)
+        self.overlap_entity_grad = bool(overlap_entity_grad)
+        self._side = torch.cuda.Stream(device=self.dev)
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
         # and replayed with one launch.  The sharded path captures its NCCL collectives into the same graph
@@ -861,10 +866,18 @@ class ConvE:
         if self.use_negative_sampling:
             self._sampled_scorer(b)
         elif self._norm_fused_now:
+            split = self.overlap_entity_grad
             call("coper_score1n_bce_fwd_bwd_norm", ptr(bg.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
                  ptr(bg.bitsT), bg.B, Ns, d, float(pos), float(neg), inv_count, ptr(bg.loss_sum),
-                 ptr(self._grad_buf(bg)), bg.ld, ptr(bg.dq), ptr(g["ent_emb"]), ptr(g["pred_bias"]), ptr(self.dE_sumsq),
-                 ptr(bg.ws), bg.ws_bytes, self.prec)
+                 ptr(self._grad_buf(bg)), bg.ld, ptr(bg.dq), None if split else ptr(g["ent_emb"]), ptr(g["pred_bias"]),
+                 ptr(self.dE_sumsq), ptr(bg.ws), bg.ws_bytes, self.prec)
+            if split:
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    call("coper_score1n_bce_dE", ptr(self._grad_buf(bg)), bg.B, Ns, d, inv_count, ptr(g["ent_emb"]),
+                         ptr(self.dE_sumsq), ptr(bg.ws), bg.ws_bytes, self.prec)
+                self._entity_grad_pending = True
         else:
             call("coper_score1n_bce_fwd_bwd", ptr(bg.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
                  ptr(bg.bits if self.prec == 0 else bg.bitsT), bg.B, Ns, d, float(pos), float(neg), inv_count,
@@ -943,6 +956,9 @@ class ConvE:
         gsq_e = self.grad_sq["ent_emb"] if self.use_negative_sampling else None
         if dp:      # every shard needs dx0 of ALL queries whose head entity it owns
             sharding.gather_batch(bg.dx0, b.dx0, self.world, self.group)
+        if getattr(self, "_entity_grad_pending", False):      # join: the scatter below adds into dE
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._entity_grad_pending = False
         if self._norm_fused_now:
             call("coper_segscatter_add_norm", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi,
                  ptr(self.norm_delta))

@@ -198,6 +198,14 @@ int coper_score1n_bce_fwd_bwd_norm(const float* q, const float* E, const void* E
                                    float* dE, float* dbias, double* dE_sumsq, void* workspace, size_t workspace_bytes,
                                    int prec, coper_stream_t stream);
 
+/* The split form of coper_score1n_bce_fwd_bwd_norm (tensor-pipe precisions): call it with dE == NULL - loss, dq, dbias
+ * and G are produced, the entity-gradient GEMM is skipped - and then coper_score1n_bce_dE with the same G / workspace
+ * (which still holds the prepared q): dE = G^T . q (+ *dE_sumsq, optional).  dE does not depend on dq, and nothing the
+ * rest of the backward pass (models.py:198 through the FC / conv layers) does depends on dE, so the host may enqueue
+ * this call on a second stream: the HBM-bound GEMM then runs under the latency-bound backward chain. */
+int coper_score1n_bce_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq,
+                         void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
+
 /* a8 / SURVEY §8f-2 — SAMPLED-label scorer (models.py:438-443), loss (:448-453) and gradients: what the shipped
  * big-dataset configs train with (training.num_labels = 100 / 1000).  lookup int32 [B, L] entity ids
  * (batch['lookup_values'], models.py:165), labels fp32 [B, L] (batch['e2_multi'] in sampled mode):
