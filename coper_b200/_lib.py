@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcoper_sm100.so")
 
 PREC = {"fp32": 0, "bf16": 1, "tf32x3": 2, "fp16x3": 3}
+# flags of coper_cpg_fc_bwd (include/coper.h)
+CPG_BWD_REUSE_FWD, CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_WEIGHT_GRADS_ONLY = 1, 2, 4
 
 vp, i32, i64, u64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 
@@ -23,14 +25,19 @@ SIGNATURES = {
     "coper_launch_count": (C.c_longlong, []),
     "coper_device_is_sm100": (i32, []),
     "coper_gather_rows": (i32, [vp, i64, i64, i32, vp, i32, vp, vp]),
+    "coper_gather_rows2": (i32, [vp, i64, i64, i32, vp, i32, vp, vp, i64, i64, i32, vp, i32, vp, vp, vp, f32, f32, f32, vp]),
     "coper_conv_fwd": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
     "coper_conv_bwd_slabs": (i32, [i32, i32, i32, i32, i32, i32, i32]),
     "coper_conv_bwd": (i32, [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "coper_colstats_chunks": (i32, [i64]),
     "coper_colstats": (i32, [vp, i64, i32, vp, vp]),
     "coper_bn_finalize": (i32, [vp, i32, i64, i32, vp, vp, vp, vp, f32, f32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "coper_bn_stats_finalize": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, f32, f32, i32, i32, vp, vp, vp, vp, vp]),
     "coper_bn_act_fwd": (i32, [vp, i64, i32, vp, vp, i32, f32, vp, u64, vp, vp]),
+    "coper_bn_act_fwd_moving": (i32, [vp, i64, i32, vp, vp, vp, vp, f32, i32, vp, vp]),
     "coper_bn_act_bwd_stats": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, i32, f32, vp, u64, vp, vp]),
+    "coper_bn_act_bwd_stats_finalize": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, i32, f32, vp, u64, vp, vp, i32, vp, vp, vp, vp,
+                                              vp]),
     "coper_bn_act_bwd_finalize": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp]),
     "coper_bn_act_bwd_apply": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, f32, vp, u64, f32, u64, vp, vp]),
     "coper_dropout_mask": (i32, [i64, f32, vp, u64, vp, vp]),
@@ -54,7 +61,7 @@ SIGNATURES = {
                                         sz, i32, vp]),
     "coper_score1n_bce_fwd_bwd_norm": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, f32, f32, f32, vp, vp, i64, vp, vp, vp, vp,
                                              vp, sz, i32, vp]),
-    "coper_score1n_bce_dE": (i32, [vp, i32, i64, i32, f32, vp, vp, vp, sz, i32, vp]),
+    "coper_score1n_bce_dE": (i32, [vp, i32, i64, i32, f32, vp, vp, vp, vp, sz, i32, vp]),
     "coper_sample_labels": (i32, [vp, vp, i32, i64, i32, i32, vp, u64, vp, vp, vp]),
     "coper_score_sampled_workspace_bytes": (sz, [i32, i32]),
     "coper_score_sampled_bce_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i32, f32, f32, f32, vp, vp, vp, vp, vp,
@@ -72,14 +79,17 @@ SIGNATURES = {
     "coper_segscatter_workspace_bytes": (sz, [i32]),
     "coper_segscatter_add_sq": (i32, [vp, i32, vp, i32, vp, vp, i64, i64, vp]),
     "coper_segscatter_add_norm": (i32, [vp, i32, vp, i32, vp, vp, i64, i64, vp, vp]),
+    "coper_segscatter_add_pair": (i32, [vp, i32, vp, i32, vp, vp, i64, i64, vp, vp, i32, vp, i32, vp, vp, i64, i64, vp]),
     "coper_segscatter_add": (i32, [vp, i32, vp, i32, vp, i64, i64, vp, sz, vp]),
     "coper_reduce_partials": (i32, [vp, i32, i64, f32, i32, vp, vp]),
+    "coper_reduce_partials2": (i32, [vp, i64, vp, vp, i64, vp, i32, f32, i32, vp]),
     "coper_sumsq": (i32, [vp, i64, i32, vp, vp]),
     "coper_clip_scale": (i32, [vp, i32, f32, vp, vp]),
     "coper_step_state_advance": (i32, [vp, vp, f32, f32, f32, vp]),
     "coper_sumsq_combine": (i32, [vp, i32, vp, i32, vp, vp]),
     "coper_mt_sumsq": (i32, [vp, i32, vp, i32, vp, vp, vp, vp]),
     "coper_clip_scale_n": (i32, [vp, i32, f32, vp, vp]),
+    "coper_mt_sumsq_clip": (i32, [vp, i32, vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, f32, vp, vp]),
     "coper_mt_amsgrad": (i32, [vp, vp, i32, vp, f32, f32, f32, vp, i32, vp]),
     "coper_amsgrad_step": (i32, [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, vp, i32, vp]),
 }

@@ -120,6 +120,10 @@ inline int sm_count() {
   return cached[dev];
 }
 
+// elementwise.cu: fixed-order reduction of S slabs, optionally with a sum of doubles riding in the same launch
+int reduce_partials_and_sum(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
+                            const double* dsum_in, int dsum_n, double* dsum_out, cudaStream_t st);
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -27,7 +27,7 @@ int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, const 
                           int d, void* ws, size_t ws_bytes, int prec, cudaStream_t st, float** slabs, int* n_slabs);
 int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* dy, int B, int dc,
                  int F, int d, float* dP, float* df, float* dc_out, void* ws, size_t ws_bytes, int prec,
-                 int reuse_fwd_operands, cudaStream_t st);
+                 int flags, cudaStream_t st);
 
 // ---------------------------------------------------------------- sources
 struct CpgFwdA {  // (b, kk) -> f[b, i] * c[b, kq],  K-contiguous
@@ -119,6 +119,43 @@ __global__ void cpg_fwd_finalize_kernel(const float* __restrict__ part, int S, c
   for (int k = 0; k < dcb; ++k) bias = fmaf(__ldg(cb + (int64_t)b * dcb + k), __ldg(Pb + (int64_t)k * d + j), bias);
   float v = (float)acc + bias;
   y[e] = v * drop_factor(keep, inv_keep, thr, seed, (uint64_t)e);
+}
+
+// float4 form (d % 4 == 0, 16-byte aligned slabs / Pb / y): four adjacent outputs per thread, same slab order and the
+// same fmaf chain per output -> same bits as cpg_fwd_finalize_kernel
+__global__ void cpg_fwd_finalize_kernel4(const float* __restrict__ part, int S, const float* __restrict__ cb,
+                                         const float* __restrict__ Pb, int B, int d, int dcb, float keep, float inv_keep,
+                                         uint32_t thr, const uint64_t* seed_dev, uint64_t salt, float* __restrict__ y) {
+  const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t n = (int64_t)B * d;
+  if (e >= n) return;
+  const int b = (int)(e / d), j = (int)(e % d);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int s = 0;
+  for (; s + 8 <= S; s += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(part + (int64_t)(s + u) * n + e));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w; }
+  }
+  for (; s < S; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (int64_t)s * n + e));
+    a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+  }
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  for (int k = 0; k < dcb; ++k) {
+    const float c = __ldg(cb + (int64_t)b * dcb + k);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(Pb + (int64_t)k * d + j));
+    b0 = fmaf(c, p.x, b0); b1 = fmaf(c, p.y, b1); b2 = fmaf(c, p.z, b2); b3 = fmaf(c, p.w, b3);
+  }
+  float4 o;
+  o.x = ((float)a0 + b0) * drop_factor(keep, inv_keep, thr, seed, (uint64_t)e);
+  o.y = ((float)a1 + b1) * drop_factor(keep, inv_keep, thr, seed, (uint64_t)e + 1);
+  o.z = ((float)a2 + b2) * drop_factor(keep, inv_keep, thr, seed, (uint64_t)e + 2);
+  o.w = ((float)a3 + b3) * drop_factor(keep, inv_keep, thr, seed, (uint64_t)e + 3);
+  *reinterpret_cast<float4*>(y + e) = o;
 }
 
 // ---------------------------------------------------------------- backward: T kernel -> df, dc partials
@@ -327,9 +364,16 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
     return COPER_ERR_UNSUPPORTED;
   }
   int64_t n = (int64_t)B * d;
-  cpg_fwd_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n_slabs, cb, Pb, B, d, dcb, keep_out,
-                                                                       1.0f / keep_out, keep_threshold(keep_out),
-                                                                       seed_dev, salt_out, y);
+  const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(Pb) |
+                                     reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (vec)
+    cpg_fwd_finalize_kernel4<<<(unsigned)((n / 4 + 127) / 128), 128, 0, st>>>(part, n_slabs, cb, Pb, B, d, dcb, keep_out,
+                                                                              1.0f / keep_out, keep_threshold(keep_out),
+                                                                              seed_dev, salt_out, y);
+  else
+    cpg_fwd_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n_slabs, cb, Pb, B, d, dcb, keep_out,
+                                                                         1.0f / keep_out, keep_threshold(keep_out),
+                                                                         seed_dev, salt_out, y);
   return check_launch();
 }
 
@@ -341,32 +385,43 @@ size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec) {
 int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
                      const float* Pb, const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
                      float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
-                     int reuse_fwd_operands, coper_stream_t stream) {
+                     int flags, coper_stream_t stream) {
   COPER_CHECK_ARG(c && f && P && cb && Pb && dy && dP && dPb && df && dc_out && dcb_out && workspace);
   COPER_CHECK_ARG(B > 0 && dc > 0 && F > 0 && d > 0 && dcb > 0);
+  const bool inputs = !(flags & COPER_CPG_BWD_WEIGHT_GRADS_ONLY), weights = !(flags & COPER_CPG_BWD_INPUT_GRADS_ONLY);
+  COPER_CHECK_ARG(inputs || weights);
   if (workspace_bytes < coper_cpg_fc_bwd_workspace_bytes(B, dc, F, d, prec)) return COPER_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   int rc;
   if (cpg_on_tensor_pipe(F, d, prec)) {
     if ((rc = umma_cpg_bwd(c, f, P, P_prepared, dy, B, dc, F, d, dP, df, dc_out, workspace, workspace_bytes, prec,
-                           reuse_fwd_operands, st)))
+                           flags, st)))
       return rc;
   } else if (prec >= COPER_PREC_FP32 && prec <= COPER_PREC_FP16X3) {
-    float* dc_part = static_cast<float*>(workspace);
-    int ftiles = ceil_div(F, BN);
-    cpg_bwd_T_kernel<<<dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st>>>(c, f, P, dy, B, dc, F, d, df, dc_part);
-    if ((rc = check_launch())) return rc;
-    if ((rc = coper_reduce_partials(dc_part, ftiles, (int64_t)B * dc, 1.0f, 0, dc_out, stream))) return rc;
-    cpg_bwd_dP_kernel<<<dim3(ceil_div(d, BN), ceil_div(F, BM), dc), THREADS, 0, st>>>(c, f, dy, B, dc, F, d, dP);
-    if ((rc = check_launch())) return rc;
+    if (inputs) {
+      float* dc_part = static_cast<float*>(workspace);
+      int ftiles = ceil_div(F, BN);
+      cpg_bwd_T_kernel<<<dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st>>>(c, f, P, dy, B, dc, F, d, df, dc_part);
+      if ((rc = check_launch())) return rc;
+      if ((rc = coper_reduce_partials(dc_part, ftiles, (int64_t)B * dc, 1.0f, 0, dc_out, stream))) return rc;
+    }
+    if (weights) {
+      cpg_bwd_dP_kernel<<<dim3(ceil_div(d, BN), ceil_div(F, BM), dc), THREADS, 0, st>>>(c, f, dy, B, dc, F, d, dP);
+      if ((rc = check_launch())) return rc;
+    }
   } else {
     return COPER_ERR_UNSUPPORTED;
   }
   // dPb [dcb, d] = cb^T . dy ;  dcb [B, dcb] = dy . Pb^T
-  cpg_dPb_kernel<<<dim3(ceil_div(d, 32), dcb), 256, 0, st>>>(cb, dy, B, d, dcb, dPb);
-  if ((rc = check_launch())) return rc;
-  cpg_dcb_kernel<<<ceil_div((int64_t)B * dcb * 32, 256), 256, 0, st>>>(dy, Pb, B, d, dcb, dcb_out);
-  return check_launch();
+  if (weights) {
+    cpg_dPb_kernel<<<dim3(ceil_div(d, 32), dcb), 256, 0, st>>>(cb, dy, B, d, dcb, dPb);
+    if ((rc = check_launch())) return rc;
+  }
+  if (inputs) {
+    cpg_dcb_kernel<<<ceil_div((int64_t)B * dcb * 32, 256), 256, 0, st>>>(dy, Pb, B, d, dcb, dcb_out);
+    if ((rc = check_launch())) return rc;
+  }
+  return COPER_OK;
 }
 
 }  // extern "C"

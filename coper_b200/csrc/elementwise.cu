@@ -31,6 +31,45 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, int64_t row_
   }
 }
 
+// Two lookups of one step in ONE launch (blocks [0, blocksA) serve table A, the rest table B); block 0 also advances
+// the optimizer / dropout step state when asked to (nothing in this kernel reads it).
+struct GatherDesc {
+  const float* table;
+  int64_t row_lo, row_hi;
+  int width;
+  const int64_t* idx;
+  int n_idx;
+  float* out;
+};
+__device__ __forceinline__ void step_state_advance(float* st, uint64_t* seed_dev, float lr, float b1, float b2) {
+  float b1p = st[1], b2p = st[2];
+  st[0] = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);  // amsgrad.py:137
+  st[1] = b1p * b1;                                // amsgrad.py:234-239
+  st[2] = b2p * b2;
+  if (seed_dev) *seed_dev += 1ull;
+}
+__global__ void gather_rows2_kernel(GatherDesc A, GatherDesc Bd, int blocksA, float* step_state, uint64_t* seed_dev,
+                                    float lr, float b1, float b2) {
+  if (step_state && blockIdx.x == 0 && threadIdx.x == 0) step_state_advance(step_state, seed_dev, lr, b1, b2);
+  const bool second = (int)blockIdx.x >= blocksA;
+  const GatherDesc& g = second ? Bd : A;
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = ((int)blockIdx.x - (second ? blocksA : 0)) * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= g.n_idx) return;
+  const int64_t id = g.idx[row];
+  const bool owned = id >= g.row_lo && id < g.row_hi;
+  const float* src = g.table + (id - g.row_lo) * (int64_t)g.width;
+  float* dst = g.out + (int64_t)row * g.width;
+  if ((g.width & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < (g.width >> 2); i += 32) d4[i] = owned ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int i = lane; i < g.width; i += 32) dst[i] = owned ? __ldg(src + i) : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------ column statistics
 // mode 0: (x, x^2); mode 1: backward (g1, g1*xhat) with g1 = dout * drop_post * relu'(a x + b)
 // rows per chunk: enough chunks to fill the machine (R = B*OH*OW = 73,728 -> 576 CTAs; R = B = 512 -> 8 per column slab)
@@ -48,11 +87,105 @@ struct StatBwdArgs {
   const uint64_t* seed_dev;
   uint64_t salt;
 };
-template <int MODE>
+// Per-channel finalisation of the forward / backward statistics: one warp per channel, lanes stride over the chunk
+// partials, fixed-order shuffle combine.  Shared by the stand-alone finalize kernels (partials of ALL ranks after the
+// all-gather of a data-parallel step) and by the last block of colstats_kernel<_, true> (single-launch statistics).
+template <bool CG>
+__device__ __forceinline__ float2 ld_partial(const float* partials, int64_t i) {
+  const float2* p = reinterpret_cast<const float2*>(partials) + i;
+  return CG ? __ldcg(p) : __ldg(p);          // CG: written by other blocks of the SAME launch -> read through L2
+}
+struct BnFwdFin {
+  const float* gamma;
+  const float* beta;
+  float* moving_mean;
+  float* moving_var;
+  float momentum, eps;
+  int use_batch, update_moving, bessel;
+  float* a;
+  float* b;
+  float* mean;
+  float* invstd;
+};
+struct BnBwdFin {
+  int use_batch;
+  float* dgamma;
+  float* dbeta;
+  float* c1;
+  float* c2;
+};
+// (sum, sum of second component) of NC channels' chunk partials at once: lanes stride over the chunks, every lane adds
+// its chunks in increasing order (the loads of 4 strides x NC channels are issued together, the adds stay ordered),
+// fixed-order shuffle combine -> the result does not depend on NC.
+template <bool CG, int NC>
+__device__ __forceinline__ void sum_partials(const float* partials, int nchunk, int C, const int (&ch)[NC], int lane,
+                                             double (&s)[NC], double (&ss)[NC]) {
+#pragma unroll
+  for (int i = 0; i < NC; ++i) s[i] = ss[i] = 0.0;
+  int k = lane;
+  for (; k + 96 < nchunk; k += 128) {
+    float2 v[NC][4];
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[i][u] = ch[i] < C ? ld_partial<CG>(partials, (int64_t)(k + 32 * u) * C + ch[i]) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s[i] += (double)v[i][u].x; ss[i] += (double)v[i][u].y; }
+  }
+  for (; k < nchunk; k += 32) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const float2 v = ch[i] < C ? ld_partial<CG>(partials, (int64_t)k * C + ch[i]) : make_float2(0.f, 0.f);
+      s[i] += (double)v.x;
+      ss[i] += (double)v.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) { s[i] = warp_sum_d(s[i]); ss[i] = warp_sum_d(ss[i]); }
+}
+// lane 0 of the warp that summed channel c
+__device__ __forceinline__ void bn_fwd_finish(double s, double ss, int64_t R, int c, const BnFwdFin& f) {
+  float mu, var;
+  if (f.use_batch) {
+    double m = s / (double)R;
+    double v = ss / (double)R - m * m;
+    if (v < 0.0) v = 0.0;
+    mu = (float)m;
+    var = (float)v;
+    if (f.update_moving) {
+      double vm = f.bessel ? v * ((double)R / (double)(R > 1 ? R - 1 : 1)) : v;
+      f.moving_mean[c] = f.moving_mean[c] * f.momentum + mu * (1.0f - f.momentum);
+      f.moving_var[c] = f.moving_var[c] * f.momentum + (float)vm * (1.0f - f.momentum);
+    }
+  } else {
+    mu = f.moving_mean[c];
+    var = f.moving_var[c];
+  }
+  float inv = 1.0f / sqrtf(var + f.eps);
+  float ac = f.gamma[c] * inv;
+  f.a[c] = ac;
+  f.b[c] = f.beta[c] - mu * ac;
+  f.mean[c] = mu;
+  f.invstd[c] = inv;
+}
+__device__ __forceinline__ void bn_bwd_finish(double s, double ss, int64_t R, int c, const BnBwdFin& f) {
+  f.dbeta[c] = (float)s;
+  f.dgamma[c] = (float)ss;
+  f.c1[c] = f.use_batch ? (float)(s / (double)R) : 0.f;
+  f.c2[c] = f.use_batch ? (float)(ss / (double)R) : 0.f;
+}
+
+// FIN: the block that arrives LAST at `sync_word` (zero on entry, left zero) finalises every channel from the chunk
+// partials of all blocks - statistics + finalize in one launch, same summation order as the two-launch form.
+template <int MODE, bool FIN>
 __global__ void colstats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ partials,
-                                StatBwdArgs bw) {
+                                StatBwdArgs bw, BnFwdFin ff, BnBwdFin fb, unsigned int* sync_word) {
   // block (32, 8): x = column in slab, y = row lane
   __shared__ float s1[8][33], s2[8][33];
+  __shared__ int s_last;
   int c = blockIdx.x * 32 + threadIdx.x;
   const int kStatRows = stat_rows(R);
   int64_t r0 = (int64_t)blockIdx.y * kStatRows;
@@ -88,48 +221,66 @@ __global__ void colstats_kernel(const float* __restrict__ x, int64_t R, int C, f
     partials[o] = t1;
     partials[o + 1] = t2;
   }
+  if (FIN) {
+    __threadfence();                       // this thread's partials are visible device-wide before the arrival below
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+      s_last = atomicAdd(sync_word, 1u) == gridDim.x * gridDim.y - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // All 256 threads finalise: thread = (channel in round, chunk lane).  Few channels -> up to 8 chunk lanes per
+    // channel (each adds its chunks k = lane, lane + lanes, ... in increasing order, the lane sums are added in lane
+    // order); every channel of a round is finished by its own thread, so the dependent loads of the finish step
+    // (gamma, beta, moving statistics) are paid once per round, not once per channel.
+    __shared__ double red[2][256];
+    const int nchunk = (int)gridDim.y;
+    const int tid = (int)(threadIdx.y * 32 + threadIdx.x);
+    const int lanes = C <= 32 ? 8 : C <= 64 ? 4 : C <= 128 ? 2 : 1;
+    const int cpr = 256 / lanes;            // channels per round
+    const int cl = tid % cpr, kl = tid / cpr;
+    for (int c0 = 0; c0 < C; c0 += cpr) {
+      const int ch = c0 + cl;
+      double sm = 0.0, sq = 0.0;
+      if (ch < C) {
+        int k = kl;
+        for (; k + 3 * lanes < nchunk; k += 4 * lanes) {
+          float2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = ld_partial<true>(partials, (int64_t)(k + u * lanes) * C + ch);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { sm += (double)v[u].x; sq += (double)v[u].y; }
+        }
+        for (; k < nchunk; k += lanes) {
+          const float2 v = ld_partial<true>(partials, (int64_t)k * C + ch);
+          sm += (double)v.x;
+          sq += (double)v.y;
+        }
+      }
+      if (lanes > 1) {
+        red[0][tid] = sm;
+        red[1][tid] = sq;
+        __syncthreads();
+        if (kl == 0) {
+          for (int l = 1; l < lanes; ++l) { sm += red[0][l * cpr + cl]; sq += red[1][l * cpr + cl]; }
+        }
+        __syncthreads();
+      }
+      if (kl == 0 && ch < C) {
+        if (MODE == 0) bn_fwd_finish(sm, sq, R, ch, ff);
+        else bn_bwd_finish(sm, sq, R, ch, fb);
+      }
+    }
+    if (tid == 0) *sync_word = 0u;
+  }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* moving_mean, float* moving_var, float momentum, float eps,
-                                   int use_batch, int update_moving, int bessel, float* a, float* b, float* mean,
-                                   float* invstd) {
-  // one warp per channel: lanes stride over the chunk partials, fixed-order shuffle combine
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
-  float mu, var;
-  if (use_batch) {
-    double s = 0.0, ss = 0.0;
-    for (int k = lane; k < nchunk; k += 32) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(partials) + (int64_t)k * C + c);
-      s += (double)v.x;
-      ss += (double)v.y;
-    }
-    s = warp_sum_d(s);
-    ss = warp_sum_d(ss);
-    double m = s / (double)R;
-    double v = ss / (double)R - m * m;
-    if (v < 0.0) v = 0.0;
-    mu = (float)m;
-    var = (float)v;
-    if (update_moving && lane == 0) {
-      double vm = bessel ? v * ((double)R / (double)(R > 1 ? R - 1 : 1)) : v;
-      moving_mean[c] = moving_mean[c] * momentum + mu * (1.0f - momentum);
-      moving_var[c] = moving_var[c] * momentum + (float)vm * (1.0f - momentum);
-    }
-  } else {
-    mu = moving_mean[c];
-    var = moving_var[c];
-  }
-  if (lane != 0) return;
-  float inv = 1.0f / sqrtf(var + eps);
-  float ac = gamma[c] * inv;
-  a[c] = ac;
-  b[c] = beta[c] - mu * ac;
-  mean[c] = mu;
-  invstd[c] = inv;
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C, BnFwdFin f) {
+  const int ch[1] = {(int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5)};
+  if (ch[0] >= C) return;
+  double s[1] = {0.0}, ss[1] = {0.0};
+  if (f.use_batch) sum_partials<false, 1>(partials, nchunk, C, ch, threadIdx.x & 31, s, ss);
+  if ((threadIdx.x & 31) == 0) bn_fwd_finish(s[0], ss[0], R, ch[0], f);
 }
 
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t n, int C, const float* __restrict__ a,
@@ -169,24 +320,57 @@ __global__ void bn_act_fwd_kernel4(const float4* __restrict__ x, int64_t n4, int
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C,
-                                       int use_batch, float* dgamma, float* dbeta, float* c1, float* c2) {
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = lane; k < nchunk; k += 32) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(partials) + (int64_t)k * C + c);
-    s += (double)v.x;
-    ss += (double)v.y;
+// Inference form (moving statistics, no dropout): coper_bn_finalize(use_batch_stats = 0) + coper_bn_act_fwd in one
+// launch - every thread derives the affine pair of its channel with the finalize kernel's expressions (same bits).
+__global__ void bn_act_fwd_moving_kernel(const float* __restrict__ x, int64_t n, int C, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, const float* __restrict__ moving_mean,
+                                         const float* __restrict__ moving_var, float eps, int relu,
+                                         float* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    int c = (int)(e % C);
+    float inv = 1.0f / sqrtf(__ldg(moving_var + c) + eps);
+    float ac = __ldg(gamma + c) * inv;
+    float bc = __ldg(beta + c) - __ldg(moving_mean + c) * ac;
+    float v = ac * x[e] + bc;
+    if (relu) v = fmaxf(v, 0.f);
+    out[e] = v;
   }
-  s = warp_sum_d(s);
-  ss = warp_sum_d(ss);
-  if (lane != 0) return;
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)ss;
-  c1[c] = use_batch ? (float)(s / (double)R) : 0.f;
-  c2[c] = use_batch ? (float)(ss / (double)R) : 0.f;
+}
+
+// float4 variant (C % 4 == 0, n % 4 == 0, 16-byte aligned pointers)
+__global__ void bn_act_fwd_moving_kernel4(const float4* __restrict__ x, int64_t n4, int C,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          const float* __restrict__ moving_mean, const float* __restrict__ moving_var,
+                                          float eps, int relu, float4* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = (int)((i * 4) % C);
+    const float4 xv = __ldg(x + i);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(moving_mean + c));
+    const float4 va = __ldg(reinterpret_cast<const float4*>(moving_var + c));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {g.x, g.y, g.z, g.w}, bs[4] = {be.x, be.y, be.z, be.w};
+    const float ms[4] = {mu.x, mu.y, mu.z, mu.w}, vs[4] = {va.x, va.y, va.z, va.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float inv = 1.0f / sqrtf(vs[k] + eps);
+      float ac = gs[k] * inv;
+      float bc = bs[k] - ms[k] * ac;
+      o[k] = ac * xs[k] + bc;
+      if (relu) o[k] = fmaxf(o[k], 0.f);
+    }
+    out[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C, BnBwdFin f) {
+  const int ch[1] = {(int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5)};
+  if (ch[0] >= C) return;
+  double s[1], ss[1];
+  sum_partials<false, 1>(partials, nchunk, C, ch, threadIdx.x & 31, s, ss);
+  if ((threadIdx.x & 31) == 0) bn_bwd_finish(s[0], ss[0], R, ch[0], f);
 }
 
 __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ x, int64_t n,
@@ -310,29 +494,98 @@ __global__ void __launch_bounds__(256) reduce_partials_few_kernel(const float* _
 }
 // out[i] = scale * sum_s in[s, i]: block = 32 outputs x 8 slab lanes; every thread sums the slabs s = ty, ty+8, ...
 // in fp64, the 8 lane sums are added in a fixed order -> deterministic, and the slab loop is 8x shorter / pipelined
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ in, int S, int64_t n,
-                                                              float scale, int accumulate, float* __restrict__ out) {
-  __shared__ double red[8][33];
+struct ReduceJob {
+  const float* in;
+  int S;
+  int64_t n;
+  float scale;
+  int accumulate;
+  float* out;
+};
+__device__ __forceinline__ void reduce_job_block(const ReduceJob& j, int block, double (&red)[8][33]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  int64_t i = (int64_t)blockIdx.x * 32 + tx;
+  int64_t i = (int64_t)block * 32 + tx;
   double acc = 0.0;
-  if (i < n) {
+  if (i < j.n) {
     int s = ty;
-    for (; s + 24 < S; s += 32) {
-      float a0 = __ldg(in + (int64_t)s * n + i), a1 = __ldg(in + (int64_t)(s + 8) * n + i);
-      float a2 = __ldg(in + (int64_t)(s + 16) * n + i), a3 = __ldg(in + (int64_t)(s + 24) * n + i);
+    for (; s + 24 < j.S; s += 32) {
+      float a0 = __ldg(j.in + (int64_t)s * j.n + i), a1 = __ldg(j.in + (int64_t)(s + 8) * j.n + i);
+      float a2 = __ldg(j.in + (int64_t)(s + 16) * j.n + i), a3 = __ldg(j.in + (int64_t)(s + 24) * j.n + i);
       acc += (double)a0; acc += (double)a1; acc += (double)a2; acc += (double)a3;
     }
-    for (; s < S; s += 8) acc += (double)__ldg(in + (int64_t)s * n + i);
+    for (; s < j.S; s += 8) acc += (double)__ldg(j.in + (int64_t)s * j.n + i);
   }
   red[ty][tx] = acc;
   __syncthreads();
-  if (ty == 0 && i < n) {
+  if (ty == 0 && i < j.n) {
     double t = red[0][tx];
 #pragma unroll
     for (int k = 1; k < 8; ++k) t += red[k][tx];
-    float r = (float)(t * (double)scale);
-    out[i] = accumulate ? out[i] + r : r;
+    float r = (float)(t * (double)j.scale);
+    j.out[i] = j.accumulate ? j.out[i] + r : r;
+  }
+}
+// float4 form of the same reduction (n % 4 == 0, 16-byte aligned): block = 32 x 4 outputs, 8 slab lanes; same slab
+// order per output as reduce_job_block -> same bits, a quarter of the load instructions
+__device__ __forceinline__ void reduce_job_block4(const ReduceJob& j, int block, double (&red)[8][33], double* red4) {
+  (void)red;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t i = ((int64_t)block * 32 + tx) * 4;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (i < j.n) {
+    int s = ty;
+    for (; s + 24 < j.S; s += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(j.in + (int64_t)(s + 8 * u) * j.n + i));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a0 += (double)v[u].x; a1 += (double)v[u].y; a2 += (double)v[u].z; a3 += (double)v[u].w; }
+    }
+    for (; s < j.S; s += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(j.in + (int64_t)s * j.n + i));
+      a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+    }
+  }
+  double* mine = red4 + ((size_t)ty * 32 + tx) * 4;
+  mine[0] = a0; mine[1] = a1; mine[2] = a2; mine[3] = a3;
+  __syncthreads();
+  if (ty == 0 && i < j.n) {
+    double t[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) t[c] = red4[(size_t)tx * 4 + c];
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) t[c] += red4[((size_t)k * 32 + tx) * 4 + c];
+    float4 r = make_float4((float)(t[0] * (double)j.scale), (float)(t[1] * (double)j.scale),
+                           (float)(t[2] * (double)j.scale), (float)(t[3] * (double)j.scale));
+    float4* o = reinterpret_cast<float4*>(j.out + i);
+    if (j.accumulate) {
+      const float4 p = *o;
+      r.x = p.x + r.x; r.y = p.y + r.y; r.z = p.z + r.z; r.w = p.w + r.w;
+    }
+    *o = r;
+  }
+}
+// blocks [0, blocks_a) reduce job A, [blocks_a, blocks_a + blocks_b) job B; one more block (if dsum_in) adds dsum_n
+// doubles in the order of sum_doubles_kernel (umma_entity.cu) - three tiny dependent-free reductions, one launch
+template <bool VEC_A>
+__global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceJob A, int blocks_a, ReduceJob Bj, int blocks_b,
+                                                              const double* __restrict__ dsum_in, int dsum_n,
+                                                              double* __restrict__ dsum_out) {
+  __shared__ double red[8][33];
+  __shared__ double red4[VEC_A ? 8 * 32 * 4 : 1];
+  const int blk = (int)blockIdx.x;
+  if (blk < blocks_a) {
+    if (VEC_A) reduce_job_block4(A, blk, red, red4);
+    else reduce_job_block(A, blk, red);
+  } else if (blk < blocks_a + blocks_b) {
+    reduce_job_block(Bj, blk - blocks_a, red);
+  } else {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < dsum_n; i += blockDim.x) acc += dsum_in[i];
+    const double t = block_sum<double>(acc, &red[0][0]);
+    if (threadIdx.x == 0) *dsum_out = t;
   }
 }
 
@@ -401,13 +654,7 @@ __global__ void amsgrad_kernel(float* __restrict__ theta, const float* __restric
 }
 
 __global__ void step_state_advance_kernel(float* st, uint64_t* seed_dev, float lr, float b1, float b2) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float b1p = st[1], b2p = st[2];
-    st[0] = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);  // amsgrad.py:137
-    st[1] = b1p * b1;                                // amsgrad.py:234-239
-    st[2] = b2p * b2;
-    if (seed_dev) *seed_dev += 1ull;
-  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) step_state_advance(st, seed_dev, lr, b1, b2);
 }
 
 
@@ -468,6 +715,52 @@ __global__ void mt_tensor_sums_kernel(const coper_param_desc* __restrict__ descs
       reinterpret_cast<int*>(tr)[0] = fp16x3_exponent_of(__uint_as_float(tr[2]));
       tr[2] = 0u;
     }
+  }
+}
+// mt_tensor_sums_kernel + sumsq_combine_kernel + clip_scale_kernel in ONE block (same summation orders): per-tensor sums
+// of the chunk partials, the producer-supplied squared norm of tensor `ext_tensor` (parts + deltas, < 0: none), and -
+// with clip_out != NULL - the clip factor over all tensors.
+__global__ void __launch_bounds__(256) mt_sumsq_finish_kernel(const coper_param_desc* __restrict__ descs,
+                                                              const double* __restrict__ chunk_partials,
+                                                              const int32_t* __restrict__ chunk_offsets, int n_tensors,
+                                                              double* tensor_sumsq, int ext_tensor,
+                                                              const double* __restrict__ ext_parts, int n_ext_parts,
+                                                              const double* __restrict__ ext_deltas, int n_ext_deltas,
+                                                              float clip, float* clip_out) {
+  __shared__ double smd[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < n_tensors; t += 8) {
+    const coper_param_desc d = descs[t];
+    double acc = 0.0;
+    if (!(d.mode & COPER_GRAD_NORM_EXTERNAL))
+      for (int c = chunk_offsets[t] + lane; c < chunk_offsets[t + 1]; c += 32) acc += chunk_partials[c];
+    acc = warp_sum_d(acc);
+    if (lane == 0) {
+      if (t != ext_tensor) tensor_sumsq[t] = acc;
+      if (d.prepared && d.prepared_prec == COPER_PREC_FP16X3) {      // see mt_tensor_sums_kernel
+        uint32_t* tr = fp16x3_trailer_of(d);
+        reinterpret_cast<int*>(tr)[0] = fp16x3_exponent_of(__uint_as_float(tr[2]));
+        tr[2] = 0u;
+      }
+    }
+  }
+  if (ext_tensor >= 0) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_ext_parts; i += blockDim.x) acc += ext_parts[i];
+    for (int i = threadIdx.x; i < n_ext_deltas; i += blockDim.x) acc += ext_deltas[i];
+    const double t = block_sum<double>(acc, smd);
+    if (threadIdx.x == 0) tensor_sumsq[ext_tensor] = t > 0.0 ? t : 0.0;
+  }
+  if (!clip_out) return;
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_tensors; i += blockDim.x) acc += tensor_sumsq[i];
+  const double t = block_sum<double>(acc, smd);
+  if (threadIdx.x == 0) {
+    double norm = sqrt(t);
+    double c = (double)clip;
+    clip_out[0] = (float)(c / (norm > c ? norm : c));
+    clip_out[1] = (float)norm;
   }
 }
 __device__ __forceinline__ void amsgrad_elem(float g, float& th, float* m, float* v, float& vh, int64_t i, float lr_t,
@@ -622,6 +915,23 @@ __global__ void sumsq_combine_kernel(const double* __restrict__ parts, int n_par
   if (threadIdx.x == 0) *out = t > 0.0 ? t : 0.0;
 }
 
+// out = scale * sum of S slabs (+ out), and - in the same launch - *dsum_out = sum of dsum_n doubles (dsum_in may be
+// NULL).  Used by the scorer: the split-K slabs of dq and the loss partials of the BCE epilogue.
+int reduce_partials_and_sum(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
+                            const double* dsum_in, int dsum_n, double* dsum_out, cudaStream_t st) {
+  ReduceJob A{in, S, n, scale, accumulate, out};
+  const bool vec = n >= 4096 && (n & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) {
+    const int ba = (int)((n / 4 + 31) / 32);
+    reduce_partials_kernel<true><<<ba + (dsum_in ? 1 : 0), 256, 0, st>>>(A, ba, ReduceJob{}, 0, dsum_in, dsum_n, dsum_out);
+  } else {
+    const int ba = (int)((n + 31) / 32);
+    reduce_partials_kernel<false><<<ba + (dsum_in ? 1 : 0), 256, 0, st>>>(A, ba, ReduceJob{}, 0, dsum_in, dsum_n, dsum_out);
+  }
+  return check_launch();
+}
+
 static inline int grid_for(int64_t n, int threads, int per_sm = 8) {
   int64_t g = (n + threads - 1) / threads;
   int64_t cap = (int64_t)kSMs * per_sm;
@@ -663,13 +973,27 @@ int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int wi
   return check_launch();
 }
 
+int coper_gather_rows2(const float* table_a, int64_t lo_a, int64_t hi_a, int width_a, const int64_t* idx_a, int n_a,
+                       float* out_a, const float* table_b, int64_t lo_b, int64_t hi_b, int width_b,
+                       const int64_t* idx_b, int n_b, float* out_b, float* step_state, uint64_t* seed_dev, float lr,
+                       float beta1, float beta2, coper_stream_t stream) {
+  COPER_CHECK_ARG(table_a && idx_a && out_a && width_a > 0 && n_a >= 0 && hi_a >= lo_a);
+  COPER_CHECK_ARG(n_b == 0 || (table_b && idx_b && out_b && width_b > 0 && n_b > 0 && hi_b >= lo_b));
+  const int blocks_a = ceil_div(n_a, 8), blocks_b = ceil_div(n_b, 8);
+  if (blocks_a + blocks_b == 0 && !step_state) return COPER_OK;
+  GatherDesc A{table_a, lo_a, hi_a, width_a, idx_a, n_a, out_a}, Bd{table_b, lo_b, hi_b, width_b, idx_b, n_b, out_b};
+  const int grid = blocks_a + blocks_b > 0 ? blocks_a + blocks_b : 1;
+  gather_rows2_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, Bd, blocks_a, step_state, seed_dev, lr, beta1, beta2);
+  return check_launch();
+}
+
 int coper_colstats_chunks(int64_t R) { return R <= 0 ? 0 : (int)((R + stat_rows(R) - 1) / stat_rows(R)); }
 
 int coper_colstats(const float* x, int64_t R, int C, float* partials, coper_stream_t stream) {
   COPER_CHECK_ARG(x && partials && R > 0 && C > 0);
   dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
-  StatBwdArgs bw{};
-  colstats_kernel<0><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw);
+  colstats_kernel<0, false><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, StatBwdArgs{}, BnFwdFin{}, BnBwdFin{},
+                                                                    nullptr);
   return check_launch();
 }
 
@@ -679,9 +1003,20 @@ int coper_bn_finalize(const float* partials, int nchunk, int64_t R, int C, const
                       coper_stream_t stream) {
   COPER_CHECK_ARG(gamma && beta && moving_mean && moving_var && a && b && mean && invstd && C > 0);
   COPER_CHECK_ARG(!use_batch_stats || (partials && nchunk > 0 && R > 0));
-  bn_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, gamma, beta, moving_mean,
-                                                                     moving_var, momentum, eps, use_batch_stats,
-                                                                     update_moving, bessel, a, b, mean, invstd);
+  BnFwdFin f{gamma, beta, moving_mean, moving_var, momentum, eps, use_batch_stats, update_moving, bessel, a, b, mean, invstd};
+  bn_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, f);
+  return check_launch();
+}
+
+int coper_bn_stats_finalize(const float* x, int64_t R, int C, float* partials, unsigned int* sync_word,
+                            const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                            float momentum, float eps, int update_moving, int bessel, float* a, float* b, float* mean,
+                            float* invstd, coper_stream_t stream) {
+  COPER_CHECK_ARG(x && partials && sync_word && R > 0 && C > 0);
+  COPER_CHECK_ARG(gamma && beta && moving_mean && moving_var && a && b && mean && invstd);
+  dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
+  BnFwdFin f{gamma, beta, moving_mean, moving_var, momentum, eps, 1, update_moving, bessel, a, b, mean, invstd};
+  colstats_kernel<0, true><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, StatBwdArgs{}, f, BnBwdFin{}, sync_word);
   return check_launch();
 }
 
@@ -705,6 +1040,24 @@ int coper_bn_act_fwd(const float* x, int64_t R, int C, const float* a, const flo
   return check_launch();
 }
 
+int coper_bn_act_fwd_moving(const float* x, int64_t R, int C, const float* gamma, const float* beta,
+                            const float* moving_mean, const float* moving_var, float eps, int relu, float* out,
+                            coper_stream_t stream) {
+  COPER_CHECK_ARG(x && gamma && beta && moving_mean && moving_var && out && R > 0 && C > 0);
+  int64_t n = R * C;
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                                     reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                                     reinterpret_cast<uintptr_t>(moving_mean) | reinterpret_cast<uintptr_t>(moving_var)) & 15) == 0;
+  if (vec)
+    bn_act_fwd_moving_kernel4<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), n / 4, C, gamma, beta, moving_mean, moving_var, eps, relu,
+        reinterpret_cast<float4*>(out));
+  else
+    bn_act_fwd_moving_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, C, gamma, beta, moving_mean, moving_var,
+                                                                              eps, relu, out);
+  return check_launch();
+}
+
 int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
                            const float* mean, const float* invstd, int relu, float keep_post,
                            const uint64_t* seed_dev, uint64_t salt_post, float* partials, coper_stream_t stream) {
@@ -712,15 +1065,30 @@ int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, 
   dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
   StatBwdArgs bw{dout, a, b, mean, invstd, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post), seed_dev,
                  salt_post};
-  colstats_kernel<1><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw);
+  colstats_kernel<1, false><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw, BnFwdFin{}, BnBwdFin{}, nullptr);
   return check_launch();
 }
 
 int coper_bn_act_bwd_finalize(const float* partials, int nchunk, int64_t R, int C, int use_batch_stats,
                               float* dgamma, float* dbeta, float* c1, float* c2, coper_stream_t stream) {
   COPER_CHECK_ARG(partials && dgamma && dbeta && c1 && c2 && nchunk > 0 && R > 0 && C > 0);
-  bn_bwd_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, use_batch_stats,
-                                                                         dgamma, dbeta, c1, c2);
+  BnBwdFin f{use_batch_stats, dgamma, dbeta, c1, c2};
+  bn_bwd_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, f);
+  return check_launch();
+}
+
+int coper_bn_act_bwd_stats_finalize(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
+                                    const float* mean, const float* invstd, int relu, float keep_post,
+                                    const uint64_t* seed_dev, uint64_t salt_post, float* partials,
+                                    unsigned int* sync_word, int use_batch_stats, float* dgamma, float* dbeta, float* c1,
+                                    float* c2, coper_stream_t stream) {
+  COPER_CHECK_ARG(dout && x && a && b && mean && invstd && partials && sync_word && R > 0 && C > 0 && keep_post > 0.f);
+  COPER_CHECK_ARG(dgamma && dbeta && c1 && c2);
+  dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
+  StatBwdArgs bw{dout, a, b, mean, invstd, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post), seed_dev,
+                 salt_post};
+  BnBwdFin f{use_batch_stats, dgamma, dbeta, c1, c2};
+  colstats_kernel<1, true><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw, BnFwdFin{}, f, sync_word);
   return check_launch();
 }
 
@@ -798,11 +1166,19 @@ int coper_dense_to_bits_t(const float* dense, int B, int64_t N, int64_t ld_dense
 int coper_reduce_partials(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
                           coper_stream_t stream) {
   COPER_CHECK_ARG(in && out && S > 0 && n > 0);
-  if (S <= 8 && n >= (1 << 16) && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+  if (S <= 8 && n >= (1 << 16) && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     reduce_partials_few_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate,
                                                                                         out);
-  else
-    reduce_partials_kernel<<<(unsigned)((n + 31) / 32), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate, out);
+    return check_launch();
+  }
+  return reduce_partials_and_sum(in, S, n, scale, accumulate, out, nullptr, 0, nullptr, as_stream(stream));
+}
+int coper_reduce_partials2(const float* in_a, int64_t n_a, float* out_a, const float* in_b, int64_t n_b, float* out_b,
+                           int S, float scale, int accumulate, coper_stream_t stream) {
+  COPER_CHECK_ARG(in_a && out_a && in_b && out_b && S > 0 && n_a > 0 && n_b > 0);
+  ReduceJob A{in_a, S, n_a, scale, accumulate, out_a}, Bj{in_b, S, n_b, scale, accumulate, out_b};
+  const int ba = (int)((n_a + 31) / 32), bb = (int)((n_b + 31) / 32);
+  reduce_partials_kernel<false><<<ba + bb, 256, 0, as_stream(stream)>>>(A, ba, Bj, bb, nullptr, 0, nullptr);
   return check_launch();
 }
 int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_stream_t stream) {
@@ -828,6 +1204,25 @@ int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* 
   if (rc) return rc;
   mt_tensor_sums_kernel<<<(n_tensors * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(descs, chunk_partials, chunk_offsets,
                                                                             n_tensors, tensor_sumsq);
+  return check_launch();
+}
+int coper_mt_sumsq_clip(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
+                        const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, int ext_tensor,
+                        const double* ext_parts, int n_ext_parts, const double* ext_deltas, int n_ext_deltas,
+                        float clip_norm, float* clip_out, coper_stream_t stream) {
+  COPER_CHECK_ARG(descs && chunk_offsets && chunk_partials && tensor_sumsq && n_tensors > 0 && n_chunks >= 0);
+  COPER_CHECK_ARG(n_chunks == 0 || chunks);
+  COPER_CHECK_ARG(ext_tensor < n_tensors && n_ext_parts >= 0 && n_ext_deltas >= 0);
+  COPER_CHECK_ARG((ext_parts || n_ext_parts == 0) && (ext_deltas || n_ext_deltas == 0));
+  COPER_CHECK_ARG(!clip_out || clip_norm > 0.f);
+  int rc;
+  if (n_chunks > 0) {
+    mt_sumsq_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, chunk_partials);
+    if ((rc = check_launch())) return rc;
+  }
+  mt_sumsq_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(descs, chunk_partials, chunk_offsets, n_tensors, tensor_sumsq,
+                                                           ext_tensor, ext_parts, n_ext_parts, ext_deltas, n_ext_deltas,
+                                                           clip_norm, clip_out);
   return check_launch();
 }
 int coper_mt_amsgrad(const coper_param_desc* descs, const int32_t* chunks, int n_chunks, const float* step_state,

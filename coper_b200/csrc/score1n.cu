@@ -22,8 +22,8 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
                              int64_t Ns, int d, float pos, float neg, float inv_count, double* loss_sum, void* G,
                              int64_t ldG, float* dq, float* dE, float* dbias, void* ws, size_t ws_bytes, int prec,
                              double* dE_sumsq, cudaStream_t st);
-int umma_score1n_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq, void* ws,
-                    size_t ws_bytes, int prec, cudaStream_t st);
+int umma_score1n_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq, float* dbias,
+                    void* ws, size_t ws_bytes, int prec, cudaStream_t st);
 
 using namespace simt;
 
@@ -285,10 +285,10 @@ int coper_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prep
                           ldG, dq, dE, dbias, workspace, workspace_bytes, prec, nullptr, stream);
 }
 int coper_score1n_bce_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq,
-                         void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
-  COPER_CHECK_ARG(G && dE && workspace && B > 0 && Ns > 0 && d > 0);
+                         float* dbias, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream) {
+  COPER_CHECK_ARG(G && dE && dbias && workspace && B > 0 && Ns > 0 && d > 0);
   if (prec != COPER_PREC_BF16 && prec != COPER_PREC_TF32X3 && prec != COPER_PREC_FP16X3) return COPER_ERR_UNSUPPORTED;
-  return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, workspace, workspace_bytes, prec, as_stream(stream));
+  return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, dbias, workspace, workspace_bytes, prec, as_stream(stream));
 }
 int coper_score1n_bce_fwd_bwd_norm(const float* q, const float* E, const void* E_prepared, const float* bias,
                                    const uint32_t* label_bits, int B, int64_t Ns, int d, float pos_target,

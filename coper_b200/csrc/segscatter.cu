@@ -43,10 +43,21 @@ constexpr int kSegSmallM = 4096;
 // norm_delta (optional, [M] doubles): position i receives sum_c (new_c^2 - old_c^2) of the destination row it updated
 // (0 if it is not a segment head / not owned) - the correction that turns a sum of squares taken BEFORE the scatter
 // (by the kernel that produced dst) into the sum of squares of the final gradient.
-__global__ void segscatter_small_kernel(const int64_t* __restrict__ idx, int M, const float* __restrict__ src, int width,
-                                        float* __restrict__ dst, float* __restrict__ dst_sq, int64_t row_lo,
-                                        int64_t row_hi, double* __restrict__ norm_delta) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+struct SegSmallJob {
+  const int64_t* idx;
+  int M;
+  const float* src;
+  int width;
+  float* dst;
+  float* dst_sq;
+  int64_t row_lo, row_hi;
+  double* norm_delta;
+};
+__device__ __forceinline__ void segscatter_small_warp(const int64_t* __restrict__ idx, int M,
+                                                      const float* __restrict__ src, int width, float* __restrict__ dst,
+                                                      float* __restrict__ dst_sq, int64_t row_lo, int64_t row_hi,
+                                                      double* __restrict__ norm_delta, int block) {
+  const int i = block * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= M) return;
   if (norm_delta && lane == 0) norm_delta[i] = 0.0;
@@ -96,6 +107,72 @@ __global__ void segscatter_small_kernel(const int64_t* __restrict__ idx, int M, 
     if (lane == 0) norm_delta[i] = delta;
   }
 }
+// Small TABLE (the relation embedding: tens to hundreds of rows, each hit by many positions of the batch): one block per
+// table row.  The block lists the positions that hold its row in index order (ballot compaction), then every thread owns
+// columns and adds the members in that order with the loads of 8 members in flight.  Same sums in the same order as
+// segscatter_small_warp - where one warp walks its 20+ members one dependent L2 round trip at a time.
+constexpr int kSegRowOwnerRows = 2048;
+__device__ __forceinline__ void segscatter_row_block(const SegSmallJob& J, int row, uint16_t* list, int* warp_cnt,
+                                                     int* base) {
+  const int64_t key = J.row_lo + row;
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *base = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < J.M; j0 += 256) {
+    const int j = j0 + tid;
+    const bool hit = j < J.M && __ldg(J.idx + j) == key;
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = *base;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += warp_cnt[w];
+      *base += t;
+    }
+    __syncthreads();
+  }
+  const int cnt = *base;
+  if (cnt == 0) return;
+  for (int c = tid; c < J.width; c += 256) {
+    float a = 0.f, q = 0.f;
+    int m = 0;
+    for (; m + 8 <= cnt; m += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(J.src + (int64_t)list[m + u] * J.width + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a += v[u]; q = fmaf(v[u], v[u], q); }
+    }
+    for (; m < cnt; ++m) {
+      const float v = __ldg(J.src + (int64_t)list[m] * J.width + c);
+      a += v;
+      q = fmaf(v, v, q);
+    }
+    float* d = J.dst + (int64_t)row * J.width + c;
+    *d = *d + a;
+    if (J.dst_sq) J.dst_sq[(int64_t)row * J.width + c] += q;
+  }
+}
+// blocks [0, blocks_a) run job A, the rest job B (two independent scatters of one step - head entities and
+// relations - in one launch; B.M == 0: single job).  b_row_owner: job B runs one block per table row.
+__global__ void __launch_bounds__(256) segscatter_small_kernel(SegSmallJob A, int blocks_a, SegSmallJob Bj,
+                                                               int b_row_owner) {
+  __shared__ uint16_t list[kSegSmallM];
+  __shared__ int warp_cnt[8];
+  __shared__ int base;
+  if ((int)blockIdx.x < blocks_a)
+    segscatter_small_warp(A.idx, A.M, A.src, A.width, A.dst, A.dst_sq, A.row_lo, A.row_hi, A.norm_delta, (int)blockIdx.x);
+  else if (b_row_owner)
+    segscatter_row_block(Bj, (int)blockIdx.x - blocks_a, list, warp_cnt, &base);
+  else
+    segscatter_small_warp(Bj.idx, Bj.M, Bj.src, Bj.width, Bj.dst, Bj.dst_sq, Bj.row_lo, Bj.row_hi, Bj.norm_delta,
+                          (int)blockIdx.x - blocks_a);
+}
 
 struct SegLayout {
   size_t off_keys_out, off_pos_in, off_pos_out, off_cub, cub_bytes, total;
@@ -127,8 +204,8 @@ int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int wid
   COPER_CHECK_ARG(idx && src && dst && M >= 0 && width > 0 && row_hi >= row_lo);
   if (M > kSegSmallM) return COPER_ERR_UNSUPPORTED;
   if (M == 0) return COPER_OK;
-  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(idx, M, src, width, dst, dst_sq, row_lo, row_hi,
-                                                                         nullptr);
+  SegSmallJob A{idx, M, src, width, dst, dst_sq, row_lo, row_hi, nullptr};
+  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(A, ceil_div(M, 8), SegSmallJob{}, 0);
   return check_launch();
 }
 
@@ -137,8 +214,23 @@ int coper_segscatter_add_norm(const int64_t* idx, int M, const float* src, int w
   COPER_CHECK_ARG(idx && src && dst && norm_delta && M >= 0 && width > 0 && row_hi >= row_lo);
   if (M > kSegSmallM) return COPER_ERR_UNSUPPORTED;
   if (M == 0) return COPER_OK;
-  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(idx, M, src, width, dst, dst_sq, row_lo, row_hi,
-                                                                         norm_delta);
+  SegSmallJob A{idx, M, src, width, dst, dst_sq, row_lo, row_hi, norm_delta};
+  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(A, ceil_div(M, 8), SegSmallJob{}, 0);
+  return check_launch();
+}
+
+int coper_segscatter_add_pair(const int64_t* idx_a, int M_a, const float* src_a, int width_a, float* dst_a,
+                              float* dst_sq_a, int64_t lo_a, int64_t hi_a, double* norm_delta_a, const int64_t* idx_b,
+                              int M_b, const float* src_b, int width_b, float* dst_b, float* dst_sq_b, int64_t lo_b,
+                              int64_t hi_b, coper_stream_t stream) {
+  COPER_CHECK_ARG(idx_a && src_a && dst_a && M_a > 0 && width_a > 0 && hi_a >= lo_a);
+  COPER_CHECK_ARG(idx_b && src_b && dst_b && M_b > 0 && width_b > 0 && hi_b >= lo_b);
+  if (M_a > kSegSmallM || M_b > kSegSmallM) return COPER_ERR_UNSUPPORTED;
+  SegSmallJob A{idx_a, M_a, src_a, width_a, dst_a, dst_sq_a, lo_a, hi_a, norm_delta_a};
+  SegSmallJob Bj{idx_b, M_b, src_b, width_b, dst_b, dst_sq_b, lo_b, hi_b, nullptr};
+  const int row_owner = hi_b - lo_b <= kSegRowOwnerRows && hi_b > lo_b;
+  const int ba = ceil_div(M_a, 8), bb = row_owner ? (int)(hi_b - lo_b) : ceil_div(M_b, 8);
+  segscatter_small_kernel<<<ba + bb, 256, 0, as_stream(stream)>>>(A, ba, Bj, row_owner);
   return check_launch();
 }
 

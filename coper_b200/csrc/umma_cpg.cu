@@ -185,6 +185,84 @@ __global__ void prepare_scaled_kernel(const float* __restrict__ dy, const float*
   }
 }
 
+// fp16x3, one batch (B <= a few thousand rows): both backward operands - dy and dy scaled by the context - in ONE launch
+// instead of prepare(dy) + absmax_scaled + prepare_scaled.  Every block reduces its rows' maxima into tr_dy[1] (max |dy|)
+// and tr_dy[4] (max |dy| * max |c| per row), a grid-wide arrive counter (tr_dy[3]) tells when all are in, then the
+// blocks emit the planes.  tr_dy words 0..7 are zero on entry; the grid is capped so that all blocks are co-resident.
+// Same maxima, same exponent rule, same rounding as the three kernels it replaces -> same bits.
+__global__ void __launch_bounds__(256) cpg_bwd_prepare_fp16x3_kernel(const float* __restrict__ dy,
+                                                                     const float* __restrict__ c, int B, int d, int dc,
+                                                                     int64_t ldp, __half* __restrict__ dyp,
+                                                                     __half* __restrict__ dycp,
+                                                                     uint32_t* __restrict__ tr_dy,
+                                                                     uint32_t* __restrict__ tr_dyc) {
+  __shared__ float wmax[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m_dy = 0.f, m_dyc = 0.f;
+  for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+    float my = 0.f, mc = 0.f;
+    for (int j = lane; j < d; j += 32) my = fmaxf(my, fabsf(__ldg(dy + (int64_t)b * d + j)));
+    for (int g = lane; g < dc; g += 32) mc = fmaxf(mc, fabsf(__ldg(c + (int64_t)b * dc + g)));
+    my = warp_max(my);
+    mc = warp_max(mc);
+    m_dy = fmaxf(m_dy, my);
+    m_dyc = fmaxf(m_dyc, my * mc);
+  }
+  if (lane == 0) { wmax[0][warp] = m_dy; wmax[1][warp] = m_dyc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { m_dy = fmaxf(m_dy, wmax[0][w]); m_dyc = fmaxf(m_dyc, wmax[1][w]); }
+    if (m_dy > 0.f) atomicMax(tr_dy + 1, __float_as_uint(m_dy));
+    if (m_dyc > 0.f) atomicMax(tr_dy + 4, __float_as_uint(m_dyc));
+    __threadfence();
+    atomicAdd(tr_dy + 3, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile uint32_t*>(tr_dy + 3) < gridDim.x) {
+      if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const uint32_t bits_dy = *reinterpret_cast<volatile uint32_t*>(tr_dy + 1);
+  const uint32_t bits_dyc = *reinterpret_cast<volatile uint32_t*>(tr_dy + 4);
+  const int e_dy = fp16x3_exponent_of(__uint_as_float(bits_dy)), e_dyc = fp16x3_exponent_of(__uint_as_float(bits_dyc));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    reinterpret_cast<int*>(tr_dy)[0] = e_dy;
+    tr_dy[2] = bits_dy;
+    reinterpret_cast<int*>(tr_dyc)[0] = e_dyc;
+    tr_dyc[1] = bits_dyc;
+  }
+  const float sc_dy = exp2f((float)e_dy), sc_dyc = exp2f((float)e_dyc);
+  // work unit = one 8-column group of one row of plane-set p (p = 0: dy, p = 1 + g: dy * c[:, g])
+  const int gpr = (int)(ldp / 8);
+  const int64_t per = (int64_t)B * gpr, units = per * (1 + dc);
+  __half* const dy_lo = dyp + (int64_t)B * ldp;
+  __half* const dyc_lo = dycp + (int64_t)dc * B * ldp;
+  for (int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x; u < units; u += (int64_t)gridDim.x * 256) {
+    const int p = (int)(u / per);
+    const int64_t v = u - (int64_t)p * per;
+    const int b = (int)(v / gpr), c0 = (int)(v - (int64_t)b * gpr) * 8;
+    const float cs = p == 0 ? 1.0f : __ldg(c + (int64_t)b * dc + (p - 1));
+    const float sc = p == 0 ? sc_dy : sc_dyc;
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = c0 + 2 * k;
+      float x0 = j < d ? __ldg(dy + (int64_t)b * d + j) : 0.f, x1 = j + 1 < d ? __ldg(dy + (int64_t)b * d + j + 1) : 0.f;
+      if (p != 0) { x0 = j < d ? x0 * cs : 0.f; x1 = j + 1 < d ? x1 * cs : 0.f; }
+      const float a0 = x0 * sc, a1 = x1 * sc;
+      h[k] = __floats2half2_rn(a0, a1);
+      const float2 hf = __half22float2(h[k]);
+      l[k] = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+    }
+    __half* hi = p == 0 ? dyp + v * 8 : dycp + ((int64_t)(p - 1) * per + v) * 8;
+    __half* lo = p == 0 ? dy_lo + v * 8 : dyc_lo + ((int64_t)(p - 1) * per + v) * 8;
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<uint4*>(l);
+  }
+}
+
 struct CpgBwdPlan {
   size_t off_f, off_P, off_dy, off_dyc, off_dcpart, total;
   int dc_slabs;
@@ -234,12 +312,13 @@ int umma_cpg_fwd_partials(const float* c, const float* f, const float* P, const 
   return rc;
 }
 
-// df, dc_out, dP through the tensor pipe.  reuse_fwd_operands: the workspace still holds the prepared f and P
-// operands written by umma_cpg_fwd_partials for the same (f, P).
+// df, dc_out, dP through the tensor pipe.  flags: COPER_CPG_BWD_* (include/coper.h).  REUSE_FWD: the workspace still
+// holds the prepared f and P operands written by umma_cpg_fwd_partials for the same (f, P).
 int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* dy, int B, int dc,
                  int F, int d, float* dP, float* df, float* dc_out, void* ws, size_t ws_bytes, int prec,
-                 int reuse_fwd_operands, cudaStream_t st) {
+                 int flags, cudaStream_t st) {
   if (F % 32 != 0 || d > 256) return COPER_ERR_UNSUPPORTED;
+  const bool inputs = !(flags & COPER_CPG_BWD_WEIGHT_GRADS_ONLY), weights = !(flags & COPER_CPG_BWD_INPUT_GRADS_ONLY);
   CpgBwdPlan L = cpg_bwd_plan(B, dc, F, d, prec);
   if (!ws || ws_bytes < L.total) return COPER_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(ws) & 255) return COPER_ERR_INVALID_ARG;
@@ -249,28 +328,40 @@ int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_p
   void* dyp = w + L.off_dy;
   void* dycp = w + L.off_dyc;
   float* dc_part = reinterpret_cast<float*>(w + L.off_dcpart);
-  int rc;
-  if (!reuse_fwd_operands) {
-    if ((rc = tc_prepare(f, B, F, F, prec, fp, st))) return rc;
-    if (!P_prepared && (rc = tc_prepare(P, (int64_t)dc * F, d, d, prec, w + L.off_P, st))) return rc;
-  }
-  if ((rc = tc_prepare(dy, B, d, d, prec, dyp, st))) return rc;
-  {
+  int rc = COPER_OK;
+  if (inputs) {
+    // ---- operands: f, P (unless the forward call left them), dy, and dy pre-scaled by the context (for dP)
+    if (!(flags & COPER_CPG_BWD_REUSE_FWD)) {
+      if ((rc = tc_prepare(f, B, F, F, prec, fp, st))) return rc;
+      if (!P_prepared && (rc = tc_prepare(P, (int64_t)dc * F, d, d, prec, w + L.off_P, st))) return rc;
+    }
     int64_t ldp = tc_prepared_ld(d, prec);
     int64_t n = (int64_t)dc * B * ldp;
-    int grid = (int)((n + 255) / 256 < sm_count() * 8 ? (n + 255) / 256 : sm_count() * 8);
-    uint32_t* trailer = nullptr;
-    if (prec == COPER_PREC_FP16X3) {
-      trailer = static_cast<uint32_t*>(tc_fp16x3_trailer(dycp, (int64_t)dc * B, d));
-      if ((rc = check_cuda(cudaMemsetAsync(trailer, 0, 8, st)))) return rc;
-      absmax_scaled_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, c, B, d, dc, trailer);
+    if (prec == COPER_PREC_FP16X3 && n <= ((int64_t)8 << 20)) {
+      // one launch for both operands (grid barrier: <= 2 co-resident blocks per SM)
+      uint32_t* tr_dy = static_cast<uint32_t*>(tc_fp16x3_trailer(dyp, B, d));
+      uint32_t* tr_dyc = static_cast<uint32_t*>(tc_fp16x3_trailer(dycp, (int64_t)dc * B, d));
+      if ((rc = check_cuda(cudaMemsetAsync(tr_dy, 0, 32, st)))) return rc;
+      const int64_t want = ((int64_t)(1 + dc) * B * (ldp / 8) + 256 * 4 - 1) / (256 * 4);
+      int g = (int)(want < (int64_t)sm_count() * 2 ? want : (int64_t)sm_count() * 2);
+      if (g < 1) g = 1;
+      cpg_bwd_prepare_fp16x3_kernel<<<g, 256, 0, st>>>(dy, c, B, d, dc, ldp, static_cast<__half*>(dyp),
+                                                       static_cast<__half*>(dycp), tr_dy, tr_dyc);
+      if ((rc = check_launch())) return rc;
+    } else {
+      if ((rc = tc_prepare(dy, B, d, d, prec, dyp, st))) return rc;
+      int grid = (int)((n + 255) / 256 < sm_count() * 8 ? (n + 255) / 256 : sm_count() * 8);
+      uint32_t* trailer = nullptr;
+      if (prec == COPER_PREC_FP16X3) {
+        trailer = static_cast<uint32_t*>(tc_fp16x3_trailer(dycp, (int64_t)dc * B, d));
+        if ((rc = check_cuda(cudaMemsetAsync(trailer, 0, 8, st)))) return rc;
+        absmax_scaled_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, c, B, d, dc, trailer);
+        if ((rc = check_launch())) return rc;
+      }
+      prepare_scaled_kernel<<<grid, 256, 0, st>>>(dy, c, B, d, dc, ldp, prec, dycp, trailer);
       if ((rc = check_launch())) return rc;
     }
-    prepare_scaled_kernel<<<grid, 256, 0, st>>>(dy, c, B, d, dc, ldp, prec, dycp, trailer);
-    if ((rc = check_launch())) return rc;
-  }
-  // ---- T kernel: df, dc partials
-  {
+    // ---- T kernel: df, dc partials
     GemmProblem p{};
     p.M = B; p.N = F; p.K = d; p.groups = dc; p.groups_inner = 1;
     p.a_group_mn = 0; p.a_group_k = 0; p.b_group_mn = F; p.b_group_k = 0;
@@ -292,7 +383,7 @@ int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_p
       return rc;
   }
   // ---- dP[k] = f^T . (c[:,k] * dy): A = f stored [K=B, M=F] (MN-major), B = dyc stored [dc*B, d] (MN-major)
-  {
+  if (weights) {
     GemmProblem p{};
     p.M = F; p.N = d; p.K = B; p.groups = dc; p.groups_inner = 0;
     p.a_group_mn = 0; p.a_group_k = 0; p.b_group_mn = 0; p.b_group_k = B;

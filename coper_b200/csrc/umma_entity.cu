@@ -597,6 +597,17 @@ static BceTcLayout bce_tc_layout(int B, int64_t Ns, int d, int prec) {
   return L;
 }
 size_t umma_bce_workspace_bytes(int B, int64_t Ns, int d, int prec) { return bce_tc_layout(B, Ns, d, prec).total; }
+// dbias slabs the scorer pass of these arguments writes: QB from the fused kernel, else one per query-block chunk row
+static int bce_dbias_slabs_used(const BceTcLayout& L, int B, int64_t Ns, int d, int prec) {
+  if (fused_enabled() && umma_fused_ok(B, Ns, d, prec)) {
+    int QB, R;
+    umma_fused_plan(B, Ns, &QB, &R);
+    return QB;
+  }
+  int bn = ent_block_n(d, prec, Ns, B);
+  (void)L;
+  return ((B + bn - 1) / bn) * (kBceEpiWarps / 4);
+}
 // GT [Ns, ldGT]: ldGT = B rounded up to 32 (whole 16-byte vectors per 32-query chunk)
 static inline int64_t gt_pitch(int B) { return (B + 31) / 32 * 32; }
 size_t umma_bce_G_bytes(int B, int64_t Ns, int prec) {
@@ -645,11 +656,18 @@ static TcOperand g_operand(const void* G, int B, int64_t Ns, int prec) {
 // Pass 3 on its own: dE = G^T . q from the G and the prepared q that umma_score1n_bce_fwd_bwd (called with dE == NULL)
 // left in `G` / `ws`.  Independent of dq and of everything the front-end backward does, so the host may enqueue it on a
 // second stream and let the HBM-bound GEMM run under the latency-bound backward chain.
-int umma_score1n_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq, void* ws,
-                    size_t ws_bytes, int prec, cudaStream_t st) {
+// dbias != NULL: also reduce the dbias slabs the scorer call left in `ws` (it skips that reduction when it is called
+// with dE == NULL, so the short dependent chain BCE -> dq on the main stream carries nothing but what dq needs).
+int umma_score1n_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq, float* dbias,
+                    void* ws, size_t ws_bytes, int prec, cudaStream_t st) {
   BceTcLayout L = bce_tc_layout(B, Ns, d, prec);
   if (!ws || ws_bytes < L.total) return COPER_ERR_WORKSPACE;
   char* w = static_cast<char*>(ws);
+  if (dbias) {
+    int rc = coper_reduce_partials(reinterpret_cast<const float*>(w + L.off_dbias), bce_dbias_slabs_used(L, B, Ns, d, prec),
+                                   Ns, 1.0f, 0, dbias, (coper_stream_t)st);
+    if (rc) return rc;
+  }
   TcOperand Qo = tc_operand(w + L.off_q, B, d, prec), Go = g_operand(G, B, Ns, prec);
   GemmProblem p{};
   p.M = (int)Ns; p.N = d; p.K = B; p.groups = 1; p.groups_inner = 0;
@@ -688,13 +706,12 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     if ((rc = umma_bce_dq_fused(Eo, Qo, bias, label_bits_t, B, Ns, d, pos, neg, inv_count, G, ldGT, dq_part, dbias_part,
                                 loss_part, &grid, st)))
       return rc;
-    sum_doubles_kernel<<<1, 256, 0, st>>>(loss_part, grid * kBceEpiWarps, loss_sum);
-    if ((rc = check_launch())) return rc;
-    if ((rc = coper_reduce_partials(dbias_part, QB, Ns, 1.0f, 0, dbias, (coper_stream_t)st))) return rc;
-    if ((rc = coper_reduce_partials(dq_part, R, (int64_t)B * d, 1.0f, 0, dq, (coper_stream_t)st))) return rc;
+    // dq slabs and the loss partials are reduced by one launch; dbias here only if the caller does not split off dE
+    if ((rc = reduce_partials_and_sum(dq_part, R, (int64_t)B * d, 1.0f, 0, dq, loss_part, grid * kBceEpiWarps, loss_sum, st)))
+      return rc;
     // ---- dE = G^T . q from the entity-major G the kernel stored (dE == NULL: the caller runs umma_score1n_dE itself)
     if (!dE) return COPER_OK;
-    return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, ws, ws_bytes, prec, st);
+    return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, dbias, ws, ws_bytes, prec, st);
   }
   // ---- pass 1: scores -> loss, G, dbias partials
   int grid = 0;
@@ -715,9 +732,6 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
                                                      dbias_part, loss_part, st, &grid);
   };
   if ((rc = run_bce())) return rc;
-  sum_doubles_kernel<<<1, 256, 0, st>>>(loss_part, grid * kBceEpiWarps, loss_sum);
-  if ((rc = check_launch())) return rc;
-  if ((rc = coper_reduce_partials(dbias_part, L.dbias_slabs, Ns, 1.0f, 0, dbias, (coper_stream_t)st))) return rc;
   TcOperand Go = g_operand(G, B, Ns, prec);
   // ---- pass 2: dq = G . E   (A(b, n): GT is the MN-major form, G the K-major form; B = E stored [K, N] -> MN-major)
   {
@@ -726,11 +740,15 @@ int umma_score1n_bce_fwd_bwd(const float* q, const float* E, const void* E_prepa
     p.post_scale = g_post;
     StoreEpi epi = make_store_epi(dq_part, d, 0, (long long)B * d);
     if ((rc = tc_gemm_store(prec, entity_major, true, Go, Eo, p, true, epi, st))) return rc;
-    if ((rc = coper_reduce_partials(dq_part, L.splits, (int64_t)B * d, 1.0f, 0, dq, (coper_stream_t)st))) return rc;
+    // dq slabs and the loss partials of pass 1: one launch
+    if ((rc = reduce_partials_and_sum(dq_part, L.splits, (int64_t)B * d, 1.0f, 0, dq, loss_part, grid * kBceEpiWarps,
+                                      loss_sum, st)))
+      return rc;
   }
-  // ---- pass 3: dE = G^T . q (A(n, b): GT is the K-major form, G the MN-major form; B = q stored [K, N] -> MN-major)
+  // ---- pass 3: dE = G^T . q (A(n, b): GT is the K-major form, G the MN-major form; B = q stored [K, N] -> MN-major),
+  // preceded by the dbias slab reduction
   if (!dE) return COPER_OK;                            // the caller runs umma_score1n_dE itself (second stream)
-  return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, ws, ws_bytes, prec, st);
+  return umma_score1n_dE(G, B, Ns, d, inv_count, dE, dE_sumsq, dbias, ws, ws_bytes, prec, st);
 }
 
 }  // namespace coper

@@ -36,7 +36,7 @@ import numpy as np
 import torch
 
 from . import _lib, sharding
-from ._lib import PREC, call, ptr
+from ._lib import CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_REUSE_FWD, CPG_BWD_WEIGHT_GRADS_ONLY, PREC, call, ptr
 from .sharding import EntityShard
 
 BN_EPS = 1e-3           # tf.layers.batch_normalization default epsilon (models.py:386-388)
@@ -185,6 +185,7 @@ class ConvE:
         # the latency-bound FC / CPG / conv backward chain (fork / join are captured into the step's CUDA graph)
         self.overlap_entity_grad = bool(overlap_entity_grad)
         self._side = torch.cuda.Stream(device=self.dev)
+        self._side_pending = False
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
         # and replayed with one launch.  The sharded path captures its NCCL collectives into the same graph
@@ -389,6 +390,8 @@ class ConvE:
         self.mt_offsets_ext = torch.tensor([0] + [max(0, o - n0) for o in offsets[1:]], dtype=torch.int32).to(self.dev)
         self.mt_nchunks_ext = len(chunks_ext)
         self.dE_sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        # arrival counter of the single-launch batch-norm statistics (coper_bn_stats_finalize); zero between launches
+        self.sync_word = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.norm_delta = torch.zeros(4096, dtype=torch.float64, device=self.dev)
         self._norm_fused_now = False
         self._norm_delta_n = 0
@@ -541,7 +544,10 @@ class ConvE:
         b.bitsT = z(max(Ns, 1), -(-B // 32), dt=torch.int32) if self.prec != 0 else None
         b.loss_sum = z(1, dt=torch.float64)
         b.gold = z(B)
-        b.n_greater, b.n_equal = z(B, dt=torch.int32), z(B, dt=torch.int32)
+        b.rank_counts = z(2, B, dt=torch.int32)       # one buffer: cleared by one fill per evaluation batch
+        b.n_greater, b.n_equal = b.rank_counts[0], b.rank_counts[1]
+        b.rank = z(B, dt=torch.int32)
+        b.loss_mean = z(1, dt=torch.float64)
         b.dwc_part, b.dbc_part = z(B, self.conv_filter_height * self.conv_filter_width * C), z(B, C)
         dcw = self.fc_weights.projections[-1].shape[0]
         dcb = self.fc_bias.projections[-1].shape[0]
@@ -685,6 +691,17 @@ class ConvE:
         lib = _lib.load()
         nch = 0
         stat, Rt = b.stat, R
+        if use_batch and not self.dp:        # statistics + finalize: one launch (the last block to arrive finalises)
+            call("coper_bn_stats_finalize", ptr(x), R, C, ptr(b.stat), ptr(self.sync_word), ptr(bn.gamma), ptr(bn.beta),
+                 ptr(bn.moving_mean), ptr(bn.moving_var), self.batch_norm_momentum, BN_EPS, int(is_train), int(bessel),
+                 ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd))
+            call("coper_bn_act_fwd", ptr(x), R, C, ptr(bn.a), ptr(bn.b), int(relu), keep_post, ptr(self.seed_dev), salt,
+                 ptr(out))
+            return
+        if not use_batch and not is_train and keep_post >= 1.0:      # inference: moving statistics, one launch
+            call("coper_bn_act_fwd_moving", ptr(x), R, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
+                 ptr(bn.moving_var), BN_EPS, int(relu), ptr(out))
+            return
         if use_batch:
             nch = lib.coper_colstats_chunks(R)
             call("coper_colstats", ptr(x), R, C, ptr(b.stat))
@@ -700,13 +717,18 @@ class ConvE:
                      salt_pre, dx):
         lib = _lib.load()
         nch = lib.coper_colstats_chunks(R)
-        call("coper_bn_act_bwd_stats", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
-             int(relu), keep_post, ptr(self.seed_dev), salt_post, ptr(b.stat))
+        if not self.dp:
+            call("coper_bn_act_bwd_stats_finalize", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean),
+                 ptr(bn.invstd), int(relu), keep_post, ptr(self.seed_dev), salt_post, ptr(b.stat), ptr(self.sync_word),
+                 int(use_batch), ptr(bn.dgamma), ptr(bn.dbeta), ptr(bn.c1), ptr(bn.c2))
+        else:
+            call("coper_bn_act_bwd_stats", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
+                 int(relu), keep_post, ptr(self.seed_dev), salt_post, ptr(b.stat))
         stat, Rt = b.stat, R
         if self.dp:              # gradient statistics over the global batch (also makes dgamma / dbeta global)
             stat, nch, Rt = self._gather_stats(b, nch * C * 2), nch * self.world, R * self.world
-        call("coper_bn_act_bwd_finalize", ptr(stat), nch, Rt, C, int(use_batch), ptr(bn.dgamma), ptr(bn.dbeta),
-             ptr(bn.c1), ptr(bn.c2))
+            call("coper_bn_act_bwd_finalize", ptr(stat), nch, Rt, C, int(use_batch), ptr(bn.dgamma), ptr(bn.dbeta),
+                 ptr(bn.c1), ptr(bn.c2))
         call("coper_bn_act_bwd_apply", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
              ptr(bn.c1), ptr(bn.c2), int(relu), keep_post, ptr(self.seed_dev), salt_post, keep_pre, salt_pre, ptr(dx))
 
@@ -774,19 +796,25 @@ class ConvE:
                 dr_out.copy_(dctx)
 
     # ------------------------------------------------------------------------------------------
-    def _forward_q(self, b, is_train: bool):
+    def _forward_q(self, b, is_train: bool, advance: bool = False):
         """Lookups -> conv block -> fused CPG-FC -> FC block; leaves q in b.q (models.py:176-183, 354-426)."""
         B, d = b.B, self.ent_emb_size
         s = self.shard
-        call("coper_gather_rows", ptr(self.ent_emb), s.lo, s.hi, d, ptr(b.e1), B, ptr(b.x0))
+        # both lookups and (training) the step-state advance: one launch
+        rel = self.rel_emb is not None
+        call("coper_gather_rows2", ptr(self.ent_emb), s.lo, s.hi, d, ptr(b.e1), B, ptr(b.x0),
+             ptr(self.rel_emb) if rel else None, 0, self.num_rel if rel else 0, self.rel_emb_size if rel else 0,
+             ptr(b.rel) if rel else None, B if rel else 0, ptr(b.r) if rel else None,
+             ptr(self.step_state) if advance else None, ptr(self.seed_dev) if advance else None,
+             self.learning_rate, self.beta1, self.beta2)
         sharding.exchange_rows(b.x0, self.world, self.group)
-        self._front_end(b, is_train)
+        self._front_end(b, is_train, gather_rel=False)
 
-    def _front_end(self, b, is_train: bool):
+    def _front_end(self, b, is_train: bool, gather_rel: bool = True):
         """b.x0, b.rel -> b.q for the rows of buffer set b (conv block, fused CPG-FC, FC block)."""
         B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
         x_img = b.x0
-        if self.rel_emb is not None:
+        if self.rel_emb is not None and gather_rel:
             call("coper_gather_rows", ptr(self.rel_emb), 0, self.num_rel, dr, ptr(b.rel), B, ptr(b.r))
         if self.variant == "plain":          # models.py:360-362: rows 0..H/2 = entity image, the rest = relation image
             b.xc[:, :d].copy_(b.x0)
@@ -852,17 +880,18 @@ class ConvE:
         B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
         s, g = self.shard, self.grads
         Ns = s.rows
-        call("coper_step_state_advance", ptr(self.step_state), ptr(self.seed_dev), self.learning_rate, self.beta1,
-             self.beta2)
         if dp:
+            call("coper_step_state_advance", ptr(self.step_state), ptr(self.seed_dev), self.learning_rate, self.beta1,
+                 self.beta2)
             self._forward_q_dp(bg, b, True)
         else:
-            self._forward_q(b, True)
+            self._forward_q(b, True, advance=True)
         pos = np.float32(np.float32(1.0 - self.label_smoothing_epsilon) * np.float32(1.0)
                          + np.float32(1.0 / self.num_ent))                     # models.py:450 in fp32
         neg = np.float32(1.0 / self.num_ent)
         inv_count = 1.0 / (float(bg.B) * float(self.num_ent))                # mean over B*N (models.py:451)
         self._norm_fused_now = self._norm_fused and bg.B <= 4096       # (the scatter correction is the small-M kernel's)
+        rel_cleared = loss_done = False
         if self.use_negative_sampling:
             self._sampled_scorer(b)
         elif self._norm_fused_now:
@@ -875,9 +904,16 @@ class ConvE:
                 main = torch.cuda.current_stream()
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
+                    if self.rel_emb is not None:     # cleared here, off the main chain, for the scatter after the join
+                        g["rel_emb"].zero_()
+                        self.grad_sq["rel_emb"].zero_()
+                        rel_cleared = True
                     call("coper_score1n_bce_dE", ptr(self._grad_buf(bg)), bg.B, Ns, d, inv_count, ptr(g["ent_emb"]),
-                         ptr(self.dE_sumsq), ptr(bg.ws), bg.ws_bytes, self.prec)
-                self._entity_grad_pending = True
+                         ptr(self.dE_sumsq), ptr(g["pred_bias"]), ptr(bg.ws), bg.ws_bytes, self.prec)
+                    if self.world == 1:              # the mean loss the caller reads (models.py:451)
+                        torch.div(bg.loss_sum, float(bg.B) * float(self.num_ent), out=bg.loss_mean)
+                        loss_done = True
+                self._side_pending = True
         else:
             call("coper_score1n_bce_fwd_bwd", ptr(bg.q), ptr(self.ent_emb), ptr(self.E_prep), ptr(self.pred_bias),
                  ptr(bg.bits if self.prec == 0 else bg.bitsT), bg.B, Ns, d, float(pos), float(neg), inv_count,
@@ -889,16 +925,27 @@ class ConvE:
             sharding.scatter_dq(bg.dq, b.dq, bg.loss_sum, self.world, self.group)
         else:
             sharding.reduce_scorer_partials(b.loss_sum, b.dq, self.world, self.group)
+        if not loss_done and not self.use_negative_sampling:
+            torch.div(bg.loss_sum, float(bg.B) * float(self.num_ent), out=bg.loss_mean)
         use_batch = self.batch_norm_train_stats
         keep1, keep2 = 1.0 - self.hidden_dropout, 1.0 - self.output_dropout
         # FC block backward: relu -> FCBN -> output dropout (models.py:414-419)
         self._bn_backward(self.fc_bn, b.dq, b.y, B, d, b, use_batch, True, 1.0, 0, keep2, SALT_OUTPUT, b.dy)
         Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
         nw, nb = len(self.fc_weights.projections) - 1, len(self.fc_bias.projections) - 1
-        call("coper_cpg_fc_bwd", ptr(b.cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(b.cb), ptr(Pb), ptr(b.dy), B,
-             Pw.shape[0], F, d,
-             Pb.shape[0], ptr(g[self._last_w_name]), ptr(g[self._last_b_name]),
-             ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec, int(self.prec != 0))
+        # the generator's weight gradients (dP^, dPb) feed nothing but the clip / optimizer: with the side stream on,
+        # they are computed there while the chain through df / dc continues
+        split_w = self.overlap_entity_grad and not dp and self.variant != "param_lookup"
+        reuse = CPG_BWD_REUSE_FWD if self.prec != 0 else 0
+        cpg_bwd_args = (ptr(b.cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(b.cb), ptr(Pb), ptr(b.dy), B,
+                        Pw.shape[0], F, d, Pb.shape[0], ptr(g[self._last_w_name]), ptr(g[self._last_b_name]),
+                        ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec)
+        call("coper_cpg_fc_bwd", *cpg_bwd_args, reuse | (CPG_BWD_INPUT_GRADS_ONLY if split_w else 0))
+        if split_w:
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                call("coper_cpg_fc_bwd", *cpg_bwd_args, reuse | CPG_BWD_WEIGHT_GRADS_ONLY)
+            self._side_pending = True
         if self.variant == "param_lookup":
             # the tables are read through embedding_lookup (models.py:91): IndexedSlices gradients, one [F*d] / [d]
             # slice per query.  The slice-wise norm and the sparse AMSGrad rule need, per table row, the sum of the
@@ -947,8 +994,8 @@ class ConvE:
                     b.dr.add_(b.df[:, self.F_conv:])
             slabs = _lib.load().coper_conv_bwd_slabs(B, self.H, self.W, self.conv_filter_height,
                                                      self.conv_filter_width, C, 0)
-            call("coper_reduce_partials", ptr(b.dwc_part), slabs, KK, 1.0, 0, ptr(g["conv1_weights"]))
-            call("coper_reduce_partials", ptr(b.dbc_part), slabs, C, 1.0, 0, ptr(g["conv1_bias"]))
+            call("coper_reduce_partials2", ptr(b.dwc_part), KK, ptr(g["conv1_weights"]), ptr(b.dbc_part), C,
+                 ptr(g["conv1_bias"]), slabs, 1.0, 0)
         # gradients of the two embedding gathers (models.py:176-178): deterministic segmented scatter
         # IndexedSlices bookkeeping (rel_emb always; ent_emb with sampled labels): the same pass also accumulates the
         # per-row sums of the SQUARED slices (slice-wise global norm + sparse AMSGrad rule)
@@ -956,10 +1003,20 @@ class ConvE:
         gsq_e = self.grad_sq["ent_emb"] if self.use_negative_sampling else None
         if dp:      # every shard needs dx0 of ALL queries whose head entity it owns
             sharding.gather_batch(bg.dx0, b.dx0, self.world, self.group)
-        if getattr(self, "_entity_grad_pending", False):      # join: the scatter below adds into dE
+        if self._side_pending:      # join: the scatter below adds into dE, the clip reads every gradient
             torch.cuda.current_stream().wait_stream(self._side)
-            self._entity_grad_pending = False
-        if self._norm_fused_now:
+            self._side_pending = False
+        pair = bg.B <= 4096 and small and self.rel_emb is not None
+        if pair:      # head-entity and relation scatters: one launch
+            if not rel_cleared:
+                g["rel_emb"].zero_()
+                self.grad_sq["rel_emb"].zero_()
+            call("coper_segscatter_add_pair", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi,
+                 ptr(self.norm_delta) if self._norm_fused_now else None, ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]),
+                 ptr(self.grad_sq["rel_emb"]), 0, self.num_rel)
+            if self._norm_fused_now:
+                self._norm_delta_n = bg.B
+        elif self._norm_fused_now:
             call("coper_segscatter_add_norm", ptr(bg.e1), bg.B, ptr(bg.dx0), d, ptr(g["ent_emb"]), ptr(gsq_e), s.lo, s.hi,
                  ptr(self.norm_delta))
             self._norm_delta_n = bg.B
@@ -976,17 +1033,19 @@ class ConvE:
             if dp:
                 raise NotImplementedError
             return self._clip_and_apply()
-        g["rel_emb"].zero_()
-        self.grad_sq["rel_emb"].zero_()
-        if small:
-            call("coper_segscatter_add_sq", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]),
-                 ptr(self.grad_sq["rel_emb"]), 0, self.num_rel)
-        else:
-            call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]), 0, self.num_rel, ptr(b.ws),
-                 b.ws_bytes)
-            torch.mul(b.dr, b.dr, out=b.dr_sq)
-            call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0,
-                 self.num_rel, ptr(b.ws), b.ws_bytes)
+        if not pair:
+            if not rel_cleared:
+                g["rel_emb"].zero_()
+                self.grad_sq["rel_emb"].zero_()
+            if small:
+                call("coper_segscatter_add_sq", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]),
+                     ptr(self.grad_sq["rel_emb"]), 0, self.num_rel)
+            else:
+                call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr), dr, ptr(g["rel_emb"]), 0, self.num_rel, ptr(b.ws),
+                     b.ws_bytes)
+                torch.mul(b.dr, b.dr, out=b.dr_sq)
+                call("coper_segscatter_add", ptr(b.rel), B, ptr(b.dr_sq), dr, ptr(self.grad_sq["rel_emb"]), 0,
+                     self.num_rel, ptr(b.ws), b.ws_bytes)
         if dp:      # partial sums over this rank's rows -> all-reduce of the flat bucket
             if big_work is not None:
                 sharding.reduce_replicated_grads(self.flat_small, self.world, self.group)
@@ -1031,18 +1090,22 @@ class ConvE:
         nt = len(self.trainables)
         fused = self._norm_fused_now
         if fused and self.mt_nchunks_ext > 0:
-            call("coper_mt_sumsq", ptr(self.mt_desc_ext), nt, ptr(self.mt_chunks_ext), self.mt_nchunks_ext,
-                 ptr(self.mt_offsets_ext), ptr(self.mt_partials), ptr(self.sumsq))
+            descs, chunks, nchunks, offsets = self.mt_desc_ext, self.mt_chunks_ext, self.mt_nchunks_ext, self.mt_offsets_ext
         else:
-            call("coper_mt_sumsq", ptr(self.mt_desc_ext if fused else self.mt_desc), nt, ptr(self.mt_chunks),
-                 self.mt_nchunks, ptr(self.mt_offsets), ptr(self.mt_partials), ptr(self.sumsq))
-        if fused:       # |dE|^2 from the dE GEMM epilogue + the change the head-entity scatter made to it
-            call("coper_sumsq_combine", ptr(self.dE_sumsq), 1, ptr(self.norm_delta), self._norm_delta_n,
-                 ptr(self.sumsq))
-        # trainables 0,1 (ent_emb, pred_bias) are row-sharded: their squared norms add across ranks;
-        # every other gradient is replicated (identical on all ranks) and is counted once.
-        sharding.reduce_sharded_sumsq(self.sumsq[:2], self.world, self.group)
-        call("coper_clip_scale_n", ptr(self.sumsq), nt, CLIP_NORM, ptr(self.clip_out))
+            descs, chunks, nchunks, offsets = (self.mt_desc_ext if fused else self.mt_desc, self.mt_chunks,
+                                               self.mt_nchunks, self.mt_offsets)
+        # per-tensor squared norms; fused: |dE|^2 (tensor 0) = the dE GEMM epilogue's sum + the change the head-entity
+        # scatter made to it; single GPU: the clip factor comes out of the same finishing launch
+        one = self.world == 1
+        call("coper_mt_sumsq_clip", ptr(descs), nt, ptr(chunks), nchunks, ptr(offsets), ptr(self.mt_partials),
+             ptr(self.sumsq), 0 if fused else -1, ptr(self.dE_sumsq) if fused else None, 1 if fused else 0,
+             ptr(self.norm_delta) if fused else None, self._norm_delta_n if fused else 0, CLIP_NORM,
+             ptr(self.clip_out) if one else None)
+        if not one:
+            # trainables 0,1 (ent_emb, pred_bias) are row-sharded: their squared norms add across ranks;
+            # every other gradient is replicated (identical on all ranks) and is counted once.
+            sharding.reduce_sharded_sumsq(self.sumsq[:2], self.world, self.group)
+            call("coper_clip_scale_n", ptr(self.sumsq), nt, CLIP_NORM, ptr(self.clip_out))
         call("coper_mt_amsgrad", ptr(self.mt_desc), ptr(self.mt_chunks), self.mt_nchunks, ptr(self.step_state),
              self.beta1, self.beta2, self.adam_eps, ptr(self.clip_out), int(self.bug_compat))
         if not self._emit_prepared:
@@ -1074,7 +1137,8 @@ class ConvE:
 
     def train_step(self, batch: Dict, apply_update: bool = True):
         """One reference training step (run_cpg.py:210-219).  Returns the loss as a 0-d device tensor
-        (float64 -> call .item() to read it; that is the step's only device->host transfer)."""
+        (float64 -> call .item() to read it; that is the step's only device->host transfer).  The tensor is a view
+        of the step's own buffer, written inside the captured step: valid until the next step of the same batch size."""
         if self.use_negative_sampling:
             return self._train_step_sampled(batch, apply_update)
         b = self.stage_batch(batch)
@@ -1088,7 +1152,7 @@ class ConvE:
         else:
             self._run_graphed(("train", b.B), lambda: self._train_device(b))
         self.global_step += 1
-        return b.loss_sum[0] / (float(b.B) * float(self.num_ent))
+        return b.loss_mean[0]
 
     def _train_step_sampled(self, batch: Dict, apply_update: bool):
         """Sampled-label step: ``batch['lookup_values']`` int32 [B, L] entity ids and ``batch['e2_multi']`` fp32 [B, L]
@@ -1159,7 +1223,8 @@ class ConvE:
     def filtered_ranks(self, batch: Dict):
         """Filtered rank of ``e2`` for each query (metrics.py:44-51) computed on device.
         ``batch['e2_multi*']`` is the filter set (all known true tails).  Returns int32 device tensors
-        (rank, n_equal); rank == the reference's rank whenever n_equal == 0."""
+        (rank, n_equal); rank == the reference's rank whenever n_equal == 0.  Both are buffers of the batch-size slot,
+        overwritten by the next call with the same batch size (clone them to keep them, as metrics.py does)."""
         if not (isinstance(batch["e2"], torch.Tensor) and batch["e2"].is_cuda):   # host batches are validated
             e2 = np.asarray(batch["e2"])
             if int(e2.min()) < 0 or int(e2.max()) >= self.num_ent:
@@ -1168,7 +1233,7 @@ class ConvE:
         if self.prec != 0:          # the gold entity joins the filter set (metrics.py:44-46 never compares it)
             call("coper_bits_t_set", ptr(b.e2), b.B, self.shard.lo, self.shard.hi, ptr(b.bitsT))
         self._run_graphed(("rank", b.B), lambda: self._rank_device(b))
-        return b.n_greater + 1, b.n_equal
+        return b.rank, b.n_equal
 
     def _rank_device(self, b):
         # (evaluation uses moving statistics and no dropout: a batch that does not split evenly over the ranks simply
@@ -1179,8 +1244,7 @@ class ConvE:
             self._forward_q(b, False)
         s = self.shard
         d = self.ent_emb_size
-        b.n_greater.zero_()
-        b.n_equal.zero_()
+        b.rank_counts.zero_()
         if self.E_prep is not None:
             # tensor-pipe engines: rank counts straight from the scorer's accumulators, logits never written
             call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
@@ -1196,4 +1260,5 @@ class ConvE:
             call("coper_filtered_rank", ptr(b.S), b.ld, b.B, s.rows, ptr(b.e2), s.lo, ptr(b.gold), ptr(b.bits),
                  ptr(b.n_greater), ptr(b.n_equal))
         sharding.reduce_counts(b.n_greater, b.n_equal, self.world, self.group)
-        return b.n_greater + 1, b.n_equal
+        torch.add(b.n_greater, 1, out=b.rank)        # inside the captured step: the caller reads b.rank
+        return b.rank, b.n_equal

@@ -62,6 +62,13 @@ int coper_device_is_sm100(void);
  * (entity-sharded lookup: an all-reduce(sum) of the outputs then delivers every row exactly). */
 int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int width,
                       const int64_t* idx, int n_idx, float* out, coper_stream_t stream);
+/* The two lookups that open a step (models.py:176 head entities, :178 relations) in ONE launch; n_b == 0: only table a.
+ * step_state != NULL: the launch also performs coper_step_state_advance(step_state, seed_dev, lr, beta1, beta2)
+ * (nothing in the lookups reads that state) - a training step then starts with one kernel instead of three. */
+int coper_gather_rows2(const float* table_a, int64_t lo_a, int64_t hi_a, int width_a, const int64_t* idx_a, int n_a,
+                       float* out_a, const float* table_b, int64_t lo_b, int64_t hi_b, int width_b,
+                       const int64_t* idx_b, int n_b, float* out_b, float* step_state, uint64_t* seed_dev, float lr,
+                       float beta1, float beta2, coper_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a5 / K4 — tf.nn.conv2d NHWC, 1 input channel, stride 1, VALID (+ bias) (models.py:355,382-385;
@@ -86,6 +93,12 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
  *                         (out = a*x + b), mean, invstd; optionally updates moving stats in place with
  *                         TF semantics moving = moving*momentum + batch*(1-momentum)
  *                         (bessel != 0: unbiased variance for the moving update, the fused 4-D path).
+ *   coper_bn_stats_finalize : coper_colstats + coper_bn_finalize(use_batch_stats = 1) in ONE launch - the block that
+ *                         arrives last at *sync_word (a device word, zero before the first call, left zero) finalises
+ *                         every channel from the chunk partials (fp64, fixed order: run-to-run identical; the
+ *                         two-call form adds the same partials in another fixed order - last-bit differences).
+ *                         (The two-call form remains for synchronised batch statistics: partials of all ranks are
+ *                         all-gathered between the calls.)  coper_bn_act_bwd_stats_finalize: the same for the backward pair.
  *   coper_bn_act_fwd    : out = dropout_post(relu?(a[c]*x + b[c]))
  *   coper_bn_act_bwd_*  : g1 = dout * dropout_post * relu'(a*x+b); stats (sum g1, sum g1*xhat) ->
  *                         dgamma, dbeta, and dx = a*(g1 - c1 - xhat*c2) [* dropout_pre]. */
@@ -95,13 +108,27 @@ int coper_bn_finalize(const float* partials, int nchunk, int64_t R, int C, const
                       float* moving_mean, float* moving_var, float momentum, float eps, int use_batch_stats,
                       int update_moving, int bessel, float* a, float* b, float* mean, float* invstd,
                       coper_stream_t stream);
+int coper_bn_stats_finalize(const float* x, int64_t R, int C, float* partials, unsigned int* sync_word,
+                            const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                            float momentum, float eps, int update_moving, int bessel, float* a, float* b, float* mean,
+                            float* invstd, coper_stream_t stream);
 int coper_bn_act_fwd(const float* x, int64_t R, int C, const float* a, const float* b, int relu,
                      float keep_post, const uint64_t* seed_dev, uint64_t salt_post, float* out, coper_stream_t stream);
+/* inference (training=False: moving statistics, no dropout): coper_bn_finalize(use_batch_stats = 0) +
+ * coper_bn_act_fwd in one launch; same bits */
+int coper_bn_act_fwd_moving(const float* x, int64_t R, int C, const float* gamma, const float* beta,
+                            const float* moving_mean, const float* moving_var, float eps, int relu, float* out,
+                            coper_stream_t stream);
 int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
                            const float* mean, const float* invstd, int relu, float keep_post,
                            const uint64_t* seed_dev, uint64_t salt_post, float* partials, coper_stream_t stream);
 int coper_bn_act_bwd_finalize(const float* partials, int nchunk, int64_t R, int C, int use_batch_stats,
                               float* dgamma, float* dbeta, float* c1, float* c2, coper_stream_t stream);
+int coper_bn_act_bwd_stats_finalize(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
+                                    const float* mean, const float* invstd, int relu, float keep_post,
+                                    const uint64_t* seed_dev, uint64_t salt_post, float* partials,
+                                    unsigned int* sync_word, int use_batch_stats, float* dgamma, float* dbeta, float* c1,
+                                    float* c2, coper_stream_t stream);
 int coper_bn_act_bwd_apply(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
                            const float* mean, const float* invstd, const float* c1, const float* c2, int relu,
                            float keep_post, const uint64_t* seed_dev, uint64_t salt_post, float keep_pre,
@@ -129,13 +156,23 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
                      coper_stream_t stream);
 /* backward (models.py:198 autodiff of the above): given dy [B,d] (already through the dropout mask)
  *   dP [dc,F*d], dPb [dcb,d], df [B,F], dc_out [B,dc], dcb_out [B,dcb].
- * reuse_fwd_operands != 0 (tensor-pipe precisions only): `workspace` is the buffer the matching
- * coper_cpg_fc_fwd call used and still holds its prepared f and P operands (f, P unchanged since). */
+ * flags (bit mask):
+ *   COPER_CPG_BWD_REUSE_FWD (tensor-pipe precisions only): `workspace` is the buffer the matching coper_cpg_fc_fwd
+ *     call used and still holds its prepared f and P operands (f, P unchanged since).
+ *   COPER_CPG_BWD_INPUT_GRADS_ONLY: compute df, dc_out, dcb_out and leave dP, dPb untouched; the workspace keeps
+ *     the operands the weight-gradient half needs.
+ *   COPER_CPG_BWD_WEIGHT_GRADS_ONLY: compute only dP, dPb from the operands an INPUT_GRADS_ONLY call with the same
+ *     arguments left in `workspace` - the two halves are independent given those operands, so a caller may run
+ *     the second on another stream while the backward chain through df / dc_out continues (models.py:198's graph
+ *     has no edge between them either). */
+#define COPER_CPG_BWD_REUSE_FWD 1
+#define COPER_CPG_BWD_INPUT_GRADS_ONLY 2
+#define COPER_CPG_BWD_WEIGHT_GRADS_ONLY 4
 size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec);
 int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
                      const float* Pb, const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
                      float* dc_out, float* dcb_out, void* workspace, size_t workspace_bytes, int prec,
-                     int reuse_fwd_operands, coper_stream_t stream);
+                     int flags, coper_stream_t stream);
 
 /* plain C = op(A) . op(B) (+C) for the small dense layers around the path (CPG hidden projections,
  * models.py:60): row-major; transX != 0 means the stored matrix is the transpose of the operand. */
@@ -198,13 +235,14 @@ int coper_score1n_bce_fwd_bwd_norm(const float* q, const float* E, const void* E
                                    float* dE, float* dbias, double* dE_sumsq, void* workspace, size_t workspace_bytes,
                                    int prec, coper_stream_t stream);
 
-/* The split form of coper_score1n_bce_fwd_bwd_norm (tensor-pipe precisions): call it with dE == NULL - loss, dq, dbias
- * and G are produced, the entity-gradient GEMM is skipped - and then coper_score1n_bce_dE with the same G / workspace
- * (which still holds the prepared q): dE = G^T . q (+ *dE_sumsq, optional).  dE does not depend on dq, and nothing the
- * rest of the backward pass (models.py:198 through the FC / conv layers) does depends on dE, so the host may enqueue
- * this call on a second stream: the HBM-bound GEMM then runs under the latency-bound backward chain. */
+/* The split form of coper_score1n_bce_fwd_bwd_norm (tensor-pipe precisions): call it with dE == NULL - loss, dq and G
+ * are produced; the entity-gradient GEMM and the reduction of the dbias slabs are skipped (`dbias` is not written) - and
+ * then coper_score1n_bce_dE with the same G / workspace (which still holds the prepared q and the dbias slabs):
+ * dE = G^T . q (+ *dE_sumsq, optional) and dbias.  Neither depends on dq, and nothing the rest of the backward pass
+ * (models.py:198 through the FC / conv layers) does depends on them, so the host may enqueue this call on a second
+ * stream: the HBM-bound GEMM then runs under the latency-bound backward chain. */
 int coper_score1n_bce_dE(const void* G, int B, int64_t Ns, int d, float inv_count, float* dE, double* dE_sumsq,
-                         void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
+                         float* dbias, void* workspace, size_t workspace_bytes, int prec, coper_stream_t stream);
 
 /* a8 / SURVEY §8f-2 — SAMPLED-label scorer (models.py:438-443), loss (:448-453) and gradients: what the shipped
  * big-dataset configs train with (training.num_labels = 100 / 1000).  lookup int32 [B, L] entity ids
@@ -299,6 +337,12 @@ int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int wid
  * norm that was taken before this scatter (tf.clip_by_global_norm over the dense ent_emb gradient, models.py:198-199). */
 int coper_segscatter_add_norm(const int64_t* idx, int M, const float* src, int width, float* dst, float* dst_sq,
                               int64_t row_lo, int64_t row_hi, double* norm_delta, coper_stream_t stream);
+/* Two independent small scatters of one step in ONE launch: a = coper_segscatter_add_norm's arguments (norm_delta_a may
+ * be NULL), b = coper_segscatter_add_sq's (the head-entity and relation gathers' gradients, models.py:176-178). */
+int coper_segscatter_add_pair(const int64_t* idx_a, int M_a, const float* src_a, int width_a, float* dst_a,
+                              float* dst_sq_a, int64_t lo_a, int64_t hi_a, double* norm_delta_a, const int64_t* idx_b,
+                              int M_b, const float* src_b, int width_b, float* dst_b, float* dst_sq_b, int64_t lo_b,
+                              int64_t hi_b, coper_stream_t stream);
 int coper_segscatter_add(const int64_t* idx, int M, const float* src, int width, float* dst, int64_t row_lo,
                          int64_t row_hi, void* workspace, size_t workspace_bytes, coper_stream_t stream);
 
@@ -311,6 +355,9 @@ int coper_segscatter_add(const int64_t* idx, int M, const float* src, int width,
 #define COPER_SUMSQ_BLOCKS 256
 int coper_reduce_partials(const float* in, int S, int64_t n, float scale, int accumulate, float* out,
                           coper_stream_t stream);
+/* two reductions with the same slab count in one launch (the conv filter / bias gradient slabs of coper_conv_bwd) */
+int coper_reduce_partials2(const float* in_a, int64_t n_a, float* out_a, const float* in_b, int64_t n_b, float* out_b,
+                           int S, float scale, int accumulate, coper_stream_t stream);
 int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_stream_t stream);
 int coper_clip_scale(const double* partials, int n_slots, float clip_norm, float* out2, coper_stream_t stream);
 
@@ -375,6 +422,13 @@ int coper_sumsq_combine(const double* parts, int n_parts, const double* deltas, 
 int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
                    const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, coper_stream_t stream);
 int coper_clip_scale_n(const double* sums, int n, float clip_norm, float* out2, coper_stream_t stream);
+/* coper_mt_sumsq + coper_sumsq_combine (into tensor_sumsq[ext_tensor]; ext_tensor < 0: none) + coper_clip_scale_n
+ * (clip_out == NULL: skipped - a multi-GPU caller all-reduces the sharded tensors' sums first) as two launches instead
+ * of four; same summation orders, same bits.  n_chunks == 0: every norm is external, only the finishing launch runs. */
+int coper_mt_sumsq_clip(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
+                        const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, int ext_tensor,
+                        const double* ext_parts, int n_ext_parts, const double* ext_deltas, int n_ext_deltas,
+                        float clip_norm, float* clip_out, coper_stream_t stream);
 int coper_mt_amsgrad(const coper_param_desc* descs, const int32_t* chunks, int n_chunks, const float* step_state,
                      float beta1, float beta2, float eps, const float* clip_scale, int bug_compat,
                      coper_stream_t stream);
