@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcoper_sm100.so")
 
 PREC = {"fp32": 0, "bf16": 1, "tf32x3": 2, "fp16x3": 3}
 # flags of coper_cpg_fc_bwd (include/coper.h)
-CPG_BWD_REUSE_FWD, CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_WEIGHT_GRADS_ONLY = 1, 2, 4
+CPG_BWD_REUSE_FWD, CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_WEIGHT_GRADS_ONLY, CPG_BWD_DCB_ACCUMULATE = 1, 2, 4, 8
 
 vp, i32, i64, u64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 

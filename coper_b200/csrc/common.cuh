@@ -33,6 +33,37 @@ inline int check_cuda(cudaError_t e) {
 
 static inline cudaStream_t as_stream(coper_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL).  The training / evaluation step is a chain of ~30 short dependent kernels;
+// with plain stream order each one is launched only after its predecessor has drained.  Every kernel of this library
+// is launched with the programmatic-stream-serialization attribute and starts with pdl_enter(): it releases ITS
+// dependent at once (griddepcontrol.launch_dependents - the next kernel's blocks may be scheduled, set up and parked as
+// soon as all blocks of this one have started) and then waits for its own predecessor to complete and flush
+// (griddepcontrol.wait), before touching any memory.  Correctness never depends on the attribute: without it (or after
+// a non-kernel stream operation, an event wait, a kernel of another library) both instructions are no-ops and the
+// launch is an ordinary one.  The tcgen05 kernels place the wait after their prologue (barrier init, TMEM allocation,
+// descriptor prefetch - nothing that reads a predecessor's output).  COPER_PDL=0 in the environment turns it off.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+bool pdl_enabled();      // elementwise.cu
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+}
+
 // Counter-based dropout hash (splitmix64 finaliser): identical on host and device.
 __host__ __device__ __forceinline__ uint32_t hash32(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;

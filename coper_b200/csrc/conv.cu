@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_fwd_kernel(const float* __r
                                                                 const float* __restrict__ wc,
                                                                 const float* __restrict__ bc, int KH, int KW, int C,
                                                                 int per_query, float* __restrict__ z) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* img = sm;                 // H*W
   float* wf = sm + H * W;          // KH*KW*C
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_bwd_kernel(const float* __r
                                                                 int per_query, float* __restrict__ dx0,
                                                                 float* __restrict__ dwc_part,
                                                                 float* __restrict__ dbc_part) {
+  pdl_enter();
   extern __shared__ float sm[];
   int OH = H - KH + 1, OW = W - KW + 1;
   int total = OH * OW * C;
@@ -104,6 +106,7 @@ template <int IMG>
 __global__ void __launch_bounds__(256) conv3x3_fwd_kernel(const float* __restrict__ x0, int B, int H, int W,
                                                           const float* __restrict__ wc, const float* __restrict__ bc,
                                                           float* __restrict__ z) {
+  pdl_enter();
   extern __shared__ float sm[];                    // IMG * H * W
   const int c = threadIdx.x & 31, hs = threadIdx.x >> 5;
   const int OH = H - 2, OW = W - 2, HW = H * W;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_kernel(const float* __restric
                                                           int B, int H, int W, const float* __restrict__ wc,
                                                           float* __restrict__ dx0, float* __restrict__ dwc_part,
                                                           float* __restrict__ dbc_part) {
+  pdl_enter();
   extern __shared__ float sm[];
   const int c = threadIdx.x & 31, hs = threadIdx.x >> 5, lane = c;
   const int OH = H - 2, OW = W - 2, HW = H * W, total = OH * OW * kFastC;
@@ -232,12 +236,12 @@ int coper_conv_fwd(const float* x0, int B, int H, int W, const float* wc, const 
   if (H * W > kMaxImg || KH * KW * C > kMaxFilt) return COPER_ERR_UNSUPPORTED;
   if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3) {
     size_t sm_fast = (size_t)kConvImgPerCta * H * W * sizeof(float);
-    conv3x3_fwd_kernel<kConvImgPerCta><<<(B + kConvImgPerCta - 1) / kConvImgPerCta, 256, sm_fast, as_stream(stream)>>>(
-        x0, B, H, W, wc, bc, z);
+    launch_pdl(conv3x3_fwd_kernel<kConvImgPerCta>, (B + kConvImgPerCta - 1) / kConvImgPerCta, 256, sm_fast,
+               as_stream(stream), x0, B, H, W, wc, bc, z);
     return check_launch();
   }
   size_t smem = (size_t)(H * W + KH * KW * C + C) * sizeof(float);
-  conv_fwd_kernel<<<B, kConvThreads, smem, as_stream(stream)>>>(x0, H, W, wc, bc, KH, KW, C, per_query, z);
+  launch_pdl(conv_fwd_kernel, B, kConvThreads, smem, as_stream(stream), x0, H, W, wc, bc, KH, KW, C, per_query, z);
   return check_launch();
 }
 
@@ -259,8 +263,8 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
   if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3) {
     size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
     if (sm_fast <= 48 * 1024 && (OH * OW * C) % 4 == 0) {
-      conv3x3_bwd_kernel<kConvImgPerCtaBwd><<<(B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd, 256, sm_fast, as_stream(stream)>>>(
-          dz, x0, B, H, W, wc, dx0, dwc_part, dbc_part);
+      launch_pdl(conv3x3_bwd_kernel<kConvImgPerCtaBwd>, (B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd, 256,
+                 sm_fast, as_stream(stream), dz, x0, B, H, W, wc, dx0, dwc_part, dbc_part);
       return check_launch();
     }
   }
@@ -273,8 +277,8 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
     if (rc) return rc;
     attr_set = true;
   }
-  conv_bwd_kernel<<<B, kConvThreads, smem, as_stream(stream)>>>(dz, x0, H, W, wc, KH, KW, C, per_query, dx0, dwc_part,
-                                                               dbc_part);
+  launch_pdl(conv_bwd_kernel, B, kConvThreads, smem, as_stream(stream), dz, x0, H, W, wc, KH, KW, C, per_query, dx0,
+             dwc_part, dbc_part);
   return check_launch();
 }
 

@@ -70,6 +70,7 @@ struct ScaledMN {  // (j, kk) -> x[b, j] * s[b, kq] with b = k index,  MN-contig
 __global__ void __launch_bounds__(THREADS) cpg_fwd_kernel(const float* __restrict__ c, const float* __restrict__ f,
                                                           const float* __restrict__ P, int B, int dc, int F, int d,
                                                           int tiles_per_split, float* __restrict__ part) {
+  pdl_enter();
   __shared__ Smem sm;
   int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, split = blockIdx.z;
   int nt = (F + BK - 1) / BK;
@@ -99,6 +100,7 @@ __global__ void cpg_fwd_finalize_kernel(const float* __restrict__ part, int S, c
                                         const float* __restrict__ Pb, int B, int d, int dcb, float keep,
                                         float inv_keep, uint32_t thr, const uint64_t* seed_dev, uint64_t salt,
                                         float* __restrict__ y) {
+  pdl_enter();
   uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t n = (int64_t)B * d;
@@ -126,6 +128,7 @@ __global__ void cpg_fwd_finalize_kernel(const float* __restrict__ part, int S, c
 __global__ void cpg_fwd_finalize_kernel4(const float* __restrict__ part, int S, const float* __restrict__ cb,
                                          const float* __restrict__ Pb, int B, int d, int dcb, float keep, float inv_keep,
                                          uint32_t thr, const uint64_t* seed_dev, uint64_t salt, float* __restrict__ y) {
+  pdl_enter();
   const uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int64_t n = (int64_t)B * d;
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(THREADS) cpg_bwd_T_kernel(const float* __restr
                                                             const float* __restrict__ P,
                                                             const float* __restrict__ dy, int B, int dc, int F, int d,
                                                             float* __restrict__ df, float* __restrict__ dc_part) {
+  pdl_enter();
   __shared__ Smem sm;
   int n0 = blockIdx.x * BN;  // feature tile
   int m0 = blockIdx.y * BM;  // batch tile
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(THREADS) cpg_bwd_T_kernel(const float* __restr
 __global__ void __launch_bounds__(THREADS) cpg_bwd_dP_kernel(const float* __restrict__ c, const float* __restrict__ f,
                                                              const float* __restrict__ dy, int B, int dc, int F,
                                                              int d, float* __restrict__ dP) {
+  pdl_enter();
   __shared__ Smem sm;
   int n0 = blockIdx.x * BN;  // output-dim tile
   int m0 = blockIdx.y * BM;  // feature tile
@@ -237,6 +242,7 @@ __global__ void __launch_bounds__(THREADS) cpg_bwd_dP_kernel(const float* __rest
 // dPb[k, j] = sum_b cb[b,k] dy[b,j] : block = (k, 32-column slab), 8 batch lanes, fixed-order combine
 __global__ void __launch_bounds__(256) cpg_dPb_kernel(const float* __restrict__ cb, const float* __restrict__ dy,
                                                       int B, int d, int dcb, float* __restrict__ dPb) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k = blockIdx.y, j = blockIdx.x * 32 + tx;
@@ -254,20 +260,22 @@ __global__ void __launch_bounds__(256) cpg_dPb_kernel(const float* __restrict__ 
 }
 // dcb[b, k] = sum_j dy[b,j] Pb[k,j] : one warp per (b, k)
 __global__ void __launch_bounds__(256) cpg_dcb_kernel(const float* __restrict__ dy, const float* __restrict__ Pb, int B,
-                                                      int d, int dcb, float* __restrict__ dcb_out) {
+                                                      int d, int dcb, float* __restrict__ dcb_out, int accumulate) {
+  pdl_enter();
   int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (w >= B * dcb) return;
   int b = w / dcb, k = w - b * dcb;
   float acc = 0.f;
   for (int j = lane; j < d; j += 32) acc = fmaf(__ldg(dy + (int64_t)b * d + j), __ldg(Pb + (int64_t)k * d + j), acc);
   acc = warp_sum(acc);
-  if (lane == 0) dcb_out[w] = acc;
+  if (lane == 0) dcb_out[w] = accumulate ? dcb_out[w] + acc : acc;
 }
 
 // ---------------------------------------------------------------- plain sgemm
 template <class SA, class SB>
 __global__ void __launch_bounds__(THREADS) sgemm_kernel(SA A, SB Bs, int M, int N, int K, float* __restrict__ C,
                                                         int ldc, int accumulate) {
+  pdl_enter();
   __shared__ Smem sm;
   int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   float acc[8][8];
@@ -318,13 +326,17 @@ int coper_sgemm(int transA, int transB, int M, int N, int K, const float* A, int
   // operand A(m,k): !transA -> A[m*lda+k] (K-contig); transA -> A[k*lda+m] (MN-contig)
   // operand B(k,n): !transB -> B[k*ldb+n] (MN-contig); transB -> B[n*ldb+k] (K-contig)
   if (!transA && !transB)
-    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcK{A, lda, M, K}, SrcMN{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+    launch_pdl(sgemm_kernel<SrcK, SrcMN>, grid, THREADS, 0, st, SrcK{A, lda, M, K}, SrcMN{B, ldb, N, K}, M, N, K, C, ldc,
+               accumulate);
   else if (!transA && transB)
-    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcK{A, lda, M, K}, SrcK{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+    launch_pdl(sgemm_kernel<SrcK, SrcK>, grid, THREADS, 0, st, SrcK{A, lda, M, K}, SrcK{B, ldb, N, K}, M, N, K, C, ldc,
+               accumulate);
   else if (transA && !transB)
-    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcMN{A, lda, M, K}, SrcMN{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+    launch_pdl(sgemm_kernel<SrcMN, SrcMN>, grid, THREADS, 0, st, SrcMN{A, lda, M, K}, SrcMN{B, ldb, N, K}, M, N, K, C, ldc,
+               accumulate);
   else
-    sgemm_kernel<<<grid, THREADS, 0, st>>>(SrcMN{A, lda, M, K}, SrcK{B, ldb, N, K}, M, N, K, C, ldc, accumulate);
+    launch_pdl(sgemm_kernel<SrcMN, SrcK>, grid, THREADS, 0, st, SrcMN{A, lda, M, K}, SrcK{B, ldb, N, K}, M, N, K, C, ldc,
+               accumulate);
   return check_launch();
 }
 
@@ -358,7 +370,7 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
     part = static_cast<float*>(workspace);
     n_slabs = L.splits;
     dim3 grid(ceil_div(d, BN), ceil_div(B, BM), L.splits);
-    cpg_fwd_kernel<<<grid, THREADS, 0, st>>>(c, f, P, B, dc, F, d, L.tiles_per_split, part);
+    launch_pdl(cpg_fwd_kernel, grid, THREADS, 0, st, c, f, P, B, dc, F, d, L.tiles_per_split, part);
     if ((rc = check_launch())) return rc;
   } else {
     return COPER_ERR_UNSUPPORTED;
@@ -367,13 +379,11 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
   const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(Pb) |
                                      reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   if (vec)
-    cpg_fwd_finalize_kernel4<<<(unsigned)((n / 4 + 127) / 128), 128, 0, st>>>(part, n_slabs, cb, Pb, B, d, dcb, keep_out,
-                                                                              1.0f / keep_out, keep_threshold(keep_out),
-                                                                              seed_dev, salt_out, y);
+    launch_pdl(cpg_fwd_finalize_kernel4, (unsigned)((n / 4 + 127) / 128), 128, 0, st, part, n_slabs, cb, Pb, B, d,
+               dcb, keep_out, 1.0f / keep_out, keep_threshold(keep_out), seed_dev, salt_out, y);
   else
-    cpg_fwd_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n_slabs, cb, Pb, B, d, dcb, keep_out,
-                                                                         1.0f / keep_out, keep_threshold(keep_out),
-                                                                         seed_dev, salt_out, y);
+    launch_pdl(cpg_fwd_finalize_kernel, (unsigned)((n + 255) / 256), 256, 0, st, part, n_slabs, cb, Pb, B, d, dcb,
+               keep_out, 1.0f / keep_out, keep_threshold(keep_out), seed_dev, salt_out, y);
   return check_launch();
 }
 
@@ -401,12 +411,14 @@ int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void*
     if (inputs) {
       float* dc_part = static_cast<float*>(workspace);
       int ftiles = ceil_div(F, BN);
-      cpg_bwd_T_kernel<<<dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st>>>(c, f, P, dy, B, dc, F, d, df, dc_part);
+      launch_pdl(cpg_bwd_T_kernel, dim3(ftiles, ceil_div(B, BM)), THREADS, 0, st, c, f, P, dy, B, dc, F, d, df,
+                 dc_part);
       if ((rc = check_launch())) return rc;
       if ((rc = coper_reduce_partials(dc_part, ftiles, (int64_t)B * dc, 1.0f, 0, dc_out, stream))) return rc;
     }
     if (weights) {
-      cpg_bwd_dP_kernel<<<dim3(ceil_div(d, BN), ceil_div(F, BM), dc), THREADS, 0, st>>>(c, f, dy, B, dc, F, d, dP);
+      launch_pdl(cpg_bwd_dP_kernel, dim3(ceil_div(d, BN), ceil_div(F, BM), dc), THREADS, 0, st, c, f, dy, B, dc, F,
+                 d, dP);
       if ((rc = check_launch())) return rc;
     }
   } else {
@@ -414,11 +426,12 @@ int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void*
   }
   // dPb [dcb, d] = cb^T . dy ;  dcb [B, dcb] = dy . Pb^T
   if (weights) {
-    cpg_dPb_kernel<<<dim3(ceil_div(d, 32), dcb), 256, 0, st>>>(cb, dy, B, d, dcb, dPb);
+    launch_pdl(cpg_dPb_kernel, dim3(ceil_div(d, 32), dcb), 256, 0, st, cb, dy, B, d, dcb, dPb);
     if ((rc = check_launch())) return rc;
   }
   if (inputs) {
-    cpg_dcb_kernel<<<ceil_div((int64_t)B * dcb * 32, 256), 256, 0, st>>>(dy, Pb, B, d, dcb, dcb_out);
+    launch_pdl(cpg_dcb_kernel, ceil_div((int64_t)B * dcb * 32, 256), 256, 0, st, dy, Pb, B, d, dcb, dcb_out,
+               (flags & COPER_CPG_BWD_DCB_ACCUMULATE) ? 1 : 0);
     if ((rc = check_launch())) return rc;
   }
   return COPER_OK;

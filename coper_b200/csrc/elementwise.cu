@@ -3,17 +3,25 @@
 // 128-bit vectorised where the shape allows, grids sized in multiples of the SM count.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
-#include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace coper {
 thread_local int g_last_cuda_error = 0;
 long long g_launch_count = 0;
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("COPER_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 constexpr int kSMs = 148;
 
 // ------------------------------------------------------------------ gather (models.py:176,178)
 __global__ void gather_rows_kernel(const float* __restrict__ table, int64_t row_lo, int64_t row_hi, int width,
                                    const int64_t* __restrict__ idx, int n_idx, float* __restrict__ out) {
+  pdl_enter();
   int warps_per_block = blockDim.x >> 5;
   int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
@@ -50,6 +58,7 @@ __device__ __forceinline__ void step_state_advance(float* st, uint64_t* seed_dev
 }
 __global__ void gather_rows2_kernel(GatherDesc A, GatherDesc Bd, int blocksA, float* step_state, uint64_t* seed_dev,
                                     float lr, float b1, float b2) {
+  pdl_enter();
   if (step_state && blockIdx.x == 0 && threadIdx.x == 0) step_state_advance(step_state, seed_dev, lr, b1, b2);
   const bool second = (int)blockIdx.x >= blocksA;
   const GatherDesc& g = second ? Bd : A;
@@ -72,8 +81,9 @@ __global__ void gather_rows2_kernel(GatherDesc A, GatherDesc Bd, int blocksA, fl
 
 // ------------------------------------------------------------------ column statistics
 // mode 0: (x, x^2); mode 1: backward (g1, g1*xhat) with g1 = dout * drop_post * relu'(a x + b)
-// rows per chunk: enough chunks to fill the machine (R = B*OH*OW = 73,728 -> 576 CTAs; R = B = 512 -> 8 per column slab)
-__host__ __device__ __forceinline__ int stat_rows(int64_t R) { return R >= 32768 ? 128 : 64; }
+// rows per chunk: enough chunks to fill the machine (R = B*OH*OW = 73,728 -> 288 CTAs, two per SM; R = B = 512 -> 8 per
+// column slab) and few enough that the finalising block's pass over the chunk partials stays short
+__host__ __device__ __forceinline__ int stat_rows(int64_t R) { return R >= 32768 ? 256 : 64; }
 struct StatBwdArgs {
   const float* dout;
   const float* a;
@@ -183,6 +193,7 @@ __device__ __forceinline__ void bn_bwd_finish(double s, double ss, int64_t R, in
 template <int MODE, bool FIN>
 __global__ void colstats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ partials,
                                 StatBwdArgs bw, BnFwdFin ff, BnBwdFin fb, unsigned int* sync_word) {
+  pdl_enter();
   // block (32, 8): x = column in slab, y = row lane
   __shared__ float s1[8][33], s2[8][33];
   __shared__ int s_last;
@@ -244,12 +255,12 @@ __global__ void colstats_kernel(const float* __restrict__ x, int64_t R, int C, f
       double sm = 0.0, sq = 0.0;
       if (ch < C) {
         int k = kl;
-        for (; k + 3 * lanes < nchunk; k += 4 * lanes) {
-          float2 v[4];
+        for (; k + 7 * lanes < nchunk; k += 8 * lanes) {
+          float2 v[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = ld_partial<true>(partials, (int64_t)(k + u * lanes) * C + ch);
+          for (int u = 0; u < 8; ++u) v[u] = ld_partial<true>(partials, (int64_t)(k + u * lanes) * C + ch);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { sm += (double)v[u].x; sq += (double)v[u].y; }
+          for (int u = 0; u < 8; ++u) { sm += (double)v[u].x; sq += (double)v[u].y; }
         }
         for (; k < nchunk; k += lanes) {
           const float2 v = ld_partial<true>(partials, (int64_t)k * C + ch);
@@ -276,6 +287,7 @@ __global__ void colstats_kernel(const float* __restrict__ x, int64_t R, int C, f
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C, BnFwdFin f) {
+  pdl_enter();
   const int ch[1] = {(int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5)};
   if (ch[0] >= C) return;
   double s[1] = {0.0}, ss[1] = {0.0};
@@ -286,6 +298,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchun
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t n, int C, const float* __restrict__ a,
                                   const float* __restrict__ b, int relu, float keep, float inv_keep, uint32_t thr,
                                   const uint64_t* seed_dev, uint64_t salt, float* __restrict__ out) {
+  pdl_enter();
   uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
@@ -299,6 +312,7 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t n, int C,
 __global__ void bn_act_fwd_kernel4(const float4* __restrict__ x, int64_t n4, int C, const float* __restrict__ a,
                                    const float* __restrict__ b, int relu, float keep, float inv_keep, uint32_t thr,
                                    const uint64_t* seed_dev, uint64_t salt, float4* __restrict__ out) {
+  pdl_enter();
   uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -326,6 +340,7 @@ __global__ void bn_act_fwd_moving_kernel(const float* __restrict__ x, int64_t n,
                                          const float* __restrict__ beta, const float* __restrict__ moving_mean,
                                          const float* __restrict__ moving_var, float eps, int relu,
                                          float* __restrict__ out) {
+  pdl_enter();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
     int c = (int)(e % C);
@@ -343,6 +358,7 @@ __global__ void bn_act_fwd_moving_kernel4(const float4* __restrict__ x, int64_t 
                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                           const float* __restrict__ moving_mean, const float* __restrict__ moving_var,
                                           float eps, int relu, float4* __restrict__ out) {
+  pdl_enter();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const int c = (int)((i * 4) % C);
@@ -366,6 +382,7 @@ __global__ void bn_act_fwd_moving_kernel4(const float4* __restrict__ x, int64_t 
 }
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunk, int64_t R, int C, BnBwdFin f) {
+  pdl_enter();
   const int ch[1] = {(int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5)};
   if (ch[0] >= C) return;
   double s[1], ss[1];
@@ -381,6 +398,7 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dout, const fl
                                         const uint64_t* seed_dev, uint64_t salt_post, float keep_pre,
                                         float inv_keep_pre, uint32_t thr_pre, uint64_t salt_pre,
                                         float* __restrict__ dx) {
+  pdl_enter();
   uint64_t sd = seed_dev ? *seed_dev : 0ull;
   uint64_t seed_post = sd + salt_post, seed_pre = sd + salt_pre;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -398,6 +416,7 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dout, const fl
 
 __global__ void dropout_mask_kernel(int64_t n, uint32_t thr, float keep, const uint64_t* seed_dev, uint64_t salt,
                                     float* mask) {
+  pdl_enter();
   uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
@@ -405,6 +424,7 @@ __global__ void dropout_mask_kernel(int64_t n, uint32_t thr, float keep, const u
 }
 __global__ void dropout_apply_kernel(float* x, int64_t n, float keep, float inv_keep, uint32_t thr,
                                      const uint64_t* seed_dev, uint64_t salt) {
+  pdl_enter();
   uint64_t seed = (seed_dev ? *seed_dev : 0ull) + salt;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
@@ -414,6 +434,7 @@ __global__ void dropout_apply_kernel(float* x, int64_t n, float keep, float inv_
 // ------------------------------------------------------------------ label / filter bit rows
 __global__ void csr_to_bits_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int B,
                                    int64_t lo, int64_t hi, int64_t words, uint32_t* bits) {
+  pdl_enter();
   int b = blockIdx.x;
   if (b >= B) return;
   int s = rowptr[b], e = rowptr[b + 1];
@@ -427,6 +448,7 @@ __global__ void csr_to_bits_kernel(const int32_t* __restrict__ rowptr, const int
 }
 __global__ void dense_to_bits_kernel(const float* __restrict__ dense, int B, int64_t N, int64_t words,
                                      uint32_t* __restrict__ bits) {
+  pdl_enter();
   // one warp per output word: lane l tests entity w*32 + l (coalesced 128 B read), ballot packs the word
   int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -442,6 +464,7 @@ __global__ void dense_to_bits_kernel(const float* __restrict__ dense, int B, int
 // entity-major bit matrix bitsT [Ns, wordsB]: bit (b & 31) of word (n, b >> 5) = entity n is a positive of query b
 __global__ void csr_to_bits_t_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int B,
                                      int64_t lo, int64_t hi, int wordsB, uint32_t* bitsT) {
+  pdl_enter();
   int b = blockIdx.x;
   if (b >= B) return;
   int s = rowptr[b], e = rowptr[b + 1];
@@ -452,6 +475,7 @@ __global__ void csr_to_bits_t_kernel(const int32_t* __restrict__ rowptr, const i
 }
 __global__ void bits_t_set_kernel(const int64_t* __restrict__ ent, int B, int64_t lo, int64_t hi, int wordsB,
                                   uint32_t* bitsT) {
+  pdl_enter();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int64_t n = ent[b];
@@ -459,6 +483,7 @@ __global__ void bits_t_set_kernel(const int64_t* __restrict__ ent, int B, int64_
 }
 __global__ void dense_to_bits_t_kernel(const float* __restrict__ dense, int B, int64_t N, int64_t ld, int wordsB,
                                        uint32_t* __restrict__ bitsT) {
+  pdl_enter();
   // one warp per output word (n, w): lane l tests query w*32 + l
   int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -476,6 +501,7 @@ __global__ void dense_to_bits_t_kernel(const float* __restrict__ dense, int B, i
 // loads, slabs added in slab order in fp64 - the same order (and bits) as the general kernel below gives for S <= 8.
 __global__ void __launch_bounds__(256) reduce_partials_few_kernel(const float* __restrict__ in, int S, int64_t n,
                                                                   float scale, int accumulate, float* __restrict__ out) {
+  pdl_enter();
   const int64_t i4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (i4 >= n) return;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -573,6 +599,7 @@ template <bool VEC_A>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceJob A, int blocks_a, ReduceJob Bj, int blocks_b,
                                                               const double* __restrict__ dsum_in, int dsum_n,
                                                               double* __restrict__ dsum_out) {
+  pdl_enter();
   __shared__ double red[8][33];
   __shared__ double red4[VEC_A ? 8 * 32 * 4 : 1];
   const int blk = (int)blockIdx.x;
@@ -590,6 +617,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceJob A, int b
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
+  pdl_enter();
   __shared__ double sm[32];
   double acc = 0.0;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -614,6 +642,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, double* __r
 }
 
 __global__ void clip_scale_kernel(const double* __restrict__ partials, int n, float clip, float* out2) {
+  pdl_enter();
   __shared__ double sm[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
@@ -631,6 +660,7 @@ __global__ void amsgrad_kernel(float* __restrict__ theta, const float* __restric
                                float* __restrict__ v, float* __restrict__ vhat, int64_t n,
                                const float* __restrict__ step_state, float b1, float b2, float eps,
                                const float* __restrict__ clip_scale, int bug_compat) {
+  pdl_enter();
   float lr_t = step_state[0];
   float cs = clip_scale ? *clip_scale : 1.0f;
   float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
@@ -654,6 +684,7 @@ __global__ void amsgrad_kernel(float* __restrict__ theta, const float* __restric
 }
 
 __global__ void step_state_advance_kernel(float* st, uint64_t* seed_dev, float lr, float b1, float b2) {
+  pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) step_state_advance(st, seed_dev, lr, b1, b2);
 }
 
@@ -663,6 +694,7 @@ __global__ void step_state_advance_kernel(float* st, uint64_t* seed_dev, float l
 __global__ void __launch_bounds__(256) mt_sumsq_kernel(const coper_param_desc* __restrict__ descs,
                                                        const int32_t* __restrict__ chunks,
                                                        double* __restrict__ chunk_partials) {
+  pdl_enter();
   __shared__ double sm[32];
   const int t = chunks[2 * blockIdx.x];
   const int64_t start = (int64_t)chunks[2 * blockIdx.x + 1] * COPER_MT_CHUNK;
@@ -697,6 +729,7 @@ __device__ __forceinline__ uint32_t* fp16x3_trailer_of(const coper_param_desc& d
 __global__ void mt_tensor_sums_kernel(const coper_param_desc* __restrict__ descs, const double* __restrict__ chunk_partials,
                                       const int32_t* __restrict__ chunk_offsets, int n_tensors,
                                       double* __restrict__ tensor_sumsq) {
+  pdl_enter();
   // one warp per tensor: lanes stride over the tensor's chunks, fixed-order shuffle combine.  A tensor whose norm is
   // supplied by its producer (COPER_GRAD_NORM_EXTERNAL) has no partials to add (160 k of them at 10 M entities).
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -727,6 +760,7 @@ __global__ void __launch_bounds__(256) mt_sumsq_finish_kernel(const coper_param_
                                                               const double* __restrict__ ext_parts, int n_ext_parts,
                                                               const double* __restrict__ ext_deltas, int n_ext_deltas,
                                                               float clip, float* clip_out) {
+  pdl_enter();
   __shared__ double smd[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t = warp; t < n_tensors; t += 8) {
@@ -799,6 +833,7 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
                                                          const float* __restrict__ step_state, float b1, float b2,
                                                          float eps, const float* __restrict__ clip_scale,
                                                          int bug_compat) {
+  pdl_enter();
   const int t = chunks[2 * blockIdx.x];
   const int64_t start = (int64_t)chunks[2 * blockIdx.x + 1] * COPER_MT_CHUNK;
   const coper_param_desc d = descs[t];
@@ -907,6 +942,7 @@ __global__ void __launch_bounds__(256) mt_amsgrad_kernel(const coper_param_desc*
 // out[0] = sum(parts[0..n_parts)) + sum(deltas[0..n_deltas)) in a fixed order (one block)
 __global__ void sumsq_combine_kernel(const double* __restrict__ parts, int n_parts, const double* __restrict__ deltas,
                                      int n_deltas, double* __restrict__ out) {
+  pdl_enter();
   __shared__ double smd[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n_parts; i += blockDim.x) acc += parts[i];
@@ -924,10 +960,12 @@ int reduce_partials_and_sum(const float* in, int S, int64_t n, float scale, int 
                    ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   if (vec) {
     const int ba = (int)((n / 4 + 31) / 32);
-    reduce_partials_kernel<true><<<ba + (dsum_in ? 1 : 0), 256, 0, st>>>(A, ba, ReduceJob{}, 0, dsum_in, dsum_n, dsum_out);
+    launch_pdl(reduce_partials_kernel<true>, ba + (dsum_in ? 1 : 0), 256, 0, st, A, ba, ReduceJob{}, 0, dsum_in,
+               dsum_n, dsum_out);
   } else {
     const int ba = (int)((n + 31) / 32);
-    reduce_partials_kernel<false><<<ba + (dsum_in ? 1 : 0), 256, 0, st>>>(A, ba, ReduceJob{}, 0, dsum_in, dsum_n, dsum_out);
+    launch_pdl(reduce_partials_kernel<false>, ba + (dsum_in ? 1 : 0), 256, 0, st, A, ba, ReduceJob{}, 0, dsum_in,
+               dsum_n, dsum_out);
   }
   return check_launch();
 }
@@ -969,7 +1007,8 @@ int coper_gather_rows(const float* table, int64_t row_lo, int64_t row_hi, int wi
                       float* out, coper_stream_t stream) {
   COPER_CHECK_ARG(table && idx && out && width > 0 && n_idx >= 0 && row_hi >= row_lo);
   if (n_idx == 0) return COPER_OK;
-  gather_rows_kernel<<<ceil_div(n_idx, 8), 256, 0, as_stream(stream)>>>(table, row_lo, row_hi, width, idx, n_idx, out);
+  launch_pdl(gather_rows_kernel, ceil_div(n_idx, 8), 256, 0, as_stream(stream), table, row_lo, row_hi, width, idx,
+             n_idx, out);
   return check_launch();
 }
 
@@ -983,7 +1022,8 @@ int coper_gather_rows2(const float* table_a, int64_t lo_a, int64_t hi_a, int wid
   if (blocks_a + blocks_b == 0 && !step_state) return COPER_OK;
   GatherDesc A{table_a, lo_a, hi_a, width_a, idx_a, n_a, out_a}, Bd{table_b, lo_b, hi_b, width_b, idx_b, n_b, out_b};
   const int grid = blocks_a + blocks_b > 0 ? blocks_a + blocks_b : 1;
-  gather_rows2_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, Bd, blocks_a, step_state, seed_dev, lr, beta1, beta2);
+  launch_pdl(gather_rows2_kernel, grid, 256, 0, as_stream(stream), A, Bd, blocks_a, step_state, seed_dev, lr, beta1,
+             beta2);
   return check_launch();
 }
 
@@ -992,8 +1032,8 @@ int coper_colstats_chunks(int64_t R) { return R <= 0 ? 0 : (int)((R + stat_rows(
 int coper_colstats(const float* x, int64_t R, int C, float* partials, coper_stream_t stream) {
   COPER_CHECK_ARG(x && partials && R > 0 && C > 0);
   dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
-  colstats_kernel<0, false><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, StatBwdArgs{}, BnFwdFin{}, BnBwdFin{},
-                                                                    nullptr);
+  launch_pdl(colstats_kernel<0, false>, grid, block, 0, as_stream(stream), x, R, C, partials, StatBwdArgs{},
+             BnFwdFin{}, BnBwdFin{}, nullptr);
   return check_launch();
 }
 
@@ -1004,7 +1044,8 @@ int coper_bn_finalize(const float* partials, int nchunk, int64_t R, int C, const
   COPER_CHECK_ARG(gamma && beta && moving_mean && moving_var && a && b && mean && invstd && C > 0);
   COPER_CHECK_ARG(!use_batch_stats || (partials && nchunk > 0 && R > 0));
   BnFwdFin f{gamma, beta, moving_mean, moving_var, momentum, eps, use_batch_stats, update_moving, bessel, a, b, mean, invstd};
-  bn_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, f);
+  launch_pdl(bn_finalize_kernel, ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream), partials, nchunk, R, C,
+             f);
   return check_launch();
 }
 
@@ -1016,7 +1057,8 @@ int coper_bn_stats_finalize(const float* x, int64_t R, int C, float* partials, u
   COPER_CHECK_ARG(gamma && beta && moving_mean && moving_var && a && b && mean && invstd);
   dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
   BnFwdFin f{gamma, beta, moving_mean, moving_var, momentum, eps, 1, update_moving, bessel, a, b, mean, invstd};
-  colstats_kernel<0, true><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, StatBwdArgs{}, f, BnBwdFin{}, sync_word);
+  launch_pdl(colstats_kernel<0, true>, grid, block, 0, as_stream(stream), x, R, C, partials, StatBwdArgs{}, f,
+             BnBwdFin{}, sync_word);
   return check_launch();
 }
 
@@ -1030,12 +1072,11 @@ int coper_bn_act_fwd(const float* x, int64_t R, int C, const float* a, const flo
                                reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
   if (vec) {
     int64_t n4 = n / 4;
-    bn_act_fwd_kernel4<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float4*>(x), n4, C, a, b, relu, keep_post, inv, thr, seed_dev, salt_post,
-        reinterpret_cast<float4*>(out));
+    launch_pdl(bn_act_fwd_kernel4, grid_for(n4, 256), 256, 0, as_stream(stream), reinterpret_cast<const float4*>(x),
+               n4, C, a, b, relu, keep_post, inv, thr, seed_dev, salt_post, reinterpret_cast<float4*>(out));
   } else {
-    bn_act_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, C, a, b, relu, keep_post, inv, thr,
-                                                                       seed_dev, salt_post, out);
+    launch_pdl(bn_act_fwd_kernel, grid_for(n, 256), 256, 0, as_stream(stream), x, n, C, a, b, relu, keep_post, inv,
+               thr, seed_dev, salt_post, out);
   }
   return check_launch();
 }
@@ -1049,12 +1090,12 @@ int coper_bn_act_fwd_moving(const float* x, int64_t R, int C, const float* gamma
                                      reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
                                      reinterpret_cast<uintptr_t>(moving_mean) | reinterpret_cast<uintptr_t>(moving_var)) & 15) == 0;
   if (vec)
-    bn_act_fwd_moving_kernel4<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float4*>(x), n / 4, C, gamma, beta, moving_mean, moving_var, eps, relu,
-        reinterpret_cast<float4*>(out));
+    launch_pdl(bn_act_fwd_moving_kernel4, grid_for(n / 4, 256), 256, 0, as_stream(stream), reinterpret_cast<const
+               float4*>(x), n / 4, C, gamma, beta, moving_mean, moving_var, eps, relu,
+               reinterpret_cast<float4*>(out));
   else
-    bn_act_fwd_moving_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, C, gamma, beta, moving_mean, moving_var,
-                                                                              eps, relu, out);
+    launch_pdl(bn_act_fwd_moving_kernel, grid_for(n, 256), 256, 0, as_stream(stream), x, n, C, gamma, beta,
+               moving_mean, moving_var, eps, relu, out);
   return check_launch();
 }
 
@@ -1065,7 +1106,8 @@ int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, 
   dim3 grid(ceil_div(C, 32), coper_colstats_chunks(R)), block(32, 8);
   StatBwdArgs bw{dout, a, b, mean, invstd, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post), seed_dev,
                  salt_post};
-  colstats_kernel<1, false><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw, BnFwdFin{}, BnBwdFin{}, nullptr);
+  launch_pdl(colstats_kernel<1, false>, grid, block, 0, as_stream(stream), x, R, C, partials, bw, BnFwdFin{},
+             BnBwdFin{}, nullptr);
   return check_launch();
 }
 
@@ -1073,7 +1115,8 @@ int coper_bn_act_bwd_finalize(const float* partials, int nchunk, int64_t R, int 
                               float* dgamma, float* dbeta, float* c1, float* c2, coper_stream_t stream) {
   COPER_CHECK_ARG(partials && dgamma && dbeta && c1 && c2 && nchunk > 0 && R > 0 && C > 0);
   BnBwdFin f{use_batch_stats, dgamma, dbeta, c1, c2};
-  bn_bwd_finalize_kernel<<<ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream)>>>(partials, nchunk, R, C, f);
+  launch_pdl(bn_bwd_finalize_kernel, ceil_div((int64_t)C * 32, 256), 256, 0, as_stream(stream), partials, nchunk, R,
+             C, f);
   return check_launch();
 }
 
@@ -1088,7 +1131,8 @@ int coper_bn_act_bwd_stats_finalize(const float* dout, const float* x, int64_t R
   StatBwdArgs bw{dout, a, b, mean, invstd, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post), seed_dev,
                  salt_post};
   BnBwdFin f{use_batch_stats, dgamma, dbeta, c1, c2};
-  colstats_kernel<1, true><<<grid, block, 0, as_stream(stream)>>>(x, R, C, partials, bw, BnFwdFin{}, f, sync_word);
+  launch_pdl(colstats_kernel<1, true>, grid, block, 0, as_stream(stream), x, R, C, partials, bw, BnFwdFin{}, f,
+             sync_word);
   return check_launch();
 }
 
@@ -1099,9 +1143,9 @@ int coper_bn_act_bwd_apply(const float* dout, const float* x, int64_t R, int C, 
   COPER_CHECK_ARG(dout && x && a && b && mean && invstd && c1 && c2 && dx && R > 0 && C > 0);
   COPER_CHECK_ARG(keep_post > 0.f && keep_pre > 0.f);
   int64_t n = R * C;
-  bn_act_bwd_apply_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-      dout, x, n, C, a, b, mean, invstd, c1, c2, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post),
-      seed_dev, salt_post, keep_pre, 1.0f / keep_pre, keep_threshold(keep_pre), salt_pre, dx);
+  launch_pdl(bn_act_bwd_apply_kernel, grid_for(n, 256), 256, 0, as_stream(stream), dout, x, n, C, a, b, mean, invstd,
+             c1, c2, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post), seed_dev, salt_post, keep_pre,
+             1.0f / keep_pre, keep_threshold(keep_pre), salt_pre, dx);
   return check_launch();
 }
 
@@ -1109,16 +1153,16 @@ int coper_dropout_mask(int64_t n, float keep, const uint64_t* seed_dev, uint64_t
                        coper_stream_t stream) {
   COPER_CHECK_ARG(mask && n >= 0 && keep > 0.f);
   if (n == 0) return COPER_OK;
-  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(n, keep_threshold(keep), keep, seed_dev, salt,
-                                                                       mask);
+  launch_pdl(dropout_mask_kernel, grid_for(n, 256), 256, 0, as_stream(stream), n, keep_threshold(keep), keep,
+             seed_dev, salt, mask);
   return check_launch();
 }
 int coper_dropout_apply(float* x, int64_t n, float keep, const uint64_t* seed_dev, uint64_t salt,
                         coper_stream_t stream) {
   COPER_CHECK_ARG(x && n >= 0 && keep > 0.f);
   if (n == 0 || keep >= 1.0f) return COPER_OK;
-  dropout_apply_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, keep, 1.0f / keep, keep_threshold(keep),
-                                                                        seed_dev, salt);
+  launch_pdl(dropout_apply_kernel, grid_for(n, 256), 256, 0, as_stream(stream), x, n, keep, 1.0f / keep,
+             keep_threshold(keep), seed_dev, salt);
   return check_launch();
 }
 
@@ -1129,14 +1173,15 @@ int coper_csr_to_bits(const int32_t* rowptr, const int32_t* col, int B, int64_t 
   int rc = check_cuda(cudaMemsetAsync(bits, 0, (size_t)B * words * sizeof(uint32_t), as_stream(stream)));
   if (rc) return rc;
   if (!col) return COPER_OK;
-  csr_to_bits_kernel<<<B, 64, 0, as_stream(stream)>>>(rowptr, col, B, ent_lo, ent_hi, words, bits);
+  launch_pdl(csr_to_bits_kernel, B, 64, 0, as_stream(stream), rowptr, col, B, ent_lo, ent_hi, words, bits);
   return check_launch();
 }
 int coper_dense_to_bits(const float* dense, int B, int64_t N, uint32_t* bits, coper_stream_t stream) {
   COPER_CHECK_ARG(dense && bits && B > 0 && N > 0);
   int64_t words = (N + 31) / 32;
   int64_t threads = (int64_t)B * words * 32;
-  dense_to_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(dense, B, N, words, bits);
+  launch_pdl(dense_to_bits_kernel, (unsigned)((threads + 255) / 256), 256, 0, as_stream(stream), dense, B, N, words,
+             bits);
   return check_launch();
 }
 
@@ -1146,20 +1191,21 @@ int coper_csr_to_bits_t(const int32_t* rowptr, const int32_t* col, int B, int64_
   int wordsB = (B + 31) / 32;
   int rc = check_cuda(cudaMemsetAsync(bits_t, 0, (size_t)(ent_hi - ent_lo) * wordsB * sizeof(uint32_t), as_stream(stream)));
   if (rc) return rc;
-  csr_to_bits_t_kernel<<<B, 128, 0, as_stream(stream)>>>(rowptr, col, B, ent_lo, ent_hi, wordsB, bits_t);
+  launch_pdl(csr_to_bits_t_kernel, B, 128, 0, as_stream(stream), rowptr, col, B, ent_lo, ent_hi, wordsB, bits_t);
   return check_launch();
 }
 int coper_bits_t_set(const int64_t* ent, int B, int64_t ent_lo, int64_t ent_hi, uint32_t* bits_t, coper_stream_t stream) {
   COPER_CHECK_ARG(ent && bits_t && B > 0 && ent_hi > ent_lo);
-  bits_t_set_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(ent, B, ent_lo, ent_hi, (B + 31) / 32, bits_t);
+  launch_pdl(bits_t_set_kernel, (B + 127) / 128, 128, 0, as_stream(stream), ent, B, ent_lo, ent_hi, (B + 31) / 32,
+             bits_t);
   return check_launch();
 }
 int coper_dense_to_bits_t(const float* dense, int B, int64_t N, int64_t ld_dense, uint32_t* bits_t, coper_stream_t stream) {
   COPER_CHECK_ARG(dense && bits_t && B > 0 && N > 0 && ld_dense >= N);
   int wordsB = (B + 31) / 32;
   int64_t threads = N * wordsB * 32;
-  dense_to_bits_t_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(dense, B, N, ld_dense, wordsB,
-                                                                                           bits_t);
+  launch_pdl(dense_to_bits_t_kernel, (unsigned)((threads + 255) / 256), 256, 0, as_stream(stream), dense, B, N,
+             ld_dense, wordsB, bits_t);
   return check_launch();
 }
 
@@ -1167,8 +1213,8 @@ int coper_reduce_partials(const float* in, int S, int64_t n, float scale, int ac
                           coper_stream_t stream) {
   COPER_CHECK_ARG(in && out && S > 0 && n > 0);
   if (S <= 8 && n >= (1 << 16) && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    reduce_partials_few_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, as_stream(stream)>>>(in, S, n, scale, accumulate,
-                                                                                        out);
+    launch_pdl(reduce_partials_few_kernel, (unsigned)((n / 4 + 255) / 256), 256, 0, as_stream(stream), in, S, n,
+               scale, accumulate, out);
     return check_launch();
   }
   return reduce_partials_and_sum(in, S, n, scale, accumulate, out, nullptr, 0, nullptr, as_stream(stream));
@@ -1178,32 +1224,34 @@ int coper_reduce_partials2(const float* in_a, int64_t n_a, float* out_a, const f
   COPER_CHECK_ARG(in_a && out_a && in_b && out_b && S > 0 && n_a > 0 && n_b > 0);
   ReduceJob A{in_a, S, n_a, scale, accumulate, out_a}, Bj{in_b, S, n_b, scale, accumulate, out_b};
   const int ba = (int)((n_a + 31) / 32), bb = (int)((n_b + 31) / 32);
-  reduce_partials_kernel<false><<<ba + bb, 256, 0, as_stream(stream)>>>(A, ba, Bj, bb, nullptr, 0, nullptr);
+  launch_pdl(reduce_partials_kernel<false>, ba + bb, 256, 0, as_stream(stream), A, ba, Bj, bb, nullptr, 0, nullptr);
   return check_launch();
 }
 int coper_sumsq(const float* x, int64_t n, int slot, double* partials, coper_stream_t stream) {
   COPER_CHECK_ARG(x && partials && n >= 0 && slot >= 0);
-  sumsq_kernel<<<COPER_SUMSQ_BLOCKS, 256, 0, as_stream(stream)>>>(x, n, partials + (int64_t)slot * COPER_SUMSQ_BLOCKS);
+  launch_pdl(sumsq_kernel, COPER_SUMSQ_BLOCKS, 256, 0, as_stream(stream), x, n, partials + (int64_t)slot *
+             COPER_SUMSQ_BLOCKS);
   return check_launch();
 }
 int coper_clip_scale(const double* partials, int n_slots, float clip_norm, float* out2, coper_stream_t stream) {
   COPER_CHECK_ARG(partials && out2 && n_slots > 0 && clip_norm > 0.f);
-  clip_scale_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, n_slots * COPER_SUMSQ_BLOCKS, clip_norm, out2);
+  launch_pdl(clip_scale_kernel, 1, 256, 0, as_stream(stream), partials, n_slots * COPER_SUMSQ_BLOCKS, clip_norm,
+             out2);
   return check_launch();
 }
 int coper_clip_scale_n(const double* sums, int n, float clip_norm, float* out2, coper_stream_t stream) {
   COPER_CHECK_ARG(sums && out2 && n > 0 && clip_norm > 0.f);
-  clip_scale_kernel<<<1, 256, 0, as_stream(stream)>>>(sums, n, clip_norm, out2);
+  launch_pdl(clip_scale_kernel, 1, 256, 0, as_stream(stream), sums, n, clip_norm, out2);
   return check_launch();
 }
 int coper_mt_sumsq(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
                    const int32_t* chunk_offsets, double* chunk_partials, double* tensor_sumsq, coper_stream_t stream) {
   COPER_CHECK_ARG(descs && chunks && chunk_offsets && chunk_partials && tensor_sumsq && n_tensors > 0 && n_chunks > 0);
-  mt_sumsq_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, chunk_partials);
+  launch_pdl(mt_sumsq_kernel, n_chunks, 256, 0, as_stream(stream), descs, chunks, chunk_partials);
   int rc = check_launch();
   if (rc) return rc;
-  mt_tensor_sums_kernel<<<(n_tensors * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(descs, chunk_partials, chunk_offsets,
-                                                                            n_tensors, tensor_sumsq);
+  launch_pdl(mt_tensor_sums_kernel, (n_tensors * 32 + 255) / 256, 256, 0, as_stream(stream), descs, chunk_partials,
+             chunk_offsets, n_tensors, tensor_sumsq);
   return check_launch();
 }
 int coper_mt_sumsq_clip(const coper_param_desc* descs, int n_tensors, const int32_t* chunks, int n_chunks,
@@ -1217,32 +1265,31 @@ int coper_mt_sumsq_clip(const coper_param_desc* descs, int n_tensors, const int3
   COPER_CHECK_ARG(!clip_out || clip_norm > 0.f);
   int rc;
   if (n_chunks > 0) {
-    mt_sumsq_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, chunk_partials);
+    launch_pdl(mt_sumsq_kernel, n_chunks, 256, 0, as_stream(stream), descs, chunks, chunk_partials);
     if ((rc = check_launch())) return rc;
   }
-  mt_sumsq_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(descs, chunk_partials, chunk_offsets, n_tensors, tensor_sumsq,
-                                                           ext_tensor, ext_parts, n_ext_parts, ext_deltas, n_ext_deltas,
-                                                           clip_norm, clip_out);
+  launch_pdl(mt_sumsq_finish_kernel, 1, 256, 0, as_stream(stream), descs, chunk_partials, chunk_offsets, n_tensors,
+             tensor_sumsq, ext_tensor, ext_parts, n_ext_parts, ext_deltas, n_ext_deltas, clip_norm, clip_out);
   return check_launch();
 }
 int coper_mt_amsgrad(const coper_param_desc* descs, const int32_t* chunks, int n_chunks, const float* step_state,
                      float beta1, float beta2, float eps, const float* clip_scale, int bug_compat,
                      coper_stream_t stream) {
   COPER_CHECK_ARG(descs && chunks && step_state && n_chunks > 0);
-  mt_amsgrad_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(descs, chunks, step_state, beta1, beta2, eps, clip_scale,
-                                                            bug_compat);
+  launch_pdl(mt_amsgrad_kernel, n_chunks, 256, 0, as_stream(stream), descs, chunks, step_state, beta1, beta2, eps,
+             clip_scale, bug_compat);
   return check_launch();
 }
 int coper_sumsq_combine(const double* parts, int n_parts, const double* deltas, int n_deltas, double* out,
                         coper_stream_t stream) {
   COPER_CHECK_ARG(out && n_parts >= 0 && n_deltas >= 0 && (parts || n_parts == 0) && (deltas || n_deltas == 0));
-  sumsq_combine_kernel<<<1, 256, 0, as_stream(stream)>>>(parts, n_parts, deltas, n_deltas, out);
+  launch_pdl(sumsq_combine_kernel, 1, 256, 0, as_stream(stream), parts, n_parts, deltas, n_deltas, out);
   return check_launch();
 }
 int coper_step_state_advance(float* step_state, uint64_t* seed_dev, float lr, float beta1, float beta2,
                              coper_stream_t stream) {
   COPER_CHECK_ARG(step_state);
-  step_state_advance_kernel<<<1, 32, 0, as_stream(stream)>>>(step_state, seed_dev, lr, beta1, beta2);
+  launch_pdl(step_state_advance_kernel, 1, 32, 0, as_stream(stream), step_state, seed_dev, lr, beta1, beta2);
   return check_launch();
 }
 int coper_amsgrad_step(float* theta, const float* grad, float* m, float* v, float* vhat, int64_t n,
@@ -1251,8 +1298,8 @@ int coper_amsgrad_step(float* theta, const float* grad, float* m, float* v, floa
   COPER_CHECK_ARG(theta && grad && vhat && step_state && n >= 0);
   COPER_CHECK_ARG(bug_compat || (m && v));
   if (n == 0) return COPER_OK;
-  amsgrad_kernel<<<grid_for(n, 256, 16), 256, 0, as_stream(stream)>>>(theta, grad, m, v, vhat, n, step_state, beta1,
-                                                                      beta2, eps, clip_scale, bug_compat);
+  launch_pdl(amsgrad_kernel, grid_for(n, 256, 16), 256, 0, as_stream(stream), theta, grad, m, v, vhat, n, step_state,
+             beta1, beta2, eps, clip_scale, bug_compat);
   return check_launch();
 }
 

@@ -13,6 +13,7 @@ constexpr int kRankChunk = 256 * 4 * 8;  // entities per CTA: 8 float4 per threa
 
 __global__ void gold_scores_kernel(const float* __restrict__ scores, int64_t ld, int B, int64_t Ns,
                                    const int64_t* __restrict__ e2, int64_t ent_lo, float* __restrict__ gold) {
+  pdl_enter();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int64_t l = e2[b] - ent_lo;
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(kRankThreads) filtered_rank_kernel(
     const float* __restrict__ scores, int64_t ld, int B, int64_t Ns, const int64_t* __restrict__ e2, int64_t ent_lo,
     const float* __restrict__ gold, const uint32_t* __restrict__ filt, int32_t* __restrict__ n_greater,
     int32_t* __restrict__ n_equal) {
+  pdl_enter();
   __shared__ int sm_g[32], sm_e[32];
   int b = blockIdx.y;
   int64_t c0 = (int64_t)blockIdx.x * kRankChunk;
@@ -80,7 +82,7 @@ extern "C" {
 int coper_gold_scores(const float* scores, int64_t ld, int B, int64_t Ns, const int64_t* e2, int64_t ent_lo,
                       float* gold, coper_stream_t stream) {
   COPER_CHECK_ARG(scores && e2 && gold && B > 0 && Ns > 0 && ld >= Ns);
-  gold_scores_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(scores, ld, B, Ns, e2, ent_lo, gold);
+  launch_pdl(gold_scores_kernel, ceil_div(B, 128), 128, 0, as_stream(stream), scores, ld, B, Ns, e2, ent_lo, gold);
   return check_launch();
 }
 
@@ -90,8 +92,8 @@ int coper_filtered_rank(const float* scores, int64_t ld, int B, int64_t Ns, cons
   COPER_CHECK_ARG(scores && e2 && gold && filter_bits && n_greater && n_equal && B > 0 && Ns > 0 && ld >= Ns);
   COPER_CHECK_ARG(B <= 65535);
   dim3 grid(ceil_div(Ns, kRankChunk), B);
-  filtered_rank_kernel<<<grid, kRankThreads, 0, as_stream(stream)>>>(scores, ld, B, Ns, e2, ent_lo, gold, filter_bits,
-                                                                    n_greater, n_equal);
+  launch_pdl(filtered_rank_kernel, grid, kRankThreads, 0, as_stream(stream), scores, ld, B, Ns, e2, ent_lo, gold,
+             filter_bits, n_greater, n_equal);
   return check_launch();
 }
 

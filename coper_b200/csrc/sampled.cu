@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kSampWarps * 32) sampled_score_bce_kernel(
     const int32_t* __restrict__ lookup, const float* __restrict__ labels, int L, int64_t N, int d, float one_minus_eps,
     float inv_num_ent, float inv_count, double* __restrict__ loss_part, float* __restrict__ scores,
     float* __restrict__ g_out, float* __restrict__ dq) {
+  pdl_enter();
   __shared__ float red[kSampWarps][256];
   __shared__ double lred[kSampWarps];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kSampWarps * 32) sampled_score_bce_kernel(
 }
 
 __global__ void sum_loss_kernel(const double* __restrict__ in, int n, double* out) {
+  pdl_enter();
   __shared__ double smd[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += in[i];
@@ -87,6 +89,7 @@ __global__ void sum_loss_kernel(const double* __restrict__ in, int n, double* ou
 }
 
 __global__ void iota32_kernel(int32_t* p, int n) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = i;
 }
@@ -96,6 +99,7 @@ __global__ void sampled_scatter_kernel(const int32_t* __restrict__ keys, const i
                                        const float* __restrict__ g, const float* __restrict__ q, int d,
                                        float* __restrict__ dE_sum, float* __restrict__ dE_sq,
                                        float* __restrict__ db_sum, float* __restrict__ db_sq) {
+  pdl_enter();
   const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (seg >= M) return;
@@ -186,6 +190,7 @@ constexpr int kSampleThreads = 128;
 __global__ void __launch_bounds__(kSampleThreads) sample_labels_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int L, int n_pos_needed,
     const uint64_t* __restrict__ seed_dev, uint64_t salt, int32_t* __restrict__ lookup, float* __restrict__ labels) {
+  pdl_enter();
   __shared__ int32_t spos[kSampleSmall];       // the row's positives (membership test)
   __shared__ uint32_t sh[kSampleSmall];        // hashes of the rank permutation
   const int b = blockIdx.x;
@@ -265,8 +270,8 @@ int coper_sample_labels(const int32_t* rowptr, const int32_t* col, int B, int64_
                         const uint64_t* seed_dev, uint64_t salt, int32_t* lookup, float* labels, coper_stream_t stream) {
   COPER_CHECK_ARG(rowptr && col && seed_dev && lookup && labels && B > 0 && L > 0 && n_pos_needed >= 0);
   COPER_CHECK_ARG(N > 0 && N < (int64_t(1) << 31) && (int64_t)L <= N);
-  sample_labels_kernel<<<B, kSampleThreads, 0, as_stream(stream)>>>(rowptr, col, N, L, n_pos_needed, seed_dev, salt,
-                                                                    lookup, labels);
+  launch_pdl(sample_labels_kernel, B, kSampleThreads, 0, as_stream(stream), rowptr, col, N, L, n_pos_needed,
+             seed_dev, salt, lookup, labels);
   return check_launch();
 }
 
@@ -288,22 +293,22 @@ int coper_score_sampled_bce_fwd_bwd(const float* q, const float* E, const float*
   int32_t* keys_out = reinterpret_cast<int32_t*>(ws + S.off_keys_out);
   int32_t* pos_in = reinterpret_cast<int32_t*>(ws + S.off_pos_in);
   int32_t* pos_out = reinterpret_cast<int32_t*>(ws + S.off_pos_out);
-  sampled_score_bce_kernel<<<B, kSampWarps * 32, 0, st>>>(q, E, bias, lookup, labels, L, N, d, one_minus_eps,
-                                                         inv_num_ent, inv_count, loss_part, scores, g, dq);
+  launch_pdl(sampled_score_bce_kernel, B, kSampWarps * 32, 0, st, q, E, bias, lookup, labels, L, N, d, one_minus_eps,
+             inv_num_ent, inv_count, loss_part, scores, g, dq);
   int rc = check_launch();
   if (rc) return rc;
-  sum_loss_kernel<<<1, 256, 0, st>>>(loss_part, B, loss_sum);
+  launch_pdl(sum_loss_kernel, 1, 256, 0, st, loss_part, B, loss_sum);
   if ((rc = check_launch())) return rc;
   const int M = B * L;
-  iota32_kernel<<<ceil_div(M, 256), 256, 0, st>>>(pos_in, M);
+  launch_pdl(iota32_kernel, ceil_div(M, 256), 256, 0, st, pos_in, M);
   if ((rc = check_launch())) return rc;
   int end_bit = 1;
   while (end_bit < 31 && (int64_t(1) << end_bit) < N) ++end_bit;
   size_t cb = S.cub_bytes;
   rc = check_cuda(cub::DeviceRadixSort::SortPairs(ws + S.off_cub, cb, lookup, keys_out, pos_in, pos_out, M, 0, end_bit, st));
   if (rc) return rc;
-  sampled_scatter_kernel<<<ceil_div(M, 8), 256, 0, st>>>(keys_out, pos_out, M, L, g, q, d, dE_sum, dE_sq, dbias_sum,
-                                                         dbias_sq);
+  launch_pdl(sampled_scatter_kernel, ceil_div(M, 8), 256, 0, st, keys_out, pos_out, M, L, g, q, d, dE_sum, dE_sq,
+             dbias_sum, dbias_sq);
   return check_launch();
 }
 

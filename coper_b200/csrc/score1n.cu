@@ -47,6 +47,7 @@ template <int MODE>  // 0: write logits, 1: BCE epilogue (write G, loss partial,
 __global__ void __launch_bounds__(THREADS) score_kernel(const float* __restrict__ q, const float* __restrict__ E,
                                                         const float* __restrict__ bias, int B, int64_t Ns, int d,
                                                         float* __restrict__ out, int64_t ld, BceArgs bce) {
+  pdl_enter();
   __shared__ Smem sm;
   __shared__ float red32[32];
   // entity tiles on x (can be ~80k at 10M entities), batch tiles on y
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const float* __restrict_
 __global__ void __launch_bounds__(THREADS) dq_kernel(const float* __restrict__ G, int64_t ldG,
                                                      const float* __restrict__ E, int B, int64_t Ns, int d,
                                                      int tiles_per_split, float* __restrict__ part) {
+  pdl_enter();
   __shared__ Smem sm;
   int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, split = blockIdx.z;
   int ktiles = (int)((Ns + BK - 1) / BK);
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(THREADS) dq_kernel(const float* __restrict__ G
 __global__ void __launch_bounds__(THREADS) dE_kernel(const float* __restrict__ G, int64_t ldG,
                                                      const float* __restrict__ q, int B, int64_t Ns, int d,
                                                      float* __restrict__ dE) {
+  pdl_enter();
   __shared__ Smem sm;
   int64_t e0 = (int64_t)blockIdx.x * BM;
   int n0 = blockIdx.y * BN;
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(THREADS) dE_kernel(const float* __restrict__ G
 }
 
 __global__ void sum_to_double_kernel(const float* __restrict__ in, int64_t n, double* out) {
+  pdl_enter();
   __shared__ double smd[32];
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)in[i];
@@ -228,7 +232,7 @@ int coper_score1n_fwd(const float* q, const float* E, const float* bias, int B, 
     return umma_score1n_fwd(q, E, bias, B, Ns, d, scores, ld_scores, workspace, workspace_bytes, prec, as_stream(stream));
   dim3 grid(ceil_div(Ns, BN), ceil_div(B, BM));
   BceArgs none{};
-  score_kernel<0><<<grid, THREADS, 0, as_stream(stream)>>>(q, E, bias, B, Ns, d, scores, ld_scores, none);
+  launch_pdl(score_kernel<0>, grid, THREADS, 0, as_stream(stream), q, E, bias, B, Ns, d, scores, ld_scores, none);
   return check_launch();
 }
 
@@ -262,18 +266,19 @@ static int score1n_bce_impl(const float* q, const float* E, const void* E_prepar
   float* dbias_part = reinterpret_cast<float*>(ws + L.off_dbias);
   float* dq_part = reinterpret_cast<float*>(ws + L.off_dq);
   BceArgs bce{label_bits, (Ns + 31) / 32, pos_target, neg_target, inv_count, loss_part, dbias_part};
-  score_kernel<1><<<dim3(L.gx, L.gy), THREADS, 0, st>>>(q, E, bias, B, Ns, d, G, ldG, bce);
+  launch_pdl(score_kernel<1>, dim3(L.gx, L.gy), THREADS, 0, st, q, E, bias, B, Ns, d, G, ldG, bce);
   int rc = check_launch();
   if (rc) return rc;
-  sum_to_double_kernel<<<1, 1024, 0, st>>>(loss_part, (int64_t)L.gx * L.gy, loss_sum);
+  launch_pdl(sum_to_double_kernel, 1, 1024, 0, st, loss_part, (int64_t)L.gx * L.gy, loss_sum);
   if ((rc = check_launch())) return rc;
   rc = coper_reduce_partials(dbias_part, L.gy, Ns, 1.0f, 0, dbias, stream);
   if (rc) return rc;
-  dq_kernel<<<dim3(ceil_div(d, BN), L.gy, L.splits), THREADS, 0, st>>>(G, ldG, E, B, Ns, d, L.tiles_per_split, dq_part);
+  launch_pdl(dq_kernel, dim3(ceil_div(d, BN), L.gy, L.splits), THREADS, 0, st, G, ldG, E, B, Ns, d,
+             L.tiles_per_split, dq_part);
   if ((rc = check_launch())) return rc;
   rc = coper_reduce_partials(dq_part, L.splits, (int64_t)B * d, 1.0f, 0, dq, stream);
   if (rc) return rc;
-  dE_kernel<<<dim3(ceil_div(Ns, BM), ceil_div(d, BN)), THREADS, 0, st>>>(G, ldG, q, B, Ns, d, dE);
+  launch_pdl(dE_kernel, dim3(ceil_div(Ns, BM), ceil_div(d, BN)), THREADS, 0, st, G, ldG, q, B, Ns, d, dE);
   return check_launch();
 }
 

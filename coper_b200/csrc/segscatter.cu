@@ -11,6 +11,7 @@
 namespace coper {
 
 __global__ void iota_kernel(int32_t* p, int n) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = i;
 }
@@ -18,6 +19,7 @@ __global__ void iota_kernel(int32_t* p, int n) {
 __global__ void segscatter_kernel(const int64_t* __restrict__ keys, const int32_t* __restrict__ pos, int M,
                                   const float* __restrict__ src, int width, float* __restrict__ dst, int64_t row_lo,
                                   int64_t row_hi) {
+  pdl_enter();
   int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // candidate head position
   int lane = threadIdx.x & 31;
   if (seg >= M) return;
@@ -63,41 +65,56 @@ __device__ __forceinline__ void segscatter_small_warp(const int64_t* __restrict_
   if (norm_delta && lane == 0) norm_delta[i] = 0.0;
   const int64_t key = idx[i];
   if (key < row_lo || key >= row_hi) return;
-  bool dup = false;
-  for (int j0 = 0; j0 < i; j0 += 32) {
-    const int j = j0 + lane;
-    dup |= (j < i) && (__ldg(idx + j) == key);
-  }
-  if (__any_sync(0xffffffffu, dup)) return;          // an earlier position owns this row
   float* drow = dst + (key - row_lo) * (int64_t)width;
   float* qrow = dst_sq ? dst_sq + (key - row_lo) * (int64_t)width : nullptr;
   double delta = 0.0;
-  for (int c0 = 0; c0 < width; c0 += 32 * 4) {       // 4 columns per lane per pass
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j0 = (i / 32) * 32; j0 < M; j0 += 32) {
+  // ONE scan of the index array per 256-column pass (a single pass for every shipped width): positions before i only
+  // decide whether an earlier position owns this row; positions from i on are the members, added in index order.
+  // 8 columns per lane, so the source loads of a member and the destination loads are each one round trip.
+  for (int c0 = 0; c0 < width; c0 += 32 * 8) {
+    float a[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = q[k] = 0.f;
+    for (int j0 = 0; j0 < M; j0 += 32) {
       const int j = j0 + lane;
-      uint32_t m = __ballot_sync(0xffffffffu, j >= i && j < M && __ldg(idx + j) == key);
+      uint32_t m = __ballot_sync(0xffffffffu, j < M && __ldg(idx + j) == key);
+      if (j0 + 32 <= i) {                              // every position of this group precedes i
+        if (m) return;                                 // an earlier position owns this row
+        continue;
+      }
+      if (j0 <= i) {                                   // the group that holds i
+        if (m & ((1u << (i - j0)) - 1u)) return;
+        m &= ~((1u << (i - j0)) - 1u);
+      }
       while (m) {
         const int jj = j0 + __ffs(m) - 1;
         m &= m - 1;
+        float v[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
           const int c = c0 + lane + 32 * k;
-          if (c < width) {
-            const float v = __ldg(src + (int64_t)jj * width + c);
-            a[k] += v;
-            q[k] = fmaf(v, v, q[k]);
-          }
+          v[k] = c < width ? __ldg(src + (int64_t)jj * width + c) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a[k] += v[k];
+          q[k] = fmaf(v[k], v[k], q[k]);
         }
       }
     }
+    float old[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + lane + 32 * k;
+      old[k] = c < width ? drow[c] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
       const int c = c0 + lane + 32 * k;
       if (c < width) {
-        const float old = drow[c], nw = old + a[k];
+        const float nw = old[k] + a[k];
         drow[c] = nw;
-        delta += (double)nw * (double)nw - (double)old * (double)old;
+        delta += (double)nw * (double)nw - (double)old[k] * (double)old[k];
         if (qrow) qrow[c] += q[k];
       }
     }
@@ -162,6 +179,7 @@ __device__ __forceinline__ void segscatter_row_block(const SegSmallJob& J, int r
 // relations - in one launch; B.M == 0: single job).  b_row_owner: job B runs one block per table row.
 __global__ void __launch_bounds__(256) segscatter_small_kernel(SegSmallJob A, int blocks_a, SegSmallJob Bj,
                                                                int b_row_owner) {
+  pdl_enter();
   __shared__ uint16_t list[kSegSmallM];
   __shared__ int warp_cnt[8];
   __shared__ int base;
@@ -205,7 +223,7 @@ int coper_segscatter_add_sq(const int64_t* idx, int M, const float* src, int wid
   if (M > kSegSmallM) return COPER_ERR_UNSUPPORTED;
   if (M == 0) return COPER_OK;
   SegSmallJob A{idx, M, src, width, dst, dst_sq, row_lo, row_hi, nullptr};
-  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(A, ceil_div(M, 8), SegSmallJob{}, 0);
+  launch_pdl(segscatter_small_kernel, ceil_div(M, 8), 256, 0, as_stream(stream), A, ceil_div(M, 8), SegSmallJob{}, 0);
   return check_launch();
 }
 
@@ -215,7 +233,7 @@ int coper_segscatter_add_norm(const int64_t* idx, int M, const float* src, int w
   if (M > kSegSmallM) return COPER_ERR_UNSUPPORTED;
   if (M == 0) return COPER_OK;
   SegSmallJob A{idx, M, src, width, dst, dst_sq, row_lo, row_hi, norm_delta};
-  segscatter_small_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(A, ceil_div(M, 8), SegSmallJob{}, 0);
+  launch_pdl(segscatter_small_kernel, ceil_div(M, 8), 256, 0, as_stream(stream), A, ceil_div(M, 8), SegSmallJob{}, 0);
   return check_launch();
 }
 
@@ -230,7 +248,7 @@ int coper_segscatter_add_pair(const int64_t* idx_a, int M_a, const float* src_a,
   SegSmallJob Bj{idx_b, M_b, src_b, width_b, dst_b, dst_sq_b, lo_b, hi_b, nullptr};
   const int row_owner = hi_b - lo_b <= kSegRowOwnerRows && hi_b > lo_b;
   const int ba = ceil_div(M_a, 8), bb = row_owner ? (int)(hi_b - lo_b) : ceil_div(M_b, 8);
-  segscatter_small_kernel<<<ba + bb, 256, 0, as_stream(stream)>>>(A, ba, Bj, row_owner);
+  launch_pdl(segscatter_small_kernel, ba + bb, 256, 0, as_stream(stream), A, ba, Bj, row_owner);
   return check_launch();
 }
 
@@ -246,13 +264,13 @@ int coper_segscatter_add(const int64_t* idx, int M, const float* src, int width,
   int64_t* keys_out = reinterpret_cast<int64_t*>(ws + L.off_keys_out);
   int32_t* pos_in = reinterpret_cast<int32_t*>(ws + L.off_pos_in);
   int32_t* pos_out = reinterpret_cast<int32_t*>(ws + L.off_pos_out);
-  iota_kernel<<<ceil_div(M, 256), 256, 0, st>>>(pos_in, M);
+  launch_pdl(iota_kernel, ceil_div(M, 256), 256, 0, st, pos_in, M);
   int rc = check_launch();
   if (rc) return rc;
   size_t cb = L.cub_bytes;
   rc = check_cuda(cub::DeviceRadixSort::SortPairs(ws + L.off_cub, cb, idx, keys_out, pos_in, pos_out, M, 0, 64, st));
   if (rc) return rc;
-  segscatter_kernel<<<ceil_div(M, 8), 256, 0, st>>>(keys_out, pos_out, M, src, width, dst, row_lo, row_hi);
+  launch_pdl(segscatter_kernel, ceil_div(M, 8), 256, 0, st, keys_out, pos_out, M, src, width, dst, row_lo, row_hi);
   return check_launch();
 }
 

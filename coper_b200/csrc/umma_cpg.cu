@@ -138,6 +138,7 @@ using CpgBwdTCfg = GemmCfg<PREC, kBwdTBlockN, (PREC == PREC_BF16 ? 4 : 3), kBwdT
 // trailer[1] (zeroed before the launch)
 __global__ void absmax_scaled_kernel(const float* __restrict__ dy, const float* __restrict__ c, int B, int d, int dc,
                                      uint32_t* __restrict__ trailer) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.x * (blockDim.x >> 5)) {
     float my = 0.f, mc = 0.f;
@@ -155,6 +156,7 @@ __global__ void absmax_scaled_kernel(const float* __restrict__ dy, const float* 
 // dyc[(g*B + b), j] = dy[b,j] * c[b,g] in prepared operand form
 __global__ void prepare_scaled_kernel(const float* __restrict__ dy, const float* __restrict__ c, int B, int d, int dc,
                                       int64_t ldp, int prec, void* __restrict__ dst, uint32_t* __restrict__ trailer) {
+  pdl_enter();
   int64_t n = (int64_t)dc * B * ldp;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float sc = 1.0f;
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(256) cpg_bwd_prepare_fp16x3_kernel(const float
                                                                      __half* __restrict__ dycp,
                                                                      uint32_t* __restrict__ tr_dy,
                                                                      uint32_t* __restrict__ tr_dyc) {
+  pdl_enter();
   __shared__ float wmax[2][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float m_dy = 0.f, m_dyc = 0.f;
@@ -345,8 +348,8 @@ int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_p
       const int64_t want = ((int64_t)(1 + dc) * B * (ldp / 8) + 256 * 4 - 1) / (256 * 4);
       int g = (int)(want < (int64_t)sm_count() * 2 ? want : (int64_t)sm_count() * 2);
       if (g < 1) g = 1;
-      cpg_bwd_prepare_fp16x3_kernel<<<g, 256, 0, st>>>(dy, c, B, d, dc, ldp, static_cast<__half*>(dyp),
-                                                       static_cast<__half*>(dycp), tr_dy, tr_dyc);
+      launch_pdl(cpg_bwd_prepare_fp16x3_kernel, g, 256, 0, st, dy, c, B, d, dc, ldp, static_cast<__half*>(dyp),
+                 static_cast<__half*>(dycp), tr_dy, tr_dyc);
       if ((rc = check_launch())) return rc;
     } else {
       if ((rc = tc_prepare(dy, B, d, d, prec, dyp, st))) return rc;
@@ -355,10 +358,10 @@ int umma_cpg_bwd(const float* c, const float* f, const float* P, const void* P_p
       if (prec == COPER_PREC_FP16X3) {
         trailer = static_cast<uint32_t*>(tc_fp16x3_trailer(dycp, (int64_t)dc * B, d));
         if ((rc = check_cuda(cudaMemsetAsync(trailer, 0, 8, st)))) return rc;
-        absmax_scaled_kernel<<<(B + 7) / 8, 256, 0, st>>>(dy, c, B, d, dc, trailer);
+        launch_pdl(absmax_scaled_kernel, (B + 7) / 8, 256, 0, st, dy, c, B, d, dc, trailer);
         if ((rc = check_launch())) return rc;
       }
-      prepare_scaled_kernel<<<grid, 256, 0, st>>>(dy, c, B, d, dc, ldp, prec, dycp, trailer);
+      launch_pdl(prepare_scaled_kernel, grid, 256, 0, st, dy, c, B, d, dc, ldp, prec, dycp, trailer);
       if ((rc = check_launch())) return rc;
     }
     // ---- T kernel: df, dc partials

@@ -379,6 +379,7 @@ struct DiagEpiT : EpiBase {
 __global__ void gather_prepared_kernel(const uint4* __restrict__ src, int64_t Ns, int vec_per_row, int planes,
                                        const int64_t* __restrict__ e2, int64_t ent_lo, int B, uint4* __restrict__ dst,
                                        const int* __restrict__ src_exp, int* __restrict__ dst_exp) {
+  pdl_enter();
   int b = blockIdx.x;
   if (src_exp && b == 0 && threadIdx.x == 0) *dst_exp = *src_exp;      // fp16x3: the gathered rows keep E's exponent
   int64_t l = e2[b] - ent_lo;
@@ -391,6 +392,7 @@ __global__ void gather_prepared_kernel(const uint4* __restrict__ src, int64_t Ns
 }
 
 __global__ void sum_doubles_kernel(const double* __restrict__ in, int n, double* out) {
+  pdl_enter();
   __shared__ double smd[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += in[i];
@@ -516,9 +518,8 @@ int umma_score1n_gold(const void* q_prep, const void* E_prep, const float* bias,
     src_exp = static_cast<const int*>(tc_fp16x3_trailer(E_prep, Ns, d));
     dst_exp = static_cast<int*>(tc_fp16x3_trailer(ws, B, d));
   }
-  gather_prepared_kernel<<<B, 64, 0, st>>>(static_cast<const uint4*>(E_prep), Ns, vec_per_row,
-                                           prec == COPER_PREC_BF16 ? 1 : 2, e2, ent_lo, B, static_cast<uint4*>(ws),
-                                           src_exp, dst_exp);
+  launch_pdl(gather_prepared_kernel, B, 64, 0, st, static_cast<const uint4*>(E_prep), Ns, vec_per_row, prec ==
+             COPER_PREC_BF16 ? 1 : 2, e2, ent_lo, B, static_cast<uint4*>(ws), src_exp, dst_exp);
   int rc = check_launch();
   if (rc) return rc;
   TcOperand Q = tc_operand(q_prep, B, d, prec), Eg = tc_operand(ws, B, d, prec);
@@ -563,7 +564,7 @@ static int dE_gemm(int prec, bool a_mn, const TcOperand& Go, const TcOperand& Qo
   }
   if ((rc = tc_gemm_store(prec, a_mn, true, Go, Qo, p, false, epi, st))) return rc;
   if (dE_sumsq) {
-    sum_doubles_kernel<<<1, 256, 0, st>>>(ss_part, n_part, dE_sumsq);
+    launch_pdl(sum_doubles_kernel, 1, 256, 0, st, ss_part, n_part, dE_sumsq);
     rc = check_launch();
   }
   return rc;

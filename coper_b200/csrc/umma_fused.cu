@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(fz::kThreads, 1)
 bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constant__ CUtensorMap tQ,
                     const __grid_constant__ CUtensorMap tG, const fz::Params p) {
   using namespace fz;
+  coper::pdl_trigger();                          // the next kernel of the stream may be scheduled (common.cuh)
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();          // the swizzled operand tiles need 1024-byte alignment
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -88,6 +89,7 @@ bce_dq_fused_kernel(const __grid_constant__ CUtensorMap tE, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  coper::pdl_wait();                             // barriers / TMEM are set up; from here on the predecessor's output is read
 
   const int qb = blockIdx.x % p.QB, rr = blockIdx.x / p.QB;
   const int t0 = (int)((int64_t)rr * p.m_tiles / p.R), t1 = (int)((int64_t)(rr + 1) * p.m_tiles / p.R);
@@ -359,7 +361,7 @@ int umma_bce_dq_fused(const TcOperand& E, const TcOperand& Q, const float* bias,
   }
   const int grid = p.QB * p.R;
   *grid_out = grid;
-  bce_dq_fused_kernel<<<grid, kThreads, kSmemBytes, st>>>(tE, tQ, tG, p);
+  launch_pdl(bce_dq_fused_kernel, grid, kThreads, kSmemBytes, st, tE, tQ, tG, p);
   return check_launch();
 }
 

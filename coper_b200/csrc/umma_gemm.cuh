@@ -289,9 +289,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tA, const __grid_constant__ CUtensorMap tAlo,
                  const __grid_constant__ CUtensorMap tB, const __grid_constant__ CUtensorMap tBlo,
                  const GemmProblem p, Epi epi) {
+  coper::pdl_trigger();                          // the next kernel of the stream may be scheduled (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   SmemLayout<Cfg> sm(smem_raw);
   uint32_t tmem_base = cta_setup<Cfg>(sm);
+  coper::pdl_wait();                             // barriers / TMEM are set up; from here on the predecessor's output is read
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const long long supers = gemm_supers(p);
   const int g_loop = p.groups_inner ? p.groups : 1;
@@ -552,7 +554,7 @@ int launch_gemm(const TcOperand& A, const TcOperand& B, const GemmProblem& p, co
   int grid = (int)(supers < sms ? supers : sms);
   if (grid_override > 0 && grid_override < grid) grid = grid_override;
   if (grid < 1) return COPER_ERR_INVALID_ARG;
-  umma_gemm_kernel<Cfg, Epi><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tAlo, tB, tBlo, pp, epi);
+  launch_pdl(umma_gemm_kernel<Cfg, Epi>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, tA, tAlo, tB, tBlo, pp, epi);
   return check_launch();
 }
 

@@ -19,6 +19,7 @@ static inline int64_t prepared_ld(int cols, int prec) { return prec == COPER_PRE
 template <int PREC>
 __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ src, int64_t rows, int cols,
                                                       int64_t ld_src, void* __restrict__ dst, int64_t ldp) {
+  pdl_enter();
   constexpr int VEC = PREC == COPER_PREC_BF16 ? 8 : 4;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int nvec = (int)(ldp / VEC);
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const float* __restrict__ 
 // from the accumulators by the consuming kernels (umma_gemm.cuh, SCALED).
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src,
                                                      uint32_t* __restrict__ trailer) {
+  pdl_enter();
   float m = 0.f;
   if (ld_src == cols) {                                // dense: one flat stream (16-byte loads when aligned)
     const int64_t n = rows * cols;
@@ -99,6 +101,7 @@ __device__ __forceinline__ int fp16x3_exponent(uint32_t absmax_bits) { return fp
 __global__ void __launch_bounds__(256) prepare_fp16x3_kernel(const float* __restrict__ src, int64_t rows, int cols,
                                                              int64_t ld_src, __half* __restrict__ dst, int64_t ldp,
                                                              uint32_t* __restrict__ trailer) {
+  pdl_enter();
   const int e = fp16x3_exponent(trailer[1]);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     reinterpret_cast<int*>(trailer)[0] = e;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256) prepare_fp16x3_kernel(const float* __rest
 __global__ void __launch_bounds__(256) prepare_fp16x3_fused_kernel(const float* __restrict__ src, int64_t rows, int cols,
                                                                    int64_t ld_src, __half* __restrict__ dst, int64_t ldp,
                                                                    uint32_t* __restrict__ trailer) {
+  pdl_enter();
   __shared__ float wmax[8];
   // work unit = one 8-column group of one row (ldp / 8 groups per row); consecutive threads take consecutive groups
   const int gpr = (int)(ldp / 8);
@@ -234,9 +238,9 @@ static int prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int
   int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
   if (grid < 1) grid = 1;
   if (prec == COPER_PREC_BF16)
-    prepare_kernel<COPER_PREC_BF16><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ldp);
+    launch_pdl(prepare_kernel<COPER_PREC_BF16>, grid, 256, 0, st, src, rows, cols, ld_src, dst, ldp);
   else if (prec == COPER_PREC_TF32X3)
-    prepare_kernel<COPER_PREC_TF32X3><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ldp);
+    launch_pdl(prepare_kernel<COPER_PREC_TF32X3>, grid, 256, 0, st, src, rows, cols, ld_src, dst, ldp);
   else if (prec == COPER_PREC_FP16X3) {
     uint32_t* trailer = static_cast<uint32_t*>(tc_fp16x3_trailer(dst, rows, cols));
     int rc = check_cuda(cudaMemsetAsync(trailer, 0, 16, st));
@@ -247,13 +251,15 @@ static int prepare(const float* src, int64_t rows, int cols, int64_t ld_src, int
       const int64_t want = (rows * (ldp / 8) + 256 * 4 - 1) / (256 * 4);
       int g = (int)(want < (int64_t)sm_count() * 2 ? want : (int64_t)sm_count() * 2);
       if (g < 1) g = 1;
-      prepare_fp16x3_fused_kernel<<<g, 256, 0, st>>>(src, rows, cols, ld_src, static_cast<__half*>(dst), ldp, trailer);
+      launch_pdl(prepare_fp16x3_fused_kernel, g, 256, 0, st, src, rows, cols, ld_src, static_cast<__half*>(dst), ldp,
+                 trailer);
       return check_launch();
     }
     int g1 = (int)((n + 2047) / 2048 < sm_count() * 8 ? (n + 2047) / 2048 : sm_count() * 8);
-    absmax_kernel<<<g1 < 1 ? 1 : g1, 256, 0, st>>>(src, rows, cols, ld_src, trailer);
+    launch_pdl(absmax_kernel, g1 < 1 ? 1 : g1, 256, 0, st, src, rows, cols, ld_src, trailer);
     if ((rc = check_launch())) return rc;
-    prepare_fp16x3_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, static_cast<__half*>(dst), ldp, trailer);
+    launch_pdl(prepare_fp16x3_kernel, grid, 256, 0, st, src, rows, cols, ld_src, static_cast<__half*>(dst), ldp,
+               trailer);
   } else
     return COPER_ERR_UNSUPPORTED;
   return check_launch();

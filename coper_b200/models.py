@@ -30,13 +30,15 @@ one fused kernel).
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 
 from . import _lib, sharding
-from ._lib import CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_REUSE_FWD, CPG_BWD_WEIGHT_GRADS_ONLY, PREC, call, ptr
+from ._lib import (CPG_BWD_DCB_ACCUMULATE, CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_REUSE_FWD, CPG_BWD_WEIGHT_GRADS_ONLY, PREC,
+                   call, ptr)
 from .sharding import EntityShard
 
 BN_EPS = 1e-3           # tf.layers.batch_normalization default epsilon (models.py:386-388)
@@ -186,6 +188,7 @@ class ConvE:
         self.overlap_entity_grad = bool(overlap_entity_grad)
         self._side = torch.cuda.Stream(device=self.dev)
         self._side_pending = False
+        self._split_cpg_bwd = os.environ.get("COPER_SPLIT_CPG_BWD", "1") != "0"      # (A/B switch for measurements)
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
         # and replayed with one launch.  The sharded path captures its NCCL collectives into the same graph
@@ -935,11 +938,17 @@ class ConvE:
         nw, nb = len(self.fc_weights.projections) - 1, len(self.fc_bias.projections) - 1
         # the generator's weight gradients (dP^, dPb) feed nothing but the clip / optimizer: with the side stream on,
         # they are computed there while the chain through df / dc continues
-        split_w = self.overlap_entity_grad and not dp and self.variant != "param_lookup"
+        split_w = self.overlap_entity_grad and not dp and self.variant != "param_lookup" and self._split_cpg_bwd
         reuse = CPG_BWD_REUSE_FWD if self.prec != 0 else 0
+        # g_linear (no hidden generator layers: both contexts ARE the relation embedding): d rel_emb = dc + dcb is formed
+        # by the call itself - dc lands in b.dr, the bias generator's dcb is added to it
+        linear = self.variant == "cpg" and not self.fc_weights.hidden and not self.fc_bias.hidden
+        if linear:
+            reuse |= CPG_BWD_DCB_ACCUMULATE
+        dcw_out, dcb_out = (b.dr, b.dr) if linear else (b.dcw, b.dcb)
         cpg_bwd_args = (ptr(b.cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(b.cb), ptr(Pb), ptr(b.dy), B,
                         Pw.shape[0], F, d, Pb.shape[0], ptr(g[self._last_w_name]), ptr(g[self._last_b_name]),
-                        ptr(b.df), ptr(b.dcw), ptr(b.dcb), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec)
+                        ptr(b.df), ptr(dcw_out), ptr(dcb_out), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec)
         call("coper_cpg_fc_bwd", *cpg_bwd_args, reuse | (CPG_BWD_INPUT_GRADS_ONLY if split_w else 0))
         if split_w:
             self._side.wait_stream(torch.cuda.current_stream())
@@ -959,7 +968,7 @@ class ConvE:
         big_work = None
         if dp and self.group_big is not None:
             big_work = sharding.reduce_replicated_grads(self.flat_big, self.world, self.group_big, async_op=True)
-        if self.variant == "cpg":
+        if self.variant == "cpg" and not linear:
             self._ctx_backward(self.fc_weights, 0, b, b.dcw, b.dr, False)
             self._ctx_backward(self.fc_bias, 1, b, b.dcb, b.dr, True)
         # conv block backward: feature-map dropout -> relu -> Conv1BN -> conv (models.py:373-391)

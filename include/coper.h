@@ -168,6 +168,9 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
 #define COPER_CPG_BWD_REUSE_FWD 1
 #define COPER_CPG_BWD_INPUT_GRADS_ONLY 2
 #define COPER_CPG_BWD_WEIGHT_GRADS_ONLY 4
+/* dcb_out += instead of = (a caller whose two generators read the same context - the reference's g_linear setup, context =
+ * relation embedding for weights and bias - passes the same [B, dc] buffer as dc_out and dcb_out and gets their sum) */
+#define COPER_CPG_BWD_DCB_ACCUMULATE 8
 size_t coper_cpg_fc_bwd_workspace_bytes(int B, int dc, int F, int d, int prec);
 int coper_cpg_fc_bwd(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
                      const float* Pb, const float* dy, int B, int dc, int F, int d, int dcb, float* dP, float* dPb, float* df,
