@@ -24,6 +24,8 @@ SIGNATURES = {
     "coper_last_cuda_error": (i32, []),
     "coper_launch_count": (C.c_longlong, []),
     "coper_device_is_sm100": (i32, []),
+    "coper_set_sm_budget": (i32, [i32]),
+    "coper_set_pdl": (i32, [i32]),
     "coper_gather_rows": (i32, [vp, i64, i64, i32, vp, i32, vp, vp]),
     "coper_gather_rows2": (i32, [vp, i64, i64, i32, vp, i32, vp, vp, i64, i64, i32, vp, i32, vp, vp, vp, f32, f32, f32, vp]),
     "coper_conv_fwd": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
@@ -137,6 +139,11 @@ def ptr(t):
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def call_plain(name, *args):
+    """Invoke a status-returning entry point that takes no stream."""
+    check(getattr(load(), name)(*args), name)
 
 
 def call(name, *args):

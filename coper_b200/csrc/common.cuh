@@ -8,6 +8,7 @@ namespace coper {
 
 extern thread_local int g_last_cuda_error;
 extern long long g_launch_count;  // kernels launched by this library (every launch is followed by check_launch)
+extern thread_local int g_sm_budget;   // coper_set_sm_budget: grid cap of the persistent tcgen05 kernels (0 = all SMs)
 
 inline int check_launch() {
   ++g_launch_count;

@@ -38,7 +38,7 @@ import torch
 
 from . import _lib, sharding
 from ._lib import (CPG_BWD_DCB_ACCUMULATE, CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_REUSE_FWD, CPG_BWD_WEIGHT_GRADS_ONLY, PREC,
-                   call, ptr)
+                   call, call_plain, ptr)
 from .sharding import EntityShard
 
 BN_EPS = 1e-3           # tf.layers.batch_normalization default epsilon (models.py:386-388)
@@ -189,6 +189,11 @@ class ConvE:
         self._side = torch.cuda.Stream(device=self.dev)
         self._side_pending = False
         self._split_cpg_bwd = os.environ.get("COPER_SPLIT_CPG_BWD", "1") != "0"      # (A/B switch for measurements)
+        # programmatic dependent launch pays on the launch-bound steps of the named datasets and costs on the HBM-bound
+        # step of a 10 M-row table: per model, by the size of the entity table
+        self._pdl = int(self.shard.rows) * int(self.ent_emb_size) <= (64 << 20)
+        # SMs the side stream's persistent GEMMs may take (coper_set_sm_budget; 0 = all)
+        self._side_sms = int(os.environ.get("COPER_SIDE_SMS", "0"))
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
         # (step counter, dropout seed and clip scale live in device memory), so it is captured once per batch size
         # and replayed with one launch.  The sharded path captures its NCCL collectives into the same graph
@@ -735,6 +740,10 @@ class ConvE:
         call("coper_bn_act_bwd_apply", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
              ptr(bn.c1), ptr(bn.c2), int(relu), keep_post, ptr(self.seed_dev), salt_post, keep_pre, salt_pre, ptr(dx))
 
+    def _side_budget(self, on: bool):
+        if self._side_sms > 0:
+            call_plain("coper_set_sm_budget", self._side_sms if on else 0)
+
     def _gather_stats(self, b, n):
         if getattr(b, "stat_all", None) is None:
             b.stat_all = torch.zeros(self.world * b.stat.numel(), dtype=torch.float32, device=self.dev)
@@ -911,8 +920,10 @@ class ConvE:
                         g["rel_emb"].zero_()
                         self.grad_sq["rel_emb"].zero_()
                         rel_cleared = True
+                    self._side_budget(True)
                     call("coper_score1n_bce_dE", ptr(self._grad_buf(bg)), bg.B, Ns, d, inv_count, ptr(g["ent_emb"]),
                          ptr(self.dE_sumsq), ptr(g["pred_bias"]), ptr(bg.ws), bg.ws_bytes, self.prec)
+                    self._side_budget(False)
                     if self.world == 1:              # the mean loss the caller reads (models.py:451)
                         torch.div(bg.loss_sum, float(bg.B) * float(self.num_ent), out=bg.loss_mean)
                         loss_done = True
@@ -953,7 +964,9 @@ class ConvE:
         if split_w:
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
+                self._side_budget(True)
                 call("coper_cpg_fc_bwd", *cpg_bwd_args, reuse | CPG_BWD_WEIGHT_GRADS_ONLY)
+                self._side_budget(False)
             self._side_pending = True
         if self.variant == "param_lookup":
             # the tables are read through embedding_lookup (models.py:91): IndexedSlices gradients, one [F*d] / [d]
@@ -1121,17 +1134,25 @@ class ConvE:
             self.refresh_prepared()
 
     # ------------------------------------------------------------------------------------------
+    def _launch_mode(self):
+        """Process-wide launch switches of the library, set before this model enqueues kernels (a replayed graph keeps
+        what it was captured with)."""
+        call_plain("coper_set_pdl", int(self._pdl))
+
     def _run_graphed(self, key, fn):
         """First call: eager (allocates buffers, sets kernel attributes).  Second call: capture, then replay."""
         if not self.use_graphs or (self.world > 1 and not self.graphs_multi_gpu):
+            self._launch_mode()
             fn()
             return
         st = self._graphs.get(key)
         if st is None:
+            self._launch_mode()
             fn()
             self._graphs[key] = "warm"
             return
         if st == "warm":
+            self._launch_mode()
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             lib = _lib.load()
@@ -1154,6 +1175,7 @@ class ConvE:
         if not apply_update:
             saved = self._clip_and_apply
             self._clip_and_apply = lambda: None
+            self._launch_mode()
             try:
                 self._train_device(b)
             finally:
@@ -1199,6 +1221,7 @@ class ConvE:
         if not apply_update:
             saved = self._clip_and_apply
             self._clip_and_apply = lambda: None
+            self._launch_mode()
             try:
                 self._train_device(b)
             finally:
@@ -1212,6 +1235,7 @@ class ConvE:
     def predict_all(self, batch: Dict):
         """Logits of every query against this rank's entity rows: [B, rows] view (metrics.py:40-42)."""
         b = self.stage_batch(batch)
+        self._launch_mode()
         if self.dp and b.B % self.world == 0:
             self._forward_q_dp(b, self._local_buffers(b), False)
         else:

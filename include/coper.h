@@ -53,6 +53,17 @@ const char* coper_status_string(int status);
 int coper_last_cuda_error(void);
 /* number of kernels this library has launched in this process (bench.py reports the per-step delta) */
 long long coper_launch_count(void);
+/* Programmatic dependent launch between consecutive kernels of a stream (every kernel of the library is launched with
+ * the programmatic-stream-serialization attribute and begins with griddepcontrol.launch_dependents / .wait): on by
+ * default; worth ~8 % on the launch-bound evaluation step of the named datasets, and measured to COST ~10 % on the
+ * HBM-bound 10 M-entity step - a caller with tables of that size switches it off.  COPER_PDL=0 in the
+ * environment forces it off. */
+int coper_set_pdl(int on);
+/* Persistent tcgen05 kernels launched by the calling thread after this call use at most n_sms CTAs (one per SM); 0 = all
+ * SMs (default).  For a caller that runs an independent GEMM of the step on a second stream (coper_score1n_bce_dE, the
+ * weight-gradient half of coper_cpg_fc_bwd): a persistent kernel on every SM leaves no room for the other stream's
+ * kernels, a share does. */
+int coper_set_sm_budget(int n_sms);
 /* 1 if the running device is compute capability 10.x (tcgen05 paths usable), 0 otherwise, <0 on error */
 int coper_device_is_sm100(void);
 
