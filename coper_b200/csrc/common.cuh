@@ -86,6 +86,17 @@ __device__ __forceinline__ float drop_factor(float keep, float inv_keep, uint32_
   return hash32(seed, idx) < thr ? inv_keep : 0.0f;
 }
 
+// dx of batch norm + relu + post-dropout for one element (without the pre-dropout factor): g1 = dout * drop_post *
+// relu'(a x + b); dx = a (g1 - c1 - xhat c2).  One definition with explicit roundings, shared by coper_bn_act_bwd_apply and
+// the conv backward that consumes dout directly (coper_conv_bwd_bn) - the two give the same bits.
+__device__ __forceinline__ float bn_bwd_dx(float dout, float post_factor, float xv, float ac, float bc, float mean,
+                                           float invstd, float c1, float c2, int relu) {
+  float g = __fmul_rn(dout, post_factor);
+  if (relu && !(fmaf(ac, xv, bc) > 0.f)) g = 0.f;
+  const float xhat = __fmul_rn(__fsub_rn(xv, mean), invstd);
+  return __fmul_rn(ac, fmaf(-xhat, c2, __fsub_rn(g, c1)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -145,19 +145,46 @@ __global__ void __launch_bounds__(256) conv3x3_fwd_kernel(const float* __restric
 // taps + bias gradient in registers with the same sliding window; phase 2 (warp per pixel, lanes = channels) forms dx.
 // The per-CTA filter / bias partials (IMG images, 8 h-slices) are combined in shared memory in a fixed order:
 // dwc_part / dbc_part get ONE slab per CTA.
-template <int IMG>
+// BN = true: `dz` is the gradient w.r.t. the OUTPUT of the batch-norm / relu / dropout block that follows the conv
+// (models.py:386-391) and `bn.z` the conv output: the block's backward (coper_bn_act_bwd_apply, keep_pre = 1) is applied
+// while the tile is staged in shared memory - its [B, OH*OW*C] result is never written to HBM.
+struct ConvBnBwd {
+  const float* z;
+  const float* a;
+  const float* b;
+  const float* mean;
+  const float* invstd;
+  const float* c1;
+  const float* c2;
+  int relu;
+  float keep, inv_keep;
+  uint32_t thr;
+  const uint64_t* seed_dev;
+  uint64_t salt;
+};
+template <int IMG, bool BN>
 __global__ void __launch_bounds__(256) conv3x3_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x0,
                                                           int B, int H, int W, const float* __restrict__ wc,
                                                           float* __restrict__ dx0, float* __restrict__ dwc_part,
-                                                          float* __restrict__ dbc_part) {
+                                                          float* __restrict__ dbc_part, ConvBnBwd bn) {
   pdl_enter();
   extern __shared__ float sm[];
+  __shared__ float bnp[BN ? 6 : 1][kFastC];
   const int c = threadIdx.x & 31, hs = threadIdx.x >> 5, lane = c;
   const int OH = H - 2, OW = W - 2, HW = H * W, total = OH * OW * kFastC;
   float* img = sm;                  // HW
   float* dzs = img + HW;            // total
   float* red = dzs + total;         // 8 * 10 * 32
   const int b0 = blockIdx.x * IMG;
+  uint64_t seed = 0;
+  if (BN) {
+    seed = (bn.seed_dev ? *bn.seed_dev : 0ull) + bn.salt;
+    if (threadIdx.x < kFastC) {
+      const int ch = threadIdx.x;
+      bnp[0][ch] = bn.a[ch]; bnp[1][ch] = bn.b[ch]; bnp[2][ch] = bn.mean[ch];
+      bnp[3][ch] = bn.invstd[ch]; bnp[4][ch] = bn.c1[ch]; bnp[5][ch] = bn.c2[ch];
+    }
+  }
   float wr[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) wr[k] = __ldg(wc + k * kFastC + c);
@@ -169,10 +196,26 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_kernel(const float* __restric
     if (b >= B) break;
     __syncthreads();
     for (int i = threadIdx.x; i < HW; i += 256) img[i] = x0[(int64_t)b * HW + i];
-    {
+    if (!BN) {
       const float4* src = reinterpret_cast<const float4*>(dz + (int64_t)b * total);
       float4* dst = reinterpret_cast<float4*>(dzs);
       for (int i = threadIdx.x; i < total / 4; i += 256) dst[i] = __ldg(src + i);
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(dz + (int64_t)b * total);
+      const float4* zsrc = reinterpret_cast<const float4*>(bn.z + (int64_t)b * total);
+      float4* dst = reinterpret_cast<float4*>(dzs);
+      for (int i = threadIdx.x; i < total / 4; i += 256) {
+        const float4 g4 = __ldg(src + i), z4 = __ldg(zsrc + i);
+        const int ch = (i * 4) & (kFastC - 1);
+        const uint64_t e = (uint64_t)b * (uint64_t)total + (uint64_t)i * 4u;
+        const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          o[k] = bn_bwd_dx(gs[k], drop_factor(bn.keep, bn.inv_keep, bn.thr, seed, e + k), zs[k], bnp[0][ch + k],
+                           bnp[1][ch + k], bnp[2][ch + k], bnp[3][ch + k], bnp[4][ch + k], bnp[5][ch + k], bn.relu);
+        dst[i] = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
     __syncthreads();
     // phase 1: filter / bias gradient, thread (c, h = hs, hs + 8, ...)
@@ -248,7 +291,7 @@ int coper_conv_fwd(const float* x0, int B, int H, int W, const float* wc, const 
 int coper_conv_bwd_slabs(int B, int H, int W, int KH, int KW, int C, int per_query) {
   int OH = H - KH + 1, OW = W - KW + 1;
   size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
-  if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3 && sm_fast <= 48 * 1024 &&
+  if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3 && sm_fast <= 47 * 1024 &&
       (OH * OW * C) % 4 == 0)
     return (B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd;
   return B;
@@ -262,9 +305,9 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
   if (H * W > kMaxImg || KH * KW * C > kMaxFilt || smem > 200 * 1024) return COPER_ERR_UNSUPPORTED;
   if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3) {
     size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
-    if (sm_fast <= 48 * 1024 && (OH * OW * C) % 4 == 0) {
-      launch_pdl(conv3x3_bwd_kernel<kConvImgPerCtaBwd>, (B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd, 256,
-                 sm_fast, as_stream(stream), dz, x0, B, H, W, wc, dx0, dwc_part, dbc_part);
+    if (sm_fast <= 47 * 1024 && (OH * OW * C) % 4 == 0) {
+      launch_pdl(conv3x3_bwd_kernel<kConvImgPerCtaBwd, false>, (B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd, 256,
+                 sm_fast, as_stream(stream), dz, x0, B, H, W, wc, dx0, dwc_part, dbc_part, ConvBnBwd{});
       return check_launch();
     }
   }
@@ -280,6 +323,34 @@ int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const 
   launch_pdl(conv_bwd_kernel, B, kConvThreads, smem, as_stream(stream), dz, x0, H, W, wc, KH, KW, C, per_query, dx0,
              dwc_part, dbc_part);
   return check_launch();
+}
+
+/* coper_bn_act_bwd_apply (keep_pre = 1) + coper_conv_bwd in one call: dout [B, OH*OW*C] is the gradient w.r.t. the
+ * output of the batch-norm / relu / dropout block, z the conv output.  3x3 x 32-channel shared filters: one kernel, the
+ * block's input gradient never exists in HBM; any other shape: the two kernels through dz_scratch [B, OH*OW*C]. */
+int coper_conv_bwd_bn(const float* dout, const float* z, const float* x0, int B, int H, int W, const float* wc, int KH,
+                      int KW, int C, int per_query, const float* a, const float* b, const float* mean,
+                      const float* invstd, const float* c1, const float* c2, int relu, float keep_post,
+                      const uint64_t* seed_dev, uint64_t salt_post, float* dx0, float* dwc_part, float* dbc_part,
+                      float* dz_scratch, coper_stream_t stream) {
+  COPER_CHECK_ARG(dout && z && x0 && wc && dx0 && dwc_part && dbc_part && dz_scratch && B > 0 && H >= KH && W >= KW && C > 0);
+  COPER_CHECK_ARG(a && b && mean && invstd && c1 && c2 && keep_post > 0.f);
+  const int OH = H - KH + 1, OW = W - KW + 1;
+  if (KH == 3 && KW == 3 && C == kFastC && !per_query && H >= 3 && W >= 3 && H * W <= kMaxImg) {
+    size_t sm_fast = (size_t)(H * W + OH * OW * C + 8 * 10 * kFastC) * sizeof(float);
+    if (sm_fast <= 47 * 1024 && (OH * OW * C) % 4 == 0 &&
+        ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(z)) & 15) == 0) {
+      ConvBnBwd bn{z, a, b, mean, invstd, c1, c2, relu, keep_post, 1.0f / keep_post, keep_threshold(keep_post), seed_dev,
+                   salt_post};
+      launch_pdl(conv3x3_bwd_kernel<kConvImgPerCtaBwd, true>, (B + kConvImgPerCtaBwd - 1) / kConvImgPerCtaBwd, 256,
+                 sm_fast, as_stream(stream), dout, x0, B, H, W, wc, dx0, dwc_part, dbc_part, bn);
+      return check_launch();
+    }
+  }
+  int rc = coper_bn_act_bwd_apply(dout, z, (int64_t)B * OH * OW, C, a, b, mean, invstd, c1, c2, relu, keep_post, seed_dev,
+                                  salt_post, 1.0f, 0, dz_scratch, stream);
+  if (rc) return rc;
+  return coper_conv_bwd(dz_scratch, x0, B, H, W, wc, KH, KW, C, per_query, dx0, dwc_part, dbc_part, stream);
 }
 
 }  // extern "C"

@@ -407,12 +407,8 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dout, const fl
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
     int c = (int)(e % C);
-    float xv = x[e];
-    float ac = a[c];
-    float g = dout[e] * drop_factor(keep_post, inv_keep_post, thr_post, seed_post, (uint64_t)e);
-    if (relu && !(ac * xv + b[c] > 0.f)) g = 0.f;
-    float xhat = (xv - mean[c]) * invstd[c];
-    float d = ac * (g - c1[c] - xhat * c2[c]);
+    float d = bn_bwd_dx(dout[e], drop_factor(keep_post, inv_keep_post, thr_post, seed_post, (uint64_t)e), x[e], a[c], b[c],
+                        mean[c], invstd[c], c1[c], c2[c], relu);
     dx[e] = d * drop_factor(keep_pre, inv_keep_pre, thr_pre, seed_pre, (uint64_t)e);
   }
 }

@@ -37,8 +37,8 @@ import numpy as np
 import torch
 
 from . import _lib, sharding
-from ._lib import (CPG_BWD_DCB_ACCUMULATE, CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_REUSE_FWD, CPG_BWD_WEIGHT_GRADS_ONLY, PREC,
-                   call, call_plain, ptr)
+from ._lib import (CPG_BWD_DCB_ACCUMULATE, CPG_BWD_INPUT_GRADS_ONLY, CPG_BWD_REUSE_FWD, CPG_BWD_WEIGHT_GRADS_ONLY,
+                   CPG_FWD_F_PREPARED, PREC, call, call_plain, ptr)
 from .sharding import EntityShard
 
 BN_EPS = 1e-3           # tf.layers.batch_normalization default epsilon (models.py:386-388)
@@ -695,20 +695,34 @@ class ConvE:
         return b
 
     # ------------------------------------------------------------------------------------------
-    def _bn_forward(self, bn: _BatchNorm, x, R, C, b, use_batch, is_train, bessel, relu, keep_post, salt, out):
+    def _bn_forward(self, bn: _BatchNorm, x, R, C, b, use_batch, is_train, bessel, relu, keep_post, salt, out,
+                    prepared=None):
+        """prepared = (device pointer, rows, cols): also emit the tensor-pipe operand form of `out` viewed [rows, cols]
+        (the activation and coper_prepare_operand in one launch)."""
         lib = _lib.load()
         nch = 0
         stat, Rt = b.stat, R
+
+        def act():
+            if prepared is None:
+                call("coper_bn_act_fwd", ptr(x), R, C, ptr(bn.a), ptr(bn.b), int(relu), keep_post, ptr(self.seed_dev),
+                     salt, ptr(out))
+            else:
+                call("coper_bn_act_fwd_prepared", ptr(x), R, C, ptr(bn.a), ptr(bn.b), int(relu), keep_post,
+                     ptr(self.seed_dev), salt, ptr(out), prepared[1], prepared[2], self.prec, prepared[0])
+
         if use_batch and not self.dp:        # statistics + finalize: one launch (the last block to arrive finalises)
             call("coper_bn_stats_finalize", ptr(x), R, C, ptr(b.stat), ptr(self.sync_word), ptr(bn.gamma), ptr(bn.beta),
                  ptr(bn.moving_mean), ptr(bn.moving_var), self.batch_norm_momentum, BN_EPS, int(is_train), int(bessel),
                  ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd))
-            call("coper_bn_act_fwd", ptr(x), R, C, ptr(bn.a), ptr(bn.b), int(relu), keep_post, ptr(self.seed_dev), salt,
-                 ptr(out))
-            return
+            return act()
         if not use_batch and not is_train and keep_post >= 1.0:      # inference: moving statistics, one launch
-            call("coper_bn_act_fwd_moving", ptr(x), R, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
-                 ptr(bn.moving_var), BN_EPS, int(relu), ptr(out))
+            if prepared is None:
+                call("coper_bn_act_fwd_moving", ptr(x), R, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
+                     ptr(bn.moving_var), BN_EPS, int(relu), ptr(out))
+            else:
+                call("coper_bn_act_fwd_moving_prepared", ptr(x), R, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
+                     ptr(bn.moving_var), BN_EPS, int(relu), ptr(out), prepared[1], prepared[2], self.prec, prepared[0])
             return
         if use_batch:
             nch = lib.coper_colstats_chunks(R)
@@ -718,11 +732,11 @@ class ConvE:
         call("coper_bn_finalize", ptr(stat), nch, Rt, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean),
              ptr(bn.moving_var), self.batch_norm_momentum, BN_EPS, int(use_batch), int(use_batch and is_train),
              int(bessel), ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd))
-        call("coper_bn_act_fwd", ptr(x), R, C, ptr(bn.a), ptr(bn.b), int(relu), keep_post, ptr(self.seed_dev), salt,
-             ptr(out))
+        act()
 
     def _bn_backward(self, bn: _BatchNorm, dout, x, R, C, b, use_batch, relu, keep_post, salt_post, keep_pre,
-                     salt_pre, dx):
+                     salt_pre, dx, apply=True):
+        """apply=False: statistics only (dgamma, dbeta, c1, c2) - the caller's next kernel forms dx itself."""
         lib = _lib.load()
         nch = lib.coper_colstats_chunks(R)
         if not self.dp:
@@ -737,8 +751,9 @@ class ConvE:
             stat, nch, Rt = self._gather_stats(b, nch * C * 2), nch * self.world, R * self.world
             call("coper_bn_act_bwd_finalize", ptr(stat), nch, Rt, C, int(use_batch), ptr(bn.dgamma), ptr(bn.dbeta),
                  ptr(bn.c1), ptr(bn.c2))
-        call("coper_bn_act_bwd_apply", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
-             ptr(bn.c1), ptr(bn.c2), int(relu), keep_post, ptr(self.seed_dev), salt_post, keep_pre, salt_pre, ptr(dx))
+        if apply:
+            call("coper_bn_act_bwd_apply", ptr(dout), ptr(x), R, C, ptr(bn.a), ptr(bn.b), ptr(bn.mean), ptr(bn.invstd),
+                 ptr(bn.c1), ptr(bn.c2), int(relu), keep_post, ptr(self.seed_dev), salt_post, keep_pre, salt_pre, ptr(dx))
 
     def _side_budget(self, on: bool):
         if self._side_sms > 0:
@@ -820,9 +835,9 @@ class ConvE:
              ptr(self.step_state) if advance else None, ptr(self.seed_dev) if advance else None,
              self.learning_rate, self.beta1, self.beta2)
         sharding.exchange_rows(b.x0, self.world, self.group)
-        self._front_end(b, is_train, gather_rel=False)
+        self._front_end(b, is_train, gather_rel=False, prepare_q=True)
 
-    def _front_end(self, b, is_train: bool, gather_rel: bool = True):
+    def _front_end(self, b, is_train: bool, gather_rel: bool = True, prepare_q: bool = False):
         """b.x0, b.rel -> b.q for the rows of buffer set b (conv block, fused CPG-FC, FC block)."""
         B, d, dr, F, C = b.B, self.ent_emb_size, self.rel_emb_size, self.F, self.C
         x_img = b.x0
@@ -849,8 +864,11 @@ class ConvE:
                  self.conv_filter_height, self.conv_filter_width, C, 1, ptr(b.z))
         use_batch = self.batch_norm_train_stats and is_train
         keep1 = 1.0 - (self.hidden_dropout if is_train else 0.0)
+        # fp16x3: the activation that produces f also writes f's operand form where coper_cpg_fc_fwd expects it (the
+        # start of its workspace) - one launch instead of two
+        f_prep = self.prec == PREC["fp16x3"] and not self.concat_rel and F % 32 == 0 and d <= 256
         self._bn_forward(self.conv1_bn, b.z, B * self.OH * self.OW, C, b, use_batch, is_train, True, True, keep1,
-                         SALT_FEATURE_MAP, b.fconv)
+                         SALT_FEATURE_MAP, b.fconv, prepared=(ptr(b.ws_cpg), B, F) if f_prep else None)
         if self.concat_rel:                  # tf.concat([fc_input, rel_emb], axis=1)  (models.py:406-407)
             b.f[:, :self.F_conv].copy_(b.fconv)
             b.f[:, self.F_conv:].copy_(b.r)
@@ -861,10 +879,14 @@ class ConvE:
             cw = cb = b.cconst
         Pw, Pb = self.fc_weights.projections[-1], self.fc_bias.projections[-1]
         keep2 = 1.0 - (self.output_dropout if is_train else 0.0)
-        call("coper_cpg_fc_fwd", ptr(cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(cb), ptr(Pb), B, Pw.shape[0], F, d,
-             Pb.shape[0],
-             keep2, ptr(self.seed_dev), SALT_OUTPUT, ptr(b.y), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec)
-        self._bn_forward(self.fc_bn, b.y, B, d, b, use_batch, is_train, False, True, 1.0, 0, b.q)
+        call("coper_cpg_fc_fwd_ex", ptr(cw), ptr(b.f), ptr(Pw), ptr(self.P_prep), ptr(cb), ptr(Pb), B, Pw.shape[0], F, d,
+             Pb.shape[0], keep2, ptr(self.seed_dev), SALT_OUTPUT, ptr(b.y), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec,
+             CPG_FWD_F_PREPARED if f_prep else 0)
+        # evaluation on the tensor-pipe scorer: q's operand form comes out of the same launch as q
+        q_prep = (prepare_q and not is_train and self.prec == PREC["fp16x3"] and b.q_prep is not None)
+        self._bn_forward(self.fc_bn, b.y, B, d, b, use_batch, is_train, False, True, 1.0, 0, b.q,
+                         prepared=(ptr(b.q_prep), B, d) if q_prep else None)
+        b.q_prepared = bool(q_prep)
         b.cw, b.cb = cw, cb
 
     def _forward_q_dp(self, bg, bl, is_train: bool):
@@ -990,7 +1012,10 @@ class ConvE:
             b.dfconv.copy_(b.df[:, :self.F_conv])
             if self.variant == "cpg":
                 b.dr.add_(b.df[:, self.F_conv:])
-        self._bn_backward(self.conv1_bn, b.dfconv, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz)
+        # shared filters: the Conv1BN backward is folded into the conv backward (dz never goes to HBM)
+        fold = self.conv_w_gen is None
+        self._bn_backward(self.conv1_bn, b.dfconv, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz,
+                          apply=not fold)
         plain = self.variant == "plain"
         KK = self.conv_filter_height * self.conv_filter_width * C
         if self.conv_w_gen is not None:
@@ -1006,9 +1031,11 @@ class ConvE:
                 call("coper_sgemm", 0, 1, B, dcc, width, ptr(dq_), width, ptr(Pl), width, ptr(dctx_), dcc, 0)
                 self._ctx_backward(gen_, net, b, dctx_, b.dr, True)
         else:
-            call("coper_conv_bwd", ptr(b.dz), ptr(b.xc if plain else b.x0), B, self.H, self.W, ptr(self.conv1_weights),
-                 self.conv_filter_height, self.conv_filter_width, C, 0, ptr(b.dxc if plain else b.dx0),
-                 ptr(b.dwc_part), ptr(b.dbc_part))
+            bn1 = self.conv1_bn
+            call("coper_conv_bwd_bn", ptr(b.dfconv), ptr(b.z), ptr(b.xc if plain else b.x0), B, self.H, self.W,
+                 ptr(self.conv1_weights), self.conv_filter_height, self.conv_filter_width, C, 0, ptr(bn1.a), ptr(bn1.b),
+                 ptr(bn1.mean), ptr(bn1.invstd), ptr(bn1.c1), ptr(bn1.c2), 1, keep1, ptr(self.seed_dev),
+                 SALT_FEATURE_MAP, ptr(b.dxc if plain else b.dx0), ptr(b.dwc_part), ptr(b.dbc_part), ptr(b.dz))
             if plain:                            # tf.concat backward: the two halves of the stacked image
                 b.dx0.copy_(b.dxc[:, :d])
                 b.dr.copy_(b.dxc[:, d:])
@@ -1246,7 +1273,8 @@ class ConvE:
     def _score(self, b):
         d = self.ent_emb_size
         if self.E_prep is not None:
-            call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
+            if not getattr(b, "q_prepared", False):
+                call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
             call("coper_score1n_fwd_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B,
                  self.shard.rows, d, ptr(self._scores_buf(b)), b.ld, self.prec)
         else:
@@ -1280,7 +1308,8 @@ class ConvE:
         b.rank_counts.zero_()
         if self.E_prep is not None:
             # tensor-pipe engines: rank counts straight from the scorer's accumulators, logits never written
-            call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
+            if not getattr(b, "q_prepared", False):
+                call("coper_prepare_operand", ptr(b.q), b.B, d, d, self.prec, ptr(b.q_prep))
             call("coper_score1n_gold_prepared", ptr(b.q_prep), ptr(self.E_prep), ptr(self.pred_bias), b.B, s.rows, d,
                  ptr(b.e2), s.lo, ptr(b.gold), ptr(b.ws), b.ws_bytes, self.prec)
             sharding.reduce_gold(b.gold, self.world, self.group)

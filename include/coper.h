@@ -95,6 +95,16 @@ int coper_conv_fwd(const float* x0, int B, int H, int W, const float* wc, const 
 int coper_conv_bwd_slabs(int B, int H, int W, int KH, int KW, int C, int per_query);
 int coper_conv_bwd(const float* dz, const float* x0, int B, int H, int W, const float* wc, int KH, int KW,
                    int C, int per_query, float* dx0, float* dwc_part, float* dbc_part, coper_stream_t stream);
+/* coper_bn_act_bwd_apply (with keep_pre = 1) + coper_conv_bwd in one call, for the Conv1BN block that follows the conv
+ * (models.py:386-391): dout [B, OH*OW*C] is the gradient w.r.t. the block's OUTPUT, z the conv output, a .. c2 as in
+ * coper_bn_act_bwd_apply.  Shared 3x3 x 32-channel filters: one kernel - the block's input gradient is formed while the
+ * tile is staged in shared memory and never written to HBM; other shapes run the two kernels through dz_scratch
+ * [B, OH*OW*C].  Same bits either way. */
+int coper_conv_bwd_bn(const float* dout, const float* z, const float* x0, int B, int H, int W, const float* wc, int KH,
+                      int KW, int C, int per_query, const float* a, const float* b, const float* mean,
+                      const float* invstd, const float* c1, const float* c2, int relu, float keep_post,
+                      const uint64_t* seed_dev, uint64_t salt_post, float* dx0, float* dwc_part, float* dbc_part,
+                      float* dz_scratch, coper_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5 — tf.layers.batch_normalization (+relu, +dropout) on x [R, C] with C fastest
@@ -135,6 +145,16 @@ int coper_bn_act_bwd_stats(const float* dout, const float* x, int64_t R, int C, 
                            const uint64_t* seed_dev, uint64_t salt_post, float* partials, coper_stream_t stream);
 int coper_bn_act_bwd_finalize(const float* partials, int nchunk, int64_t R, int C, int use_batch_stats,
                               float* dgamma, float* dbeta, float* c1, float* c2, coper_stream_t stream);
+/* coper_bn_act_fwd / coper_bn_act_fwd_moving that ALSO emit the tensor-pipe operand form of their output, viewed as
+ * [op_rows, op_cols] (op_rows * op_cols == R * C; `prepared` sized by coper_prepared_bytes): the activation that produces
+ * f (conv block) or q (FC block) and coper_prepare_operand in one launch (fp16x3; other precisions run the two kernels).
+ * Same bits as the two calls. */
+int coper_bn_act_fwd_prepared(const float* x, int64_t R, int C, const float* a, const float* b, int relu, float keep_post,
+                              const uint64_t* seed_dev, uint64_t salt_post, float* out, int64_t op_rows, int op_cols,
+                              int prec, void* prepared, coper_stream_t stream);
+int coper_bn_act_fwd_moving_prepared(const float* x, int64_t R, int C, const float* gamma, const float* beta,
+                                     const float* moving_mean, const float* moving_var, float eps, int relu, float* out,
+                                     int64_t op_rows, int op_cols, int prec, void* prepared, coper_stream_t stream);
 int coper_bn_act_bwd_stats_finalize(const float* dout, const float* x, int64_t R, int C, const float* a, const float* b,
                                     const float* mean, const float* invstd, int relu, float keep_post,
                                     const uint64_t* seed_dev, uint64_t salt_post, float* partials,
@@ -165,6 +185,15 @@ int coper_cpg_fc_fwd(const float* c, const float* f, const float* P, const void*
                      const float* Pb, int B, int dc, int F, int d, int dcb, float keep_out, const uint64_t* seed_dev,
                      uint64_t salt_out, float* y, void* workspace, size_t workspace_bytes, int prec,
                      coper_stream_t stream);
+/* coper_cpg_fc_fwd with flags.  COPER_CPG_FWD_F_PREPARED (tensor-pipe precisions): the operand form of f already lies
+ * at the START of `workspace` (coper_prepared_bytes(B, F, prec) bytes - where the call would put it itself), written
+ * e.g. by coper_bn_act_fwd_prepared; the call does not convert f again.  Ignored where the contraction does not run on
+ * the tensor pipe (see the F % 32 / d <= 256 rule above). */
+#define COPER_CPG_FWD_F_PREPARED 1
+int coper_cpg_fc_fwd_ex(const float* c, const float* f, const float* P, const void* P_prepared, const float* cb,
+                        const float* Pb, int B, int dc, int F, int d, int dcb, float keep_out, const uint64_t* seed_dev,
+                        uint64_t salt_out, float* y, void* workspace, size_t workspace_bytes, int prec, int flags,
+                        coper_stream_t stream);
 /* backward (models.py:198 autodiff of the above): given dy [B,d] (already through the dropout mask)
  *   dP [dc,F*d], dPb [dcb,d], df [B,F], dc_out [B,dc], dcb_out [B,dcb].
  * flags (bit mask):
