@@ -192,6 +192,9 @@ class ConvE:
         # programmatic dependent launch pays on the launch-bound steps of the named datasets and costs on the HBM-bound
         # step of a 10 M-row table: per model, by the size of the entity table
         self._pdl = int(self.shard.rows) * int(self.ent_emb_size) <= (64 << 20)
+        # (A/B switches for measurements) activation + operand form in one launch; Conv1BN backward inside the conv backward
+        self._fuse_act_prepare = os.environ.get("COPER_FUSE_ACT_PREPARE", "1") != "0"
+        self._fold_conv_bn = os.environ.get("COPER_FOLD_CONV_BN", "1") != "0"
         # SMs the side stream's persistent GEMMs may take (coper_set_sm_budget; 0 = all)
         self._side_sms = int(os.environ.get("COPER_SIDE_SMS", "0"))
         # CUDA graphs: the device side of a train / eval step is a fixed kernel sequence over pointer-stable buffers
@@ -866,7 +869,8 @@ class ConvE:
         keep1 = 1.0 - (self.hidden_dropout if is_train else 0.0)
         # fp16x3: the activation that produces f also writes f's operand form where coper_cpg_fc_fwd expects it (the
         # start of its workspace) - one launch instead of two
-        f_prep = self.prec == PREC["fp16x3"] and not self.concat_rel and F % 32 == 0 and d <= 256
+        f_prep = (self._fuse_act_prepare and self.prec == PREC["fp16x3"] and not self.concat_rel and F % 32 == 0
+                  and d <= 256)
         self._bn_forward(self.conv1_bn, b.z, B * self.OH * self.OW, C, b, use_batch, is_train, True, True, keep1,
                          SALT_FEATURE_MAP, b.fconv, prepared=(ptr(b.ws_cpg), B, F) if f_prep else None)
         if self.concat_rel:                  # tf.concat([fc_input, rel_emb], axis=1)  (models.py:406-407)
@@ -883,7 +887,8 @@ class ConvE:
              Pb.shape[0], keep2, ptr(self.seed_dev), SALT_OUTPUT, ptr(b.y), ptr(b.ws_cpg), b.ws_cpg_bytes, self.prec,
              CPG_FWD_F_PREPARED if f_prep else 0)
         # evaluation on the tensor-pipe scorer: q's operand form comes out of the same launch as q
-        q_prep = (prepare_q and not is_train and self.prec == PREC["fp16x3"] and b.q_prep is not None)
+        q_prep = (self._fuse_act_prepare and prepare_q and not is_train and self.prec == PREC["fp16x3"]
+                  and b.q_prep is not None)
         self._bn_forward(self.fc_bn, b.y, B, d, b, use_batch, is_train, False, True, 1.0, 0, b.q,
                          prepared=(ptr(b.q_prep), B, d) if q_prep else None)
         b.q_prepared = bool(q_prep)
@@ -1013,7 +1018,7 @@ class ConvE:
             if self.variant == "cpg":
                 b.dr.add_(b.df[:, self.F_conv:])
         # shared filters: the Conv1BN backward is folded into the conv backward (dz never goes to HBM)
-        fold = self.conv_w_gen is None
+        fold = self.conv_w_gen is None and self._fold_conv_bn
         self._bn_backward(self.conv1_bn, b.dfconv, b.z, R1, C, b, use_batch, True, keep1, SALT_FEATURE_MAP, 1.0, 0, b.dz,
                           apply=not fold)
         plain = self.variant == "plain"
@@ -1032,10 +1037,15 @@ class ConvE:
                 self._ctx_backward(gen_, net, b, dctx_, b.dr, True)
         else:
             bn1 = self.conv1_bn
-            call("coper_conv_bwd_bn", ptr(b.dfconv), ptr(b.z), ptr(b.xc if plain else b.x0), B, self.H, self.W,
-                 ptr(self.conv1_weights), self.conv_filter_height, self.conv_filter_width, C, 0, ptr(bn1.a), ptr(bn1.b),
-                 ptr(bn1.mean), ptr(bn1.invstd), ptr(bn1.c1), ptr(bn1.c2), 1, keep1, ptr(self.seed_dev),
-                 SALT_FEATURE_MAP, ptr(b.dxc if plain else b.dx0), ptr(b.dwc_part), ptr(b.dbc_part), ptr(b.dz))
+            if fold:
+                call("coper_conv_bwd_bn", ptr(b.dfconv), ptr(b.z), ptr(b.xc if plain else b.x0), B, self.H, self.W,
+                     ptr(self.conv1_weights), self.conv_filter_height, self.conv_filter_width, C, 0, ptr(bn1.a),
+                     ptr(bn1.b), ptr(bn1.mean), ptr(bn1.invstd), ptr(bn1.c1), ptr(bn1.c2), 1, keep1, ptr(self.seed_dev),
+                     SALT_FEATURE_MAP, ptr(b.dxc if plain else b.dx0), ptr(b.dwc_part), ptr(b.dbc_part), ptr(b.dz))
+            else:
+                call("coper_conv_bwd", ptr(b.dz), ptr(b.xc if plain else b.x0), B, self.H, self.W,
+                     ptr(self.conv1_weights), self.conv_filter_height, self.conv_filter_width, C, 0,
+                     ptr(b.dxc if plain else b.dx0), ptr(b.dwc_part), ptr(b.dbc_part))
             if plain:                            # tf.concat backward: the two halves of the stacked image
                 b.dx0.copy_(b.dxc[:, :d])
                 b.dr.copy_(b.dxc[:, d:])
