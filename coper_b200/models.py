@@ -192,8 +192,10 @@ class ConvE:
         # programmatic dependent launch pays on the launch-bound steps of the named datasets and costs on the HBM-bound
         # step of a 10 M-row table: per model, by the size of the entity table
         self._pdl = int(self.shard.rows) * int(self.ent_emb_size) <= (64 << 20)
-        # (A/B switches for measurements) activation + operand form in one launch; Conv1BN backward inside the conv backward
-        self._fuse_act_prepare = os.environ.get("COPER_FUSE_ACT_PREPARE", "1") != "0"
+        # (A/B switches for measurements) activation + operand form in one launch: measured SLOWER than the two
+        # launches at the dataset shapes (the co-resident grid of its barrier caps the parallelism over the 9 MB feature
+        # map) - off unless asked for; Conv1BN backward inside the conv backward: on
+        self._fuse_act_prepare = os.environ.get("COPER_FUSE_ACT_PREPARE", "0") == "1"
         self._fold_conv_bn = os.environ.get("COPER_FOLD_CONV_BN", "1") != "0"
         # SMs the side stream's persistent GEMMs may take (coper_set_sm_budget; 0 = all)
         self._side_sms = int(os.environ.get("COPER_SIDE_SMS", "0"))
