@@ -62,3 +62,44 @@ def test_integration_doc_names_every_entry_point():
     wild = [w[:-1] for w in re.findall(r"`(coper_[a-z0-9_]*\*)", doc) if len(w) > len("coper_*") + 1]
     missing = [s for s in syms if s not in doc and not any(s.startswith(w) for w in wild)]
     assert not missing, missing
+
+
+def test_every_kernel_waits_for_its_programmatic_predecessor():
+    """Programmatic dependent launch: every kernel of the library is launched through launch_pdl, i.e. it may
+    be scheduled before its stream predecessor has finished - so every __global__ function must execute
+    griddepcontrol.wait (pdl_enter() first thing, or pdl_trigger() ... pdl_wait() around a prologue that touches no
+    global memory) and no launch may bypass launch_pdl."""
+    import re
+    csrc = os.path.join(ROOT, "coper_b200", "csrc")
+    pat = re.compile(r"__global__\s+void\s+(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(")
+    n_kernels = 0
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cu", ".cuh")):
+            continue
+        src = open(os.path.join(csrc, f)).read()
+        code = re.sub(r"//[^\n]*", "", src)
+        assert "<<<" not in code, "%s launches a kernel without launch_pdl" % f
+        for m in pat.finditer(src):
+            depth, i = 0, m.end() - 1
+            while True:                       # end of the parameter list
+                depth += src[i] == "("
+                depth -= src[i] == ")"
+                if depth == 0:
+                    break
+                i += 1
+            b = src.find("{", i)
+            if src[i + 1:b].strip():
+                continue                      # a declaration
+            depth, j = 0, b
+            while True:                       # end of the body
+                depth += src[j] == "{"
+                depth -= src[j] == "}"
+                if depth == 0:
+                    break
+                j += 1
+            body = src[b:j]
+            head = body[:200]
+            ok = "pdl_enter();" in head or ("pdl_trigger();" in head and "pdl_wait();" in body)
+            assert ok, "%s: kernel %s does not wait for its programmatic predecessor" % (f, m.group(1))
+            n_kernels += 1
+    assert n_kernels >= 60
